@@ -1,0 +1,299 @@
+"""bspy_b200._cuda -- ctypes binding of libbspy_cuda.so (include/bspy_cuda.h).
+
+This is the thin layer the north star calls ``bspy/_cuda``: Python host code hands raw device
+pointers (taken from torch tensors) and a CUDA stream to hand-written sm_100a kernels through a
+C ABI.  torch is used for device memory, streams and copies only.
+
+There is NO CPU fallback: if the shared library is missing it is built with nvcc, and if that is
+impossible, or no CUDA device is present when a computation is requested, the call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import torch
+
+MAX_IND = 8
+MAX_ORDER = 32
+E_ARG, E_UNSUPPORTED, E_NORMAL_DIMS = -1, -2, -3
+NORMALIZE = 1
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libbspy_cuda.so")
+
+# every symbol include/bspy_cuda.h declares (tests check the library exports exactly these)
+SYMBOLS = (
+    "bspy_cuda_abi_version", "bspy_cuda_last_error_string", "bspy_cuda_launch_count",
+    "bspy_cuda_spans", "bspy_cuda_basis", "bspy_cuda_eval_points", "bspy_cuda_eval_grid",
+    "bspy_cuda_eval_grid_batch", "bspy_cuda_eval_many", "bspy_cuda_probe_fp64", "bspy_cuda_probe_hbm",
+)
+
+
+class CSpline(C.Structure):
+    """``struct bspy_spline`` of include/bspy_cuda.h."""
+    _fields_ = [
+        ("nInd", C.c_int32), ("nDep", C.c_int32),
+        ("order", C.c_int32 * MAX_IND), ("nCoef", C.c_int32 * MAX_IND),
+        ("knots", C.c_void_p * MAX_IND), ("coefs", C.c_void_p),
+        ("normalSign", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+class CudaPathError(RuntimeError):
+    """The CUDA path is unavailable or a kernel launch failed.  Never caught to fall back."""
+
+
+_lock = threading.Lock()
+_lib = None
+
+
+def library():
+    """Load (building first if needed) libbspy_cuda.so.  Raises CudaPathError if impossible."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            try:
+                from . import build as _build
+                _build.build()
+            except Exception as exc:  # no nvcc, compile error
+                raise CudaPathError(f"libbspy_cuda.so is missing and could not be built: {exc}") from exc
+        try:
+            lib = C.CDLL(LIB_PATH)
+        except OSError as exc:
+            raise CudaPathError(f"cannot load {LIB_PATH}: {exc}") from exc
+        lib.bspy_cuda_abi_version.restype = C.c_int
+        lib.bspy_cuda_last_error_string.restype = C.c_char_p
+        lib.bspy_cuda_launch_count.restype = C.c_int64
+        vp, i32, i64, u32 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint32
+        sig = {
+            "bspy_cuda_spans": [vp, i32, i32, vp, i64, vp, vp],
+            "bspy_cuda_basis": [vp, i32, i32, vp, vp, i64, i32, i32, vp, vp, vp],
+            "bspy_cuda_eval_points": [C.POINTER(CSpline), vp, i64, i64, i64, C.POINTER(i32), u32, u32, vp, vp, vp, vp, vp, vp, vp],
+            "bspy_cuda_eval_grid": [C.POINTER(CSpline), C.POINTER(vp), C.POINTER(i64), u32, u32, vp, vp, vp, vp, vp],
+            "bspy_cuda_eval_grid_batch": [C.POINTER(CSpline), i64, C.POINTER(i64), i64, C.POINTER(vp), C.POINTER(i64), u32, u32, vp, vp, vp, vp, vp],
+            "bspy_cuda_eval_many": [i32, i32, i32, i64, vp, i64, vp, i64, vp, i32, vp, vp, vp, vp],
+            "bspy_cuda_probe_fp64": [i32, i32, vp, C.POINTER(C.c_double), vp],
+            "bspy_cuda_probe_hbm": [i32, vp, vp, i64, C.POINTER(C.c_double), vp],
+        }
+        for name, args in sig.items():
+            fn = getattr(lib, name)
+            fn.argtypes = args
+            fn.restype = C.c_int
+        if lib.bspy_cuda_abi_version() != 1:
+            raise CudaPathError("libbspy_cuda.so ABI version mismatch; rebuild with python -m bspy_b200._cuda.build --force")
+        _lib = lib
+    return _lib
+
+
+def launch_count() -> int:
+    return int(library().bspy_cuda_launch_count())
+
+
+def device(index=None) -> torch.device:
+    """The CUDA device computations run on.  Raises when there is none (no CPU fallback)."""
+    if not torch.cuda.is_available():
+        raise CudaPathError("bspy_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    if isinstance(index, torch.device):
+        if index.type != "cuda":
+            raise CudaPathError(f"bspy_b200 computes on CUDA devices only, not {index}")
+        return index if index.index is not None else torch.device("cuda", torch.cuda.current_device())
+    return torch.device("cuda", torch.cuda.current_device() if index is None else int(index))
+
+
+def _check(rc: int, what: str):
+    if rc == 0:
+        return
+    msg = library().bspy_cuda_last_error_string().decode("utf-8", "replace")
+    if rc == E_NORMAL_DIMS:
+        raise ValueError(msg)
+    if rc == E_ARG:
+        raise ValueError(f"{what}: {msg}")
+    if rc == E_UNSUPPORTED:
+        raise NotImplementedError(f"{what}: {msg}")
+    raise CudaPathError(f"{what}: CUDA error {rc}: {msg}")
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream(dev):
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _f64(t, dev):
+    assert t.dtype == torch.float64 and t.device == dev and t.is_contiguous(), "expected contiguous float64 device tensor"
+    return t
+
+
+class DeviceSpline:
+    """Knots and coefficients of one spline resident on a device + the C struct describing them."""
+
+    def __init__(self, nInd, nDep, order, nCoef, knots, coefs, normal_sign=1):
+        self.nInd, self.nDep = int(nInd), int(nDep)
+        self.order, self.nCoef = tuple(int(o) for o in order), tuple(int(n) for n in nCoef)
+        if self.nInd > MAX_IND:
+            raise NotImplementedError(f"nInd {self.nInd} > {MAX_IND} is not supported by the CUDA kernels")
+        if any(o > MAX_ORDER for o in self.order):
+            raise NotImplementedError(f"order > {MAX_ORDER} is not supported by the CUDA kernels")
+        self.knots = list(knots)      # device float64 tensors
+        self.coefs = coefs            # device float64 tensor, (nDep, *nCoef) contiguous
+        self.device = coefs.device
+        self.normal_sign = -1 if normal_sign < 0 else 1
+        c = CSpline()
+        c.nInd, c.nDep = self.nInd, self.nDep
+        for i in range(self.nInd):
+            c.order[i], c.nCoef[i] = self.order[i], self.nCoef[i]
+            c.knots[i] = self.knots[i].data_ptr()
+        c.coefs = self.coefs.data_ptr()
+        c.normalSign = self.normal_sign
+        self.c = c
+
+    @property
+    def normal_dim(self):
+        return max(self.nInd, self.nDep)
+
+
+# ------------------------------------------------------------------------------ entry points
+
+def spans(knots, order, u):
+    """int32 spans for a 1-D device tensor of parameters (bspy_cuda_spans)."""
+    dev = u.device
+    out = torch.empty(u.numel(), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        rc = library().bspy_cuda_spans(_ptr(_f64(knots, dev)), knots.numel(), int(order), _ptr(_f64(u, dev)), u.numel(),
+                                       _ptr(out), _stream(dev))
+    _check(rc, "bspy_cuda_spans")
+    return out
+
+
+def basis(knots, order, u, deriv=0, taylor=False, spans_in=None):
+    """(spans int32[N], basis float64[N, order]) -- bit-exact bspline_values (bspy_cuda_basis)."""
+    dev = u.device
+    N = u.numel()
+    sp = torch.empty(N, dtype=torch.int32, device=dev)
+    out = torch.empty((N, int(order)), dtype=torch.float64, device=dev)
+    if spans_in is not None:
+        assert spans_in.dtype == torch.int32 and spans_in.device == dev and spans_in.is_contiguous()
+    with torch.cuda.device(dev):
+        rc = library().bspy_cuda_basis(_ptr(_f64(knots, dev)), knots.numel(), int(order), _ptr(_f64(u, dev)), _ptr(spans_in),
+                                       N, int(deriv), int(bool(taylor)), _ptr(sp), _ptr(out), _stream(dev))
+    _check(rc, "bspy_cuda_basis")
+    return sp, out
+
+
+def new_flag(dev):
+    return torch.full((1,), -1, dtype=torch.int64, device=dev)
+
+
+def eval_points(ds: DeviceSpline, uvw, point_stride, var_stride, N, *, wrt=None, values=True, jacobian=False,
+                normal=False, normalize=True, normal_mask=0, spans=False, flag=None):
+    """Launch bspy_cuda_eval_points.  ``uvw`` is a float64 device tensor addressed through the two
+    strides (elements).  Returns a dict of SoA device tensors; ``flag`` (int64[1], -1) receives the
+    first out-of-domain index."""
+    dev = ds.device
+    D = ds.normal_dim
+    out = {
+        "values": torch.empty((ds.nDep, N), dtype=torch.float64, device=dev) if values else None,
+        "derivative": torch.empty((ds.nDep, N), dtype=torch.float64, device=dev) if wrt is not None else None,
+        "jacobian": torch.empty((ds.nDep, ds.nInd, N), dtype=torch.float64, device=dev) if jacobian else None,
+        "normal": torch.empty((D, N), dtype=torch.float64, device=dev) if normal else None,
+        "spans": torch.empty((ds.nInd, N), dtype=torch.int32, device=dev) if spans else None,
+    }
+    w = None
+    if wrt is not None:
+        w = (C.c_int32 * max(ds.nInd, 1))(*[int(x) for x in wrt])
+    with torch.cuda.device(dev):
+        rc = library().bspy_cuda_eval_points(C.byref(ds.c), _ptr(uvw), int(point_stride), int(var_stride), int(N), w,
+                                             NORMALIZE if normalize else 0, int(normal_mask), _ptr(out["values"]),
+                                             _ptr(out["derivative"]), _ptr(out["jacobian"]), _ptr(out["normal"]),
+                                             _ptr(out["spans"]), _ptr(flag), _stream(dev))
+    _check(rc, "bspy_cuda_eval_points")
+    return out
+
+
+def eval_grid(ds: DeviceSpline, axes, *, values=True, jacobian=False, normal=False, normalize=True, normal_mask=0,
+              flag=None):
+    """Launch bspy_cuda_eval_grid; outputs (nDep, *nAxis), (nDep, nInd, *nAxis), (D, *nAxis)."""
+    dev = ds.device
+    shape = tuple(int(a.numel()) for a in axes)
+    out = {
+        "values": torch.empty((ds.nDep, *shape), dtype=torch.float64, device=dev) if values else None,
+        "jacobian": torch.empty((ds.nDep, ds.nInd, *shape), dtype=torch.float64, device=dev) if jacobian else None,
+        "normal": torch.empty((ds.normal_dim, *shape), dtype=torch.float64, device=dev) if normal else None,
+    }
+    n = max(ds.nInd, 1)
+    ax = (C.c_void_p * n)(*[a.data_ptr() for a in axes])
+    na = (C.c_int64 * n)(*shape)
+    for a in axes:
+        _f64(a, dev)
+    with torch.cuda.device(dev):
+        rc = library().bspy_cuda_eval_grid(C.byref(ds.c), ax, na, NORMALIZE if normalize else 0, int(normal_mask),
+                                           _ptr(out["values"]), _ptr(out["jacobian"]), _ptr(out["normal"]), _ptr(flag),
+                                           _stream(dev))
+    _check(rc, "bspy_cuda_eval_grid")
+    return out
+
+
+def eval_grid_batch(ds: DeviceSpline, n_splines, knot_strides, coef_stride, axes, *, values=True, jacobian=False,
+                    normal=False, normalize=True, normal_mask=0, flag=None, out=None):
+    """Launch bspy_cuda_eval_grid_batch for ``n_splines`` surfaces; ``ds`` describes element 0."""
+    dev = ds.device
+    shape = tuple(int(a.numel()) for a in axes)
+    S = int(n_splines)
+    if out is None:
+        out = {
+            "values": torch.empty((S, ds.nDep, *shape), dtype=torch.float64, device=dev) if values else None,
+            "jacobian": torch.empty((S, ds.nDep, 2, *shape), dtype=torch.float64, device=dev) if jacobian else None,
+            "normal": torch.empty((S, ds.normal_dim, *shape), dtype=torch.float64, device=dev) if normal else None,
+        }
+    ax = (C.c_void_p * 2)(*[a.data_ptr() for a in axes])
+    na = (C.c_int64 * 2)(*shape)
+    ks = (C.c_int64 * 2)(*[int(k) for k in knot_strides])
+    with torch.cuda.device(dev):
+        rc = library().bspy_cuda_eval_grid_batch(C.byref(ds.c), S, ks, int(coef_stride), ax, na,
+                                                 NORMALIZE if normalize else 0, int(normal_mask), _ptr(out.get("values")),
+                                                 _ptr(out.get("jacobian")), _ptr(out.get("normal")), _ptr(flag), _stream(dev))
+    _check(rc, "bspy_cuda_eval_grid_batch")
+    return out
+
+
+def eval_many(order, nCoef, nDep, knots, coefs, u, *, deriv1=False, flag=None, out=None):
+    """Launch bspy_cuda_eval_many: knots (S, order+nCoef), coefs (S, nDep, nCoef), u (S, nPts)
+    -> values (S, nDep, nPts) [, first derivatives of the same shape]."""
+    dev = u.device
+    S, nPts = int(u.shape[0]), int(u.shape[1])
+    _f64(knots, dev), _f64(coefs, dev), _f64(u, dev)
+    if out is None:
+        out = {"values": torch.empty((S, nDep, nPts), dtype=torch.float64, device=dev),
+               "derivative": torch.empty((S, nDep, nPts), dtype=torch.float64, device=dev) if deriv1 else None}
+    with torch.cuda.device(dev):
+        rc = library().bspy_cuda_eval_many(int(order), int(nCoef), int(nDep), S, _ptr(knots), int(knots.stride(0)),
+                                           _ptr(coefs), int(coefs.stride(0)), _ptr(u), nPts, _ptr(out["values"]),
+                                           _ptr(out.get("derivative")), _ptr(flag), _stream(dev))
+    _check(rc, "bspy_cuda_eval_many")
+    return out
+
+
+def probe_fp64(kind, iters, dev):
+    sink = torch.zeros(8, dtype=torch.float64, device=dev)
+    flops = C.c_double(0.0)
+    with torch.cuda.device(dev):
+        rc = library().bspy_cuda_probe_fp64(int(kind), int(iters), _ptr(sink), C.byref(flops), _stream(dev))
+    _check(rc, "bspy_cuda_probe_fp64")
+    return flops.value
+
+
+def probe_hbm(kind, src, dst):
+    nbytes = C.c_double(0.0)
+    dev = dst.device
+    with torch.cuda.device(dev):
+        rc = library().bspy_cuda_probe_hbm(int(kind), _ptr(src), _ptr(dst), dst.numel(), C.byref(nbytes), _stream(dev))
+    _check(rc, "bspy_cuda_probe_hbm")
+    return nbytes.value

@@ -1,0 +1,170 @@
+// Shared device/host helpers of libbspy_cuda.so (sm_100a).
+// Algorithm provenance: the semantics restated here are those of the reference's
+// bspy/_spline_evaluation.py:4-27 (span + basis recurrence); the code is written for the GPU
+// (registers, unrolled triangular recurrence, shared stages for values and derivatives).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../../include/bspy_cuda.h"
+
+namespace bspy {
+
+// ---- host side ------------------------------------------------------------------------------
+void set_error(const char *fmt, ...);
+void count_launch(int n = 1);
+int check_launch(const char *what);   // cudaGetLastError -> status code (+ error string)
+
+static inline int num_sms()
+{
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    return sms;
+}
+
+// ---- device side ----------------------------------------------------------------------------
+
+// Number of knots <= u clamped to [order, nKnots - order]  (reference: np.searchsorted(.., 'right')
+// + clamp).  NaN compares false against everything; numpy sorts it after every knot, so it
+// selects the last span.  Branch-free bisection over a power-of-two ladder.
+__device__ __forceinline__ int span_search(const double *__restrict__ knots, int nKnots, int order, double u)
+{
+    int lo = 0;           // invariant: knots[0..lo) <= u
+    int n = nKnots;
+    if (u != u) return nKnots - order;
+    while (n > 0) {
+        int half = n >> 1;
+        int mid = lo + half;
+        bool le = __ldg(knots + mid) <= u;
+        lo = le ? mid + 1 : lo;
+        n = le ? n - half - 1 : half;
+    }
+    lo = max(lo, order);
+    lo = min(lo, nKnots - order);
+    return lo;
+}
+
+// Restricted search: the caller guarantees the answer lies in [order, nKnots-order]; only the
+// knots strictly inside that range are probed (saves the steps spent on the clamped ends).
+__device__ __forceinline__ int span_search_inner(const double *__restrict__ knots, int nKnots, int order, double u)
+{
+    if (u != u) return nKnots - order;
+    int lo = order;                  // answer in [lo, lo+n]
+    int n = nKnots - 2 * order;      // candidates knots[order .. nKnots-order)
+    while (n > 0) {
+        int half = n >> 1;
+        int mid = lo + half;
+        bool le = __ldg(knots + mid) <= u;
+        lo = le ? mid + 1 : lo;
+        n = le ? n - half - 1 : half;
+    }
+    return lo;
+}
+
+// Strict (bit-exact) recurrence: IEEE operations in the reference's order, no FMA contraction.
+// b has `order` entries (any addressable memory through the accessor).  Used by bspy_cuda_basis.
+template <class Acc>
+__device__ __forceinline__ void basis_strict(const double *__restrict__ knots, int order, int ix, double u,
+                                             int deriv, bool taylor, Acc b)
+{
+    for (int j = 0; j < order; ++j) b(j) = 0.0;
+    if (deriv >= order) return;
+    b(order - 1) = 1.0;
+    const int nValue = order - deriv;
+    for (int deg = 1; deg < order; ++deg) {
+        int slot = order - deg;
+        if (deg < nValue) {
+            for (int i = ix - deg; i < ix; ++i, ++slot) {
+                const double ki = __ldg(knots + i);
+                const double a = __ddiv_rn(__dsub_rn(u, ki), __dsub_rn(__ldg(knots + i + deg), ki));
+                b(slot - 1) = __dadd_rn(b(slot - 1), __dmul_rn(__dsub_rn(1.0, a), b(slot)));
+                b(slot) = __dmul_rn(b(slot), a);
+            }
+        } else {
+            const double scale = __ddiv_rn((double)deg, taylor ? (double)(order - deg) : 1.0);
+            for (int i = ix - deg; i < ix; ++i, ++slot) {
+                const double ki = __ldg(knots + i);
+                const double a = __ddiv_rn(scale, __dsub_rn(__ldg(knots + i + deg), ki));
+                b(slot - 1) = __dadd_rn(b(slot - 1), __dmul_rn(-a, b(slot)));
+                b(slot) = __dmul_rn(b(slot), a);
+            }
+        }
+    }
+}
+
+// Register-resident recurrence for a compile-time order.  kw[] is the knot window
+// kw[j] = knots[ix - (O-1) + j], j = 0 .. 2(O-1)-1, so knots[i] with i = ix-deg+t is
+// kw[O-1-deg+t] and knots[i+deg] is kw[O-1+t].
+//   DER == false : b0 = basis of derivative order `d` (runtime, 0 = values)
+//   DER == true  : b0 = values, b1 = first derivatives; the O-2 lower stages are shared.
+template <int O, bool DER>
+__device__ __forceinline__ void basis_regs(const double (&kw)[2 * (O - 1) > 0 ? 2 * (O - 1) : 1], double u, int d,
+                                           double (&b0)[O], double (&b1)[O])
+{
+#pragma unroll
+    for (int j = 0; j < O; ++j) { b0[j] = 0.0; b1[j] = 0.0; }
+    if (!DER && d >= O) return;
+    b0[O - 1] = 1.0;
+    const int nValue = DER ? O - 1 : O - d;   // value stages: deg < nValue
+#pragma unroll
+    for (int deg = 1; deg < O; ++deg) {
+        if (DER && deg == O - 1) {
+            // last stage twice: once as a value stage into b0, once as a derivative stage into b1
+#pragma unroll
+            for (int j = 0; j < O; ++j) b1[j] = b0[j];
+#pragma unroll
+            for (int t = 0; t < deg; ++t) {
+                const int slot = O - deg + t;
+                const double kl = kw[O - 1 - deg + t];
+                const double r = 1.0 / (kw[O - 1 + t] - kl);
+                const double a = (u - kl) * r;
+                b0[slot - 1] += (1.0 - a) * b0[slot];
+                b0[slot] *= a;
+                const double g = (double)deg * r;
+                b1[slot - 1] -= g * b1[slot];
+                b1[slot] *= g;
+            }
+        } else if (deg < nValue) {
+#pragma unroll
+            for (int t = 0; t < deg; ++t) {
+                const int slot = O - deg + t;
+                const double kl = kw[O - 1 - deg + t];
+                const double a = (u - kl) / (kw[O - 1 + t] - kl);
+                b0[slot - 1] += (1.0 - a) * b0[slot];
+                b0[slot] *= a;
+            }
+        } else {
+#pragma unroll
+            for (int t = 0; t < deg; ++t) {
+                const int slot = O - deg + t;
+                const double kl = kw[O - 1 - deg + t];
+                const double g = (double)deg / (kw[O - 1 + t] - kl);
+                b0[slot - 1] -= g * b0[slot];
+                b0[slot] *= g;
+            }
+        }
+    }
+}
+
+template <int O>
+__device__ __forceinline__ void load_knot_window(const double *__restrict__ knots, int ix, double (&kw)[2 * (O - 1) > 0 ? 2 * (O - 1) : 1])
+{
+#pragma unroll
+    for (int j = 0; j < 2 * (O - 1); ++j) kw[j] = __ldg(knots + ix - (O - 1) + j);
+}
+
+// first point outside the domain: keep the smallest index
+__device__ __forceinline__ void report_outside(int64_t *flag, int64_t p)
+{
+    // flag holds a negative value when nothing was reported yet; compare as unsigned so that
+    // "negative" (huge unsigned) loses against every real index
+    atomicMin(reinterpret_cast<unsigned long long *>(flag), (unsigned long long)p);
+}
+
+}  // namespace bspy

@@ -1,0 +1,144 @@
+// libbspy_cuda.so: error handling, launch accounting, spans and (bit-exact) basis kernels.
+#include <stdarg.h>
+
+#include <atomic>
+
+#include "common.cuh"
+
+namespace bspy {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int check_launch(const char *what)
+{
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("%s: %s", what, cudaGetErrorString(e));
+        return (int)e;
+    }
+    return 0;
+}
+
+// ---- spans ------------------------------------------------------------------------------------
+// One thread per parameter, grid-stride; knots are staged in shared memory when they fit so the
+// log2(nKnots) probes of every thread stay on-chip.
+__global__ void __launch_bounds__(256) spans_kernel(const double *__restrict__ knots, int nKnots, int order,
+                                                    const double *__restrict__ u, int64_t N, int32_t *__restrict__ out,
+                                                    int useSmem)
+{
+    extern __shared__ double sk[];
+    const double *k = knots;
+    if (useSmem) {
+        for (int i = threadIdx.x; i < nKnots; i += blockDim.x) sk[i] = knots[i];
+        __syncthreads();
+        k = sk;
+    }
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < N; p += (int64_t)gridDim.x * blockDim.x) {
+        const double x = u[p];
+        int lo = 0, n = nKnots;
+        if (x != x) {
+            lo = nKnots;
+        } else {
+            while (n > 0) {
+                const int half = n >> 1;
+                const bool le = k[lo + half] <= x;
+                lo = le ? lo + half + 1 : lo;
+                n = le ? n - half - 1 : half;
+            }
+        }
+        out[p] = min(max(lo, order), nKnots - order);
+    }
+}
+
+// ---- basis (strict) ---------------------------------------------------------------------------
+// Thread per parameter.  The `order` running values live in shared memory, one column per thread
+// ([slot][thread], conflict-free), because `order` is a runtime value up to BSPY_MAX_ORDER.
+struct SmemColumn {
+    double *base;
+    int stride;
+    __device__ __forceinline__ double &operator()(int j) const { return base[j * stride]; }
+};
+
+__global__ void __launch_bounds__(128) basis_kernel(const double *__restrict__ knots, int nKnots, int order,
+                                                    const double *__restrict__ u, const int32_t *__restrict__ spansIn,
+                                                    int64_t N, int deriv, int taylor, int32_t *__restrict__ spansOut,
+                                                    double *__restrict__ basis)
+{
+    extern __shared__ double scratch[];
+    SmemColumn col{scratch + threadIdx.x, (int)blockDim.x};
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < N; p += (int64_t)gridDim.x * blockDim.x) {
+        const double x = u[p];
+        const int ix = spansIn ? spansIn[p] : span_search(knots, nKnots, order, x);
+        if (spansOut) spansOut[p] = ix;
+        basis_strict(knots, order, ix, x, deriv, taylor != 0, col);
+        for (int j = 0; j < order; ++j) basis[p * order + j] = col(j);
+    }
+}
+
+}  // namespace bspy
+
+using namespace bspy;
+
+extern "C" {
+
+int bspy_cuda_abi_version(void) { return BSPY_ABI_VERSION; }
+
+const char *bspy_cuda_last_error_string(void) { return g_err; }
+
+int64_t bspy_cuda_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int bspy_cuda_spans(const double *knots, int32_t nKnots, int32_t order, const double *u, int64_t N,
+                    int32_t *spans, void *stream)
+{
+    if (!knots || !u || !spans || N < 0 || order < 1 || nKnots < 2 * order) {
+        set_error("bspy_cuda_spans: bad argument");
+        return BSPY_E_ARG;
+    }
+    if (N == 0) return 0;
+    const int threads = 256;
+    int64_t blocks = (N + threads - 1) / threads;
+    const int64_t cap = (int64_t)num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    const size_t smem = (size_t)nKnots * sizeof(double);
+    const int useSmem = smem <= 48 * 1024;
+    spans_kernel<<<(unsigned)blocks, threads, useSmem ? smem : 0, (cudaStream_t)stream>>>(knots, nKnots, order, u, N,
+                                                                                          spans, useSmem);
+    count_launch();
+    return check_launch("bspy_cuda_spans");
+}
+
+int bspy_cuda_basis(const double *knots, int32_t nKnots, int32_t order, const double *u, const int32_t *spansIn,
+                    int64_t N, int32_t derivOrder, int32_t taylorCoefs, int32_t *spansOut, double *basis, void *stream)
+{
+    if (!knots || !u || !basis || N < 0 || order < 1 || nKnots < 2 * order || derivOrder < 0) {
+        set_error("bspy_cuda_basis: bad argument");
+        return BSPY_E_ARG;
+    }
+    if (order > BSPY_MAX_ORDER) {
+        set_error("bspy_cuda_basis: order %d > BSPY_MAX_ORDER", order);
+        return BSPY_E_UNSUPPORTED;
+    }
+    if (N == 0) return 0;
+    const int threads = 128;
+    int64_t blocks = (N + threads - 1) / threads;
+    const int64_t cap = (int64_t)num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    const size_t smem = (size_t)order * threads * sizeof(double);
+    basis_kernel<<<(unsigned)blocks, threads, smem, (cudaStream_t)stream>>>(knots, nKnots, order, u, spansIn, N, derivOrder,
+                                                                          taylorCoefs, spansOut, basis);
+    count_launch();
+    return check_launch("bspy_cuda_basis");
+}
+
+}  // extern "C"

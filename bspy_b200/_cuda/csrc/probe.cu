@@ -1,0 +1,81 @@
+// Measurement probes for bench.py: achievable FP64 FMA / DMMA rate and HBM copy / write-only
+// bandwidth on the device the library runs on.  Not part of the evaluation path; they give the
+// roofline denominators that MEASURED_PEAKS.json does not carry (FP64, write-only stream).
+#include "common.cuh"
+
+namespace bspy {
+
+__global__ void __launch_bounds__(256) probe_dfma_kernel(int iters, double *sink)
+{
+    double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    const double r = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (r == 123.456) sink[0] = r;
+}
+
+__global__ void __launch_bounds__(256) probe_dmma_kernel(int iters, double *sink)
+{
+    double c[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+    const double a = 1.0 + threadIdx.x * 1e-6, b = 1.0 - threadIdx.x * 1e-6;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c[k][0]), "+d"(c[k][1])
+                         : "d"(a), "d"(b));
+    }
+    const double r = c[0][0] + c[1][1] + c[2][0] + c[3][1];
+    if (r == 123.456) sink[0] = r;
+}
+
+__global__ void __launch_bounds__(256) probe_copy_kernel(const double2 *__restrict__ src, double2 *__restrict__ dst, long long n2)
+{
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x)
+        __stcs(dst + i, __ldcs(src + i));
+}
+
+__global__ void __launch_bounds__(256) probe_fill_kernel(double2 *__restrict__ dst, long long n2)
+{
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x)
+        __stcs(dst + i, make_double2((double)i, 1.0));
+}
+
+}  // namespace bspy
+
+using namespace bspy;
+
+extern "C" int bspy_cuda_probe_fp64(int32_t kind, int32_t iters, double *sink, double *flopsOut_host, void *stream)
+{
+    if (!sink || iters <= 0) { set_error("bspy_cuda_probe_fp64: bad argument"); return BSPY_E_ARG; }
+    const int blocks = num_sms() * 8, threads = 256;
+    if (kind == 0) {
+        probe_dfma_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(iters, sink);
+        if (flopsOut_host) *flopsOut_host = (double)blocks * threads * (double)iters * 8.0 * 2.0;
+    } else {
+        probe_dmma_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(iters, sink);
+        if (flopsOut_host) *flopsOut_host = (double)blocks * (threads / 32) * (double)iters * 4.0 * 512.0;
+    }
+    count_launch();
+    return check_launch("bspy_cuda_probe_fp64");
+}
+
+extern "C" int bspy_cuda_probe_hbm(int32_t kind, const double *src, double *dst, int64_t nDoubles, double *bytesOut_host,
+                                   void *stream)
+{
+    if (!dst || nDoubles <= 0 || (kind == 0 && !src)) { set_error("bspy_cuda_probe_hbm: bad argument"); return BSPY_E_ARG; }
+    const long long n2 = nDoubles / 2;
+    const int blocks = num_sms() * 16, threads = 256;
+    if (kind == 0) {
+        probe_copy_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>((const double2 *)src, (double2 *)dst, n2);
+        if (bytesOut_host) *bytesOut_host = 32.0 * (double)n2;
+    } else {
+        probe_fill_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>((double2 *)dst, n2);
+        if (bytesOut_host) *bytesOut_host = 16.0 * (double)n2;
+    }
+    count_launch();
+    return check_launch("bspy_cuda_probe_hbm");
+}

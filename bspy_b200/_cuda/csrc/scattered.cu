@@ -1,0 +1,639 @@
+// Scattered-point evaluation: bspy_cuda_eval_points.
+//
+// Replaces evaluate / derivative / jacobian / normal of bspy/_spline_evaluation.py:109-246 for N
+// points per launch.  One thread per point:
+//   1. knot span per variable (upper-bound bisection, bit-exact with np.searchsorted 'right'),
+//   2. Cox-de Boor basis values (and first derivatives) in registers from the 2(o-1)-knot window,
+//      the o-2 lower stages shared between values and derivatives,
+//   3. sum-factorised tensor-product contraction, last variable first (the reference's order),
+//      carrying one "derivative already taken" slot per variable so that the value and the whole
+//      jacobian come out of ONE pass over the coefficient window (the reference makes nInd+1
+//      passes and nInd^2 + nInd basis evaluations),
+//   4. optional normal: signed cofactors of the jacobian, optional 2-norm division,
+//   5. struct-of-arrays stores: consecutive threads write consecutive doubles.
+// Two implementations: eval_fixed<> (compile-time nInd/orders/nDep, everything in registers) for
+// the common shapes, eval_generic for any nInd <= 8, order <= 32 and any nDep.
+#include "common.cuh"
+
+namespace bspy {
+
+struct SplineDev {
+    int nInd, nDep;
+    int order[BSPY_MAX_IND];
+    int nCoef[BSPY_MAX_IND];
+    const double *knots[BSPY_MAX_IND];
+    const double *coefs;
+    long long stride[BSPY_MAX_IND];  // coefficient stride of variable i (elements)
+    long long depStride;
+    int normalSign;
+};
+
+struct PointsDev {
+    const double *uvw;      // scattered: parameter i of point p at uvw[p*pointStride + i*varStride]
+    long long pointStride, varStride;
+    const double *axes[BSPY_MAX_IND];  // grid mode: axes[i][idx_i]
+    long long nAxis[BSPY_MAX_IND];
+    int grid;               // 0 = scattered, 1 = tensor grid (last variable fastest)
+};
+
+struct OutDev {
+    double *values;    // (nDep, N)
+    double *jacobian;  // (nDep, nInd, N)
+    double *normal;    // (D, N)
+    int32_t *spans;    // (nInd, N)
+    long long *firstOutside;
+    unsigned normalize, normalMask;
+};
+
+struct WrtDev {
+    int d[BSPY_MAX_IND];
+};
+
+__device__ __forceinline__ double fetch_param(const PointsDev &in, long long p, int iv, long long &rem)
+{
+    // grid mode: decode the multi-index from the flat index, last variable fastest; callers walk
+    // iv from nInd-1 down to 0 and thread `rem` through.
+    if (in.grid) {
+        const long long n = in.nAxis[iv];
+        const long long idx = rem % n;
+        rem /= n;
+        return __ldg(in.axes[iv] + idx);
+    }
+    return __ldg(in.uvw + p * in.pointStride + iv * in.varStride);
+}
+
+// ---- cofactor normals -------------------------------------------------------------------------
+// T is D x (D-1) (row r = dependent/independent index r of the larger dimension), n[i] =
+// sign * (-1)^i * det(T without row i).  Closed forms for D <= 4, LU with partial pivoting above.
+template <int D>
+__device__ __forceinline__ double det_small(const double (&m)[(D > 0 ? D : 1) * (D > 0 ? D : 1)])
+{
+    if constexpr (D == 0) {
+        return 1.0;
+    } else if constexpr (D == 1) {
+        return m[0];
+    } else if constexpr (D == 2) {
+        return m[0] * m[3] - m[1] * m[2];
+    } else if constexpr (D == 3) {
+        return m[0] * (m[4] * m[8] - m[5] * m[7]) - m[1] * (m[3] * m[8] - m[5] * m[6]) + m[2] * (m[3] * m[7] - m[4] * m[6]);
+    } else {
+        double a[D * D];
+#pragma unroll
+        for (int i = 0; i < D * D; ++i) a[i] = m[i];
+        double det = 1.0;
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+            int piv = c;
+            double best = fabs(a[c * D + c]);
+#pragma unroll
+            for (int r = c + 1; r < D; ++r) {
+                const double v = fabs(a[r * D + c]);
+                if (v > best) { best = v; piv = r; }
+            }
+            if (piv != c) {
+#pragma unroll
+                for (int r = c + 1; r < D; ++r)
+                    if (r == piv) {
+#pragma unroll
+                        for (int k = 0; k < D; ++k) { const double t = a[c * D + k]; a[c * D + k] = a[r * D + k]; a[r * D + k] = t; }
+                    }
+                det = -det;
+            }
+            const double pv = a[c * D + c];
+            if (pv == 0.0) return 0.0;
+#pragma unroll
+            for (int r = c + 1; r < D; ++r) {
+                const double l = a[r * D + c] / pv;
+#pragma unroll
+                for (int k = c + 1; k < D; ++k) a[r * D + k] -= l * a[c * D + k];
+            }
+            det *= pv;
+        }
+        return det;
+    }
+}
+
+// J is (NDEP, NIND) row-major in registers; writes D = max(NIND,NDEP) components.
+template <int NIND, int NDEP>
+__device__ __forceinline__ void normal_from_jacobian(const double (&J)[NDEP * NIND], int sign, unsigned normalize,
+                                                      unsigned mask, double (&n)[(NIND > NDEP ? NIND : NDEP)])
+{
+    constexpr int D = NIND > NDEP ? NIND : NDEP;
+    constexpr int M = D - 1;
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+        double minor[(M > 0 ? M : 1) * (M > 0 ? M : 1)];
+        int rr = 0;
+#pragma unroll
+        for (int r = 0; r < D; ++r) {
+            if (r == i) continue;
+#pragma unroll
+            for (int c = 0; c < M; ++c) minor[rr * M + c] = (NIND > NDEP) ? J[c * NIND + r] : J[r * NIND + c];
+            ++rr;
+        }
+        const double det = det_small<M>(minor);
+        n[i] = ((i & 1) ? -det : det) * (double)sign;
+    }
+    if (normalize) {
+        double sq = 0.0;
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+            if (mask & (1u << i)) sq += n[i] * n[i];
+        const double len = sqrt(sq);
+#pragma unroll
+        for (int i = 0; i < D; ++i) n[i] = n[i] / len;
+    }
+}
+
+// ---- compile-time shape kernel ----------------------------------------------------------------
+template <int NIND, int O0, int O1, int O2, int O3>
+struct Orders {
+    static constexpr int n = NIND;
+    __host__ __device__ static constexpr int at(int i) { return i == 0 ? O0 : i == 1 ? O1 : i == 2 ? O2 : O3; }
+    static constexpr int omax = (O0 > O1 ? O0 : O1) > (O2 > O3 ? O2 : O3) ? (O0 > O1 ? O0 : O1) : (O2 > O3 ? O2 : O3);
+};
+
+template <class Ord, int NDEP, bool JAC>
+struct FixedCtx {
+    double B[Ord::n][Ord::omax];   // values (or wrt-derivative) basis
+    double dB[Ord::n][Ord::omax];  // first-derivative basis (JAC only)
+    long long stride[Ord::n];
+    long long depStride;
+};
+
+// Contract variables L .. NIND-1 of the window whose corner (for variables >= L the corner, for
+// variables < L the fixed index) is at `cp`.  v[d]: value part, g[m][d]: derivative w.r.t. m >= L.
+template <int L, class Ord, int NDEP, bool JAC>
+struct Contract {
+    __device__ __forceinline__ static void run(const double *__restrict__ cp, const FixedCtx<Ord, NDEP, JAC> &c,
+                                               double (&v)[NDEP], double (&g)[Ord::n][NDEP])
+    {
+        constexpr int O = Ord::at(L);
+#pragma unroll
+        for (int d = 0; d < NDEP; ++d) v[d] = 0.0;
+        if constexpr (JAC) {
+#pragma unroll
+            for (int m = L; m < Ord::n; ++m)
+#pragma unroll
+                for (int d = 0; d < NDEP; ++d) g[m][d] = 0.0;
+        }
+        if constexpr (L == Ord::n - 1) {
+            // innermost variable: contiguous coefficients
+#pragma unroll
+            for (int d = 0; d < NDEP; ++d) {
+                const double *row = cp + d * c.depStride;
+#pragma unroll
+                for (int i = 0; i < O; ++i) {
+                    const double x = __ldg(row + i);
+                    v[d] = fma(x, c.B[L][i], v[d]);
+                    if constexpr (JAC) g[L][d] = fma(x, c.dB[L][i], g[L][d]);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < O; ++i) {
+                double cv[NDEP];
+                double cg[Ord::n][NDEP];
+                Contract<L + 1, Ord, NDEP, JAC>::run(cp + i * c.stride[L], c, cv, cg);
+#pragma unroll
+                for (int d = 0; d < NDEP; ++d) {
+                    v[d] = fma(cv[d], c.B[L][i], v[d]);
+                    if constexpr (JAC) {
+                        g[L][d] = fma(cv[d], c.dB[L][i], g[L][d]);
+#pragma unroll
+                        for (int m = L + 1; m < Ord::n; ++m) g[m][d] = fma(cg[m][d], c.B[L][i], g[m][d]);
+                    }
+                }
+            }
+        }
+    }
+};
+
+template <int IV, class Ord, int NDEP, bool JAC>
+__device__ __forceinline__ void setup_variable(const SplineDev &s, double u, int d, FixedCtx<Ord, NDEP, JAC> &c,
+                                               int (&ix)[Ord::n], bool &outside)
+{
+    constexpr int O = Ord::at(IV);
+    const double *k = s.knots[IV];
+    const int nKnots = O + s.nCoef[IV];
+    outside |= (u < __ldg(k + O - 1)) | (u > __ldg(k + s.nCoef[IV]));
+    const int span = span_search_inner(k, nKnots, O, u);
+    ix[IV] = span;
+    double kw[2 * (O - 1) > 0 ? 2 * (O - 1) : 1];
+    load_knot_window<O>(k, span, kw);
+    double b0[O], b1[O];
+    basis_regs<O, JAC>(kw, u, d, b0, b1);
+#pragma unroll
+    for (int j = 0; j < O; ++j) {
+        c.B[IV][j] = b0[j];
+        if constexpr (JAC) c.dB[IV][j] = b1[j];
+    }
+}
+
+template <int NIND, int O0, int O1, int O2, int O3, int NDEP, bool JAC>
+__global__ void __launch_bounds__(128) eval_fixed_kernel(const SplineDev s, const PointsDev in, const long long N,
+                                                         const WrtDev wrt, const OutDev out)
+{
+    using Ord = Orders<NIND, O0, O1, O2, O3>;
+    for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < N; p += (long long)gridDim.x * blockDim.x) {
+        FixedCtx<Ord, NDEP, JAC> c;
+        int ix[NIND];
+        double u[NIND];
+        bool outside = false;
+        long long rem = p;
+#pragma unroll
+        for (int iv = NIND - 1; iv >= 0; --iv) u[iv] = fetch_param(in, p, iv, rem);
+        setup_variable<0, Ord, NDEP, JAC>(s, u[0], wrt.d[0], c, ix, outside);
+        if constexpr (NIND > 1) setup_variable<1, Ord, NDEP, JAC>(s, u[1], wrt.d[1], c, ix, outside);
+        if constexpr (NIND > 2) setup_variable<2, Ord, NDEP, JAC>(s, u[2], wrt.d[2], c, ix, outside);
+        if constexpr (NIND > 3) setup_variable<3, Ord, NDEP, JAC>(s, u[3], wrt.d[3], c, ix, outside);
+        if (outside && out.firstOutside) report_outside((int64_t *)out.firstOutside, p);
+        long long off = 0;
+#pragma unroll
+        for (int iv = 0; iv < NIND; ++iv) {
+            c.stride[iv] = s.stride[iv];
+            off += (long long)(ix[iv] - Ord::at(iv)) * s.stride[iv];
+        }
+        c.depStride = s.depStride;
+        double v[NDEP];
+        double g[NIND][NDEP];
+        Contract<0, Ord, NDEP, JAC>::run(s.coefs + off, c, v, g);
+        if (out.values) {
+#pragma unroll
+            for (int d = 0; d < NDEP; ++d) __stcs(out.values + d * N + p, v[d]);
+        }
+        if (out.spans) {
+#pragma unroll
+            for (int iv = 0; iv < NIND; ++iv) __stcs(out.spans + iv * N + p, ix[iv]);
+        }
+        if constexpr (JAC) {
+            if (out.jacobian) {
+#pragma unroll
+                for (int d = 0; d < NDEP; ++d)
+#pragma unroll
+                    for (int iv = 0; iv < NIND; ++iv) __stcs(out.jacobian + (d * NIND + iv) * N + p, g[iv][d]);
+            }
+            if constexpr (NIND - NDEP == 1 || NDEP - NIND == 1) {
+                if (out.normal) {
+                    constexpr int D = NIND > NDEP ? NIND : NDEP;
+                    double J[NDEP * NIND];
+#pragma unroll
+                    for (int d = 0; d < NDEP; ++d)
+#pragma unroll
+                        for (int iv = 0; iv < NIND; ++iv) J[d * NIND + iv] = g[iv][d];
+                    double n[D];
+                    normal_from_jacobian<NIND, NDEP>(J, s.normalSign, out.normalize, out.normalMask, n);
+#pragma unroll
+                    for (int i = 0; i < D; ++i) __stcs(out.normal + i * N + p, n[i]);
+                }
+            }
+        }
+    }
+}
+
+// ---- any-shape kernel -------------------------------------------------------------------------
+// Runtime nInd / orders / nDep.  Per-thread basis rows live in shared memory ([slot][thread]);
+// the window is walked with an odometer over all variables but the last, the last variable is
+// contracted in the inner loop; one pass per dependent variable.
+__device__ double det_lu_runtime(double *a, int n)
+{
+    double det = 1.0;
+    for (int c = 0; c < n; ++c) {
+        int piv = c;
+        double best = fabs(a[c * n + c]);
+        for (int r = c + 1; r < n; ++r)
+            if (fabs(a[r * n + c]) > best) { best = fabs(a[r * n + c]); piv = r; }
+        if (piv != c) {
+            for (int k = 0; k < n; ++k) { const double t = a[c * n + k]; a[c * n + k] = a[piv * n + k]; a[piv * n + k] = t; }
+            det = -det;
+        }
+        const double pv = a[c * n + c];
+        if (pv == 0.0) return 0.0;
+        for (int r = c + 1; r < n; ++r) {
+            const double l = a[r * n + c] / pv;
+            for (int k = c + 1; k < n; ++k) a[r * n + k] -= l * a[c * n + k];
+        }
+        det *= pv;
+    }
+    return det;
+}
+
+struct SmemCol {
+    double *base;
+    int stride;
+    __device__ __forceinline__ double &operator()(int j) const { return base[j * stride]; }
+};
+
+// Relaxed (FMA allowed) runtime-order recurrence into shared-memory columns.
+__device__ __forceinline__ void basis_runtime(const double *__restrict__ knots, int order, int ix, double u, int deriv,
+                                              SmemCol b)
+{
+    for (int j = 0; j < order; ++j) b(j) = 0.0;
+    if (deriv >= order) return;
+    b(order - 1) = 1.0;
+    const int nValue = order - deriv;
+    for (int deg = 1; deg < order; ++deg) {
+        int slot = order - deg;
+        for (int i = ix - deg; i < ix; ++i, ++slot) {
+            const double ki = __ldg(knots + i);
+            const double gap = __ldg(knots + i + deg) - ki;
+            if (deg < nValue) {
+                const double a = (u - ki) / gap;
+                b(slot - 1) += (1.0 - a) * b(slot);
+                b(slot) *= a;
+            } else {
+                const double a = (double)deg / gap;
+                b(slot - 1) -= a * b(slot);
+                b(slot) *= a;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) eval_generic_kernel(const SplineDev s, const PointsDev in, const long long N,
+                                                           const WrtDev wrt, const OutDev out, const int jac,
+                                                           const int rowLen /* sum of orders */)
+{
+    extern __shared__ double scratch[];
+    const int T = blockDim.x;
+    // column layout: [B rows (rowLen)] [dB rows (rowLen) if jac], each slot strided by T
+    double *colB = scratch + threadIdx.x;
+    double *colD = colB + (long long)rowLen * T;
+    const int nInd = s.nInd, nDep = s.nDep;
+    const int D = nInd > nDep ? nInd : nDep;
+    for (long long p = blockIdx.x * (long long)T + threadIdx.x; p < N; p += (long long)gridDim.x * T) {
+        int ix[BSPY_MAX_IND];
+        int rowAt[BSPY_MAX_IND];
+        bool outside = false;
+        long long rem = p;
+        double uu[BSPY_MAX_IND];
+        for (int iv = nInd - 1; iv >= 0; --iv) uu[iv] = fetch_param(in, p, iv, rem);
+        int at = 0;
+        long long off = 0;
+        for (int iv = 0; iv < nInd; ++iv) {
+            const double *k = s.knots[iv];
+            const int o = s.order[iv];
+            const double u = uu[iv];
+            outside |= (u < __ldg(k + o - 1)) | (u > __ldg(k + s.nCoef[iv]));
+            ix[iv] = span_search(k, o + s.nCoef[iv], o, u);
+            rowAt[iv] = at;
+            basis_runtime(k, o, ix[iv], u, jac ? 0 : wrt.d[iv], SmemCol{colB + (long long)at * T, T});
+            if (jac) basis_runtime(k, o, ix[iv], u, 1, SmemCol{colD + (long long)at * T, T});
+            at += o;
+            off += (long long)(ix[iv] - o) * s.stride[iv];
+            if (out.spans) out.spans[iv * N + p] = ix[iv];
+        }
+        if (outside && out.firstOutside) report_outside((int64_t *)out.firstOutside, p);
+        double J[(BSPY_MAX_IND + 1) * BSPY_MAX_IND];  // (nDep, nInd) only when a normal is requested (nDep <= nInd+1)
+        const int last = nInd - 1;
+        for (int d = 0; d < nDep; ++d) {
+            const double *cd = s.coefs + d * s.depStride + off;
+            double val = 0.0;
+            double der[BSPY_MAX_IND];
+            for (int iv = 0; iv < nInd; ++iv) der[iv] = 0.0;
+            if (nInd == 0) {
+                val = __ldg(cd);
+            } else {
+                int idx[BSPY_MAX_IND];
+                for (int iv = 0; iv < nInd; ++iv) idx[iv] = 0;
+                bool more = true;
+                while (more) {
+                    long long o2 = 0;
+                    for (int iv = 0; iv < last; ++iv) o2 += idx[iv] * s.stride[iv];
+                    double s0 = 0.0, s1 = 0.0;
+                    const int ol = s.order[last];
+                    for (int k = 0; k < ol; ++k) {
+                        const double x = __ldg(cd + o2 + k);
+                        s0 = fma(x, colB[(long long)(rowAt[last] + k) * T], s0);
+                        if (jac) s1 = fma(x, colD[(long long)(rowAt[last] + k) * T], s1);
+                    }
+                    double w = 1.0;
+                    for (int iv = 0; iv < last; ++iv) w *= colB[(long long)(rowAt[iv] + idx[iv]) * T];
+                    val = fma(w, s0, val);
+                    if (jac) {
+                        der[last] = fma(w, s1, der[last]);
+                        for (int m = 0; m < last; ++m) {
+                            double wm = 1.0;
+                            for (int iv = 0; iv < last; ++iv)
+                                wm *= (iv == m ? colD : colB)[(long long)(rowAt[iv] + idx[iv]) * T];
+                            der[m] = fma(wm, s0, der[m]);
+                        }
+                    }
+                    // odometer over variables 0 .. last-1 (last-1 fastest)
+                    int iv = last - 1;
+                    for (; iv >= 0; --iv) {
+                        if (++idx[iv] < s.order[iv]) break;
+                        idx[iv] = 0;
+                    }
+                    more = iv >= 0;
+                }
+            }
+            if (out.values) out.values[d * N + p] = val;
+            if (jac) {
+                if (out.jacobian)
+                    for (int iv = 0; iv < nInd; ++iv) out.jacobian[((long long)d * nInd + iv) * N + p] = der[iv];
+                if (out.normal)
+                    for (int iv = 0; iv < nInd; ++iv) J[d * nInd + iv] = der[iv];
+            }
+        }
+        if (jac && out.normal) {
+            double minor[BSPY_MAX_IND * BSPY_MAX_IND];
+            double n[BSPY_MAX_IND + 1];
+            const int M = D - 1;
+            double sq = 0.0;
+            for (int i = 0; i < D; ++i) {
+                int rr = 0;
+                for (int r = 0; r < D; ++r) {
+                    if (r == i) continue;
+                    for (int c = 0; c < M; ++c) minor[rr * M + c] = (nInd > nDep) ? J[c * nInd + r] : J[r * nInd + c];
+                    ++rr;
+                }
+                const double det = det_lu_runtime(minor, M);
+                n[i] = ((i & 1) ? -det : det) * (double)s.normalSign;
+                if (out.normalMask & (1u << i)) sq += n[i] * n[i];
+            }
+            const double len = sqrt(sq);
+            for (int i = 0; i < D; ++i) out.normal[(long long)i * N + p] = out.normalize ? n[i] / len : n[i];
+        }
+    }
+}
+
+// ---- host dispatch ----------------------------------------------------------------------------
+typedef void (*FixedFn)(const SplineDev, const PointsDev, const long long, const WrtDev, const OutDev);
+
+struct FixedEntry {
+    int nInd, o[4], nDep, jac;
+    FixedFn fn;
+};
+
+#define BSPY_FIXED(NI, A, B, C, D_, ND)                                        \
+    {NI, {A, B, C, D_}, ND, 0, eval_fixed_kernel<NI, A, B, C, D_, ND, false>}, \
+    {NI, {A, B, C, D_}, ND, 1, eval_fixed_kernel<NI, A, B, C, D_, ND, true>}
+
+static const FixedEntry kFixed[] = {
+    // curves
+    BSPY_FIXED(1, 2, 0, 0, 0, 1), BSPY_FIXED(1, 2, 0, 0, 0, 2), BSPY_FIXED(1, 2, 0, 0, 0, 3),
+    BSPY_FIXED(1, 3, 0, 0, 0, 1), BSPY_FIXED(1, 3, 0, 0, 0, 2), BSPY_FIXED(1, 3, 0, 0, 0, 3),
+    BSPY_FIXED(1, 4, 0, 0, 0, 1), BSPY_FIXED(1, 4, 0, 0, 0, 2), BSPY_FIXED(1, 4, 0, 0, 0, 3),
+    BSPY_FIXED(1, 5, 0, 0, 0, 1), BSPY_FIXED(1, 5, 0, 0, 0, 2), BSPY_FIXED(1, 5, 0, 0, 0, 3),
+    BSPY_FIXED(1, 6, 0, 0, 0, 2), BSPY_FIXED(1, 6, 0, 0, 0, 3),
+    // surfaces
+    BSPY_FIXED(2, 2, 2, 0, 0, 1), BSPY_FIXED(2, 2, 2, 0, 0, 3),
+    BSPY_FIXED(2, 3, 3, 0, 0, 1), BSPY_FIXED(2, 3, 3, 0, 0, 2), BSPY_FIXED(2, 3, 3, 0, 0, 3),
+    BSPY_FIXED(2, 4, 4, 0, 0, 1), BSPY_FIXED(2, 4, 4, 0, 0, 2), BSPY_FIXED(2, 4, 4, 0, 0, 3),
+    BSPY_FIXED(2, 3, 4, 0, 0, 3), BSPY_FIXED(2, 4, 3, 0, 0, 3), BSPY_FIXED(2, 4, 5, 0, 0, 3),
+    BSPY_FIXED(2, 5, 5, 0, 0, 3),
+    // volumes
+    BSPY_FIXED(3, 2, 2, 2, 0, 3), BSPY_FIXED(3, 3, 3, 3, 0, 1), BSPY_FIXED(3, 3, 3, 3, 0, 3),
+    BSPY_FIXED(3, 4, 4, 4, 0, 1), BSPY_FIXED(3, 4, 4, 4, 0, 3), BSPY_FIXED(3, 4, 4, 4, 0, 4),
+    // 4-variate manifolds
+    BSPY_FIXED(4, 2, 2, 2, 2, 3), BSPY_FIXED(4, 3, 3, 3, 3, 3), BSPY_FIXED(4, 3, 3, 3, 3, 5),
+    BSPY_FIXED(4, 3, 3, 3, 3, 6),
+};
+
+static FixedFn find_fixed(const SplineDev &s, int jac)
+{
+    if (s.nInd < 1 || s.nInd > 4) return nullptr;
+    for (const FixedEntry &e : kFixed) {
+        if (e.nInd != s.nInd || e.nDep != s.nDep || e.jac != jac) continue;
+        bool same = true;
+        for (int i = 0; i < s.nInd; ++i) same &= e.o[i] == s.order[i];
+        if (same) return e.fn;
+    }
+    return nullptr;
+}
+
+int make_spline_dev(const bspy_spline *sp, SplineDev &s, const char *who)
+{
+    if (!sp) { set_error("%s: spline is NULL", who); return BSPY_E_ARG; }
+    if (sp->nInd < 0 || sp->nDep < 0 || !sp->coefs) { set_error("%s: bad spline header", who); return BSPY_E_ARG; }
+    if (sp->nInd > BSPY_MAX_IND) { set_error("%s: nInd %d > BSPY_MAX_IND", who, sp->nInd); return BSPY_E_UNSUPPORTED; }
+    s.nInd = sp->nInd;
+    s.nDep = sp->nDep;
+    s.coefs = sp->coefs;
+    s.normalSign = sp->normalSign < 0 ? -1 : 1;
+    long long stride = 1;
+    for (int i = sp->nInd - 1; i >= 0; --i) {
+        if (sp->order[i] < 1 || sp->nCoef[i] < sp->order[i] || !sp->knots[i]) {
+            set_error("%s: bad order/nCoef/knots for variable %d", who, i);
+            return BSPY_E_ARG;
+        }
+        if (sp->order[i] > BSPY_MAX_ORDER) { set_error("%s: order %d > BSPY_MAX_ORDER", who, sp->order[i]); return BSPY_E_UNSUPPORTED; }
+        s.stride[i] = stride;
+        stride *= sp->nCoef[i];
+    }
+    s.depStride = stride;
+    for (int i = 0; i < BSPY_MAX_IND; ++i) {
+        s.order[i] = i < sp->nInd ? sp->order[i] : 0;
+        s.nCoef[i] = i < sp->nInd ? sp->nCoef[i] : 0;
+        s.knots[i] = i < sp->nInd ? sp->knots[i] : nullptr;
+        if (i >= sp->nInd) s.stride[i] = 0;
+    }
+    return 0;
+}
+
+// Launch one pass (values-or-wrt pass when jac == 0, value+jacobian(+normal) pass when jac == 1).
+int launch_eval(const SplineDev &s, const PointsDev &in, long long N, const WrtDev &wrt, const OutDev &out, int jac,
+                cudaStream_t stream)
+{
+    if (N <= 0) return 0;
+    FixedFn fn = find_fixed(s, jac);
+    const int threads = 128;
+    long long blocks = (N + threads - 1) / threads;
+    if (fn) {
+        const long long cap = (long long)num_sms() * 32;
+        if (blocks > cap) blocks = cap;
+        fn<<<(unsigned)blocks, threads, 0, stream>>>(s, in, N, wrt, out);
+    } else {
+        int rowLen = 0;
+        for (int i = 0; i < s.nInd; ++i) rowLen += s.order[i];
+        int t = threads;
+        size_t smem = (size_t)rowLen * (jac ? 2 : 1) * t * sizeof(double);
+        while (smem > 160 * 1024 && t > 32) { t >>= 1; smem >>= 1; }
+        if (smem > 200 * 1024) { set_error("eval_generic: basis scratch too large"); return BSPY_E_UNSUPPORTED; }
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(eval_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+        }
+        blocks = (N + t - 1) / t;
+        const long long cap = (long long)num_sms() * 16;
+        if (blocks > cap) blocks = cap;
+        eval_generic_kernel<<<(unsigned)blocks, t, smem, stream>>>(s, in, N, wrt, out, jac, rowLen);
+    }
+    count_launch();
+    return check_launch("bspy_cuda_eval");
+}
+
+int eval_common(const bspy_spline *spline, const PointsDev &in, long long N, const int32_t *wrt, uint32_t flags,
+                uint32_t normalMask, double *values, double *deriv, double *jacobian, double *normal, int32_t *spans,
+                int64_t *firstOutside, void *stream, const char *who)
+{
+    SplineDev s;
+    int rc = make_spline_dev(spline, s, who);
+    if (rc) return rc;
+    if (N < 0) { set_error("%s: N < 0", who); return BSPY_E_ARG; }
+    if ((deriv != nullptr) != (wrt != nullptr)) { set_error("%s: wrt and deriv must be given together", who); return BSPY_E_ARG; }
+    const int D = s.nInd > s.nDep ? s.nInd : s.nDep;
+    if (normal && (s.nInd - s.nDep != 1 && s.nDep - s.nInd != 1)) {
+        set_error("The number of independent variables must be one different than the number of dependent variables.");
+        return BSPY_E_NORMAL_DIMS;
+    }
+    if (normalMask == 0 || D >= 32) normalMask = 0xffffffffu;
+    WrtDev zero{};
+    OutDev out{};
+    out.firstOutside = (long long *)firstOutside;
+    out.normalize = (flags & BSPY_NORMALIZE) ? 1u : 0u;
+    out.normalMask = normalMask;
+    bool spansDone = false, oobDone = false;
+    if (jacobian || normal) {
+        out.values = values;
+        out.jacobian = jacobian;
+        out.normal = normal;
+        out.spans = spans;
+        rc = launch_eval(s, in, N, zero, out, 1, (cudaStream_t)stream);
+        if (rc) return rc;
+        spansDone = oobDone = true;
+    } else if (values || spans || (firstOutside && !deriv)) {
+        out.values = values;
+        out.spans = spans;
+        rc = launch_eval(s, in, N, zero, out, 0, (cudaStream_t)stream);
+        if (rc) return rc;
+        spansDone = oobDone = true;
+    }
+    if (deriv) {
+        WrtDev w{};
+        for (int i = 0; i < s.nInd; ++i) {
+            if (wrt[i] < 0) { set_error("%s: negative derivative order", who); return BSPY_E_ARG; }
+            w.d[i] = wrt[i];
+        }
+        OutDev o2{};
+        o2.values = deriv;
+        o2.spans = spansDone ? nullptr : spans;
+        o2.firstOutside = oobDone ? nullptr : (long long *)firstOutside;
+        rc = launch_eval(s, in, N, w, o2, 0, (cudaStream_t)stream);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+}  // namespace bspy
+
+using namespace bspy;
+
+extern "C" int bspy_cuda_eval_points(const bspy_spline *spline, const double *uvw, int64_t pointStride, int64_t varStride,
+                                     int64_t N, const int32_t *wrt, uint32_t flags, uint32_t normalMask, double *values,
+                                     double *deriv, double *jacobian, double *normal, int32_t *spans,
+                                     int64_t *firstOutside, void *stream)
+{
+    if (!uvw && N > 0 && spline && spline->nInd > 0) {
+        set_error("bspy_cuda_eval_points: uvw is NULL");
+        return BSPY_E_ARG;
+    }
+    PointsDev in{};
+    in.uvw = uvw;
+    in.pointStride = pointStride;
+    in.varStride = varStride;
+    in.grid = 0;
+    return eval_common(spline, in, N, wrt, flags, normalMask, values, deriv, jacobian, normal, spans, firstOutside, stream,
+                       "bspy_cuda_eval_points");
+}

@@ -1,0 +1,399 @@
+"""Host side of the evaluation path: same module-level functions as the reference's
+``bspy/_spline_evaluation.py`` (``bspline_values, domain, evaluate, derivative, jacobian, normal``;
+spline first, same argument meaning, same exceptions and messages), each of which launches the
+sm_100a kernels of ``bspy_b200._cuda`` -- plus the vectorised entries ``evaluate_points`` and
+``evaluate_grid`` that the reference lacks.
+
+No arithmetic of the path happens in this file: it validates arguments, moves bytes (torch is the
+plumbing for device memory, pinned host memory and streams) and reshapes results.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Any, Optional
+
+import numpy as np
+import torch
+
+from bspy_b200 import _cuda
+
+__all__ = ["EvalResult", "bspline_values", "bspline_values_batch", "domain", "evaluate", "derivative", "jacobian",
+           "normal", "evaluate_points", "evaluate_grid", "device_spline", "freeze"]
+
+# points per chunk when the input lives in host memory (H2D / kernel / D2H of consecutive
+# chunks overlap on a small ring of streams)
+HOST_CHUNK = 1 << 22
+_N_STREAMS = 3
+
+
+@dataclass
+class EvalResult:
+    """Struct-of-arrays results of a batched evaluation (None = not requested).
+
+    values (nDep, N) | derivative (nDep, N) | jacobian (nDep, nInd, N) |
+    normal (len(indices) or max(nInd, nDep), N) | spans (nInd, N) int32.
+    Arrays are numpy when the points were numpy / array-like, CPU tensors for CPU tensors and CUDA
+    tensors for CUDA tensors.  For grids, N is replaced by the grid shape."""
+    values: Any = None
+    derivative: Any = None
+    jacobian: Any = None
+    normal: Any = None
+    spans: Any = None
+
+
+# ----------------------------------------------------------------------------- device residency
+
+def _result_dtype(self):
+    dt = np.result_type(np.asarray(self.coefs).dtype, *[np.asarray(k).dtype for k in self.knots])
+    return dt if np.issubdtype(dt, np.floating) else np.dtype(np.float64)
+
+
+def _normal_sign(self):
+    meta = getattr(self, "metadata", None)
+    return -1 if (meta and meta.get("negateNormal", False)) else 1
+
+
+class _Resident:
+    __slots__ = ("knots_host", "coefs_host", "ds")
+
+
+def device_spline(self, dev=None) -> _cuda.DeviceSpline:
+    """The spline's knots and coefficients on ``dev`` (float64, contiguous).  Splines are mutable
+    objects (users assign into ``spline.coefs``), so the cached device copy is revalidated against
+    a host snapshot on every call and re-uploaded when anything changed; ``freeze`` skips that."""
+    dev = _cuda.device(dev)
+    frozen = getattr(self, "_bspy_frozen", None)
+    if frozen is not None and frozen.device == dev:
+        frozen.normal_sign = _normal_sign(self)
+        frozen.c.normalSign = frozen.normal_sign
+        return frozen
+    cache = self.__dict__.setdefault("_bspy_device_cache", {})
+    coefs = np.ascontiguousarray(self.coefs, dtype=np.float64)
+    knots = [np.ascontiguousarray(k, dtype=np.float64) for k in self.knots]
+    if coefs.shape != (self.nDep, *self.nCoef):
+        raise ValueError(f"coefs shape {coefs.shape} does not match (nDep, *nCoef) = {(self.nDep, *self.nCoef)}")
+    for i, k in enumerate(knots):
+        if k.shape != (self.order[i] + self.nCoef[i],):
+            raise ValueError(f"Knots array for variable {i} should have length {self.order[i] + self.nCoef[i]}")
+    hit = cache.get(dev)
+    if hit is not None and hit.coefs_host.shape == coefs.shape and np.array_equal(hit.coefs_host, coefs, equal_nan=True) \
+            and len(hit.knots_host) == len(knots) and all(a.shape == b.shape and np.array_equal(a, b, equal_nan=True)
+                                                          for a, b in zip(hit.knots_host, knots)):
+        hit.ds.normal_sign = _normal_sign(self)
+        hit.ds.c.normalSign = hit.ds.normal_sign
+        return hit.ds
+    res = _Resident()
+    res.knots_host = [k.copy() for k in knots]
+    res.coefs_host = coefs.copy()
+    res.ds = _cuda.DeviceSpline(self.nInd, self.nDep, self.order, self.nCoef,
+                                [torch.from_numpy(k).to(dev) for k in res.knots_host],
+                                torch.from_numpy(res.coefs_host).to(dev), _normal_sign(self))
+    cache[dev] = res
+    return res.ds
+
+
+def freeze(self, dev=None):
+    """Upload once and stop revalidating: later calls reuse the device copy even if the host arrays
+    are mutated (call ``freeze`` again, or ``unfreeze``, after editing the spline)."""
+    self.__dict__.pop("_bspy_frozen", None)
+    ds = device_spline(self, dev)
+    self.__dict__["_bspy_frozen"] = ds
+    return self
+
+
+def unfreeze(self):
+    self.__dict__.pop("_bspy_frozen", None)
+    return self
+
+
+# ----------------------------------------------------------------------------- reference API
+
+def bspline_values(knot, knots, splineOrder, u, derivativeOrder=0, taylorCoefs=False):
+    """``(knot, basis[splineOrder])`` for one parameter -- reference
+    ``bspy/_spline_evaluation.py:4-27`` -- computed by ``bspy_cuda_basis`` (bit-identical)."""
+    ix, b = bspline_values_batch(knot, knots, splineOrder, np.array([u], dtype=np.float64), derivativeOrder, taylorCoefs)
+    return (int(ix[0]) if knot is None else knot), b[0]
+
+
+def bspline_values_batch(knot, knots, splineOrder, u, derivativeOrder=0, taylorCoefs=False, dev=None):
+    """Vectorised ``bspline_values``: ``u`` is a 1-D array / tensor of N parameters, ``knot`` is
+    None (search), an int (same span for all) or an int array.  Returns ``(spans[N], basis[N, order])``
+    as numpy arrays, or as CUDA tensors when ``u`` is a CUDA tensor."""
+    on_device = isinstance(u, torch.Tensor) and u.is_cuda
+    dev = u.device if on_device else _cuda.device(dev)
+    kt = knots if (isinstance(knots, torch.Tensor) and knots.is_cuda) else \
+        torch.from_numpy(np.ascontiguousarray(knots, dtype=np.float64)).to(dev)
+    ut = u.contiguous().to(torch.float64) if on_device else \
+        torch.from_numpy(np.ascontiguousarray(u, dtype=np.float64).reshape(-1)).to(dev)
+    spans_in = None
+    if knot is not None:
+        if np.isscalar(knot):
+            spans_in = torch.full((ut.numel(),), int(knot), dtype=torch.int32, device=dev)
+        elif isinstance(knot, torch.Tensor):
+            spans_in = knot.to(device=dev, dtype=torch.int32).contiguous()
+        else:
+            spans_in = torch.from_numpy(np.ascontiguousarray(knot, dtype=np.int32)).to(dev)
+    sp, b = _cuda.basis(kt, int(splineOrder), ut, int(derivativeOrder), bool(taylorCoefs), spans_in)
+    if on_device:
+        return sp, b
+    kdt = np.asarray(knots).dtype if not isinstance(knots, torch.Tensor) else np.dtype(np.float64)
+    b = b.cpu().numpy()
+    if np.issubdtype(kdt, np.floating) and kdt != np.float64:
+        b = b.astype(kdt)
+    return sp.cpu().numpy(), b
+
+
+def domain(self):
+    """``(nInd, 2)`` array of parameter bounds (reference ``:135-138``).  Pure indexing."""
+    return np.array([[self.knots[i][self.order[i] - 1], self.knots[i][self.nCoef[i]]] for i in range(self.nInd)])
+
+
+def _single_point(self, uvw):
+    uvw = np.atleast_1d(uvw)
+    if len(uvw) != self.nInd:
+        raise ValueError(f"Incorrect number of parameter values: {len(uvw)}")
+    box = domain(self)
+    for i in range(self.nInd):
+        if uvw[i] < box[i][0] or uvw[i] > box[i][1]:
+            raise ValueError(f"Spline evaluation outside domain: {uvw}")
+    return uvw
+
+
+def _launch_single(self, uvw, **request):
+    ds = device_spline(self)
+    pts = torch.from_numpy(np.ascontiguousarray(uvw, dtype=np.float64).reshape(1, self.nInd)).to(ds.device)
+    return _cuda.eval_points(ds, pts, self.nInd, 1, 1, **request)
+
+
+def evaluate(self, uvw):
+    """Value at one point, ``ndarray (nDep,)`` (reference ``:140-164``)."""
+    uvw = _single_point(self, uvw)
+    if self.nInd == 0:
+        return np.array(self.coefs)
+    out = _launch_single(self, uvw, values=True)
+    return out["values"][:, 0].cpu().numpy().astype(_result_dtype(self), copy=False)
+
+
+def derivative(self, with_respect_to, uvw):
+    """Mixed partial at one point, ``ndarray (nDep,)`` (reference ``:109-133``)."""
+    uvw = _single_point(self, uvw)
+    if self.nInd == 0:
+        return np.array(self.coefs)
+    wrt = [int(with_respect_to[i]) for i in range(self.nInd)]
+    out = _launch_single(self, uvw, values=False, wrt=wrt)
+    return out["derivative"][:, 0].cpu().numpy().astype(_result_dtype(self), copy=False)
+
+
+def jacobian(self, uvw):
+    """``(nDep, nInd)`` matrix of first partials at one point (reference ``:205-213``); one fused
+    launch instead of nInd derivative calls."""
+    uvw = _single_point(self, uvw)
+    if self.nInd == 0:
+        return np.empty((self.nDep, 0), np.asarray(self.coefs).dtype)
+    out = _launch_single(self, uvw, values=False, jacobian=True)
+    return out["jacobian"][:, :, 0].cpu().numpy().astype(np.asarray(self.coefs).dtype, copy=False)
+
+
+def _normal_request(self, indices):
+    if abs(self.nInd - self.nDep) != 1:
+        raise ValueError("The number of independent variables must be one different than the number of dependent variables.")
+    D = max(self.nInd, self.nDep)
+    if indices is None:
+        return None, 0
+    idx = [int(i) for i in indices]
+    if any(i < 0 or i >= D for i in idx):
+        raise IndexError(f"normal index out of range for a normal of length {D}")
+    if len(set(idx)) != len(idx):
+        raise NotImplementedError("duplicate normal indices are not supported by the CUDA path")
+    mask = 0
+    for i in idx:
+        mask |= 1 << i
+    return idx, mask
+
+
+def normal(self, uvw, normalize=True, indices=None):
+    """Cofactor normal at one point (reference ``:215-246``): ``ndarray (max(nInd,nDep),)`` or
+    ``(len(indices),)``; the norm is taken over the selected components."""
+    uvw = np.atleast_1d(uvw)
+    idx, mask = _normal_request(self, indices)
+    uvw = _single_point(self, uvw)
+    out = _launch_single(self, uvw, values=False, normal=True, normalize=bool(normalize), normal_mask=mask)
+    n = out["normal"][:, 0].cpu().numpy()
+    if idx is not None:
+        n = n[idx]
+    dt = np.asarray(self.coefs).dtype if hasattr(self, "coefs") else getattr(self, "coefsDtype", np.float64)
+    return n.astype(dt if np.issubdtype(dt, np.floating) else np.float64, copy=False)
+
+
+# ----------------------------------------------------------------------------- vectorised entries
+
+def _classify(points):
+    if isinstance(points, torch.Tensor):
+        return "cuda" if points.is_cuda else "cpu_tensor"
+    return "numpy"
+
+
+def _raise_outside(self, flag_value, fetch_point):
+    if flag_value >= 0:
+        raise ValueError(f"Spline evaluation outside domain: {fetch_point(int(flag_value))}")
+
+
+def evaluate_points(self, uvw, *, with_respect_to=None, values=True, jacobian=False, normal=False, normalize=True,
+                    indices=None, spans=False, layout="points", check_domain=True, device=None) -> EvalResult:
+    """Evaluate the spline at N points in one go (the vectorised entry point the reference lacks).
+
+    uvw : (N, nInd) array-like, numpy array, CPU tensor or CUDA tensor of float64
+          (``layout="variables"``: (nInd, N); for curves a flat (N,) is accepted).
+    with_respect_to : optional derivative multi-index -> ``derivative`` (nDep, N)
+    values / jacobian / normal / spans : which outputs to produce (one fused pass over the window)
+    normalize, indices : as in ``Spline.normal``
+    check_domain : raise ``ValueError("Spline evaluation outside domain: ...")`` like the reference
+          when any point is outside the closed domain (costs one device->host flag read)
+
+    Returns an ``EvalResult`` of struct-of-arrays outputs of the same kind as ``uvw``."""
+    kind = _classify(uvw)
+    idx, mask = (None, 0)
+    if normal:
+        idx, mask = _normal_request(self, indices)
+    wrt = None if with_respect_to is None else [int(with_respect_to[i]) for i in range(self.nInd)]
+    if layout not in ("points", "variables"):
+        raise ValueError("layout must be 'points' or 'variables'")
+    request = dict(wrt=wrt, values=bool(values), jacobian=bool(jacobian), normal=bool(normal), normalize=bool(normalize),
+                   normal_mask=mask, spans=bool(spans))
+
+    if kind == "cuda":
+        pts = uvw if uvw.dtype == torch.float64 else uvw.to(torch.float64)
+        if pts.dim() == 1 and self.nInd == 1:
+            pts = pts.reshape(-1, 1) if layout == "points" else pts.reshape(1, -1)
+        if pts.dim() != 2 or pts.shape[1 if layout == "points" else 0] != self.nInd:
+            raise ValueError(f"Incorrect number of parameter values: {pts.shape}")
+        N = pts.shape[0] if layout == "points" else pts.shape[1]
+        ps, vs = (pts.stride(0), pts.stride(1)) if layout == "points" else (pts.stride(1), pts.stride(0))
+        ds = device_spline(self, pts.device)
+        flag = _cuda.new_flag(pts.device) if check_domain else None
+        out = _cuda.eval_points(ds, pts, ps, vs, N, flag=flag, **request)
+        if check_domain:
+            _raise_outside(self, int(flag.item()),
+                           lambda p: (pts[p] if layout == "points" else pts[:, p]).cpu().numpy())
+        nrm = out["normal"]
+        if nrm is not None and idx is not None:
+            nrm = nrm[idx]
+        return EvalResult(out["values"], out["derivative"], out["jacobian"], nrm, out["spans"])
+
+    # ---- host input: chunked H2D -> kernel -> D2H pipeline over a ring of streams ----
+    if kind == "numpy":
+        arr = np.asarray(uvw, dtype=np.float64)
+        host = torch.from_numpy(np.ascontiguousarray(arr))
+    else:
+        host = uvw.to(torch.float64).contiguous()
+    if host.dim() == 1 and self.nInd == 1:
+        host = host.reshape(-1, 1) if layout == "points" else host.reshape(1, -1)
+    if host.dim() != 2 or host.shape[1 if layout == "points" else 0] != self.nInd:
+        raise ValueError(f"Incorrect number of parameter values: {tuple(host.shape)}")
+    N = host.shape[0] if layout == "points" else host.shape[1]
+    ds = device_spline(self, device)
+    dev = ds.device
+    D = ds.normal_dim
+    pin = True
+
+    def host_out(shape, dtype=torch.float64):
+        return torch.empty(shape, dtype=dtype, pin_memory=pin)
+
+    res = {
+        "values": host_out((self.nDep, N)) if values else None,
+        "derivative": host_out((self.nDep, N)) if wrt is not None else None,
+        "jacobian": host_out((self.nDep, self.nInd, N)) if jacobian else None,
+        "normal": host_out((D, N)) if normal else None,
+        "spans": host_out((self.nInd, N), torch.int32) if spans else None,
+    }
+    flag = _cuda.new_flag(dev) if check_domain else None
+    streams = [torch.cuda.Stream(dev) for _ in range(min(_N_STREAMS, max(1, (N + HOST_CHUNK - 1) // HOST_CHUNK)))]
+    ready = torch.cuda.Event()
+    ready.record(torch.cuda.current_stream(dev))
+    for c, start in enumerate(range(0, max(N, 1), HOST_CHUNK)):
+        n = min(HOST_CHUNK, N - start)
+        if n <= 0:
+            break
+        st = streams[c % len(streams)]
+        st.wait_event(ready)
+        with torch.cuda.stream(st):
+            if layout == "points":
+                d_pts = host[start:start + n].to(dev, non_blocking=True)
+                ps, vs = self.nInd, 1
+            else:
+                d_pts = torch.empty((self.nInd, n), dtype=torch.float64, device=dev)
+                for i in range(self.nInd):
+                    d_pts[i].copy_(host[i, start:start + n], non_blocking=True)
+                ps, vs = 1, n
+            out = _cuda.eval_points(ds, d_pts, ps, vs, n, flag=flag, **request)
+            for key, full in res.items():
+                if full is None:
+                    continue
+                part = out[key]
+                dst = full.reshape(-1, N)
+                src = part.reshape(-1, n)
+                for r in range(dst.shape[0]):
+                    dst[r, start:start + n].copy_(src[r], non_blocking=True)
+    for st in streams:
+        st.synchronize()
+    if check_domain and N > 0:
+        off = int(flag.item())
+        if off >= 0:
+            # chunks report chunk-local indices; find the first offender on the host side of the API
+            box = domain(self)
+            pts_np = host.numpy() if layout == "points" else host.numpy().T
+            bad = np.zeros(N, bool)
+            for i in range(self.nInd):
+                bad |= (pts_np[:, i] < box[i, 0]) | (pts_np[:, i] > box[i, 1])
+            first = int(np.flatnonzero(bad)[0]) if bad.any() else off
+            raise ValueError(f"Spline evaluation outside domain: {pts_np[first]}")
+    if res["normal"] is not None and idx is not None:
+        res["normal"] = res["normal"][idx]
+    if kind == "numpy":
+        res = {k: (None if v is None else v.numpy()) for k, v in res.items()}
+    return EvalResult(res["values"], res["derivative"], res["jacobian"], res["normal"], res["spans"])
+
+
+def evaluate_grid(self, *axes, values=True, jacobian=False, normal=False, normalize=True, indices=None,
+                  check_domain=True, device=None) -> EvalResult:
+    """Evaluate on the tensor grid ``axes[0] x axes[1] x ...`` (one 1-D axis per independent
+    variable).  Outputs have the grid shape in place of N, last variable fastest: values
+    ``(nDep, n_0, .., n_last)``, jacobian ``(nDep, nInd, n_0, ..)``, normal ``(D, n_0, ..)`` -- the same
+    numbers as ``spline(*np.meshgrid(*axes, indexing="ij"))`` in the reference.  Surfaces run on the
+    FP64 tensor pipe."""
+    if len(axes) == 1 and self.nInd != 1 and not np.isscalar(axes[0]) and len(axes[0]) == self.nInd \
+            and not isinstance(axes[0], (np.ndarray, torch.Tensor)):
+        axes = tuple(axes[0])
+    if len(axes) != self.nInd:
+        raise ValueError(f"Incorrect number of parameter values: {len(axes)}")
+    kinds = {_classify(a) for a in axes}
+    on_device = kinds == {"cuda"}
+    idx, mask = (None, 0)
+    if normal:
+        idx, mask = _normal_request(self, indices)
+    dev = axes[0].device if on_device else _cuda.device(device)
+    ds = device_spline(self, dev)
+    d_axes = []
+    for a in axes:
+        if isinstance(a, torch.Tensor):
+            d_axes.append(a.to(device=dev, dtype=torch.float64).contiguous().reshape(-1))
+        else:
+            d_axes.append(torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64).reshape(-1)).to(dev))
+    flag = _cuda.new_flag(dev) if check_domain else None
+    out = _cuda.eval_grid(ds, d_axes, values=bool(values), jacobian=bool(jacobian), normal=bool(normal),
+                          normalize=bool(normalize), normal_mask=mask, flag=flag)
+    if check_domain:
+        off = int(flag.item())
+        if off >= 0:
+            shape = [int(a.numel()) for a in d_axes]
+            multi = np.unravel_index(off, shape)
+            raise ValueError(f"Spline evaluation outside domain: {np.array([float(d_axes[i][multi[i]]) for i in range(self.nInd)])}")
+    nrm = out["normal"]
+    if nrm is not None and idx is not None:
+        nrm = nrm[idx]
+    res = EvalResult(out["values"], None, out["jacobian"], nrm, None)
+    if not on_device:
+        conv = (lambda t: None if t is None else t.cpu().numpy()) if kinds <= {"numpy"} else \
+               (lambda t: None if t is None else t.cpu())
+        res = EvalResult(conv(res.values), None, conv(res.jacobian), conv(res.normal), None)
+    return res

@@ -1,0 +1,174 @@
+"""``SplineBatch``: many splines of one shape packed for the device.
+
+The reference evaluates a list of splines with a Python loop (``[s(u) for s in splines]``, or the
+viewer's per-patch loop in ``examples/teapot.py:350-359``); here the list is one packed tensor per
+attribute -- ``knots[i]``: ``(S, order[i]+nCoef[i])`` (or 1-D when all splines share the knots),
+``coefs``: ``(S, nDep, *nCoef)`` -- and one launch evaluates all of them:
+
+* curves (``nInd == 1``): ``evaluate(u)`` with ``u`` of shape ``(S, nPts)`` -> ``(S, nDep, nPts)``
+  (``bspy_cuda_eval_many``: one warp per curve, knots/coefficients staged in shared memory);
+* surfaces (``nInd == 2``): ``evaluate_grid(uAxis, vAxis)`` -> ``(S, nDep, nU, nV)`` (+ jacobian,
+  normal) on the FP64 tensor pipe (``bspy_cuda_eval_grid_batch``).
+
+``shard(rank, world)`` gives the contiguous slice of splines a rank owns: batches are sharded across
+GPUs by splitting the spline index range, no collective on the data path.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from bspy_b200 import _cuda
+from bspy_b200._spline_evaluation import EvalResult, _normal_request
+from bspy_b200.sharding import shard_range
+
+
+def _to_device(x, dev):
+    if isinstance(x, torch.Tensor):
+        return x.to(device=dev, dtype=torch.float64).contiguous()
+    return torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64)).to(dev)
+
+
+class SplineBatch:
+    def __init__(self, nInd, nDep, order, nCoef, knots, coefs, metadata=None, device=None):
+        self.nInd, self.nDep = int(nInd), int(nDep)
+        self.order = tuple(int(o) for o in order)
+        self.nCoef = tuple(int(n) for n in nCoef)
+        if len(self.order) != self.nInd or len(self.nCoef) != self.nInd or len(knots) != self.nInd:
+            raise ValueError("order, nCoef and knots must have nInd entries")
+        dev = coefs.device if isinstance(coefs, torch.Tensor) and coefs.is_cuda else _cuda.device(device)
+        self.device = dev
+        self.coefs = _to_device(coefs, dev)
+        if self.coefs.dim() != 2 + self.nInd or tuple(self.coefs.shape[1:]) != (self.nDep, *self.nCoef):
+            raise ValueError(f"coefs must have shape (S, nDep, *nCoef) = (S, {self.nDep}, {self.nCoef})")
+        self.nSplines = int(self.coefs.shape[0])
+        self.knots = []
+        for i, k in enumerate(knots):
+            k = _to_device(k, dev)
+            want = self.order[i] + self.nCoef[i]
+            if k.dim() == 1 and k.shape[0] == want:
+                pass                                    # shared by all splines
+            elif k.dim() == 2 and tuple(k.shape) == (self.nSplines, want):
+                pass
+            else:
+                raise ValueError(f"Knots array for variable {i} should have length {want}")
+            self.knots.append(k)
+        self.metadata = dict(metadata or {})
+
+    # ---- construction helpers --------------------------------------------------------------
+    @classmethod
+    def from_splines(cls, splines, device=None):
+        """Pack a list of ``Spline`` objects of identical nInd / nDep / order / nCoef."""
+        first = splines[0]
+        for s in splines:
+            if (s.nInd, s.nDep, s.order, s.nCoef) != (first.nInd, first.nDep, first.order, first.nCoef):
+                raise ValueError("all splines of a batch must share nInd, nDep, order and nCoef")
+        coefs = np.stack([np.ascontiguousarray(s.coefs, dtype=np.float64) for s in splines])
+        knots = []
+        for i in range(first.nInd):
+            kk = np.stack([np.asarray(s.knots[i], dtype=np.float64) for s in splines])
+            knots.append(kk[0] if np.all(kk == kk[0]) else kk)
+        negate = {bool(s.metadata.get("negateNormal", False)) for s in splines}
+        if len(negate) > 1:
+            raise ValueError("all splines of a batch must agree on metadata['negateNormal']")
+        return cls(first.nInd, first.nDep, first.order, first.nCoef, knots, coefs,
+                   {"negateNormal": True} if negate == {True} else {}, device)
+
+    def __len__(self):
+        return self.nSplines
+
+    def spline(self, i):
+        """Host-side ``Spline`` copy of element ``i``."""
+        from bspy_b200.spline import Spline
+        knots = [(k if k.dim() == 1 else k[i]).cpu().numpy() for k in self.knots]
+        return Spline(self.nInd, self.nDep, self.order, self.nCoef, knots, self.coefs[i].cpu().numpy(), self.metadata)
+
+    def shard(self, rank, world):
+        """The contiguous slice of splines owned by ``rank`` of ``world`` (views, no copy)."""
+        lo, hi = shard_range(self.nSplines, rank, world)
+        knots = [k if k.dim() == 1 else k[lo:hi] for k in self.knots]
+        return SplineBatch(self.nInd, self.nDep, self.order, self.nCoef, knots, self.coefs[lo:hi], self.metadata)
+
+    def _descriptor(self):
+        first_knots = [k if k.dim() == 1 else k[0] for k in self.knots]
+        sign = -1 if self.metadata.get("negateNormal", False) else 1
+        return _cuda.DeviceSpline(self.nInd, self.nDep, self.order, self.nCoef, first_knots, self.coefs[0], sign)
+
+    # ---- curves ------------------------------------------------------------------------------
+    def evaluate(self, u, derivative=False, check_domain=True, out=None) -> EvalResult:
+        """Curves only: ``u`` is ``(S, nPts)`` (numpy or CUDA tensor); returns values
+        ``(S, nDep, nPts)`` and, with ``derivative=True``, first derivatives of the same shape."""
+        if self.nInd != 1:
+            raise NotImplementedError("SplineBatch.evaluate handles curves (nInd == 1); use evaluate_grid for surfaces")
+        on_device = isinstance(u, torch.Tensor) and u.is_cuda
+        ut = _to_device(u, self.device)
+        if ut.dim() != 2 or ut.shape[0] != self.nSplines:
+            raise ValueError(f"u must have shape (nSplines, nPts) = ({self.nSplines}, nPts)")
+        k = self.knots[0]
+        if k.dim() == 1:
+            k = k.unsqueeze(0).expand(self.nSplines, -1)       # stride 0: every warp stages the same knots
+        flag = _cuda.new_flag(self.device) if check_domain else None
+        coefs = self.coefs.reshape(self.nSplines, self.nDep, self.nCoef[0])
+        res = _cuda.eval_many(self.order[0], self.nCoef[0], self.nDep, _ExpandedKnots(k), coefs, ut, deriv1=derivative,
+                              flag=flag, out=out)
+        if check_domain:
+            off = int(flag.item())
+            if off >= 0:
+                s, p = divmod(off, ut.shape[1])
+                raise ValueError(f"Spline evaluation outside domain: spline {s}, u = {float(ut[s, p])}")
+        vals, der = res["values"], res.get("derivative")
+        if not on_device:
+            vals = vals.cpu().numpy()
+            der = None if der is None else der.cpu().numpy()
+        return EvalResult(values=vals, derivative=der)
+
+    # ---- surfaces ----------------------------------------------------------------------------
+    def evaluate_grid(self, uAxis, vAxis, values=True, jacobian=False, normal=False, normalize=True, indices=None,
+                      check_domain=True, out=None) -> EvalResult:
+        """Surfaces only: every spline of the batch on the grid ``uAxis x vAxis``; outputs
+        ``(S, nDep, nU, nV)``, ``(S, nDep, 2, nU, nV)``, ``(S, D, nU, nV)`` (v fastest)."""
+        if self.nInd != 2:
+            raise NotImplementedError("SplineBatch.evaluate_grid handles surfaces (nInd == 2)")
+        idx, mask = (None, 0)
+        if normal:
+            idx, mask = _normal_request(self, indices)
+        on_device = all(isinstance(a, torch.Tensor) and a.is_cuda for a in (uAxis, vAxis))
+        axes = [_to_device(uAxis, self.device).reshape(-1), _to_device(vAxis, self.device).reshape(-1)]
+        strides = [0 if k.dim() == 1 else int(k.stride(0)) for k in self.knots]
+        flag = _cuda.new_flag(self.device) if check_domain else None
+        res = _cuda.eval_grid_batch(self._descriptor(), self.nSplines, strides, int(self.coefs.stride(0)), axes,
+                                    values=values, jacobian=jacobian, normal=normal, normalize=normalize,
+                                    normal_mask=mask, flag=flag, out=out)
+        if check_domain:
+            off = int(flag.item())
+            if off >= 0:
+                nU, nV = int(axes[0].numel()), int(axes[1].numel())
+                s, rem = divmod(off, nU * nV)
+                a, b = divmod(rem, nV)
+                raise ValueError(f"Spline evaluation outside domain: spline {s}, uv = [{float(axes[0][a])} {float(axes[1][b])}]")
+        nrm = res.get("normal")
+        if nrm is not None and idx is not None:
+            nrm = nrm[:, idx]
+        r = EvalResult(values=res.get("values"), jacobian=res.get("jacobian"), normal=nrm)
+        if not on_device:
+            conv = lambda t: None if t is None else t.cpu().numpy()
+            r = EvalResult(values=conv(r.values), jacobian=conv(r.jacobian), normal=conv(r.normal))
+        return r
+
+
+class _ExpandedKnots:
+    """Adapter so that a stride-0 (shared) knot tensor passes the contiguity check of the binding:
+    the kernel only needs a base pointer and the per-spline stride."""
+
+    def __init__(self, t):
+        self._t = t
+        self.dtype, self.device = t.dtype, t.device
+
+    def is_contiguous(self):
+        return True
+
+    def data_ptr(self):
+        return self._t.data_ptr()
+
+    def stride(self, i):
+        return self._t.stride(i)

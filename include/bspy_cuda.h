@@ -1,0 +1,148 @@
+/* bspy_cuda.h -- C ABI of libbspy_cuda.so: batched float64 B-spline evaluation on sm_100a.
+ *
+ * This is the drop-in boundary for ONE path of ericbrec/BSpy: the evaluation functions of
+ * bspy/_spline_evaluation.py.  The reference has no FFI for that path (it is plain Python
+ * calling numpy); every entry point below names the reference function it replaces so a
+ * maintainer can bind it from a new `bspy/_cuda` module with ctypes.
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes, no C++/torch types.
+ *  - Every function returns int: 0 = ok, negative = BSPY_E_* (bad argument / unsupported),
+ *    positive = cudaError_t of a failed CUDA call.  bspy_cuda_last_error_string() gives text
+ *    for the last non-zero return on the calling thread.
+ *  - All data pointers are DEVICE pointers owned by the caller unless the name ends in
+ *    `_host`.  The library never allocates or frees caller-visible memory, never
+ *    synchronises, and launches everything on the stream passed in (`void*` = cudaStream_t;
+ *    NULL = legacy default stream).
+ *  - `bspy_spline` / `axes` / `nAxis` / `wrt` / `knotStride` arguments are HOST structures (they
+ *    hold device pointers); they are read during the call and need not outlive it.
+ *  - float64 throughout; spans are int32; coefficients are `(nDep, nCoef[0], ..,
+ *    nCoef[nInd-1])` C-contiguous, exactly `Spline.coefs` (bspy/spline.py:70-75) made
+ *    contiguous; knots[i] has order[i] + nCoef[i] entries (bspy/spline.py:57-59).
+ *  - Batched outputs are struct-of-arrays so that consecutive points are consecutive in
+ *    memory: values (nDep, N), deriv (nDep, N), jacobian (nDep, nInd, N),
+ *    normal (max(nInd,nDep), N), spans (nInd, N).  Any output pointer may be NULL (= not
+ *    requested).
+ */
+#ifndef BSPY_CUDA_H
+#define BSPY_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BSPY_MAX_IND 8     /* independent variables supported by the kernels            */
+#define BSPY_MAX_ORDER 32  /* polynomial order per variable supported by the kernels    */
+#define BSPY_ABI_VERSION 1
+
+/* error codes (negative returns) */
+#define BSPY_E_ARG (-1)          /* NULL / negative / inconsistent argument              */
+#define BSPY_E_UNSUPPORTED (-2)  /* nInd > BSPY_MAX_IND, order > BSPY_MAX_ORDER, ...     */
+#define BSPY_E_NORMAL_DIMS (-3)  /* normal requested with |nInd - nDep| != 1 (reference:
+                                    ValueError, bspy/_spline_evaluation.py:219)          */
+
+/* The attributes of `Spline` the evaluation path reads (bspy/spline.py:46-76). */
+typedef struct bspy_spline {
+    int32_t nInd;
+    int32_t nDep;
+    int32_t order[BSPY_MAX_IND];
+    int32_t nCoef[BSPY_MAX_IND];
+    const double *knots[BSPY_MAX_IND]; /* device; knots[i] has order[i] + nCoef[i] entries */
+    const double *coefs;               /* device; (nDep, nCoef[0..nInd-1]) C-contiguous   */
+    int32_t normalSign;                /* -1 iff metadata["negateNormal"], else +1         */
+    int32_t reserved;
+} bspy_spline;
+
+/* what bspy_cuda_eval_* computes */
+#define BSPY_NORMALIZE 1u /* divide the normal by its 2-norm over the selected components */
+
+/* ---- library ------------------------------------------------------------------------- */
+int bspy_cuda_abi_version(void);
+const char *bspy_cuda_last_error_string(void);
+/* number of kernels launched by this library in this process so far (bench.py reports it) */
+int64_t bspy_cuda_launch_count(void);
+
+/* ---- knot spans: replaces the search in bspline_values
+ *      (bspy/_spline_evaluation.py:7-8: np.searchsorted(knots, u, 'right') clamped to
+ *      [order, len(knots)-order]).  Bit-exact.  NaN selects the last span like numpy.    */
+int bspy_cuda_spans(const double *knots, int32_t nKnots, int32_t order, const double *u, int64_t N,
+                    int32_t *spans, void *stream);
+
+/* ---- basis values: replaces bspline_values (bspy/_spline_evaluation.py:4-27; facade
+ *      Spline.bspline_values, bspy/spline.py:207-252) for N parameters at once.
+ *      spansIn == NULL searches (the reference's `knot is None`); spansOut may be NULL.
+ *      basis is (N, order) row-major: row p is the array the reference returns for u[p].
+ *      Arithmetic is IEEE with separate multiply/add and true divisions, in the reference's
+ *      order: the result is bit-identical to the reference.  derivOrder >= order gives zeros. */
+int bspy_cuda_basis(const double *knots, int32_t nKnots, int32_t order, const double *u,
+                    const int32_t *spansIn, int64_t N, int32_t derivOrder, int32_t taylorCoefs,
+                    int32_t *spansOut, double *basis, void *stream);
+
+/* ---- scattered points: replaces evaluate / derivative / jacobian / normal
+ *      (bspy/_spline_evaluation.py:140-164, 109-133, 205-213, 215-246) for N points.
+ *      Point p has parameter i at uvw[p*pointStride + i*varStride] (elements): (N,nInd)
+ *      row-major is (nInd,1); (nInd,N) is (1,N).
+ *      values  : spline value                               (nDep, N)      or NULL
+ *      wrt/deriv: mixed partial of order wrt[i] in variable i (nDep, N)    or both NULL
+ *                 (wrt is a HOST array of nInd ints)
+ *      jacobian: first partials, [d][i][p]                  (nDep, nInd, N) or NULL
+ *      normal  : sign * (-1)^i * det(J without row i)       (max(nInd,nDep), N) or NULL;
+ *                with BSPY_NORMALIZE divided by the norm over the components in normalMask
+ *                (bit i = component i; 0 = all), as `indices` does in the reference
+ *      spans   : rightmost-knot index per variable          (nInd, N) int32 or NULL
+ *      firstOutside: device int64, must hold -1 (or any negative) on entry; receives the
+ *                smallest point index with a parameter outside the closed domain
+ *                [knots[o-1], knots[nCoef]] (reference raises ValueError there,
+ *                bspy/_spline_evaluation.py:149-152; NaN is inside).  May be NULL.        */
+int bspy_cuda_eval_points(const bspy_spline *spline, const double *uvw, int64_t pointStride,
+                          int64_t varStride, int64_t N, const int32_t *wrt, uint32_t flags,
+                          uint32_t normalMask, double *values, double *deriv, double *jacobian,
+                          double *normal, int32_t *spans, int64_t *firstOutside, void *stream);
+
+/* ---- regular grid: the tensor product of one parameter axis per variable; axis i has
+ *      nAxis[i] device doubles.  Outputs as above with N = prod(nAxis) laid out C-order with
+ *      the LAST variable fastest: values (nDep, nAxis[0], .., nAxis[nInd-1]) etc.  This is
+ *      `spline(*np.meshgrid(*axes, indexing="ij"))` in the reference's ufunc style
+ *      (bspy/spline.py:940-947), plus jacobian / normal which the reference can only do one
+ *      point at a time.  Surfaces (nInd == 2) run the B_u * C * B_v^T contraction on the
+ *      FP64 tensor pipe.                                                                  */
+int bspy_cuda_eval_grid(const bspy_spline *spline, const double *const *axes, const int64_t *nAxis,
+                        uint32_t flags, uint32_t normalMask, double *values, double *jacobian,
+                        double *normal, int64_t *firstOutside, void *stream);
+
+/* ---- the same for a batch of nSplines surfaces of identical shape (nInd == 2, nDep <= 4,
+ *      orders <= 8) on ONE shared pair of axes, in one launch: element s uses
+ *      first->knots[i] + s*knotStride[i] (0 = shared knots) and first->coefs + s*coefStride.
+ *      Outputs gain a leading batch dimension: values (S, nDep, nU, nV), jacobian
+ *      (S, nDep, 2, nU, nV), normal (S, D, nU, nV).  This is the bulk container for a list of
+ *      patches such as examples/teapot.py's 32 bicubic patches.                            */
+int bspy_cuda_eval_grid_batch(const bspy_spline *first, int64_t nSplines, const int64_t *knotStride,
+                              int64_t coefStride, const double *const *axes, const int64_t *nAxis,
+                              uint32_t flags, uint32_t normalMask, double *values, double *jacobian,
+                              double *normal, int64_t *firstOutside, void *stream);
+
+/* ---- many independent curves/splines of identical shape (nInd == 1): spline s has knots
+ *      knots[s*knotStride ..][order+nCoef], coefficients coefs[s*coefStride ..] as
+ *      (nDep, nCoef), and nPts parameters u[s*nPts ..].  values is (nSplines, nDep, nPts),
+ *      deriv1 (first derivative, same shape) may be NULL.  firstOutside receives the
+ *      smallest flat index s*nPts + p outside its curve's domain.                         */
+int bspy_cuda_eval_many(int32_t order, int32_t nCoef, int32_t nDep, int64_t nSplines,
+                        const double *knots, int64_t knotStride, const double *coefs, int64_t coefStride,
+                        const double *u, int32_t nPts, double *values, double *deriv1,
+                        int64_t *firstOutside, void *stream);
+
+/* ---- measurement helpers used by bench.py (not part of the evaluation path) --------------
+ *      bspy_cuda_probe_fp64: runs `iters` dependent-free FP64 FMA (kind 0) or DMMA m8n8k4
+ *      (kind 1) chains on every SM and returns the flop count; time it with events on `stream`.
+ *      bspy_cuda_probe_hbm: kind 0 = copy src->dst (bytes read + bytes written),
+ *      kind 1 = write-only fill of dst; returns bytes moved.                               */
+int bspy_cuda_probe_fp64(int32_t kind, int32_t iters, double *sink, double *flopsOut_host, void *stream);
+int bspy_cuda_probe_hbm(int32_t kind, const double *src, double *dst, int64_t nDoubles,
+                        double *bytesOut_host, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BSPY_CUDA_H */

@@ -273,6 +273,8 @@ def main():
     scalar = Spline(1, 1, (3,), (5,), [np.array([0, 0, 0, .3, .6, 1, 1, 1.])], np.array([[1., 2, 0, -1, 3]]))
     disp["scalar_ufunc"] = np.array(scalar(uu), float)           # nDep == 1: 1-D array
     disp["scalar_point"] = np.array(scalar(0.5), float)
+    disp["uu2d"] = np.linspace(0, 1, 12).reshape(3, 4)
+    disp["scalar_ufunc_2d"] = np.array(scalar(disp["uu2d"]), float)   # the reference's row-iteration quirk
     disp["scalar_knots"] = np.asarray(scalar.knots[0], float)
     disp["scalar_coefs"] = np.asarray(scalar.coefs, float)
     disp["uu"] = uu

@@ -1,0 +1,354 @@
+"""Parity tests proper: the CUDA path (through the C ABI) against the goldens generated from the
+unmodified reference and against the oracle.  Spans and basis values bit-exact; values, derivatives,
+jacobians and normals within |x - ref| <= 1e-13 + 1e-12 |ref| (+ the condition term for the
+reference's ill-conditioned fixtures, see oracle/bspy_oracle.py)."""
+import numpy as np
+import pytest
+import torch
+
+from golden_io import close, close_cond, load_cases, load_npz, well_conditioned_subset
+
+pytestmark = pytest.mark.gpu
+
+CASES = load_cases()
+EPS = np.finfo(float).eps
+
+
+def _mods():
+    import bspy_b200
+    from bspy_b200 import _cuda
+    from oracle import bspy_oracle as O
+    from oracle import c_oracle as CO
+    return bspy_b200, _cuda, O, CO
+
+
+def _spline(c):
+    import bspy_b200
+    return bspy_b200.Spline(c.nInd, c.nDep, c.order, c.nCoef, c.knots, c.coefs, c.metadata)
+
+
+def _ospline(c):
+    from oracle import bspy_oracle as O
+    return O.OracleSpline(c.nInd, c.nDep, c.order, c.nCoef, c.knots, c.coefs, c.metadata)
+
+
+def test_library_loaded_and_counts_launches():
+    _, _cuda, _, _ = _mods()
+    before = _cuda.launch_count()
+    k = torch.tensor([0, 0, 0, 0.5, 1, 1, 1.0], dtype=torch.float64, device="cuda")
+    u = torch.tensor([0.1, 0.5, 1.0], dtype=torch.float64, device="cuda")
+    assert _cuda.spans(k, 3, u).tolist() == [3, 4, 4]
+    assert _cuda.launch_count() == before + 1
+
+
+@pytest.mark.parametrize("c", CASES, ids=lambda c: c.tag)
+def test_spans_and_basis_bit_exact(c):
+    bspy, _cuda, _, _ = _mods()
+    for i in range(c.nInd):
+        k = torch.from_numpy(c.knots[i]).cuda()
+        u = torch.from_numpy(np.ascontiguousarray(c.uvw[:, i])).cuda()
+        assert np.array_equal(_cuda.spans(k, c.order[i], u).cpu().numpy(), c["spans"][:, i])
+        for d in range(c.order[i] + 2):
+            for taylor in (False, True):
+                key = f"basis{i}_d{d}{'t' if taylor else ''}"
+                if not c.has(key):
+                    continue
+                sp, B = _cuda.basis(k, c.order[i], u, d, taylor)
+                assert np.array_equal(sp.cpu().numpy(), c["spans"][:, i])
+                assert np.array_equal(B.cpu().numpy(), c[key], equal_nan=True), (c.tag, key)
+        # given spans are used and returned unchanged (reference: `knot` argument)
+        sp_in = torch.from_numpy(c["spans"][:, i].copy()).cuda()
+        sp, B = _cuda.basis(k, c.order[i], u, 1, False, sp_in)
+        assert np.array_equal(B.cpu().numpy(), c[f"basis{i}_d1"], equal_nan=True)
+    # the single-parameter facade
+    ix, b = bspy.Spline.bspline_values(None, c.knots[0], c.order[0], c.uvw[5, 0], 1)
+    assert ix == c["spans"][5, 0] and np.array_equal(b, c["basis0_d1"][5], equal_nan=True)
+    ix, b = bspy.Spline.bspline_values(int(c["spans"][7, 0]), c.knots[0], c.order[0], c.uvw[7, 0])
+    assert ix == c["spans"][7, 0] and np.array_equal(b, c["basis0_d0"][7], equal_nan=True)
+
+
+@pytest.mark.parametrize("c", CASES, ids=lambda c: c.tag)
+def test_points_vs_reference(c):
+    _, _, O, _ = _mods()
+    s, so = _spline(c), _ospline(c)
+    r = s.evaluate_points(c.uvw, values=True, jacobian=True, spans=True)
+    assert np.array_equal(r.spans.T, c["spans"])
+    S0 = O.derivative_abs_vec(so, [0] * c.nInd, c.uvw)
+    assert close_cond(r.values.T, c["values"], S0), c.tag
+    SJ = O.jacobian_abs_vec(so, c.uvw)
+    assert close_cond(np.transpose(r.jacobian, (2, 0, 1)), c["jacobian"], SJ), c.tag
+    for w in c.meta["wrt"]:
+        ref = c["deriv_" + "_".join(map(str, w))]
+        got = s.evaluate_points(c.uvw, values=False, with_respect_to=w).derivative.T
+        assert close_cond(got, ref, O.derivative_abs_vec(so, w, c.uvw)), (c.tag, w)
+        if w[0] >= c.order[0]:
+            assert not got.any()
+    # values-only pass (different kernel instantiation) and CUDA-tensor input, (nInd, N) layout
+    pts = torch.from_numpy(np.ascontiguousarray(c.uvw.T)).cuda()
+    r2 = s.evaluate_points(pts, layout="variables")
+    assert isinstance(r2.values, torch.Tensor) and r2.values.is_cuda
+    assert close_cond(r2.values.cpu().numpy().T, c["values"], S0)
+
+
+@pytest.mark.parametrize("c", [c for c in CASES if c.meta["normal"]], ids=lambda c: c.tag)
+def test_normals_vs_reference(c):
+    _, _, O, _ = _mods()
+    s, so = _spline(c), _ospline(c)
+    Sn = O.normal_abs_vec(so, c.uvw)
+    with np.errstate(all="ignore"):
+        Su = (Sn.max(axis=1) / np.sqrt((c["normal_raw"] ** 2).sum(axis=1)))[:, None]
+    raw = s.evaluate_points(c.uvw, values=False, normal=True, normalize=False).normal.T
+    assert close_cond(raw, c["normal_raw"], Sn, k=64), c.tag
+    unit = s.evaluate_points(c.uvw, values=False, normal=True).normal.T
+    assert close_cond(unit, c["normal_unit"], Su, k=64), c.tag
+    idx = c.meta["normal_indices"]
+    ok = well_conditioned_subset(c["normal_raw"], idx)
+    sub = s.evaluate_points(c.uvw, values=False, normal=True, indices=idx).normal.T
+    with np.errstate(all="ignore"):
+        Si = (Sn[:, idx].max(axis=1) / np.sqrt((c["normal_idx_raw"] ** 2).sum(axis=1)))[:, None]
+    assert sub.shape == c["normal_idx_unit"].shape
+    assert close_cond(sub[ok], c["normal_idx_unit"][ok], Si[ok], k=64), c.tag
+    subraw = s.evaluate_points(c.uvw, values=False, normal=True, normalize=False, indices=idx).normal.T
+    assert close_cond(subraw, c["normal_idx_raw"], Sn[:, idx], k=64)
+    # negate_normal() flips the sign exactly
+    flipped = s.negate_normal().evaluate_points(c.uvw, values=False, normal=True, normalize=False).normal.T
+    assert np.array_equal(flipped, -raw, equal_nan=True)
+
+
+def test_reference_golden_tables():
+    """truthCurve / truthSurface of the reference's tests (bspy_test.py:743-757)."""
+    bspy, _, _, _ = _mods()
+    t = load_npz("ref_tables.npz")
+    curve = bspy.Spline(1, 2, t["curve/order"], (5,), [t["curve/knots0"]], t["curve/coefs"])
+    tab = t["curve/table"]
+    got = curve.evaluate_points(tab[:, 0]).values.T
+    assert np.sqrt(((got - tab[:, 1:]) ** 2).sum(axis=1)).max() <= 4 * EPS
+    for u, x, y in tab[::10]:
+        assert np.hypot(*(curve.evaluate([u]) - (x, y))) <= 4 * EPS
+    surf = bspy.Spline(2, 3, t["surface/order"], (4, 5), [t["surface/knots0"], t["surface/knots1"]], t["surface/coefs"])
+    g = np.linspace(0, 1, 21)
+    uv = np.array([(u, v) for v in g for u in g])
+    got = surf.evaluate_points(uv).values.T
+    assert np.sqrt(((got - t["surface/table"]) ** 2).sum(axis=1)).max() <= 4 * EPS
+    grid = surf.evaluate_grid(g, g).values           # (3, nU, nV)
+    assert np.sqrt(((grid.transpose(2, 1, 0).reshape(-1, 3) - t["surface/table"]) ** 2).sum(axis=1)).max() <= 4 * EPS
+    # derivative of order >= spline order is exactly zero (bspy_test.py:759-761)
+    assert not curve.derivative([4], [0.5]).any()
+
+
+@pytest.mark.parametrize("c", [CASES[3], CASES[13], CASES[17], CASES[20], CASES[21]], ids=lambda c: c.tag)
+def test_single_point_api(c):
+    s = _spline(c)
+    for p in range(0, c.uvw.shape[0], 11):
+        uvw = c.uvw[p]
+        v = s(uvw) if c.nInd > 1 else s(uvw[0])
+        assert v.shape == (c.nDep,) and close(v, c["values"][p])
+        assert close(s.evaluate(list(uvw)), c["values"][p])
+        J = s.jacobian(uvw)
+        assert J.shape == (c.nDep, c.nInd) and close(J, c["jacobian"][p])
+        assert close(s.tangent_space(uvw), c["jacobian"][p])
+        w = c.meta["wrt"][0]
+        assert close(s.derivative(w, uvw), c["deriv_" + "_".join(map(str, w))][p])
+        if c.meta["normal"]:
+            assert close(s.normal(uvw), c["normal_unit"][p])
+            assert close(s.normal(uvw, False), c["normal_raw"][p], atol=1e-13 * max(1, np.abs(c["normal_raw"][p]).max()))
+            idx = c.meta["normal_indices"]
+            n = s.normal(uvw, True, idx)
+            assert n.shape == (len(idx),)
+            if well_conditioned_subset(c["normal_raw"][p:p + 1], idx)[0]:
+                assert close(n, c["normal_idx_unit"][p])
+
+
+def test_dispatch_forms():
+    """Argument forms of Spline.evaluate / derivative (bspy/spline.py:757-770, 936-949)."""
+    bspy, _, _, _ = _mods()
+    t, d = load_npz("ref_tables.npz"), load_npz("ref_dispatch.npz")
+    curve = bspy.Spline(1, 2, t["curve/order"], (5,), [t["curve/knots0"]], t["curve/coefs"])
+    surf = bspy.Spline(2, 3, t["surface/order"], (4, 5), [t["surface/knots0"], t["surface/knots1"]], t["surface/coefs"])
+    r = curve(d["uu"])
+    assert isinstance(r, tuple) and len(r) == 2 and r[0].shape == d["uu"].shape
+    assert close(np.array(r), d["curve_ufunc"])
+    assert close(np.array(curve.derivative([1], d["uu"])), d["curve_deriv_ufunc"])
+    r = surf(d["U"], d["V"])
+    assert isinstance(r, tuple) and len(r) == 3 and r[0].shape == d["U"].shape
+    assert close(np.array(r), d["surf_ufunc"])
+    assert close(np.array(surf.derivative([1, 1], d["U"], d["V"])), d["surf_deriv_ufunc"])
+    assert close(surf([0.25, 0.5]), d["surf_point_list"]) and close(surf(0.25, 0.5), d["surf_point_scalars"])
+    scalar = bspy.Spline(1, 1, (3,), (5,), [d["scalar_knots"]], d["scalar_coefs"])
+    r = scalar(d["uu"])
+    assert isinstance(r, np.ndarray) and r.shape == d["scalar_ufunc"].shape and close(r, d["scalar_ufunc"])
+    assert close(scalar(0.5), d["scalar_point"])
+    if "scalar_ufunc_2d" in d:
+        r = scalar(d["uu2d"])
+        assert r.shape == d["scalar_ufunc_2d"].shape and close(r, d["scalar_ufunc_2d"])
+
+
+def test_errors_match_reference():
+    bspy, _, _, _ = _mods()
+    c = CASES[13]
+    s = _spline(c)
+    with pytest.raises(ValueError, match="Spline evaluation outside domain"):
+        s([0.5, 1.5])
+    with pytest.raises(ValueError, match="Incorrect number of parameter values"):
+        s([0.5, 0.5, 0.5])
+    pts = c.uvw.copy()
+    pts[17, 1] = 2.0
+    with pytest.raises(ValueError, match="Spline evaluation outside domain"):
+        s.evaluate_points(pts)
+    with pytest.raises(ValueError, match="Spline evaluation outside domain"):
+        s.evaluate_points(torch.from_numpy(pts).cuda())
+    with pytest.raises(ValueError, match="Spline evaluation outside domain"):
+        s.evaluate_grid(np.linspace(0, 1, 5), np.linspace(0, 1.1, 5))
+    r = s.evaluate_points(pts, check_domain=False)       # no check requested: extrapolates silently
+    assert np.isfinite(r.values).all()
+    space_curve = bspy.Spline(1, 3, (3,), (4,), [[0, 0, 0, .5, 1, 1, 1]], np.arange(12.0).reshape(3, 4))
+    with pytest.raises(ValueError, match="must be one different"):
+        space_curve.normal([0.5])
+    with pytest.raises(ValueError, match="must be one different"):
+        space_curve.evaluate_points(np.array([[0.5]]), normal=True)
+    # NaN parameter: inside the domain for the reference's comparisons, NaN result, last span
+    r = s.evaluate_points(np.array([[np.nan, 0.5]]), spans=True)
+    assert np.isnan(r.values).all() and r.spans[0, 0] == c.nCoef[0]
+
+
+def test_teapot_grid_and_batch():
+    bspy, _, _, _ = _mods()
+    t = load_npz("teapot.npz")
+    g = t["grid"]
+    kn = t["knots"]
+    splines = [bspy.Spline(2, 3, (4, 4), (4, 4), (kn, kn), t["coefs"][p]) for p in range(32)]
+    for p in (0, 5, 19, 20, 28, 31):     # 19/20/28+ include the degenerate lid / bottom patches
+        r = splines[p].evaluate_grid(g, g, jacobian=True, normal=True)
+        assert close(r.values, t["values"][p]) and close(r.jacobian[:, 0], t["du"][p]) and close(r.jacobian[:, 1], t["dv"][p])
+        assert close(r.normal, t["normal"][p]), p     # NaN unit normals at collapsed control rows must match
+    batch = bspy.SplineBatch.from_splines(splines)
+    r = batch.evaluate_grid(g, g, jacobian=True, normal=True)
+    assert r.values.shape == (32, 3, 9, 9)
+    assert close(r.values, t["values"]) and close(r.jacobian[:, :, 0], t["du"]) and close(r.jacobian[:, :, 1], t["dv"])
+    assert close(r.normal, t["normal"])
+    assert int(np.isnan(t["normal"]).any(axis=1).sum()) == int(np.isnan(r.normal).any(axis=1).sum()) == 56
+
+
+@pytest.mark.parametrize("c", [c for c in CASES if c.nInd in (2, 3)], ids=lambda c: c.tag)
+def test_grid_vs_oracle(c):
+    """Tensor-grid entry against the oracle on ragged (non-multiple-of-tile) axes that include every
+    knot, both ends and their 1-ulp neighbours."""
+    _, _, O, _ = _mods()
+    s, so = _spline(c), _ospline(c)
+    rng = np.random.default_rng(7)
+    axes = []
+    for i in range(c.nInd):
+        a = np.unique(c.uvw[:, i])
+        a = a[~np.isnan(a)]
+        n = {0: 37, 1: 301 if c.nInd == 2 else 13, 2: 11}[i]
+        axes.append(np.sort(rng.choice(a, size=min(n, a.size), replace=False)))
+    mesh = np.meshgrid(*axes, indexing="ij")
+    uvw = np.stack([m.reshape(-1) for m in mesh], axis=1)
+    want_normal = abs(c.nInd - c.nDep) == 1
+    r = s.evaluate_grid(*axes, jacobian=True, normal=want_normal, normalize=False)
+    shape = tuple(len(a) for a in axes)
+    assert r.values.shape == (c.nDep, *shape) and r.jacobian.shape == (c.nDep, c.nInd, *shape)
+    assert close_cond(r.values.reshape(c.nDep, -1).T, O.evaluate_vec(so, uvw), O.derivative_abs_vec(so, [0] * c.nInd, uvw))
+    assert close_cond(np.transpose(r.jacobian.reshape(c.nDep, c.nInd, -1), (2, 0, 1)), O.jacobian_vec(so, uvw),
+                      O.jacobian_abs_vec(so, uvw))
+    if want_normal:
+        assert close_cond(r.normal.reshape(max(c.nInd, c.nDep), -1).T, O.normal_vec(so, uvw, False),
+                          O.normal_abs_vec(so, uvw), k=64)
+
+
+def test_many_curves_vs_oracle():
+    bspy, _, O, _ = _mods()
+    rng = np.random.default_rng(1003)
+    for order, nCoef, nDep, S, nPts in ((4, 32, 3, 257, 256), (3, 9, 2, 40, 77), (6, 11, 1, 9, 33), (2, 5, 3, 5, 1)):
+        knots = np.empty((S, order + nCoef))
+        for s in range(S):
+            w = rng.uniform(0.25, 1.75, nCoef - order + 1)
+            inner = np.concatenate(([0.0], np.cumsum(w))); inner /= inner[-1]
+            knots[s] = np.concatenate((np.zeros(order - 1), inner, np.ones(order - 1)))
+        coefs = rng.standard_normal((S, nDep, nCoef))
+        u = rng.uniform(0, 1, (S, nPts))
+        u[0, 0], u[-1, -1] = 0.0, 1.0
+        if nPts > 4:
+            u[1, :3] = knots[1, order:order + 3]
+        batch = bspy.SplineBatch(1, nDep, (order,), (nCoef,), [knots], coefs)
+        r = batch.evaluate(u, derivative=True)
+        assert r.values.shape == (S, nDep, nPts)
+        for s in range(0, S, max(1, S // 9)):
+            so = O.OracleSpline(1, nDep, (order,), (nCoef,), [knots[s]], coefs[s])
+            assert close(r.values[s].T, O.evaluate_vec(so, u[s][:, None]))
+            assert close_cond(r.derivative[s].T, O.derivative_vec(so, [1], u[s][:, None]),
+                              O.derivative_abs_vec(so, [1], u[s][:, None]))
+        with pytest.raises(ValueError, match="outside domain"):
+            u2 = u.copy(); u2[S // 2, 0] = -0.5
+            batch.evaluate(u2)
+    # shared knots (1-D) broadcast to every curve
+    shared = bspy.SplineBatch(1, 3, (4,), (32,), [np.concatenate((np.zeros(3), np.linspace(0, 1, 30), np.ones(3)))],
+                              rng.standard_normal((6, 3, 32)))
+    uu = rng.uniform(0, 1, (6, 50))
+    r = shared.evaluate(uu)
+    so = O.OracleSpline(1, 3, (4,), (32,), [shared.knots[0].cpu().numpy()], shared.coefs[4].cpu().numpy())
+    assert close(r.values[4].T, O.evaluate_vec(so, uu[4][:, None]))
+
+
+def test_large_sample_vs_c_oracle_and_properties():
+    """Config-4-shaped spline at a size the C oracle finishes in seconds, plus size-independent
+    properties at a larger size: partition of unity, linearity in the coefficients, jacobian of an
+    affine map."""
+    bspy, _, _, CO = _mods()
+    CO.build()
+    rng = np.random.default_rng(1004)
+
+    def K(o, n):
+        w = rng.uniform(0.25, 1.75, n - o + 1)
+        inner = np.concatenate(([0.0], np.cumsum(w))); inner /= inner[-1]
+        return np.concatenate((np.zeros(o - 1), inner, np.ones(o - 1)))
+
+    kn = [K(4, 32) for _ in range(3)]
+    c1, c2 = rng.standard_normal((2, 3, 32, 32, 32))
+    s1 = bspy.Spline(3, 3, (4, 4, 4), (32, 32, 32), kn, c1)
+    N = 200_000
+    uvw = rng.uniform(0, 1, (N, 3))
+    r = s1.evaluate_points(uvw, jacobian=True, spans=True)
+    ref = CO.evaluate(s1, uvw, jacobian=True, spans=True)
+    assert np.array_equal(r.spans.T, ref["spans"])
+    assert close(r.values.T, ref["values"])
+    assert close(np.transpose(r.jacobian, (2, 0, 1)), ref["jacobian"], atol=1e-12)   # entries up to ~1e3: 1e-12 rel dominates
+    # properties on the device at 4M points
+    M = 4_000_000
+    g = torch.Generator(device="cuda").manual_seed(5)
+    pts = torch.rand((M, 3), dtype=torch.float64, device="cuda", generator=g)
+    ones = bspy.Spline(3, 1, (4, 4, 4), (32, 32, 32), kn, np.ones((1, 32, 32, 32)))
+    one = ones.evaluate_points(pts, jacobian=True)
+    assert float((one.values - 1).abs().max()) <= 8 * EPS and float(one.jacobian.abs().max()) <= 1e-11
+    s2 = bspy.Spline(3, 3, (4, 4, 4), (32, 32, 32), kn, c2)
+    s12 = bspy.Spline(3, 3, (4, 4, 4), (32, 32, 32), kn, 2.0 * c1 - 0.5 * c2)
+    a, b, ab = (s.evaluate_points(pts).values for s in (s1, s2, s12))
+    assert float((ab - (2.0 * a - 0.5 * b)).abs().max()) <= 1e-13 * 40
+
+
+def test_strided_input_and_zero_points():
+    bspy, _, _, _ = _mods()
+    c = CASES[17]
+    s = _spline(c)
+    wide = torch.zeros((c.uvw.shape[0], 7), dtype=torch.float64, device="cuda")
+    wide[:, 1:6:2] = torch.from_numpy(c.uvw).cuda()
+    view = wide[:, 1:6:2]                       # (N, 3) with strides (7, 2)
+    assert close(s.evaluate_points(view).values.cpu().numpy().T, c["values"])
+    r = s.evaluate_points(np.empty((0, c.nInd)))
+    assert r.values.shape == (c.nDep, 0)
+
+
+def test_mutation_is_seen_and_freeze_is_not():
+    bspy, _, _, _ = _mods()
+    c = CASES[3]
+    s = _spline(c)
+    u = c.uvw[:9]
+    before = s.evaluate_points(u).values.copy()
+    s.coefs[0, 2] += 1.0
+    after = s.evaluate_points(u).values
+    assert not np.array_equal(before, after)
+    s.freeze()
+    s.coefs[0, 2] -= 1.0
+    assert np.array_equal(s.evaluate_points(u).values, after)     # frozen handle: device copy reused
+    s.unfreeze()
+    assert np.array_equal(s.evaluate_points(u).values, before)
