@@ -297,3 +297,125 @@ def probe_hbm(kind, src, dst):
         rc = library().bspy_cuda_probe_hbm(int(kind), _ptr(src), _ptr(dst), dst.numel(), C.byref(nbytes), _stream(dev))
     _check(rc, "bspy_cuda_probe_hbm")
     return nbytes.value
+
+
+# ------------------------------------------------------------------ host-buffer pipelines
+# Inputs / outputs in HOST memory: consecutive chunks go to a small ring of streams so that the
+# H2D copy of chunk i+1, the kernel of chunk i and the D2H copy of chunk i-1 overlap (PCIe is full
+# duplex).  Results land in pinned host tensors (torch's caching host allocator recycles them).
+
+HOST_CHUNK = 1 << 22      # points per chunk
+_RING = 3
+
+
+def eval_points_host(ds: DeviceSpline, host, layout, *, check=True, chunk=None, **request):
+    """``host``: CPU float64 tensor, (N, nInd) for layout "points" or (nInd, N) for "variables".
+    Returns (dict of pinned CPU tensors in SoA layout, index of the first out-of-domain point or -1)."""
+    dev = ds.device
+    chunk = int(chunk or HOST_CHUNK)
+    N = host.shape[0] if layout == "points" else host.shape[1]
+    D = ds.normal_dim
+
+    def pinned(shape, dtype=torch.float64):
+        return torch.empty(shape, dtype=dtype, pin_memory=True)
+
+    res = {
+        "values": pinned((ds.nDep, N)) if request.get("values") else None,
+        "derivative": pinned((ds.nDep, N)) if request.get("wrt") is not None else None,
+        "jacobian": pinned((ds.nDep, ds.nInd, N)) if request.get("jacobian") else None,
+        "normal": pinned((D, N)) if request.get("normal") else None,
+        "spans": pinned((ds.nInd, N), torch.int32) if request.get("spans") else None,
+    }
+    starts = list(range(0, N, chunk))
+    flags = torch.full((max(len(starts), 1),), -1, dtype=torch.int64, device=dev) if check else None
+    streams = [torch.cuda.Stream(dev) for _ in range(min(_RING, max(1, len(starts))))]
+    ready = torch.cuda.Event()
+    ready.record(torch.cuda.current_stream(dev))
+    for c, start in enumerate(starts):
+        n = min(chunk, N - start)
+        st = streams[c % len(streams)]
+        st.wait_event(ready)
+        with torch.cuda.stream(st):
+            if layout == "points":
+                d_pts = host[start:start + n].to(dev, non_blocking=True)
+                ps, vs = ds.nInd, 1
+            else:
+                d_pts = torch.empty((ds.nInd, n), dtype=torch.float64, device=dev)
+                for i in range(ds.nInd):
+                    d_pts[i].copy_(host[i, start:start + n], non_blocking=True)
+                ps, vs = 1, n
+            out = eval_points(ds, d_pts, ps, vs, n, flag=None if flags is None else flags[c:c + 1], **request)
+            for key, full in res.items():
+                if full is None:
+                    continue
+                dst, src = full.reshape(-1, N), out[key].reshape(-1, n)
+                for r in range(dst.shape[0]):
+                    dst[r, start:start + n].copy_(src[r], non_blocking=True)
+    for st in streams:
+        st.synchronize()
+    first = -1
+    if check and starts:
+        f = flags.cpu()
+        for c, start in enumerate(starts):
+            if int(f[c]) >= 0:
+                first = start + int(f[c])
+                break
+    return res, first
+
+
+def eval_grid_batch_host(ds: DeviceSpline, n_splines, knot_strides, coef_stride, axes, *, group=None, check=True, **request):
+    """Batch-of-surfaces grid evaluation with HOST outputs: groups of splines are evaluated into
+    device buffers on alternating streams while the previous group's results stream back into pinned
+    host tensors.  ``ds`` describes element 0; coefficient / knot pointers advance by the strides."""
+    dev = ds.device
+    S = int(n_splines)
+    nU, nV = (int(a.numel()) for a in axes)
+    D = ds.normal_dim
+    per_spline = nU * nV * 8 * (ds.nDep * (1 if request.get("values", True) else 0) +
+                                ds.nDep * 2 * (1 if request.get("jacobian") else 0) + D * (1 if request.get("normal") else 0))
+    if group is None:
+        group = max(1, min(S, int((1 << 30) // max(per_spline, 1))))      # ~1 GiB of results per group
+
+    def pinned(shape):
+        return torch.empty(shape, dtype=torch.float64, pin_memory=True)
+
+    res = {
+        "values": pinned((S, ds.nDep, nU, nV)) if request.get("values", True) else None,
+        "jacobian": pinned((S, ds.nDep, 2, nU, nV)) if request.get("jacobian") else None,
+        "normal": pinned((S, D, nU, nV)) if request.get("normal") else None,
+    }
+    starts = list(range(0, S, group))
+    flags = torch.full((max(len(starts), 1),), -1, dtype=torch.int64, device=dev) if check else None
+    streams = [torch.cuda.Stream(dev) for _ in range(min(2, max(1, len(starts))))]
+    ready = torch.cuda.Event()
+    ready.record(torch.cuda.current_stream(dev))
+    base_k = [int(ds.c.knots[i]) for i in range(2)]
+    base_c = int(ds.c.coefs)
+    sub = CSpline()
+    C.memmove(C.byref(sub), C.byref(ds.c), C.sizeof(CSpline))
+    view = DeviceSpline.__new__(DeviceSpline)
+    view.__dict__.update(ds.__dict__)
+    view.c = sub
+    for g, start in enumerate(starts):
+        n = min(group, S - start)
+        st = streams[g % len(streams)]
+        st.wait_event(ready)
+        with torch.cuda.stream(st):
+            for i in range(2):
+                sub.knots[i] = base_k[i] + 8 * int(knot_strides[i]) * start
+            sub.coefs = base_c + 8 * int(coef_stride) * start
+            out = eval_grid_batch(view, n, knot_strides, coef_stride, axes, flag=None if flags is None else flags[g:g + 1],
+                                  **request)
+            for key, full in res.items():
+                if full is not None:
+                    full[start:start + n].copy_(out[key], non_blocking=True)
+    for st in streams:
+        st.synchronize()
+    first = -1
+    if check and starts:
+        f = flags.cpu()
+        for g, start in enumerate(starts):
+            if int(f[g]) >= 0:
+                first = start * nU * nV + int(f[g])
+                break
+    return res, first

@@ -20,11 +20,6 @@ from bspy_b200 import _cuda
 __all__ = ["EvalResult", "bspline_values", "bspline_values_batch", "domain", "evaluate", "derivative", "jacobian",
            "normal", "evaluate_points", "evaluate_grid", "device_spline", "freeze"]
 
-# points per chunk when the input lives in host memory (H2D / kernel / D2H of consecutive
-# chunks overlap on a small ring of streams)
-HOST_CHUNK = 1 << 22
-_N_STREAMS = 3
-
 
 @dataclass
 class EvalResult:
@@ -280,73 +275,19 @@ def evaluate_points(self, uvw, *, with_respect_to=None, values=True, jacobian=Fa
             nrm = nrm[idx]
         return EvalResult(out["values"], out["derivative"], out["jacobian"], nrm, out["spans"])
 
-    # ---- host input: chunked H2D -> kernel -> D2H pipeline over a ring of streams ----
+    # ---- host input: chunked H2D -> kernel -> D2H pipeline (bspy_b200._cuda.eval_points_host) ----
     if kind == "numpy":
-        arr = np.asarray(uvw, dtype=np.float64)
-        host = torch.from_numpy(np.ascontiguousarray(arr))
+        host = torch.from_numpy(np.ascontiguousarray(np.asarray(uvw, dtype=np.float64)))
     else:
         host = uvw.to(torch.float64).contiguous()
     if host.dim() == 1 and self.nInd == 1:
         host = host.reshape(-1, 1) if layout == "points" else host.reshape(1, -1)
     if host.dim() != 2 or host.shape[1 if layout == "points" else 0] != self.nInd:
         raise ValueError(f"Incorrect number of parameter values: {tuple(host.shape)}")
-    N = host.shape[0] if layout == "points" else host.shape[1]
     ds = device_spline(self, device)
-    dev = ds.device
-    D = ds.normal_dim
-    pin = True
-
-    def host_out(shape, dtype=torch.float64):
-        return torch.empty(shape, dtype=dtype, pin_memory=pin)
-
-    res = {
-        "values": host_out((self.nDep, N)) if values else None,
-        "derivative": host_out((self.nDep, N)) if wrt is not None else None,
-        "jacobian": host_out((self.nDep, self.nInd, N)) if jacobian else None,
-        "normal": host_out((D, N)) if normal else None,
-        "spans": host_out((self.nInd, N), torch.int32) if spans else None,
-    }
-    flag = _cuda.new_flag(dev) if check_domain else None
-    streams = [torch.cuda.Stream(dev) for _ in range(min(_N_STREAMS, max(1, (N + HOST_CHUNK - 1) // HOST_CHUNK)))]
-    ready = torch.cuda.Event()
-    ready.record(torch.cuda.current_stream(dev))
-    for c, start in enumerate(range(0, max(N, 1), HOST_CHUNK)):
-        n = min(HOST_CHUNK, N - start)
-        if n <= 0:
-            break
-        st = streams[c % len(streams)]
-        st.wait_event(ready)
-        with torch.cuda.stream(st):
-            if layout == "points":
-                d_pts = host[start:start + n].to(dev, non_blocking=True)
-                ps, vs = self.nInd, 1
-            else:
-                d_pts = torch.empty((self.nInd, n), dtype=torch.float64, device=dev)
-                for i in range(self.nInd):
-                    d_pts[i].copy_(host[i, start:start + n], non_blocking=True)
-                ps, vs = 1, n
-            out = _cuda.eval_points(ds, d_pts, ps, vs, n, flag=flag, **request)
-            for key, full in res.items():
-                if full is None:
-                    continue
-                part = out[key]
-                dst = full.reshape(-1, N)
-                src = part.reshape(-1, n)
-                for r in range(dst.shape[0]):
-                    dst[r, start:start + n].copy_(src[r], non_blocking=True)
-    for st in streams:
-        st.synchronize()
-    if check_domain and N > 0:
-        off = int(flag.item())
-        if off >= 0:
-            # chunks report chunk-local indices; find the first offender on the host side of the API
-            box = domain(self)
-            pts_np = host.numpy() if layout == "points" else host.numpy().T
-            bad = np.zeros(N, bool)
-            for i in range(self.nInd):
-                bad |= (pts_np[:, i] < box[i, 0]) | (pts_np[:, i] > box[i, 1])
-            first = int(np.flatnonzero(bad)[0]) if bad.any() else off
-            raise ValueError(f"Spline evaluation outside domain: {pts_np[first]}")
+    res, first = _cuda.eval_points_host(ds, host, layout, check=check_domain, **request)
+    if first >= 0:
+        raise ValueError(f"Spline evaluation outside domain: {(host[first] if layout == 'points' else host[:, first]).numpy()}")
     if res["normal"] is not None and idx is not None:
         res["normal"] = res["normal"][idx]
     if kind == "numpy":

@@ -135,23 +135,26 @@ class SplineBatch:
         on_device = all(isinstance(a, torch.Tensor) and a.is_cuda for a in (uAxis, vAxis))
         axes = [_to_device(uAxis, self.device).reshape(-1), _to_device(vAxis, self.device).reshape(-1)]
         strides = [0 if k.dim() == 1 else int(k.stride(0)) for k in self.knots]
-        flag = _cuda.new_flag(self.device) if check_domain else None
-        res = _cuda.eval_grid_batch(self._descriptor(), self.nSplines, strides, int(self.coefs.stride(0)), axes,
-                                    values=values, jacobian=jacobian, normal=normal, normalize=normalize,
-                                    normal_mask=mask, flag=flag, out=out)
-        if check_domain:
-            off = int(flag.item())
-            if off >= 0:
-                nU, nV = int(axes[0].numel()), int(axes[1].numel())
-                s, rem = divmod(off, nU * nV)
-                a, b = divmod(rem, nV)
-                raise ValueError(f"Spline evaluation outside domain: spline {s}, uv = [{float(axes[0][a])} {float(axes[1][b])}]")
+        request = dict(values=values, jacobian=jacobian, normal=normal, normalize=normalize, normal_mask=mask)
+        if on_device or out is not None:
+            flag = _cuda.new_flag(self.device) if check_domain else None
+            res = _cuda.eval_grid_batch(self._descriptor(), self.nSplines, strides, int(self.coefs.stride(0)), axes,
+                                        flag=flag, out=out, **request)
+            off = int(flag.item()) if check_domain else -1
+        else:
+            res, off = _cuda.eval_grid_batch_host(self._descriptor(), self.nSplines, strides, int(self.coefs.stride(0)),
+                                                  axes, check=check_domain, **request)
+        if off >= 0:
+            nU, nV = int(axes[0].numel()), int(axes[1].numel())
+            s, rem = divmod(off, nU * nV)
+            a, b = divmod(rem, nV)
+            raise ValueError(f"Spline evaluation outside domain: spline {s}, uv = [{float(axes[0][a])} {float(axes[1][b])}]")
         nrm = res.get("normal")
         if nrm is not None and idx is not None:
             nrm = nrm[:, idx]
         r = EvalResult(values=res.get("values"), jacobian=res.get("jacobian"), normal=nrm)
         if not on_device:
-            conv = lambda t: None if t is None else t.cpu().numpy()
+            conv = lambda t: None if t is None else (t.numpy() if not t.is_cuda else t.cpu().numpy())
             r = EvalResult(values=conv(r.values), jacobian=conv(r.jacobian), normal=conv(r.normal))
         return r
 

@@ -1,0 +1,102 @@
+"""Oracle-backed stand-in for the bspy_b200._cuda entry points, so that the HOST logic of the
+package (argument-form dispatch, shapes, dtypes, error messages, caching, sharding) can be tested
+on a machine without a GPU.  Test infrastructure only: it is monkeypatched over the binding by
+tests/test_host_logic.py; the product never imports it and has no CPU path of its own."""
+import numpy as np
+import torch
+
+from oracle import bspy_oracle as O
+
+CPU = torch.device("cpu")
+launches = [0]
+
+
+def device(index=None):
+    return CPU
+
+
+def new_flag(dev):
+    return torch.full((1,), -1, dtype=torch.int64)
+
+
+def launch_count():
+    return launches[0]
+
+
+def _ospline(ds):
+    return O.OracleSpline(ds.nInd, ds.nDep, ds.order, ds.nCoef, [k.numpy() for k in ds.knots], ds.coefs.numpy(),
+                          {"negateNormal": ds.normal_sign < 0})
+
+
+def _mask_indices(mask, D):
+    return [i for i in range(D) if (mask >> i) & 1] if mask else list(range(D))
+
+
+def _evaluate(ds, pts, *, wrt=None, values=True, jacobian=False, normal=False, normalize=True, normal_mask=0, spans=False,
+              flag=None):
+    launches[0] += 1
+    s = _ospline(ds)
+    N = pts.shape[0]
+    out = {"values": None, "derivative": None, "jacobian": None, "normal": None, "spans": None}
+    with np.errstate(all="ignore"):
+        if values:
+            out["values"] = torch.from_numpy(np.ascontiguousarray(O.evaluate_vec(s, pts).T.reshape(ds.nDep, N)))
+        if wrt is not None:
+            out["derivative"] = torch.from_numpy(np.ascontiguousarray(O.derivative_vec(s, wrt, pts).T.reshape(ds.nDep, N)))
+        if jacobian:
+            out["jacobian"] = torch.from_numpy(np.ascontiguousarray(np.transpose(O.jacobian_vec(s, pts), (1, 2, 0))))
+        if normal:
+            D = max(ds.nInd, ds.nDep)
+            raw = O.normal_vec(s, pts, False)
+            if normalize:
+                sel = _mask_indices(normal_mask, D)
+                raw = raw / np.sqrt((raw[:, sel] ** 2).sum(axis=1))[:, None]
+            out["normal"] = torch.from_numpy(np.ascontiguousarray(raw.T))
+        if spans:
+            sp = np.stack([O.span_vec(s.knots[i], s.order[i], pts[:, i]) for i in range(ds.nInd)]) if ds.nInd else np.empty((0, N), np.int32)
+            out["spans"] = torch.from_numpy(sp.astype(np.int32))
+    if flag is not None:
+        bad = O.check_domain_vec(s, pts)
+        if bad >= 0 and (int(flag[0]) < 0 or bad < int(flag[0])):
+            flag[0] = bad
+    return out
+
+
+def eval_points(ds, uvw, point_stride, var_stride, N, **request):
+    pts = torch.as_strided(uvw, (N, ds.nInd), (point_stride, var_stride)).numpy().astype(np.float64)
+    return _evaluate(ds, pts, **request)
+
+
+def eval_points_host(ds, host, layout, *, check=True, chunk=None, **request):
+    pts = host.numpy() if layout == "points" else host.numpy().T
+    flag = new_flag(CPU) if check else None
+    out = _evaluate(ds, np.ascontiguousarray(pts), flag=flag, **request)
+    return out, (int(flag[0]) if check else -1)
+
+
+def eval_grid(ds, axes, *, values=True, jacobian=False, normal=False, normalize=True, normal_mask=0, flag=None):
+    shape = tuple(int(a.numel()) for a in axes)
+    mesh = np.meshgrid(*[a.numpy() for a in axes], indexing="ij") if axes else []
+    pts = np.stack([m.reshape(-1) for m in mesh], axis=1) if axes else np.empty((1, 0))
+    r = _evaluate(ds, pts, values=values, jacobian=jacobian, normal=normal, normalize=normalize, normal_mask=normal_mask, flag=flag)
+    return {"values": None if r["values"] is None else r["values"].reshape(ds.nDep, *shape),
+            "jacobian": None if r["jacobian"] is None else r["jacobian"].reshape(ds.nDep, ds.nInd, *shape),
+            "normal": None if r["normal"] is None else r["normal"].reshape(-1, *shape)}
+
+
+def spans(knots, order, u):
+    launches[0] += 1
+    return torch.from_numpy(O.span_vec(knots.numpy(), order, u.numpy()))
+
+
+def basis(knots, order, u, deriv=0, taylor=False, spans_in=None):
+    launches[0] += 1
+    ix, b = O.basis_vec(knots.numpy(), order, u.numpy(), deriv, taylor, None if spans_in is None else spans_in.numpy())
+    return torch.from_numpy(ix), torch.from_numpy(b)
+
+
+def install(monkeypatch):
+    from bspy_b200 import _cuda
+    for name in ("device", "new_flag", "launch_count", "eval_points", "eval_points_host", "eval_grid", "spans", "basis"):
+        monkeypatch.setattr(_cuda, name, globals()[name])
+    launches[0] = 0

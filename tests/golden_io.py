@@ -90,3 +90,15 @@ def well_conditioned_subset(normal_raw, idx, floor=1e-6):
     part = np.sqrt((normal_raw[:, list(idx)] ** 2).sum(axis=1))
     with np.errstate(all="ignore"):
         return (part >= floor * full) | (full == 0.0) | np.isnan(full)
+
+
+def nondegenerate_normal(normal_raw, scale, floor=1e-9):
+    """Rows where the raw normal is more than rounding noise next to the terms it is summed from
+    (|n| > floor * max sum|terms|).  At singular points of a surface -- the collapsed control rows
+    of the Utah teapot's lid and bottom patches -- the raw normal is an exact or inexact zero
+    depending on how the terms happen to cancel, so the reference's unit normal there is either
+    NaN (0/0) or an arbitrary unit vector; that is not a parity question.  Elsewhere NaNs must match."""
+    normal_raw = np.asarray(normal_raw)
+    with np.errstate(all="ignore"):
+        n = np.sqrt((normal_raw ** 2).sum(axis=-1))
+        return n > floor * np.asarray(scale).max(axis=-1)
