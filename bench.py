@@ -84,7 +84,7 @@ def _spline_payload(s):
 
 class Cfg2Teapot(Workload):
     name = "cfg2: 32 bicubic Utah-teapot patches, value+du+dv+unit normal on a 2048x2048 grid per patch"
-    kernel = "grid2_dmma_kernel<3>"
+    kernel = "grid2_dmma_kernel<3,4>"
     bytes_per_point = 96.0
     flops_per_point = 92.0
     bound = "hbm"
@@ -119,7 +119,7 @@ class Cfg2Teapot(Workload):
         r = batch.evaluate_grid(self.axis_host, self.axis_host, jacobian=True, normal=True)
         h2d = self.coefs_host.nbytes + self.kn.nbytes * 2 + self.axis_host.nbytes * 2
         d2h = r.values.nbytes + r.jacobian.nbytes + r.normal.nbytes
-        self.last = r
+        del r                     # the pinned result buffers go back to torch's host allocator for the next step
         return h2d, d2h
 
     def reference_task(self, n):
@@ -164,7 +164,7 @@ class ScatteredBase(Workload):
             self.host_pts.copy_(self.pts)
         r = self.spline.evaluate_points(self.host_pts, values=True, jacobian=self.jac)
         d2h = r.values.numel() * 8 + (r.jacobian.numel() * 8 if r.jacobian is not None else 0)
-        self.last = r
+        del r
         return self.host_pts.numel() * 8, d2h
 
     def reference_task(self, n):
@@ -487,6 +487,27 @@ def run_ours(args):
                             "peak_tflops_probe": fp64_peak, "flops_per_point": wl.flops_per_point}
     except Exception as exc:  # pragma: no cover
         roofline["fp64"] = {"error": str(exc)}
+
+    # live HBM probes on this device: copy (read+write bytes) and write-only fill of 2 GiB
+    try:
+        nd = 1 << 28
+        src = torch.empty(nd, dtype=torch.float64, device=dev)
+        dst = torch.empty(nd, dtype=torch.float64, device=dev)
+        probes = {}
+        for kind, label in ((0, "copy_gbs"), (1, "write_only_gbs")):
+            best = 0.0
+            for _ in range(4):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                nbytes = _cuda.probe_hbm(kind, src, dst)
+                b.record()
+                torch.cuda.synchronize()
+                best = max(best, nbytes / (a.elapsed_time(b) * 1e-3) / 1e9)
+            probes[label] = best
+        roofline["hbm_probe"] = probes
+        del src, dst
+    except Exception as exc:  # pragma: no cover
+        roofline["hbm_probe"] = {"error": str(exc)}
 
     cpu = None
     if world == 1 or rank == 0:

@@ -28,6 +28,7 @@ SYMBOLS = (
     "bspy_cuda_abi_version", "bspy_cuda_last_error_string", "bspy_cuda_launch_count",
     "bspy_cuda_spans", "bspy_cuda_basis", "bspy_cuda_eval_points", "bspy_cuda_eval_grid",
     "bspy_cuda_eval_grid_batch", "bspy_cuda_eval_many", "bspy_cuda_probe_fp64", "bspy_cuda_probe_hbm",
+    "bspy_cuda_probe_tiles",
 )
 
 
@@ -80,6 +81,7 @@ def library():
             "bspy_cuda_eval_many": [i32, i32, i32, i64, vp, i64, vp, i64, vp, i32, vp, vp, vp, vp],
             "bspy_cuda_probe_fp64": [i32, i32, vp, C.POINTER(C.c_double), vp],
             "bspy_cuda_probe_hbm": [i32, vp, vp, i64, C.POINTER(C.c_double), vp],
+            "bspy_cuda_probe_tiles": [vp, i32, i64, i64, i32, i32, C.POINTER(C.c_double), vp],
         }
         for name, args in sig.items():
             fn = getattr(lib, name)
@@ -288,6 +290,16 @@ def probe_fp64(kind, iters, dev):
         rc = library().bspy_cuda_probe_fp64(int(kind), int(iters), _ptr(sink), C.byref(flops), _stream(dev))
     _check(rc, "bspy_cuda_probe_fp64")
     return flops.value
+
+
+def probe_tiles(dst, planes, nU, nV, tile_rows, tile_cols):
+    nbytes = C.c_double(0.0)
+    dev = dst.device
+    with torch.cuda.device(dev):
+        rc = library().bspy_cuda_probe_tiles(_ptr(dst), int(planes), int(nU), int(nV), int(tile_rows), int(tile_cols),
+                                             C.byref(nbytes), _stream(dev))
+    _check(rc, "bspy_cuda_probe_tiles")
+    return nbytes.value
 
 
 def probe_hbm(kind, src, dst):

@@ -16,6 +16,8 @@
 //
 // Everything else (nInd != 2, orders above 8, nDep above 4) goes through the scattered kernels in
 // grid mode: parameters are decoded from the flat index, nothing is materialised.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace bspy {
@@ -43,16 +45,18 @@ int eval_common(const bspy_spline *spline, const PointsDev &in, long long N, con
                 uint32_t normalMask, double *values, double *deriv, double *jacobian, double *normal, int32_t *spans,
                 int64_t *firstOutside, void *stream, const char *who);
 
-constexpr int GRID_WARPS = 4;             // warps per CTA, one 8-row strip each
-constexpr int GRID_ROWS = 8 * GRID_WARPS; // rows of a CTA tile
-constexpr int GRID_COLS = 256;            // columns of a CTA tile
-constexpr int GRID_COLS_PAD = GRID_COLS + 8;  // table row stride: == 8 (mod 16) doubles -> 2-wavefront B loads
+constexpr int GRID_WARPS = 8;              // warps per CTA, side by side along the row: 16 columns each per step
+constexpr int GRID_ROWS = 8;               // rows of a work unit (one MMA row strip)
+constexpr int GRID_STEP = 16 * GRID_WARPS; // columns a CTA covers per step: 128 (1 KB contiguous per row and plane)
+constexpr int GRID_TILE_ROWS = 64;         // rows of a CTA tile (8 strips)
+constexpr int GRID_GROUP = 4;              // splines of a batch that share one CTA's axis tables (shared knots only)
 constexpr int GRID_MAX_ORDER = 8;
 
 struct Grid2Params {
     // spline batch: element s uses knots0 + s*knotStride0, knots1 + s*knotStride1, coefs + s*coefStride
     const double *knots0, *knots1, *coefs;
     long long knotStride0, knotStride1, coefStride;
+    long long nSplines;
     int ou, ov, nCu, nCv;      // orders and coefficient counts of the two variables
     long long depStride;       // nCu * nCv
     const double *axisU, *axisV;
@@ -61,8 +65,12 @@ struct Grid2Params {
     long long *firstOutside;
     int normalSign;
     unsigned normalize, normalMask;
-    int vec2;                  // 16-byte stores allowed (nV even and bases 16-byte aligned)
-    int colChunks, rowBlocks;
+    int vec;                   // widest store allowed: 4 (32 B), 2 (16 B) or 1 doubles
+    int chunkCols;             // columns of a CTA's chunk (multiple of GRID_STEP); table row stride = chunkCols + 2
+    int colChunks;             // ceil(nV / chunkCols)
+    int tileRows;              // rows of a CTA tile (multiple of 8, <= GRID_TILE_ROWS)
+    long long rowBlocks;       // ceil(nU / tileRows)
+    int group;                 // splines per CTA
 };
 
 __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b)
@@ -72,27 +80,31 @@ __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double
                  : "d"(a), "d"(b));
 }
 
-// runtime-order recurrence, values and first derivatives, into strided table columns
-__device__ __forceinline__ void axis_basis(const double *__restrict__ knots, int order, int ix, double u,
-                                           double *__restrict__ val, double *__restrict__ der, int stride, int padTo)
+__device__ __forceinline__ void st_cs_v4(double *p, double a, double b, double c, double d)
 {
-    double b0[GRID_MAX_ORDER], b1[GRID_MAX_ORDER];
+    asm volatile("st.global.cs.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+
+// Runtime order <= MAXO: values (b0) and first derivatives (b1) in registers.  Rows are addressed from the
+// top so that every index is a compile-time constant: slot s of the order-long row is b[MAXO - order + s].
+template <int MAXO>
+__device__ __forceinline__ void axis_basis(const double *__restrict__ knots, int order, int ix, double u,
+                                           double (&b0)[MAXO], double (&b1)[MAXO])
+{
 #pragma unroll
-    for (int j = 0; j < GRID_MAX_ORDER; ++j) { b0[j] = 0.0; b1[j] = 0.0; }
-    // slots are addressed from the top so that indices stay compile-time: slot s <-> b[GRID_MAX_ORDER-order+s]
-    // (runtime `order` only shifts which stages execute)
-    b0[GRID_MAX_ORDER - 1] = 1.0;
+    for (int j = 0; j < MAXO; ++j) { b0[j] = 0.0; b1[j] = 0.0; }
+    b0[MAXO - 1] = 1.0;
 #pragma unroll
-    for (int deg = 1; deg < GRID_MAX_ORDER; ++deg) {
+    for (int deg = 1; deg < MAXO; ++deg) {
         if (deg < order) {
             const bool lastStage = deg == order - 1;
             if (lastStage) {
 #pragma unroll
-                for (int j = 0; j < GRID_MAX_ORDER; ++j) b1[j] = b0[j];
+                for (int j = 0; j < MAXO; ++j) b1[j] = b0[j];
             }
 #pragma unroll
             for (int t = 0; t < deg; ++t) {
-                const int slot = GRID_MAX_ORDER - deg + t;
+                const int slot = MAXO - deg + t;
                 const double kl = __ldg(knots + ix - deg + t);
                 const double r = 1.0 / (__ldg(knots + ix + t) - kl);
                 const double a = (u - kl) * r;
@@ -106,218 +118,250 @@ __device__ __forceinline__ void axis_basis(const double *__restrict__ knots, int
             }
         }
     }
-#pragma unroll
-    for (int j = 0; j < GRID_MAX_ORDER; ++j) {
-        const int s = j - (GRID_MAX_ORDER - order);   // slot within the order-long row
-        if (s >= 0) {
-            val[s * stride] = b0[j];
-            der[s * stride] = order > 1 ? b1[j] : 0.0;
-        }
-    }
-    for (int s = order; s < padTo; ++s) { val[s * stride] = 0.0; der[s * stride] = 0.0; }
 }
 
-template <int NDEP>
-__global__ void __launch_bounds__(GRID_WARPS * 32) grid2_dmma_kernel(const Grid2Params P)
+// CTA = (column chunk of chunkCols columns) x (block of GRID_TILE_ROWS rows) x (group of splines that share the
+// axis tables).  The 8 warps work SIDE BY SIDE on one 8-row strip (16 columns each per step, so the CTA writes
+// 1 KB contiguous per row and output plane per step), finish the strip's chunk, then move to the next strip.
+// Measured with a pure store-pattern probe (tools/pattern_probe*.py): HBM sustains the most when the set of
+// rows being written at any moment is small and each row receives long contiguous runs; one warp per strip
+// sweeping along the row (the previous layout) topped out at 5.0 TB/s of the 6.5 TB/s a linear fill reaches.
+template <int NDEP, int MAXO>
+__global__ void __launch_bounds__(GRID_WARPS * 32, 2) grid2_dmma_kernel(const Grid2Params P)
 {
     constexpr int D = NDEP > 2 ? NDEP : 2;
-    const int ksteps = (P.ov + 3) >> 2;
-    const int kpad = ksteps * 4;
-    // shared tables: V-axis basis [kind][j][col], U-axis basis [kind][i][row], spans
+    constexpr int KS = MAXO / 4;
     extern __shared__ double sm[];
-    double *tabV = sm;                                        // 2 * kpad * GRID_COLS_PAD
-    double *tabU = tabV + 2 * kpad * GRID_COLS_PAD;           // 2 * GRID_MAX_ORDER * GRID_ROWS
-    int *spanV = reinterpret_cast<int *>(tabU + 2 * GRID_MAX_ORDER * GRID_ROWS);  // GRID_COLS
-    int *spanU = spanV + GRID_COLS;                           // GRID_ROWS
+    // table row stride == 2 (mod 16) doubles: the B-fragment loads of a warp take the minimum 2 wavefronts
+    const int VS = P.chunkCols + 2;
+    double *tabV = sm;                                          // [kind][j][col]: 2 * MAXO * VS
+    double *tabU = tabV + 2 * MAXO * VS;                        // [kind][i][row]: 2 * MAXO * GRID_TILE_ROWS
+    int *spanV = reinterpret_cast<int *>(tabU + 2 * MAXO * GRID_TILE_ROWS);  // chunkCols
+    int *spanU = spanV + P.chunkCols;                           // GRID_TILE_ROWS
 
     const long long tile = blockIdx.x;
     const int cc = (int)(tile % P.colChunks);
-    const int rb = (int)((tile / P.colChunks) % P.rowBlocks);
-    const long long sIdx = tile / ((long long)P.colChunks * P.rowBlocks);
-    const double *ku = P.knots0 + sIdx * P.knotStride0;
-    const double *kv = P.knots1 + sIdx * P.knotStride1;
-    const double *coefs = P.coefs + sIdx * P.coefStride;
-    const long long row0 = (long long)rb * GRID_ROWS;
-    const long long col0 = (long long)cc * GRID_COLS;
+    const long long rb = (tile / P.colChunks) % P.rowBlocks;
+    const long long s0 = tile / ((long long)P.colChunks * P.rowBlocks) * P.group;
+    const long long s1 = min(s0 + P.group, P.nSplines);
+    const double *ku = P.knots0 + s0 * P.knotStride0;
+    const double *kv = P.knots1 + s0 * P.knotStride1;
+    const long long row0 = rb * P.tileRows;
+    const long long col0 = (long long)cc * P.chunkCols;
     const long long plane = P.nU * P.nV;
 
-    // ---- per-tile axis tables ----
-    for (int c = threadIdx.x; c < GRID_COLS; c += blockDim.x) {
+    // ---- axis tables of this tile (shared by the `group` splines of this CTA: their knots are shared) ----
+    for (int c = threadIdx.x; c < P.chunkCols; c += blockDim.x) {
         const long long b = col0 + c;
         int ix = P.ov;
-        double v = 0.0;
+        double v = __ldg(kv + P.ov - 1);
         if (b < P.nV) {
             v = __ldg(P.axisV + b);
             ix = span_search_inner(kv, P.ov + P.nCv, P.ov, v);
             if ((v < __ldg(kv + P.ov - 1)) | (v > __ldg(kv + P.nCv)))
-                if (P.firstOutside) report_outside((int64_t *)P.firstOutside, sIdx * plane + b);
-        } else {
-            v = __ldg(kv + P.ov - 1);
+                if (P.firstOutside) report_outside((int64_t *)P.firstOutside, s0 * plane + b);
         }
         spanV[c] = ix;
-        axis_basis(kv, P.ov, ix, v, tabV + c, tabV + kpad * GRID_COLS_PAD + c, GRID_COLS_PAD, kpad);
+        double b0[MAXO], b1[MAXO];
+        axis_basis<MAXO>(kv, P.ov, ix, v, b0, b1);
+#pragma unroll
+        for (int j = 0; j < MAXO; ++j) {
+            const int sl = j - (MAXO - P.ov);
+            const int row = sl >= 0 ? sl : P.ov + j;     // slots ov .. MAXO-1 are the zero padding of K
+            tabV[row * VS + c] = sl >= 0 ? b0[j] : 0.0;
+            tabV[(MAXO + row) * VS + c] = sl >= 0 ? b1[j] : 0.0;
+        }
     }
-    for (int r = threadIdx.x; r < GRID_ROWS; r += blockDim.x) {
+    for (int r = threadIdx.x; r < P.tileRows; r += blockDim.x) {
         const long long a = row0 + r;
         int ix = P.ou;
-        double u = 0.0;
+        double u = __ldg(ku + P.ou - 1);
         if (a < P.nU) {
             u = __ldg(P.axisU + a);
             ix = span_search_inner(ku, P.ou + P.nCu, P.ou, u);
-            if ((u < __ldg(ku + P.ou - 1)) | (u > __ldg(ku + P.nCu)))
-                if (P.firstOutside) report_outside((int64_t *)P.firstOutside, sIdx * plane + a * P.nV);
-        } else {
-            u = __ldg(ku + P.ou - 1);
+            if (((u < __ldg(ku + P.ou - 1)) | (u > __ldg(ku + P.nCu))) && cc == 0)
+                if (P.firstOutside) report_outside((int64_t *)P.firstOutside, s0 * plane + a * P.nV);
         }
         spanU[r] = ix;
-        axis_basis(ku, P.ou, ix, u, tabU + r, tabU + GRID_MAX_ORDER * GRID_ROWS + r, GRID_ROWS, P.ou);
+        double b0[MAXO], b1[MAXO];
+        axis_basis<MAXO>(ku, P.ou, ix, u, b0, b1);
+#pragma unroll
+        for (int j = 0; j < MAXO; ++j) {
+            const int sl = j - (MAXO - P.ou);
+            const int row = sl >= 0 ? sl : P.ou + j;
+            tabU[row * GRID_TILE_ROWS + r] = sl >= 0 ? b0[j] : 0.0;
+            tabU[(MAXO + row) * GRID_TILE_ROWS + r] = sl >= 0 ? b1[j] : 0.0;
+        }
     }
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q = lane >> 2;        // row of the A fragment / column of the B fragment
     const int r4 = lane & 3;        // k index of the fragments
-    const int myRow = warp * 8 + q;
-    const long long a = row0 + myRow;
-    const int su = spanU[myRow];
-    // this thread's u-basis row (values and derivatives)
-    double bu[GRID_MAX_ORDER], dbu[GRID_MAX_ORDER];
-#pragma unroll
-    for (int i = 0; i < GRID_MAX_ORDER; ++i) {
-        bu[i] = i < P.ou ? tabU[i * GRID_ROWS + myRow] : 0.0;
-        dbu[i] = i < P.ou ? tabU[(GRID_MAX_ORDER + i) * GRID_ROWS + myRow] : 0.0;
-    }
-    // A fragments for the cached v-span: T[d][kind][ks]
-    double tv[NDEP][2], td[NDEP][2];
-    int cached = -1;
+    // B-fragment column n = q of MMA tile t is grid column c0 + 4*(q>>1) + 2*t + (q&1): the four accumulator
+    // entries a thread ends up with (two per tile) are then the four CONSECUTIVE columns c0 + 4*r4 .. +3, so
+    // every thread stores 32 contiguous bytes and a quad covers a full 128-byte line of the row.
+    const int bcol = 4 * (q >> 1) + (q & 1);
+    const long long nColsHere = min((long long)P.chunkCols, P.nV - col0);
+    const int nStrips = (int)min((long long)(P.tileRows / 8), (P.nU - row0 + 7) / 8);
 
-    const long long nColsHere = min((long long)GRID_COLS, P.nV - col0);
-    for (int c0 = 0; c0 < nColsHere; c0 += 8) {
-        const int myCol = c0 + q;
-        const int sv = spanV[myCol];
-        double acc[NDEP][3][2];
+    for (long long sIdx = s0; sIdx < s1; ++sIdx)
+    for (int strip = 0; strip < nStrips; ++strip) {
+        const double *coefs = P.coefs + sIdx * P.coefStride;
+        const int myRow = strip * 8 + q;
+        const long long a = row0 + myRow;
+        const int su = spanU[myRow];
+        double tv[NDEP][KS], td[NDEP][KS];   // A fragments for the cached v-span
+        int cached = -1;
+
+        for (int c0 = warp * 16; c0 < nColsHere; c0 += GRID_STEP) {
+            const int colA = c0 + bcol, colB = colA + 2;
+            const int svA = spanV[colA], svB = spanV[colB];
+            double acc[NDEP][3][4];
 #pragma unroll
-        for (int d = 0; d < NDEP; ++d)
+            for (int d = 0; d < NDEP; ++d)
 #pragma unroll
-            for (int k = 0; k < 3; ++k) acc[d][k][0] = acc[d][k][1] = 0.0;
-        unsigned todo = 0xffffffffu;
-        while (todo) {
-            const int leader = __ffs(todo) - 1;
-            const int cur = __shfl_sync(0xffffffffu, sv, leader);
-            const bool mine = sv == cur;
-            if (cur != cached) {
-                // T[a][j] = sum_i Bu[a][i] * C[d][su-ou+i][cur-ov+j],  j = r4 + 4 ks
+                for (int k = 0; k < 3; ++k)
 #pragma unroll
-                for (int ks = 0; ks < 2; ++ks) {
+                    for (int e = 0; e < 4; ++e) acc[d][k][e] = 0.0;
+            unsigned todoA = 0xffffffffu, todoB = 0xffffffffu;
+            while (todoA | todoB) {
+                const int cur = todoA ? __shfl_sync(0xffffffffu, svA, __ffs(todoA) - 1)
+                                      : __shfl_sync(0xffffffffu, svB, __ffs(todoB) - 1);
+                const bool mineA = svA == cur, mineB = svB == cur;
+                if (cur != cached) {
+                    // T[a][j] = sum_i Bu[a][i] * C[d][su-ou+i][cur-ov+j],  j = r4 + 4 ks
+#pragma unroll
+                    for (int ks = 0; ks < KS; ++ks) {
+                        const int j = r4 + 4 * ks;
+#pragma unroll
+                        for (int d = 0; d < NDEP; ++d) {
+                            double t0 = 0.0, t1 = 0.0;
+                            if (j < P.ov) {
+                                const double *cp = coefs + d * P.depStride + (long long)(su - P.ou) * P.nCv + (cur - P.ov + j);
+#pragma unroll
+                                for (int i = 0; i < MAXO; ++i)
+                                    if (i < P.ou) {
+                                        const double x = __ldg(cp + (long long)i * P.nCv);
+                                        t0 = fma(x, tabU[i * GRID_TILE_ROWS + myRow], t0);
+                                        t1 = fma(x, tabU[(MAXO + i) * GRID_TILE_ROWS + myRow], t1);
+                                    }
+                            }
+                            tv[d][ks] = t0;
+                            td[d][ks] = t1;
+                        }
+                    }
+                    cached = cur;
+                }
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks) {
                     const int j = r4 + 4 * ks;
+                    const double bvA = mineA ? tabV[j * VS + colA] : 0.0;
+                    const double dvA = mineA ? tabV[(MAXO + j) * VS + colA] : 0.0;
+                    const double bvB = mineB ? tabV[j * VS + colB] : 0.0;
+                    const double dvB = mineB ? tabV[(MAXO + j) * VS + colB] : 0.0;
+                    if (P.values) {
+#pragma unroll
+                        for (int d = 0; d < NDEP; ++d) {
+                            dmma884(acc[d][0][0], acc[d][0][1], tv[d][ks], bvA);
+                            dmma884(acc[d][0][2], acc[d][0][3], tv[d][ks], bvB);
+                        }
+                    }
+                    if (P.jacobian || P.normal) {
+#pragma unroll
+                        for (int d = 0; d < NDEP; ++d) {
+                            dmma884(acc[d][1][0], acc[d][1][1], td[d][ks], bvA);
+                            dmma884(acc[d][1][2], acc[d][1][3], td[d][ks], bvB);
+                            dmma884(acc[d][2][0], acc[d][2][1], tv[d][ks], dvA);
+                            dmma884(acc[d][2][2], acc[d][2][3], tv[d][ks], dvB);
+                        }
+                    }
+                }
+                todoA &= ~__ballot_sync(0xffffffffu, mineA);
+                todoB &= ~__ballot_sync(0xffffffffu, mineB);
+            }
+            // ---- epilogue: this thread owns row `a`, columns col0 + c0 + 4*r4 + {0,1,2,3} ----
+            const long long b = col0 + c0 + 4 * r4;
+            if (a < P.nU && b < P.nV) {
+                const int left = (int)min((long long)4, P.nV - b);
+                const long long at = a * P.nV + b;
+                auto put = [&](double *base, const double (&x)[4]) {
+                    double *p = base + at;
+                    if (P.vec == 4 && left == 4) {
+                        st_cs_v4(p, x[0], x[1], x[2], x[3]);
+                    } else if (P.vec >= 2 && left == 4) {
+                        __stcs(reinterpret_cast<double2 *>(p), make_double2(x[0], x[1]));
+                        __stcs(reinterpret_cast<double2 *>(p + 2), make_double2(x[2], x[3]));
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            if (e < left) __stcs(p + e, x[e]);
+                    }
+                };
+                if (P.values) {
+#pragma unroll
+                    for (int d = 0; d < NDEP; ++d) put(P.values + (sIdx * NDEP + d) * plane, acc[d][0]);
+                }
+                if (P.jacobian) {
 #pragma unroll
                     for (int d = 0; d < NDEP; ++d) {
-                        double s0 = 0.0, s1 = 0.0;
-                        if (ks < ksteps && j < P.ov) {
-                            const double *cp = coefs + d * P.depStride + (long long)(su - P.ou) * P.nCv + (cur - P.ov + j);
-#pragma unroll
-                            for (int i = 0; i < GRID_MAX_ORDER; ++i)
-                                if (i < P.ou) {
-                                    const double x = __ldg(cp + (long long)i * P.nCv);
-                                    s0 = fma(x, bu[i], s0);
-                                    s1 = fma(x, dbu[i], s1);
-                                }
-                        }
-                        tv[d][ks] = s0;
-                        td[d][ks] = s1;
+                        put(P.jacobian + ((sIdx * NDEP + d) * 2 + 0) * plane, acc[d][1]);
+                        put(P.jacobian + ((sIdx * NDEP + d) * 2 + 1) * plane, acc[d][2]);
                     }
                 }
-                cached = cur;
-            }
+                if constexpr (NDEP == 3 || NDEP == 1) {
+                    if (P.normal) {
+                        double n[D][4];
 #pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {
-                if (ks < ksteps) {
-                    const int j = r4 + 4 * ks;
-                    const double bv = mine ? tabV[j * GRID_COLS_PAD + myCol] : 0.0;
-                    const double dbv = mine ? tabV[(kpad + j) * GRID_COLS_PAD + myCol] : 0.0;
+                        for (int e = 0; e < 4; ++e) {
+                            if constexpr (NDEP == 3) {
+                                const double ux = acc[0][1][e], uy = acc[1][1][e], uz = acc[2][1][e];
+                                const double vx = acc[0][2][e], vy = acc[1][2][e], vz = acc[2][2][e];
+                                n[0][e] = (uy * vz - uz * vy) * P.normalSign;
+                                n[1][e] = -(ux * vz - uz * vx) * P.normalSign;
+                                n[2][e] = (ux * vy - uy * vx) * P.normalSign;
+                            } else {
+                                // nInd 2 > nDep 1: T = J^T is 2x1, n = (dv, -du) * sign
+                                n[0][e] = acc[0][2][e] * P.normalSign;
+                                n[1][e] = -acc[0][1][e] * P.normalSign;
+                            }
+                            if (P.normalize) {
+                                double sq = 0.0;
 #pragma unroll
-                    for (int d = 0; d < NDEP; ++d) {
-                        dmma884(acc[d][0][0], acc[d][0][1], tv[d][ks], bv);
-                        dmma884(acc[d][1][0], acc[d][1][1], td[d][ks], bv);
-                        dmma884(acc[d][2][0], acc[d][2][1], tv[d][ks], dbv);
-                    }
-                }
-            }
-            todo &= ~__ballot_sync(0xffffffffu, mine);
-        }
-        // ---- epilogue: this thread owns row `a`, columns col0 + c0 + 2*r4 + {0,1} ----
-        const long long b = col0 + c0 + 2 * r4;
-        if (a < P.nU && b < P.nV) {
-            const bool two = b + 1 < P.nV;
-            const long long at = a * P.nV + b;
-            auto put = [&](double *base, double x0, double x1) {
-                if (P.vec2 && two) {
-                    __stcs(reinterpret_cast<double2 *>(base + at), make_double2(x0, x1));
-                } else {
-                    __stcs(base + at, x0);
-                    if (two) __stcs(base + at + 1, x1);
-                }
-            };
-            if (P.values) {
+                                for (int i = 0; i < D; ++i)
+                                    if (P.normalMask & (1u << i)) sq = fma(n[i][e], n[i][e], sq);
+                                // n / |n| as n * (1/sqrt(sq)): zero normal -> 0 * inf = NaN like the reference's 0/0
+                                const double inv = 1.0 / sqrt(sq);
 #pragma unroll
-                for (int d = 0; d < NDEP; ++d) put(P.values + (sIdx * NDEP + d) * plane, acc[d][0][0], acc[d][0][1]);
-            }
-            if (P.jacobian) {
-#pragma unroll
-                for (int d = 0; d < NDEP; ++d) {
-                    put(P.jacobian + ((sIdx * NDEP + d) * 2 + 0) * plane, acc[d][1][0], acc[d][1][1]);
-                    put(P.jacobian + ((sIdx * NDEP + d) * 2 + 1) * plane, acc[d][2][0], acc[d][2][1]);
-                }
-            }
-            if constexpr (NDEP == 3 || NDEP == 1) {
-                if (P.normal) {
-                    double n[2][D];
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        if constexpr (NDEP == 3) {
-                            const double ux = acc[0][1][e], uy = acc[1][1][e], uz = acc[2][1][e];
-                            const double vx = acc[0][2][e], vy = acc[1][2][e], vz = acc[2][2][e];
-                            n[e][0] = (uy * vz - uz * vy) * P.normalSign;
-                            n[e][1] = -(ux * vz - uz * vx) * P.normalSign;
-                            n[e][2] = (ux * vy - uy * vx) * P.normalSign;
-                        } else {
-                            // nInd 2 > nDep 1: T = J^T is 2x1, n = (dv, -du) * sign
-                            n[e][0] = acc[0][2][e] * P.normalSign;
-                            n[e][1] = -acc[0][1][e] * P.normalSign;
+                                for (int i = 0; i < D; ++i) n[i][e] *= inv;
+                            }
                         }
-                        if (P.normalize) {
-                            double sq = 0.0;
 #pragma unroll
-                            for (int i = 0; i < D; ++i)
-                                if (P.normalMask & (1u << i)) sq += n[e][i] * n[e][i];
-                            const double len = sqrt(sq);
-#pragma unroll
-                            for (int i = 0; i < D; ++i) n[e][i] = n[e][i] / len;
-                        }
+                        for (int i = 0; i < D; ++i) put(P.normal + (sIdx * D + i) * plane, n[i]);
                     }
-#pragma unroll
-                    for (int i = 0; i < D; ++i) put(P.normal + (sIdx * D + i) * plane, n[0][i], n[1][i]);
                 }
             }
         }
     }
 }
 
-static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+static bool aligned_to(const void *p, unsigned n) { return (reinterpret_cast<uintptr_t>(p) & (n - 1)) == 0; }
 
-template <int NDEP>
-static int launch_grid2(const Grid2Params &P, long long nSplines, cudaStream_t stream)
+template <int NDEP, int MAXO>
+static int launch_grid2(const Grid2Params &P, cudaStream_t stream)
 {
-    const int kpad = ((P.ov + 3) / 4) * 4;
-    const size_t smem = sizeof(double) * (2 * kpad * GRID_COLS_PAD + 2 * GRID_MAX_ORDER * GRID_ROWS) +
-                        sizeof(int) * (GRID_COLS + GRID_ROWS);
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(grid2_dmma_kernel<NDEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem = sizeof(double) * (2 * MAXO * (P.chunkCols + 2) + 2 * MAXO * GRID_TILE_ROWS) +
+                        sizeof(int) * (P.chunkCols + GRID_TILE_ROWS);
+    static size_t allowed = 48 * 1024;
+    if (smem > allowed) {
+        cudaError_t e = cudaFuncSetAttribute(grid2_dmma_kernel<NDEP, MAXO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+        allowed = smem;
     }
-    const long long tiles = nSplines * P.colChunks * P.rowBlocks;
+    const long long groups = (P.nSplines + P.group - 1) / P.group;
+    const long long tiles = groups * P.colChunks * P.rowBlocks;
     if (tiles > 0x7fffffffLL) { set_error("grid too large for one launch"); return BSPY_E_UNSUPPORTED; }
-    grid2_dmma_kernel<NDEP><<<(unsigned)tiles, GRID_WARPS * 32, smem, stream>>>(P);
+    grid2_dmma_kernel<NDEP, MAXO><<<(unsigned)tiles, GRID_WARPS * 32, smem, stream>>>(P);
     count_launch();
     return check_launch("bspy_cuda_eval_grid");
 }
@@ -336,6 +380,7 @@ static int grid2_run(const bspy_spline *sp, long long nSplines, long long knotSt
     Grid2Params P{};
     P.knots0 = sp->knots[0]; P.knots1 = sp->knots[1]; P.coefs = sp->coefs;
     P.knotStride0 = knotStride0; P.knotStride1 = knotStride1; P.coefStride = coefStride;
+    P.nSplines = nSplines;
     P.ou = sp->order[0]; P.ov = sp->order[1]; P.nCu = sp->nCoef[0]; P.nCv = sp->nCoef[1];
     P.depStride = (long long)P.nCu * P.nCv;
     P.axisU = axes[0]; P.axisV = axes[1]; P.nU = nAxis[0]; P.nV = nAxis[1];
@@ -344,15 +389,39 @@ static int grid2_run(const bspy_spline *sp, long long nSplines, long long knotSt
     P.normalSign = sp->normalSign < 0 ? -1 : 1;
     P.normalize = (flags & BSPY_NORMALIZE) ? 1u : 0u;
     P.normalMask = normalMask ? normalMask : 0xffffffffu;
-    P.vec2 = (P.nV % 2 == 0) && aligned16(values) && aligned16(jacobian) && aligned16(normal);
-    P.colChunks = (int)((P.nV + GRID_COLS - 1) / GRID_COLS);
-    P.rowBlocks = (int)((P.nU + GRID_ROWS - 1) / GRID_ROWS);
+    P.vec = 1;
+    if (P.nV % 2 == 0 && aligned_to(values, 16) && aligned_to(jacobian, 16) && aligned_to(normal, 16)) P.vec = 2;
+    if (P.nV % 4 == 0 && aligned_to(values, 32) && aligned_to(jacobian, 32) && aligned_to(normal, 32)) P.vec = 4;
+    {
+        // Tile shape.  Write-heavy requests (>= 6 doubles per point, e.g. value + jacobian + normal = 12) are bound
+        // by the HBM store stream, which is fastest when CTAs are short-lived and close together: 16 rows x 256
+        // columns, one spline per CTA (measured 6.76 TB/s against 5.0 TB/s for 64 x 256 x 4 splines).  Light
+        // requests are bound by the per-CTA table set-up instead and take the large tile.
+        const int D = sp->nDep > 2 ? sp->nDep : 2;
+        const int doubles = (values ? sp->nDep : 0) + (jacobian ? 2 * sp->nDep : 0) + (normal ? D : 0);
+        const bool heavy = doubles >= 6;
+        const char *e = getenv("BSPY_GRID_CHUNK");
+        const long long cap = e ? atoi(e) : 256;
+        const long long chunks = (P.nV + cap - 1) / cap;
+        long long per = (P.nV + chunks - 1) / chunks;
+        per = (per + GRID_STEP - 1) / GRID_STEP * GRID_STEP;
+        P.chunkCols = (int)per;
+        P.colChunks = (int)((P.nV + per - 1) / per);
+        e = getenv("BSPY_GRID_ROWS");
+        P.tileRows = e ? atoi(e) : (heavy ? 16 : GRID_TILE_ROWS);
+        if (P.tileRows < 8 || P.tileRows > GRID_TILE_ROWS || P.tileRows % 8) P.tileRows = GRID_TILE_ROWS;
+        P.rowBlocks = (P.nU + P.tileRows - 1) / P.tileRows;
+        e = getenv("BSPY_GRID_GROUP");
+        const int g = e ? atoi(e) : (heavy ? 1 : GRID_GROUP);
+        P.group = (knotStride0 == 0 && knotStride1 == 0) ? (int)(nSplines < g ? nSplines : g) : 1;
+    }
     if (P.nU == 0 || P.nV == 0 || nSplines == 0) return 0;
+    const bool small = P.ou <= 4 && P.ov <= 4;
     switch (sp->nDep) {
-        case 1: return launch_grid2<1>(P, nSplines, stream);
-        case 2: return launch_grid2<2>(P, nSplines, stream);
-        case 3: return launch_grid2<3>(P, nSplines, stream);
-        default: return launch_grid2<4>(P, nSplines, stream);
+        case 1: return small ? launch_grid2<1, 4>(P, stream) : launch_grid2<1, 8>(P, stream);
+        case 2: return small ? launch_grid2<2, 4>(P, stream) : launch_grid2<2, 8>(P, stream);
+        case 3: return small ? launch_grid2<3, 4>(P, stream) : launch_grid2<3, 8>(P, stream);
+        default: return small ? launch_grid2<4, 4>(P, stream) : launch_grid2<4, 8>(P, stream);
     }
 }
 

@@ -44,9 +44,58 @@ __global__ void __launch_bounds__(256) probe_fill_kernel(double2 *__restrict__ d
         __stcs(dst + i, make_double2((double)i, 1.0));
 }
 
+// Write-pattern probe: `planes` arrays of nU x nV doubles, written tile by tile exactly like the grid
+// kernel does (one warp = 8 rows x 16 columns per step, 32-byte stores, a CTA = (tileRows x tileCols)),
+// with no arithmetic: the attainable HBM rate of the store pattern itself.
+__global__ void __launch_bounds__(256) probe_tiles_kernel(double *dst, int planes, long long nU, long long nV,
+                                                          int tileRows, int tileCols, int colChunks, int rowBlocks)
+{
+    const long long tile = blockIdx.x;
+    const int cc = (int)(tile % colChunks);
+    const int rb = (int)(tile / colChunks);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, q = lane >> 2, r4 = lane & 3;
+    const int stripsPerCol = tileRows / 8;            // warps stacked along rows
+    const int colGroups = 8 / stripsPerCol;           // the remaining warps split the columns
+    const int strip = warp % stripsPerCol, cg = warp / stripsPerCol;
+    const long long a = (long long)rb * tileRows + strip * 8 + q;
+    const long long plane = nU * nV;
+    // tileRows == 8 with a NEGATIVE tileCols request (passed as interleave flag) is handled by the caller:
+    // interleave = 1 makes the 8 warps write side by side (16 columns each, 1 KB per row per step).
+    const bool interleave = stripsPerCol == 1 && (tileCols & 1);
+    const int tc = tileCols & ~1;
+    const int first = interleave ? warp * 16 : cg * (tc / colGroups);
+    const int last = interleave ? tc : (cg + 1) * (tc / colGroups);
+    const int step = interleave ? 128 : 16;
+    for (int c0 = first; c0 < last; c0 += step) {
+        const long long b = (long long)cc * tc + c0 + 4 * r4;
+        if (a < nU && b + 3 < nV) {
+            for (int p = 0; p < planes; ++p) {
+                double *ptr = dst + p * plane + a * nV + b;
+                asm volatile("st.global.cs.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(ptr), "d"(1.0), "d"((double)c0), "d"(3.0), "d"(4.0) : "memory");
+            }
+        }
+    }
+}
+
 }  // namespace bspy
 
 using namespace bspy;
+
+extern "C" int bspy_cuda_probe_tiles(double *dst, int32_t planes, int64_t nU, int64_t nV, int32_t tileRows, int32_t tileCols,
+                                     double *bytesOut_host, void *stream)
+{
+    if (!dst || planes <= 0 || tileRows % 8 || 64 % tileRows || (tileCols & ~1) % (16 * (64 / tileRows)) || nV % 4) {
+        set_error("bspy_cuda_probe_tiles: bad argument");
+        return BSPY_E_ARG;
+    }
+    const int tcols = tileCols & ~1;   // bit 0 of tileCols = "interleave the warps along the row"
+    const int colChunks = (int)((nV + tcols - 1) / tcols), rowBlocks = (int)((nU + tileRows - 1) / tileRows);
+    probe_tiles_kernel<<<(unsigned)(colChunks * rowBlocks), 256, 0, (cudaStream_t)stream>>>(dst, planes, nU, nV, tileRows, tileCols,
+                                                                                          colChunks, rowBlocks);
+    if (bytesOut_host) *bytesOut_host = 8.0 * planes * (double)nU * (double)nV;
+    count_launch();
+    return check_launch("bspy_cuda_probe_tiles");
+}
 
 extern "C" int bspy_cuda_probe_fp64(int32_t kind, int32_t iters, double *sink, double *flopsOut_host, void *stream)
 {

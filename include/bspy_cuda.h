@@ -141,6 +141,10 @@ int bspy_cuda_eval_many(int32_t order, int32_t nCoef, int32_t nDep, int64_t nSpl
 int bspy_cuda_probe_fp64(int32_t kind, int32_t iters, double *sink, double *flopsOut_host, void *stream);
 int bspy_cuda_probe_hbm(int32_t kind, const double *src, double *dst, int64_t nDoubles,
                         double *bytesOut_host, void *stream);
+/*      bspy_cuda_probe_tiles: writes `planes` arrays of nU x nV doubles tile by tile with the grid
+ *      kernel's store pattern and no arithmetic (the attainable rate of the pattern itself).      */
+int bspy_cuda_probe_tiles(double *dst, int32_t planes, int64_t nU, int64_t nV, int32_t tileRows,
+                          int32_t tileCols, double *bytesOut_host, void *stream);
 
 #ifdef __cplusplus
 }
