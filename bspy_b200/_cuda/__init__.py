@@ -26,7 +26,8 @@ LIB_PATH = os.path.join(HERE, "libbspy_cuda.so")
 # every symbol include/bspy_cuda.h declares (tests check the library exports exactly these)
 SYMBOLS = (
     "bspy_cuda_abi_version", "bspy_cuda_last_error_string", "bspy_cuda_launch_count",
-    "bspy_cuda_spans", "bspy_cuda_basis", "bspy_cuda_eval_points", "bspy_cuda_eval_grid",
+    "bspy_cuda_spans", "bspy_cuda_basis", "bspy_cuda_eval_points", "bspy_cuda_eval_points_binned",
+    "bspy_cuda_binned_workspace_bytes", "bspy_cuda_eval_grid",
     "bspy_cuda_eval_grid_batch", "bspy_cuda_eval_many", "bspy_cuda_probe_fp64", "bspy_cuda_probe_hbm",
     "bspy_cuda_probe_tiles",
 )
@@ -76,6 +77,7 @@ def library():
             "bspy_cuda_spans": [vp, i32, i32, vp, i64, vp, vp],
             "bspy_cuda_basis": [vp, i32, i32, vp, vp, i64, i32, i32, vp, vp, vp],
             "bspy_cuda_eval_points": [C.POINTER(CSpline), vp, i64, i64, i64, C.POINTER(i32), u32, u32, vp, vp, vp, vp, vp, vp, vp],
+            "bspy_cuda_eval_points_binned": [C.POINTER(CSpline), vp, i64, i64, i64, C.POINTER(i32), u32, u32, vp, vp, vp, vp, vp, vp, vp, i64, vp],
             "bspy_cuda_eval_grid": [C.POINTER(CSpline), C.POINTER(vp), C.POINTER(i64), u32, u32, vp, vp, vp, vp, vp],
             "bspy_cuda_eval_grid_batch": [C.POINTER(CSpline), i64, C.POINTER(i64), i64, C.POINTER(vp), C.POINTER(i64), u32, u32, vp, vp, vp, vp, vp],
             "bspy_cuda_eval_many": [i32, i32, i32, i64, vp, i64, vp, i64, vp, i32, vp, vp, vp, vp],
@@ -87,6 +89,8 @@ def library():
             fn = getattr(lib, name)
             fn.argtypes = args
             fn.restype = C.c_int
+        lib.bspy_cuda_binned_workspace_bytes.argtypes = [C.POINTER(CSpline), i64]
+        lib.bspy_cuda_binned_workspace_bytes.restype = C.c_int64
         if lib.bspy_cuda_abi_version() != 1:
             raise CudaPathError("libbspy_cuda.so ABI version mismatch; rebuild with python -m bspy_b200._cuda.build --force")
         _lib = lib
@@ -195,7 +199,7 @@ def new_flag(dev):
 
 
 def eval_points(ds: DeviceSpline, uvw, point_stride, var_stride, N, *, wrt=None, values=True, jacobian=False,
-                normal=False, normalize=True, normal_mask=0, spans=False, flag=None):
+                normal=False, normalize=True, normal_mask=0, spans=False, flag=None, binned=True):
     """Launch bspy_cuda_eval_points.  ``uvw`` is a float64 device tensor addressed through the two
     strides (elements).  Returns a dict of SoA device tensors; ``flag`` (int64[1], -1) receives the
     first out-of-domain index."""
@@ -211,11 +215,21 @@ def eval_points(ds: DeviceSpline, uvw, point_stride, var_stride, N, *, wrt=None,
     w = None
     if wrt is not None:
         w = (C.c_int32 * max(ds.nInd, 1))(*[int(x) for x in wrt])
+    lib = library()
+    ws_bytes = int(lib.bspy_cuda_binned_workspace_bytes(C.byref(ds.c), int(N))) if binned else 0
     with torch.cuda.device(dev):
-        rc = library().bspy_cuda_eval_points(C.byref(ds.c), _ptr(uvw), int(point_stride), int(var_stride), int(N), w,
-                                             NORMALIZE if normalize else 0, int(normal_mask), _ptr(out["values"]),
-                                             _ptr(out["derivative"]), _ptr(out["jacobian"]), _ptr(out["normal"]),
-                                             _ptr(out["spans"]), _ptr(flag), _stream(dev))
+        if ws_bytes > 0:
+            # big scattered batch on a spline that lives in L2: cell-binned evaluation (workspace is ours)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            rc = lib.bspy_cuda_eval_points_binned(C.byref(ds.c), _ptr(uvw), int(point_stride), int(var_stride), int(N), w,
+                                                  NORMALIZE if normalize else 0, int(normal_mask), _ptr(out["values"]),
+                                                  _ptr(out["derivative"]), _ptr(out["jacobian"]), _ptr(out["normal"]),
+                                                  _ptr(out["spans"]), _ptr(flag), _ptr(ws), ws_bytes, _stream(dev))
+        else:
+            rc = lib.bspy_cuda_eval_points(C.byref(ds.c), _ptr(uvw), int(point_stride), int(var_stride), int(N), w,
+                                           NORMALIZE if normalize else 0, int(normal_mask), _ptr(out["values"]),
+                                           _ptr(out["derivative"]), _ptr(out["jacobian"]), _ptr(out["normal"]),
+                                           _ptr(out["spans"]), _ptr(flag), _stream(dev))
     _check(rc, "bspy_cuda_eval_points")
     return out
 

@@ -28,6 +28,45 @@ static inline int num_sms()
     return sms;
 }
 
+// ---- kernel parameter blocks shared by scattered.cu and grid.cu ------------------------------------
+struct SplineDev {
+    int nInd, nDep;
+    int order[BSPY_MAX_IND];
+    int nCoef[BSPY_MAX_IND];
+    const double *knots[BSPY_MAX_IND];
+    const double *coefs;
+    long long stride[BSPY_MAX_IND];  // coefficient stride of variable i (elements)
+    long long depStride;
+    int normalSign;
+};
+
+struct PointsDev {
+    const double *uvw;      // scattered: parameter i of point p at uvw[p*pointStride + i*varStride]
+    long long pointStride, varStride;
+    const double *axes[BSPY_MAX_IND];  // grid mode: axes[i][idx_i]
+    long long nAxis[BSPY_MAX_IND];
+    int grid;               // 0 = scattered, 1 = tensor grid (last variable fastest)
+    // cell-binned mode (perm != nullptr): thread t evaluates point base + perm[t]; its knot spans are packed in
+    // cellKey[t] = ((ix0-o0) * m1 + (ix1-o1)) * m2 + ...  with m_i = nCoef_i - o_i + 1 spans in variable i
+    const int *perm;
+    const int *cellKey;
+    long long base;
+};
+
+struct OutDev {
+    long long ld;      // leading dimension of the outputs = total number of points
+    double *values;    // (nDep, N)
+    double *jacobian;  // (nDep, nInd, N)
+    double *normal;    // (D, N)
+    int32_t *spans;    // (nInd, N)
+    long long *firstOutside;
+    unsigned normalize, normalMask;
+};
+
+struct WrtDev {
+    int d[BSPY_MAX_IND];
+};
+
 // ---- device side ----------------------------------------------------------------------------
 
 // Number of knots <= u clamped to [order, nKnots - order]  (reference: np.searchsorted(.., 'right')

@@ -23,23 +23,6 @@
 namespace bspy {
 
 // from scattered.cu
-struct SplineDev {
-    int nInd, nDep;
-    int order[BSPY_MAX_IND];
-    int nCoef[BSPY_MAX_IND];
-    const double *knots[BSPY_MAX_IND];
-    const double *coefs;
-    long long stride[BSPY_MAX_IND];
-    long long depStride;
-    int normalSign;
-};
-struct PointsDev {
-    const double *uvw;
-    long long pointStride, varStride;
-    const double *axes[BSPY_MAX_IND];
-    long long nAxis[BSPY_MAX_IND];
-    int grid;
-};
 int make_spline_dev(const bspy_spline *sp, SplineDev &s, const char *who);
 int eval_common(const bspy_spline *spline, const PointsDev &in, long long N, const int32_t *wrt, uint32_t flags,
                 uint32_t normalMask, double *values, double *deriv, double *jacobian, double *normal, int32_t *spans,

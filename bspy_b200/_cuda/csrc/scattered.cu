@@ -13,41 +13,11 @@
 //   5. struct-of-arrays stores: consecutive threads write consecutive doubles.
 // Two implementations: eval_fixed<> (compile-time nInd/orders/nDep, everything in registers) for
 // the common shapes, eval_generic for any nInd <= 8, order <= 32 and any nDep.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace bspy {
-
-struct SplineDev {
-    int nInd, nDep;
-    int order[BSPY_MAX_IND];
-    int nCoef[BSPY_MAX_IND];
-    const double *knots[BSPY_MAX_IND];
-    const double *coefs;
-    long long stride[BSPY_MAX_IND];  // coefficient stride of variable i (elements)
-    long long depStride;
-    int normalSign;
-};
-
-struct PointsDev {
-    const double *uvw;      // scattered: parameter i of point p at uvw[p*pointStride + i*varStride]
-    long long pointStride, varStride;
-    const double *axes[BSPY_MAX_IND];  // grid mode: axes[i][idx_i]
-    long long nAxis[BSPY_MAX_IND];
-    int grid;               // 0 = scattered, 1 = tensor grid (last variable fastest)
-};
-
-struct OutDev {
-    double *values;    // (nDep, N)
-    double *jacobian;  // (nDep, nInd, N)
-    double *normal;    // (D, N)
-    int32_t *spans;    // (nInd, N)
-    long long *firstOutside;
-    unsigned normalize, normalMask;
-};
-
-struct WrtDev {
-    int d[BSPY_MAX_IND];
-};
 
 __device__ __forceinline__ double fetch_param(const PointsDev &in, long long p, int iv, long long &rem)
 {
@@ -211,14 +181,17 @@ struct Contract {
 
 template <int IV, class Ord, int NDEP, bool JAC>
 __device__ __forceinline__ void setup_variable(const SplineDev &s, double u, int d, FixedCtx<Ord, NDEP, JAC> &c,
-                                               int (&ix)[Ord::n], bool &outside)
+                                               int (&ix)[Ord::n], bool &outside, bool given)
 {
     constexpr int O = Ord::at(IV);
     const double *k = s.knots[IV];
     const int nKnots = O + s.nCoef[IV];
-    outside |= (u < __ldg(k + O - 1)) | (u > __ldg(k + s.nCoef[IV]));
-    const int span = span_search_inner(k, nKnots, O, u);
-    ix[IV] = span;
+    int span = ix[IV];
+    if (!given) {   // binned mode hands the span in (searched and domain-checked by bin_keys_kernel)
+        outside |= (u < __ldg(k + O - 1)) | (u > __ldg(k + s.nCoef[IV]));
+        span = span_search_inner(k, nKnots, O, u);
+        ix[IV] = span;
+    }
     double kw[2 * (O - 1) > 0 ? 2 * (O - 1) : 1];
     load_knot_window<O>(k, span, kw);
     double b0[O], b1[O];
@@ -235,18 +208,30 @@ __global__ void __launch_bounds__(128) eval_fixed_kernel(const SplineDev s, cons
                                                          const WrtDev wrt, const OutDev out)
 {
     using Ord = Orders<NIND, O0, O1, O2, O3>;
-    for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < N; p += (long long)gridDim.x * blockDim.x) {
+    const bool binned = in.perm != nullptr;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < N; t += (long long)gridDim.x * blockDim.x) {
         FixedCtx<Ord, NDEP, JAC> c;
         int ix[NIND];
         double u[NIND];
         bool outside = false;
+        long long p = t;
+        if (binned) {
+            p = in.base + __ldg(in.perm + t);
+            int key = __ldg(in.cellKey + t);
+#pragma unroll
+            for (int iv = NIND - 1; iv >= 0; --iv) {
+                const int m = s.nCoef[iv] - Ord::at(iv) + 1;
+                ix[iv] = Ord::at(iv) + key % m;
+                key /= m;
+            }
+        }
         long long rem = p;
 #pragma unroll
         for (int iv = NIND - 1; iv >= 0; --iv) u[iv] = fetch_param(in, p, iv, rem);
-        setup_variable<0, Ord, NDEP, JAC>(s, u[0], wrt.d[0], c, ix, outside);
-        if constexpr (NIND > 1) setup_variable<1, Ord, NDEP, JAC>(s, u[1], wrt.d[1], c, ix, outside);
-        if constexpr (NIND > 2) setup_variable<2, Ord, NDEP, JAC>(s, u[2], wrt.d[2], c, ix, outside);
-        if constexpr (NIND > 3) setup_variable<3, Ord, NDEP, JAC>(s, u[3], wrt.d[3], c, ix, outside);
+        setup_variable<0, Ord, NDEP, JAC>(s, u[0], wrt.d[0], c, ix, outside, binned);
+        if constexpr (NIND > 1) setup_variable<1, Ord, NDEP, JAC>(s, u[1], wrt.d[1], c, ix, outside, binned);
+        if constexpr (NIND > 2) setup_variable<2, Ord, NDEP, JAC>(s, u[2], wrt.d[2], c, ix, outside, binned);
+        if constexpr (NIND > 3) setup_variable<3, Ord, NDEP, JAC>(s, u[3], wrt.d[3], c, ix, outside, binned);
         if (outside && out.firstOutside) report_outside((int64_t *)out.firstOutside, p);
         long long off = 0;
 #pragma unroll
@@ -260,18 +245,18 @@ __global__ void __launch_bounds__(128) eval_fixed_kernel(const SplineDev s, cons
         Contract<0, Ord, NDEP, JAC>::run(s.coefs + off, c, v, g);
         if (out.values) {
 #pragma unroll
-            for (int d = 0; d < NDEP; ++d) __stcs(out.values + d * N + p, v[d]);
+            for (int d = 0; d < NDEP; ++d) __stcs(out.values + d * out.ld + p, v[d]);
         }
         if (out.spans) {
 #pragma unroll
-            for (int iv = 0; iv < NIND; ++iv) __stcs(out.spans + iv * N + p, ix[iv]);
+            for (int iv = 0; iv < NIND; ++iv) __stcs(out.spans + iv * out.ld + p, ix[iv]);
         }
         if constexpr (JAC) {
             if (out.jacobian) {
 #pragma unroll
                 for (int d = 0; d < NDEP; ++d)
 #pragma unroll
-                    for (int iv = 0; iv < NIND; ++iv) __stcs(out.jacobian + (d * NIND + iv) * N + p, g[iv][d]);
+                    for (int iv = 0; iv < NIND; ++iv) __stcs(out.jacobian + (d * NIND + iv) * out.ld + p, g[iv][d]);
             }
             if constexpr (NIND - NDEP == 1 || NDEP - NIND == 1) {
                 if (out.normal) {
@@ -284,7 +269,7 @@ __global__ void __launch_bounds__(128) eval_fixed_kernel(const SplineDev s, cons
                     double n[D];
                     normal_from_jacobian<NIND, NDEP>(J, s.normalSign, out.normalize, out.normalMask, n);
 #pragma unroll
-                    for (int i = 0; i < D; ++i) __stcs(out.normal + i * N + p, n[i]);
+                    for (int i = 0; i < D; ++i) __stcs(out.normal + i * out.ld + p, n[i]);
                 }
             }
         }
@@ -381,7 +366,7 @@ __global__ void __launch_bounds__(128) eval_generic_kernel(const SplineDev s, co
             if (jac) basis_runtime(k, o, ix[iv], u, 1, SmemCol{colD + (long long)at * T, T});
             at += o;
             off += (long long)(ix[iv] - o) * s.stride[iv];
-            if (out.spans) out.spans[iv * N + p] = ix[iv];
+            if (out.spans) out.spans[iv * out.ld + p] = ix[iv];
         }
         if (outside && out.firstOutside) report_outside((int64_t *)out.firstOutside, p);
         double J[(BSPY_MAX_IND + 1) * BSPY_MAX_IND];  // (nDep, nInd) only when a normal is requested (nDep <= nInd+1)
@@ -428,10 +413,10 @@ __global__ void __launch_bounds__(128) eval_generic_kernel(const SplineDev s, co
                     more = iv >= 0;
                 }
             }
-            if (out.values) out.values[d * N + p] = val;
+            if (out.values) out.values[d * out.ld + p] = val;
             if (jac) {
                 if (out.jacobian)
-                    for (int iv = 0; iv < nInd; ++iv) out.jacobian[((long long)d * nInd + iv) * N + p] = der[iv];
+                    for (int iv = 0; iv < nInd; ++iv) out.jacobian[((long long)d * nInd + iv) * out.ld + p] = der[iv];
                 if (out.normal)
                     for (int iv = 0; iv < nInd; ++iv) J[d * nInd + iv] = der[iv];
             }
@@ -453,10 +438,91 @@ __global__ void __launch_bounds__(128) eval_generic_kernel(const SplineDev s, co
                 if (out.normalMask & (1u << i)) sq += n[i] * n[i];
             }
             const double len = sqrt(sq);
-            for (int i = 0; i < D; ++i) out.normal[(long long)i * N + p] = out.normalize ? n[i] / len : n[i];
+            for (int i = 0; i < D; ++i) out.normal[(long long)i * out.ld + p] = out.normalize ? n[i] / len : n[i];
         }
     }
 }
+
+// ---- cell binning --------------------------------------------------------------------------------
+// Scattered points on a spline whose coefficients do not fit in L1 gather a window of prod(order)*nDep doubles
+// per point from L2 (1.5 KB for a tricubic volume, 3.9 KB for the 4-variate manifold): measured, the
+// thread-per-point kernel is then bound by L2->SM traffic (~7 TB/s) at 10% of the FP64 roofline.  Binning makes
+// the lanes of a warp share their window: the points of a chunk (small enough that its outputs stay in L2) are
+// counting-sorted by knot-span cell, evaluated in cell order (window loads become L1 broadcasts) and written
+// straight back to their original positions.  Same arithmetic per point, so results are bit-identical to the
+// unbinned kernel.
+__global__ void __launch_bounds__(256) bin_keys_kernel(const SplineDev s, const PointsDev in, const long long base, const int n,
+                                                       int *__restrict__ keys, int *__restrict__ hist, const OutDev out)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const long long p = base + t;
+    int key = 0;
+    bool outside = false;
+    for (int iv = 0; iv < s.nInd; ++iv) {
+        const double *k = s.knots[iv];
+        const int o = s.order[iv];
+        const double u = __ldg(in.uvw + p * in.pointStride + iv * in.varStride);
+        outside |= (u < __ldg(k + o - 1)) | (u > __ldg(k + s.nCoef[iv]));
+        const int ix = span_search_inner(k, o + s.nCoef[iv], o, u);
+        if (out.spans) __stcs(out.spans + iv * out.ld + p, ix);
+        key = key * (s.nCoef[iv] - o + 1) + (ix - o);
+    }
+    if (outside && out.firstOutside) report_outside((int64_t *)out.firstOutside, p);
+    keys[t] = key;
+    atomicAdd(hist + key, 1);
+}
+
+// exclusive scan of hist[0..cells) in place, one CTA
+__global__ void __launch_bounds__(1024) bin_scan_kernel(int *__restrict__ hist, const int cells)
+{
+    __shared__ int part[1024];
+    const int per = (cells + 1023) / 1024;
+    const int lo = threadIdx.x * per, hi = min(lo + per, cells);
+    int sum = 0;
+    for (int i = lo; i < hi; ++i) sum += hist[i];
+    part[threadIdx.x] = sum;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {
+        const int v = threadIdx.x >= off ? part[threadIdx.x - off] : 0;
+        __syncthreads();
+        part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    int run = part[threadIdx.x] - sum;
+    for (int i = lo; i < hi; ++i) {
+        const int c = hist[i];
+        hist[i] = run;
+        run += c;
+    }
+}
+
+__global__ void __launch_bounds__(256) bin_scatter_kernel(const int *__restrict__ keys, int *__restrict__ cursor, const int n,
+                                                          int *__restrict__ perm, int *__restrict__ sortedKey)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int key = keys[t];
+    const int pos = atomicAdd(cursor + key, 1);
+    perm[pos] = t;
+    sortedKey[pos] = key;
+}
+
+constexpr long long BIN_CHUNK_MAX = 1 << 20;  // workspace is sized for this many points per chunk
+
+// Points per chunk: the outputs of a chunk are scattered back to their original positions 8 bytes at a time, which
+// is only cheap while the chunk's output region stays in L2 (measured optimum: ~56 MB of outputs per chunk; larger
+// chunks give more points per cell but turn the scatter into DRAM read-modify-writes and are 2x slower).
+static long long bin_chunk(long long outBytesPerPoint)
+{
+    const char *e = getenv("BSPY_BIN_CHUNK");
+    long long v = e ? atoll(e) : (56LL << 20) / (outBytesPerPoint > 0 ? outBytesPerPoint : 8);
+    v = v / 1024 * 1024;
+    if (v < 65536) v = 65536;
+    if (v > BIN_CHUNK_MAX) v = BIN_CHUNK_MAX;
+    return v;
+}
+constexpr long long BIN_MAX_CELLS = 1 << 18;  // histogram / scan size limit
 
 // ---- host dispatch ----------------------------------------------------------------------------
 typedef void (*FixedFn)(const SplineDev, const PointsDev, const long long, const WrtDev, const OutDev);
@@ -581,6 +647,7 @@ int eval_common(const bspy_spline *spline, const PointsDev &in, long long N, con
     if (normalMask == 0 || D >= 32) normalMask = 0xffffffffu;
     WrtDev zero{};
     OutDev out{};
+    out.ld = N;
     out.firstOutside = (long long *)firstOutside;
     out.normalize = (flags & BSPY_NORMALIZE) ? 1u : 0u;
     out.normalMask = normalMask;
@@ -607,6 +674,7 @@ int eval_common(const bspy_spline *spline, const PointsDev &in, long long N, con
             w.d[i] = wrt[i];
         }
         OutDev o2{};
+        o2.ld = N;
         o2.values = deriv;
         o2.spans = spansDone ? nullptr : spans;
         o2.firstOutside = oobDone ? nullptr : (long long *)firstOutside;
@@ -616,9 +684,122 @@ int eval_common(const bspy_spline *spline, const PointsDev &in, long long N, con
     return 0;
 }
 
+static long long binned_cells(const SplineDev &s)
+{
+    long long cells = 1;
+    for (int i = 0; i < s.nInd; ++i) {
+        cells *= (s.nCoef[i] - s.order[i] + 1);
+        if (cells > BIN_MAX_CELLS) return 0;
+    }
+    return cells;
+}
+
+// bytes of workspace for the binned path, 0 when binning does not apply to this spline
+long long binned_workspace(const SplineDev &s, long long N)
+{
+    if (s.nInd < 2 || N < 65536) return 0;
+    long long window = s.nDep;
+    for (int i = 0; i < s.nInd; ++i) window *= s.order[i];
+    if (window * 8 < 512) return 0;                         // small windows: the gather is cheap anyway
+    if (s.depStride * s.nDep * 8 < 128 * 1024) return 0;    // the whole spline fits in L1
+    const long long cells = binned_cells(s);
+    if (!cells) return 0;
+    if (!find_fixed(s, 0)) return 0;
+    const long long chunk = N < BIN_CHUNK_MAX ? N : BIN_CHUNK_MAX;
+    return 3 * 4 * ((chunk + 63) / 64 * 64) + 4 * ((cells + 1 + 63) / 64 * 64);
+}
+
+int eval_binned(const SplineDev &s, PointsDev in, long long N, const WrtDev &wrt, OutDev out, int jac, void *workspace,
+                cudaStream_t stream)
+{
+    const long long cells = binned_cells(s);
+    const int D = s.nInd > s.nDep ? s.nInd : s.nDep;
+    const long long outBytes = 8LL * ((out.values ? s.nDep : 0) + (out.jacobian ? s.nDep * s.nInd : 0) + (out.normal ? D : 0));
+    const long long cap = N < BIN_CHUNK_MAX ? N : BIN_CHUNK_MAX;      // what the workspace was sized for
+    const long long chunk = bin_chunk(outBytes) < cap ? bin_chunk(outBytes) : cap;
+    const long long cpad = (cap + 63) / 64 * 64;
+    int *keys = (int *)workspace, *perm = keys + cpad, *skey = perm + cpad, *hist = skey + cpad;
+    FixedFn fn = find_fixed(s, jac);
+    int32_t *spans = out.spans;
+    long long *flag = out.firstOutside;
+    for (long long base = 0; base < N; base += chunk) {
+        const int n = (int)(N - base < chunk ? N - base : chunk);
+        cudaError_t e = cudaMemsetAsync(hist, 0, sizeof(int) * (cells + 1), stream);
+        if (e != cudaSuccess) { set_error("cudaMemsetAsync: %s", cudaGetErrorString(e)); return (int)e; }
+        OutDev o1{};
+        o1.ld = out.ld; o1.spans = spans; o1.firstOutside = flag;
+        bin_keys_kernel<<<(n + 255) / 256, 256, 0, stream>>>(s, in, base, n, keys, hist, o1);
+        bin_scan_kernel<<<1, 1024, 0, stream>>>(hist, (int)cells);
+        bin_scatter_kernel<<<(n + 255) / 256, 256, 0, stream>>>(keys, hist, n, perm, skey);
+        PointsDev pin = in;
+        pin.perm = perm; pin.cellKey = skey; pin.base = base;
+        OutDev o2 = out;
+        o2.spans = nullptr; o2.firstOutside = nullptr;
+        long long blocks = (n + 127) / 128;
+        fn<<<(unsigned)blocks, 128, 0, stream>>>(s, pin, n, wrt, o2);
+        count_launch(4);
+        int rc = check_launch("bspy_cuda_eval_points_binned");
+        if (rc) return rc;
+    }
+    return 0;
+}
+
 }  // namespace bspy
 
 using namespace bspy;
+
+extern "C" int64_t bspy_cuda_binned_workspace_bytes(const bspy_spline *spline, int64_t N)
+{
+    SplineDev s;
+    if (make_spline_dev(spline, s, "bspy_cuda_binned_workspace_bytes")) return 0;
+    return binned_workspace(s, N);
+}
+
+extern "C" int bspy_cuda_eval_points_binned(const bspy_spline *spline, const double *uvw, int64_t pointStride, int64_t varStride,
+                                            int64_t N, const int32_t *wrt, uint32_t flags, uint32_t normalMask, double *values,
+                                            double *deriv, double *jacobian, double *normal, int32_t *spans,
+                                            int64_t *firstOutside, void *workspace, int64_t workspaceBytes, void *stream)
+{
+    const char *who = "bspy_cuda_eval_points_binned";
+    SplineDev s;
+    int rc = make_spline_dev(spline, s, who);
+    if (rc) return rc;
+    const long long need = binned_workspace(s, N);
+    const bool onePass = !(deriv && (values || jacobian || normal));
+    if (!need || !workspace || workspaceBytes < need || !onePass || !uvw)
+        return bspy_cuda_eval_points(spline, uvw, pointStride, varStride, N, wrt, flags, normalMask, values, deriv, jacobian,
+                                     normal, spans, firstOutside, stream);
+    if ((deriv != nullptr) != (wrt != nullptr)) { set_error("%s: wrt and deriv must be given together", who); return BSPY_E_ARG; }
+    const int D = s.nInd > s.nDep ? s.nInd : s.nDep;
+    if (normal && (s.nInd - s.nDep != 1 && s.nDep - s.nInd != 1)) {
+        set_error("The number of independent variables must be one different than the number of dependent variables.");
+        return BSPY_E_NORMAL_DIMS;
+    }
+    if (normalMask == 0 || D >= 32) normalMask = 0xffffffffu;
+    PointsDev in{};
+    in.uvw = uvw; in.pointStride = pointStride; in.varStride = varStride;
+    OutDev out{};
+    out.ld = N;
+    out.firstOutside = (long long *)firstOutside;
+    out.spans = spans;
+    out.normalize = (flags & BSPY_NORMALIZE) ? 1u : 0u;
+    out.normalMask = normalMask;
+    WrtDev w{};
+    int jac = 0;
+    if (jacobian || normal) {
+        jac = 1;
+        out.values = values; out.jacobian = jacobian; out.normal = normal;
+    } else if (deriv) {
+        for (int i = 0; i < s.nInd; ++i) {
+            if (wrt[i] < 0) { set_error("%s: negative derivative order", who); return BSPY_E_ARG; }
+            w.d[i] = wrt[i];
+        }
+        out.values = deriv;
+    } else {
+        out.values = values;
+    }
+    return eval_binned(s, in, N, w, out, jac, workspace, (cudaStream_t)stream);
+}
 
 extern "C" int bspy_cuda_eval_points(const bspy_spline *spline, const double *uvw, int64_t pointStride, int64_t varStride,
                                      int64_t N, const int32_t *wrt, uint32_t flags, uint32_t normalMask, double *values,

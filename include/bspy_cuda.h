@@ -101,6 +101,21 @@ int bspy_cuda_eval_points(const bspy_spline *spline, const double *uvw, int64_t 
                           uint32_t normalMask, double *values, double *deriv, double *jacobian,
                           double *normal, int32_t *spans, int64_t *firstOutside, void *stream);
 
+/* ---- the same with cell binning for big scattered batches: the points of each 512 Ki chunk are
+ *      counting-sorted by knot-span cell (in `workspace`, caller-owned device memory) so that the
+ *      lanes of a warp share their coefficient window, evaluated in that order and written to their
+ *      original positions.  Results are bit-identical to bspy_cuda_eval_points.
+ *      bspy_cuda_binned_workspace_bytes returns the workspace size for (spline, N), or 0 when
+ *      binning does not apply (curves, small windows, splines that fit in L1, N < 65536, shapes
+ *      without a compiled kernel); with a NULL / too small workspace the call falls back to
+ *      bspy_cuda_eval_points.                                                               */
+int64_t bspy_cuda_binned_workspace_bytes(const bspy_spline *spline, int64_t N);
+int bspy_cuda_eval_points_binned(const bspy_spline *spline, const double *uvw, int64_t pointStride,
+                                 int64_t varStride, int64_t N, const int32_t *wrt, uint32_t flags,
+                                 uint32_t normalMask, double *values, double *deriv, double *jacobian,
+                                 double *normal, int32_t *spans, int64_t *firstOutside,
+                                 void *workspace, int64_t workspaceBytes, void *stream);
+
 /* ---- regular grid: the tensor product of one parameter axis per variable; axis i has
  *      nAxis[i] device doubles.  Outputs as above with N = prod(nAxis) laid out C-order with
  *      the LAST variable fastest: values (nDep, nAxis[0], .., nAxis[nInd-1]) etc.  This is

@@ -374,3 +374,42 @@ def test_mutation_is_seen_and_freeze_is_not():
     assert np.array_equal(s.evaluate_points(u).values, after)     # frozen handle: device copy reused
     s.unfreeze()
     assert np.array_equal(s.evaluate_points(u).values, before)
+
+
+def test_binned_path_is_bit_identical_to_unbinned():
+    """Big scattered batches on a spline that lives in L2 are counting-sorted by knot-span cell and
+    evaluated in cell order (bspy_cuda_eval_points_binned); per-point arithmetic is unchanged."""
+    bspy, _cuda, _, _ = _mods()
+    from bspy_b200._spline_evaluation import device_spline
+    rng = np.random.default_rng(11)
+
+    def K(o, n):
+        w = rng.uniform(0.25, 1.75, n - o + 1)
+        inner = np.concatenate(([0.0], np.cumsum(w))); inner /= inner[-1]
+        return np.concatenate((np.zeros(o - 1), inner, np.ones(o - 1)))
+
+    for shape in (dict(nInd=3, nDep=3, order=(4, 4, 4), nCoef=(32, 32, 32)), dict(nInd=4, nDep=6, order=(3,) * 4, nCoef=(16,) * 4)):
+        s = bspy.Spline(shape["nInd"], shape["nDep"], shape["order"], shape["nCoef"],
+                        [K(o, n) for o, n in zip(shape["order"], shape["nCoef"])], rng.standard_normal((shape["nDep"], *shape["nCoef"])))
+        ds = device_spline(s)
+        N = (1 << 19) + 12345                                  # more than one chunk, ragged tail
+        assert _cuda.library().bspy_cuda_binned_workspace_bytes(ds.c, N) > 0
+        g = torch.Generator(device="cuda").manual_seed(3)
+        pts = torch.rand((N, s.nInd), dtype=torch.float64, device="cuda", generator=g)
+        pts[5, 0], pts[N - 1, s.nInd - 1], pts[777, 1] = 0.0, 1.0, float(s.knots[1][7])
+        for request in (dict(values=True, jacobian=True, spans=True), dict(values=True), dict(values=False, wrt=[1] + [0] * (s.nInd - 1))):
+            a = _cuda.eval_points(ds, pts, s.nInd, 1, N, binned=True, **request)
+            b = _cuda.eval_points(ds, pts, s.nInd, 1, N, binned=False, **request)
+            for key in a:
+                assert (a[key] is None) == (b[key] is None)
+                if a[key] is not None:
+                    assert torch.equal(a[key], b[key]), (shape, key)
+        bad = pts.clone()
+        bad[(1 << 19) + 5, 1] = 1.5
+        bad[(1 << 19) + 900, 0] = -0.1
+        flag = _cuda.new_flag(pts.device)
+        _cuda.eval_points(ds, bad, s.nInd, 1, N, flag=flag, binned=True)
+        assert int(flag.item()) == (1 << 19) + 5
+    # curves / small splines / small N keep the direct kernel
+    small = bspy.Spline(2, 3, (4, 4), (8, 8), [K(4, 8), K(4, 8)], rng.standard_normal((3, 8, 8)))
+    assert _cuda.library().bspy_cuda_binned_workspace_bytes(device_spline(small).c, 1 << 20) == 0
