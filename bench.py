@@ -436,13 +436,39 @@ def run_ours(args):
     for _ in range(max(args.warmup, 3)):
         wl.step()
     barrier()
+    # Launch-bound steps (config 1: 5 us of HBM traffic; the binned path: hundreds of small launches) are
+    # captured once in a CUDA graph and replayed, so that the timed region holds GPU work, not Python overhead.
+    step_fn, graphed = wl.step, False
+    if args.graph:
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                wl.step()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                wl.step()
+            graph.replay()
+            torch.cuda.synchronize()
+            step_fn, graphed = graph.replay, True
+        except Exception as exc:  # capture not possible: time eager launches
+            sys.stderr.write(f"CUDA graph capture failed, timing eager launches: {exc}\n")
+            torch.cuda.synchronize()
+    launches_per_step = None
+    if graphed:
+        c0 = _cuda.launch_count()
+        wl.step()
+        torch.cuda.synchronize()
+        launches_per_step = _cuda.launch_count() - c0
     sampler = ClockSampler(local) if rank == 0 else None
     l0 = _cuda.launch_count()
     t0 = time.perf_counter()
-    per_step = timed(wl.step, args.steps)
+    per_step = timed(step_fn, args.steps)
     barrier()
     t1 = time.perf_counter()
-    launches = _cuda.launch_count() - l0
+    launches = launches_per_step * args.steps if graphed else _cuda.launch_count() - l0
     clocks = sampler.stop(t0, t1) if sampler else None
     total = torch.tensor([sum(per_step)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -527,7 +553,8 @@ def run_ours(args):
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": wl.name, "points_per_step_per_gpu": wl.points, "note": wl.note,
                        "l2": "L2 flushed (write of 252 MB) between timed steps" if flush is not None else "per-step working set larger than L2",
-                       "sharding": "each rank evaluates its own shard (no data-path collective)"},
+                       "sharding": "each rank evaluates its own shard (no data-path collective)",
+                       "cuda_graph": graphed},
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps},
             "roofline": roofline, "cpu_baseline": cpu}
@@ -546,6 +573,7 @@ def main():
     ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (testing only; 1.0 = BASELINE size)")
     ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-graph", dest="graph", action="store_false", help="time eager launches instead of a CUDA-graph replay")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     args = ap.parse_args()
     return run_reference(args) if args.impl == "reference" else run_ours(args)

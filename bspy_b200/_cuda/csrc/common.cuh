@@ -198,6 +198,19 @@ __device__ __forceinline__ void load_knot_window(const double *__restrict__ knot
     for (int j = 0; j < 2 * (O - 1); ++j) kw[j] = __ldg(knots + ix - (O - 1) + j);
 }
 
+__device__ __forceinline__ double fetch_param(const PointsDev &in, long long p, int iv, long long &rem)
+{
+    // grid mode: decode the multi-index from the flat index, last variable fastest; callers walk
+    // iv from nInd-1 down to 0 and thread `rem` through.
+    if (in.grid) {
+        const long long n = in.nAxis[iv];
+        const long long idx = rem % n;
+        rem /= n;
+        return __ldg(in.axes[iv] + idx);
+    }
+    return __ldg(in.uvw + p * in.pointStride + iv * in.varStride);
+}
+
 // first point outside the domain: keep the smallest index
 __device__ __forceinline__ void report_outside(int64_t *flag, int64_t p)
 {

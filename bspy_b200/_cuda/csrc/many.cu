@@ -3,11 +3,15 @@
 // Replaces a Python loop of `spline(uArray)` over a list of splines (reference ufunc-style
 // evaluate, bspy/spline.py:940-947, one interpreter pass per point) for S curves that share
 // order / nCoef / nDep but have their own knots, coefficients and parameters.
-// One warp per curve: the curve's knots and coefficients (a few hundred bytes) are staged once in
-// the warp's slice of shared memory with coalesced loads, each lane then evaluates every 32nd
-// parameter (span bisection over the staged knots, register recurrence, window dot products) and
-// stores are coalesced along the point index.  No block-level synchronisation.
-#include "common.cuh"
+// One warp per curve, no block-level synchronisation:
+//   1. the curve's knots and coefficients (a few hundred bytes) are staged in the warp's slice of shared memory
+//      with coalesced loads, coefficients interleaved as cf[i][dep];
+//   2. the lanes build the per-span records (left knots + reciprocal knot gaps, curve.cuh) once per curve --
+//      the only divisions of the whole evaluation;
+//   3. each lane evaluates every 32nd parameter: bisection over the staged knots, one record fetch (16-byte
+//      loads), subtract/multiply/fma recurrence, window dot products;
+//   4. stores are coalesced along the point index.
+#include "curve.cuh"
 
 namespace bspy {
 
@@ -21,60 +25,73 @@ struct ManyParams {
     int slice;  // doubles of shared memory per warp
 };
 
-template <int O, bool DER>
+// NDEP == 0: runtime nDep (one dot product per dependent variable)
+template <int O, int NDEP, bool DER>
 __global__ void __launch_bounds__(256) many_kernel(const ManyParams P)
 {
+    using R = SpanRec<O>;
     extern __shared__ double sm[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int warpsPerBlock = blockDim.x >> 5;
-    double *sk = sm + (long long)warp * P.slice;   // knots
     const int nKnots = O + P.nCoef;
-    double *sc = sk + ((nKnots + 1) & ~1);          // coefs (nDep, nCoef)
-    const int nC = P.nDep * P.nCoef;
+    const int nDep = NDEP ? NDEP : P.nDep;
+    double *kn = sm + (long long)warp * P.slice;                 // knots
+    double *rec = kn + ((nKnots + 1) & ~1);                      // (nCoef-O+1) records
+    double *cf = rec + (P.nCoef - O + 1) * R::stride;            // cf[i * nDep + d]
+    const int nC = nDep * P.nCoef;
     for (long long s = (long long)blockIdx.x * warpsPerBlock + warp; s < P.nSplines; s += (long long)gridDim.x * warpsPerBlock) {
         const double *gk = P.knots + s * P.knotStride;
         const double *gc = P.coefs + s * P.coefStride;
         __syncwarp();
-        for (int i = lane; i < nKnots; i += 32) sk[i] = __ldcs(gk + i);
-        for (int i = lane; i < nC; i += 32) sc[i] = __ldcs(gc + i);
+        for (int i = lane; i < nKnots; i += 32) kn[i] = __ldcs(gk + i);
+        for (int i = lane; i < nC; i += 32) {
+            const int d = i / P.nCoef, c = i - d * P.nCoef;      // global layout (nDep, nCoef)
+            cf[c * nDep + d] = __ldcs(gc + i);
+        }
         __syncwarp();
-        const double lo = sk[O - 1], hi = sk[P.nCoef];
+        build_span_records<O>(kn, P.nCoef, rec, lane, 32);
+        __syncwarp();
+        const double lo = kn[O - 1], hi = kn[P.nCoef];
         const double *gu = P.u + s * P.nPts;
+        double *ov = P.values + s * nDep * P.nPts;
+        double *og = DER ? P.deriv1 + s * nDep * P.nPts : nullptr;
+#pragma unroll 2
         for (int p = lane; p < P.nPts; p += 32) {
             const double u = __ldcs(gu + p);
             if (((u < lo) | (u > hi)) && P.firstOutside) report_outside((int64_t *)P.firstOutside, s * P.nPts + p);
-            // span: knots <= u among sk[O .. nCoef)
-            int ix = O, n = P.nCoef - O;
-            if (u != u) { ix = P.nCoef; n = 0; }
-            while (n > 0) {
-                const int half = n >> 1;
-                const bool le = sk[ix + half] <= u;
-                ix = le ? ix + half + 1 : ix;
-                n = le ? n - half - 1 : half;
-            }
-            double kw[2 * (O - 1) > 0 ? 2 * (O - 1) : 1];
+            if constexpr (NDEP > 0) {
+                double v[NDEP], g[NDEP];
+                curve_point<O, NDEP, DER>(kn, rec, cf, P.nCoef, u, v, g);
 #pragma unroll
-            for (int j = 0; j < 2 * (O - 1); ++j) kw[j] = sk[ix - (O - 1) + j];
-            double b0[O], b1[O];
-            basis_regs<O, DER>(kw, u, 0, b0, b1);
-            for (int d = 0; d < P.nDep; ++d) {
-                const double *row = sc + d * P.nCoef + ix - O;
-                double v = 0.0, g = 0.0;
-#pragma unroll
-                for (int j = 0; j < O; ++j) {
-                    const double x = row[j];
-                    v = fma(x, b0[j], v);
-                    if (DER) g = fma(x, b1[j], g);
+                for (int d = 0; d < NDEP; ++d) {
+                    __stcs(ov + d * P.nPts + p, v[d]);
+                    if (DER) __stcs(og + d * P.nPts + p, g[d]);
                 }
-                __stcs(P.values + (s * P.nDep + d) * P.nPts + p, v);
-                if (DER) __stcs(P.deriv1 + (s * P.nDep + d) * P.nPts + p, g);
+            } else {
+                const int ix = curve_span(kn, O, P.nCoef, u);
+                double r[R::stride > 0 ? R::stride : 1];
+#pragma unroll
+                for (int j = 0; j < R::stride; ++j) r[j] = rec[(ix - O) * R::stride + j];
+                double b0[O], b1[O];
+                basis_from_record<O, DER>(r, u, b0, b1);
+                for (int d = 0; d < nDep; ++d) {
+                    double v = 0.0, g = 0.0;
+#pragma unroll
+                    for (int j = 0; j < O; ++j) {
+                        const double x = cf[(ix - O + j) * nDep + d];
+                        v = fma(x, b0[j], v);
+                        if (DER) g = fma(x, b1[j], g);
+                    }
+                    __stcs(ov + d * P.nPts + p, v);
+                    if (DER) __stcs(og + d * P.nPts + p, g);
+                }
             }
         }
     }
 }
 
-template <int O>
-static int launch_many(const ManyParams &P, cudaStream_t stream)
+template <int O, int NDEP, bool DER>
+static int launch_many3(const ManyParams &P, cudaStream_t stream)
 {
     const int threads = 256, warps = threads / 32;
     const size_t smem = (size_t)P.slice * warps * sizeof(double);
@@ -82,17 +99,25 @@ static int launch_many(const ManyParams &P, cudaStream_t stream)
     long long blocks = (P.nSplines + warps - 1) / warps;
     const long long cap = (long long)num_sms() * 8;
     if (blocks > cap) blocks = cap;
-    cudaError_t e = cudaSuccess;
-    if (P.deriv1) {
-        if (smem > 48 * 1024) e = cudaFuncSetAttribute(many_kernel<O, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) many_kernel<O, true><<<(unsigned)blocks, threads, smem, stream>>>(P);
-    } else {
-        if (smem > 48 * 1024) e = cudaFuncSetAttribute(many_kernel<O, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) many_kernel<O, false><<<(unsigned)blocks, threads, smem, stream>>>(P);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(many_kernel<O, NDEP, DER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
     }
-    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+    many_kernel<O, NDEP, DER><<<(unsigned)blocks, threads, smem, stream>>>(P);
     count_launch();
     return check_launch("bspy_cuda_eval_many");
+}
+
+template <int O>
+static int launch_many(const ManyParams &P, cudaStream_t stream)
+{
+    const bool der = P.deriv1 != nullptr;
+    switch (P.nDep) {
+        case 1: return der ? launch_many3<O, 1, true>(P, stream) : launch_many3<O, 1, false>(P, stream);
+        case 2: return der ? launch_many3<O, 2, true>(P, stream) : launch_many3<O, 2, false>(P, stream);
+        case 3: return der ? launch_many3<O, 3, true>(P, stream) : launch_many3<O, 3, false>(P, stream);
+        default: return der ? launch_many3<O, 0, true>(P, stream) : launch_many3<O, 0, false>(P, stream);
+    }
 }
 
 }  // namespace bspy
@@ -108,13 +133,18 @@ extern "C" int bspy_cuda_eval_many(int32_t order, int32_t nCoef, int32_t nDep, i
         return BSPY_E_ARG;
     }
     if (nSplines == 0 || nPts == 0) return 0;
+    if (order > 8) {
+        set_error("bspy_cuda_eval_many: order %d not supported (1..8)", order);
+        return BSPY_E_UNSUPPORTED;
+    }
     ManyParams P{};
     P.nCoef = nCoef; P.nDep = nDep; P.nPts = nPts; P.nSplines = nSplines;
     P.knots = knots; P.coefs = coefs; P.u = u;
     P.knotStride = knotStride; P.coefStride = coefStride;
     P.values = values; P.deriv1 = deriv1;
     P.firstOutside = (long long *)firstOutside;
-    P.slice = ((order + nCoef + 1) & ~1) + ((nDep * nCoef + 1) & ~1);
+    const int recStride = ((order - 1 + order * (order - 1) / 2) + 1) & ~1;
+    P.slice = ((order + nCoef + 1) & ~1) + (nCoef - order + 1) * recStride + ((nDep * nCoef + 1) & ~1);
     cudaStream_t st = (cudaStream_t)stream;
     switch (order) {
         case 1: return launch_many<1>(P, st);
@@ -124,9 +154,6 @@ extern "C" int bspy_cuda_eval_many(int32_t order, int32_t nCoef, int32_t nDep, i
         case 5: return launch_many<5>(P, st);
         case 6: return launch_many<6>(P, st);
         case 7: return launch_many<7>(P, st);
-        case 8: return launch_many<8>(P, st);
-        default:
-            set_error("bspy_cuda_eval_many: order %d not supported (1..8)", order);
-            return BSPY_E_UNSUPPORTED;
+        default: return launch_many<8>(P, st);
     }
 }

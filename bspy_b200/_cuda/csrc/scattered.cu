@@ -19,19 +19,6 @@
 
 namespace bspy {
 
-__device__ __forceinline__ double fetch_param(const PointsDev &in, long long p, int iv, long long &rem)
-{
-    // grid mode: decode the multi-index from the flat index, last variable fastest; callers walk
-    // iv from nInd-1 down to 0 and thread `rem` through.
-    if (in.grid) {
-        const long long n = in.nAxis[iv];
-        const long long idx = rem % n;
-        rem /= n;
-        return __ldg(in.axes[iv] + idx);
-    }
-    return __ldg(in.uvw + p * in.pointStride + iv * in.varStride);
-}
-
 // ---- cofactor normals -------------------------------------------------------------------------
 // T is D x (D-1) (row r = dependent/independent index r of the larger dimension), n[i] =
 // sign * (-1)^i * det(T without row i).  Closed forms for D <= 4, LU with partial pivoting above.
@@ -525,6 +512,9 @@ static long long bin_chunk(long long outBytesPerPoint)
 constexpr long long BIN_MAX_CELLS = 1 << 18;  // histogram / scan size limit
 
 // ---- host dispatch ----------------------------------------------------------------------------
+int launch_curve(const SplineDev &s, const PointsDev &in, long long N, const WrtDev &wrt, const OutDev &out, int jac,
+                 cudaStream_t stream);
+
 typedef void (*FixedFn)(const SplineDev, const PointsDev, const long long, const WrtDev, const OutDev);
 
 struct FixedEntry {
@@ -603,6 +593,10 @@ int launch_eval(const SplineDev &s, const PointsDev &in, long long N, const WrtD
                 cudaStream_t stream)
 {
     if (N <= 0) return 0;
+    if (!in.perm) {
+        const int rc = launch_curve(s, in, N, wrt, out, jac, stream);   // lean single-curve path (curve.cu)
+        if (rc != -1000) return rc;
+    }
     FixedFn fn = find_fixed(s, jac);
     const int threads = 128;
     long long blocks = (N + threads - 1) / threads;
