@@ -303,50 +303,76 @@ def cpu_native_points_per_second(workload, n_points):
 # ------------------------------------------------------------------------------- utilities
 
 class ClockSampler:
+    """SM clock / power / throttle reasons sampled DURING the timed region: NVML in a background thread
+    (~1 ms period, so that even a 10 ms region gets samples), `nvidia-smi -lms` as a fallback."""
     FIELDS = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, gpu_index):
-        self.rows, self.proc = [], None
+        self.rows, self.proc, self.nvml, self.stop_flag = [], None, None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[gpu_index]) if visible and visible.split(",")[gpu_index].isdigit() else gpu_index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20", "-i", str(gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        bits = {"hw_slowdown": n.nvmlClocksEventReasonHwSlowdown if hasattr(n, "nvmlClocksEventReasonHwSlowdown") else 0x8,
+                "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        while not self.stop_flag:
+            try:
+                clk = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                pw = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+                try:
+                    mask = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                except Exception:
+                    mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                self.rows.append((time.perf_counter(), clk, pw, [k for k, b in bits.items() if mask & b]))
+            except Exception:
+                pass
+            time.sleep(0.001)
+
     def _read(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in self.proc.stdout:
-            self.rows.append((time.perf_counter(), line.strip()))
+            f = [x.strip() for x in line.split(",")]
+            try:
+                self.smax = float(f[1])
+                self.rows.append((time.perf_counter(), float(f[0]), float(f[2]) if f[2][:1].isdigit() else None,
+                                  [nm for nm, v in zip(names, f[3:7]) if v.lower().startswith("active")]))
+            except Exception:
+                continue
 
     def stop(self, t0, t1):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, smax, reasons, power = [], None, set(), []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for t, line in self.rows:
-            f = [x.strip() for x in line.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                clk, mx = float(f[0]), float(f[1])
-            except ValueError:
-                continue
-            smax = mx
-            if t0 - 0.05 <= t <= t1 + 0.05:
-                sm.append(clk)
-                try:
-                    power.append(float(f[2]))
-                except ValueError:
-                    pass
-                for name, val in zip(names, f[3:7]):
-                    if val.lower().startswith("active"):
-                        reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
-                "samples": len(sm), "power_w_max": max(power) if power else None}
+        if self.nvml is None and self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML / nvidia-smi"], "samples": 0}
+        time.sleep(0.03)
+        self.stop_flag = True
+        if self.proc is not None:
+            self.proc.terminate()
+        inside = [r for r in self.rows if t0 <= r[0] <= t1]
+        sm = [r[1] for r in inside]
+        power = [r[2] for r in inside if r[2] is not None]
+        reasons = sorted({x for r in inside for x in r[3]})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": getattr(self, "smax", None), "reasons": reasons,
+                "samples": len(sm), "power_w_max": max(power) if power else None,
+                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def measured_peaks():

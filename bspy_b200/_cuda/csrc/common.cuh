@@ -51,6 +51,11 @@ struct PointsDev {
     const int *perm;
     const int *cellKey;
     long long base;
+    // sorted-record mode (records != nullptr): thread t evaluates the point whose parameters are
+    // records[4t .. 4t+nInd) (32-byte records written in cell order by bin_scatter_records_kernel); the packed
+    // span key is the int64 bit pattern of records[4t+3] for nInd <= 3, recKey[t] for nInd == 4
+    const double *records;
+    const int *recKey;
 };
 
 struct OutDev {
@@ -61,6 +66,10 @@ struct OutDev {
     int32_t *spans;    // (nInd, N)
     long long *firstOutside;
     unsigned normalize, normalMask;
+    // array-of-structs results (sorted-record mode): point t writes [values | jacobian (d, iv) | normal] to
+    // aos[t * aosStride ..]; aosStride is a multiple of 4 doubles so that records are whole 32-byte sectors
+    double *aos;
+    int aosStride;
 };
 
 struct WrtDev {

@@ -195,7 +195,8 @@ __global__ void __launch_bounds__(128) eval_fixed_kernel(const SplineDev s, cons
                                                          const WrtDev wrt, const OutDev out)
 {
     using Ord = Orders<NIND, O0, O1, O2, O3>;
-    const bool binned = in.perm != nullptr;
+    const bool recs = in.records != nullptr;
+    const bool binned = in.perm != nullptr || recs;
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < N; t += (long long)gridDim.x * blockDim.x) {
         FixedCtx<Ord, NDEP, JAC> c;
         int ix[NIND];
@@ -203,8 +204,19 @@ __global__ void __launch_bounds__(128) eval_fixed_kernel(const SplineDev s, cons
         bool outside = false;
         long long p = t;
         if (binned) {
-            p = in.base + __ldg(in.perm + t);
-            int key = __ldg(in.cellKey + t);
+            int key;
+            if (recs) {
+                const double2 *rp = reinterpret_cast<const double2 *>(in.records + 4 * t);
+                const double2 r0 = __ldcs(rp), r1 = __ldcs(rp + 1);
+                u[0] = r0.x;
+                if constexpr (NIND > 1) u[1] = r0.y;
+                if constexpr (NIND > 2) u[2] = r1.x;
+                if constexpr (NIND > 3) u[3] = r1.y;
+                key = NIND > 3 ? __ldcs(in.recKey + t) : (int)__double_as_longlong(r1.y);
+            } else {
+                p = in.base + __ldg(in.perm + t);
+                key = __ldg(in.cellKey + t);
+            }
 #pragma unroll
             for (int iv = NIND - 1; iv >= 0; --iv) {
                 const int m = s.nCoef[iv] - Ord::at(iv) + 1;
@@ -212,9 +224,11 @@ __global__ void __launch_bounds__(128) eval_fixed_kernel(const SplineDev s, cons
                 key /= m;
             }
         }
-        long long rem = p;
+        if (!recs) {
+            long long rem = p;
 #pragma unroll
-        for (int iv = NIND - 1; iv >= 0; --iv) u[iv] = fetch_param(in, p, iv, rem);
+            for (int iv = NIND - 1; iv >= 0; --iv) u[iv] = fetch_param(in, p, iv, rem);
+        }
         setup_variable<0, Ord, NDEP, JAC>(s, u[0], wrt.d[0], c, ix, outside, binned);
         if constexpr (NIND > 1) setup_variable<1, Ord, NDEP, JAC>(s, u[1], wrt.d[1], c, ix, outside, binned);
         if constexpr (NIND > 2) setup_variable<2, Ord, NDEP, JAC>(s, u[2], wrt.d[2], c, ix, outside, binned);
@@ -230,6 +244,41 @@ __global__ void __launch_bounds__(128) eval_fixed_kernel(const SplineDev s, cons
         double v[NDEP];
         double g[NIND][NDEP];
         Contract<0, Ord, NDEP, JAC>::run(s.coefs + off, c, v, g);
+        if (out.aos) {
+            // sorted-record mode: one contiguous, sector-aligned result record per point
+            constexpr int DN = (NIND - NDEP == 1 || NDEP - NIND == 1) ? (NIND > NDEP ? NIND : NDEP) : 0;
+            constexpr int R = JAC ? NDEP + NDEP * NIND + DN : NDEP;
+            constexpr int RP = (R + 3) & ~3;
+            double rec[RP];
+#pragma unroll
+            for (int j = 0; j < RP; ++j) rec[j] = 0.0;
+#pragma unroll
+            for (int d = 0; d < NDEP; ++d) rec[d] = v[d];
+            if constexpr (JAC) {
+#pragma unroll
+                for (int d = 0; d < NDEP; ++d)
+#pragma unroll
+                    for (int iv = 0; iv < NIND; ++iv) rec[NDEP + d * NIND + iv] = g[iv][d];
+                if constexpr (DN > 0) {
+                    if (out.normal) {
+                        double J[NDEP * NIND];
+#pragma unroll
+                        for (int d = 0; d < NDEP; ++d)
+#pragma unroll
+                            for (int iv = 0; iv < NIND; ++iv) J[d * NIND + iv] = g[iv][d];
+                        double n[DN];
+                        normal_from_jacobian<NIND, NDEP>(J, s.normalSign, out.normalize, out.normalMask, n);
+#pragma unroll
+                        for (int i = 0; i < DN; ++i) rec[NDEP + NDEP * NIND + i] = n[i];
+                    }
+                }
+            }
+            double2 *q = reinterpret_cast<double2 *>(out.aos + t * out.aosStride);
+#pragma unroll
+            for (int j = 0; j < RP / 2; ++j)
+                if (2 * j < out.aosStride) __stcs(q + j, make_double2(rec[2 * j], rec[2 * j + 1]));
+            continue;
+        }
         if (out.values) {
 #pragma unroll
             for (int d = 0; d < NDEP; ++d) __stcs(out.values + d * out.ld + p, v[d]);
@@ -495,6 +544,68 @@ __global__ void __launch_bounds__(256) bin_scatter_kernel(const int *__restrict_
     sortedKey[pos] = key;
 }
 
+// ---- sorted-record variant (large chunks; no L2-residency assumption) --------------------------------------
+// scatter: 32-byte point records in cell order (a full sector per point, so the scattered write needs no
+// read-modify-write) + the inverse permutation (coalesced)
+__global__ void __launch_bounds__(256) bin_scatter_records_kernel(const SplineDev s, const PointsDev in, const long long base,
+                                                                  const int n, const int *__restrict__ keys,
+                                                                  int *__restrict__ cursor, double *__restrict__ records,
+                                                                  int *__restrict__ recKey, int *__restrict__ inv)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const long long p = base + t;
+    const int key = keys[t];
+    const int pos = atomicAdd(cursor + key, 1);
+    double r[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int iv = 0; iv < s.nInd; ++iv) r[iv] = __ldg(in.uvw + p * in.pointStride + iv * in.varStride);
+    if (s.nInd <= 3) r[3] = __longlong_as_double((long long)key);
+    else recKey[pos] = key;
+    double2 *q = reinterpret_cast<double2 *>(records + 4LL * pos);
+    q[0] = make_double2(r[0], r[1]);
+    q[1] = make_double2(r[2], r[3]);
+    inv[t] = pos;
+}
+
+// un-permute: a warp takes 32 consecutive points, reads their 32 result records with lanes running along each
+// record (every sector is requested once, 12 lanes per 96-byte record), transposes through shared memory and
+// writes the struct-of-arrays outputs coalesced.
+constexpr int UNPERM_WARPS = 8;
+__global__ void __launch_bounds__(UNPERM_WARPS * 32) bin_unpermute_kernel(const double *__restrict__ aos, const int aosStride,
+                                                                          const int *__restrict__ inv, const long long base,
+                                                                          const int n, const int nDep, const int nJ,
+                                                                          const int nNormal, const OutDev out)
+{
+    extern __shared__ double tile[];                       // per warp: aosStride x 33 doubles
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *tw = tile + (long long)warp * aosStride * 33;
+    const int first = (blockIdx.x * (blockDim.x >> 5) + warp) * 32;
+    if (first >= n) return;
+    const int t = first + lane;
+    const long long myRec = t < n ? (long long)__ldg(inv + t) * aosStride : 0;
+    const int total = 32 * aosStride;
+    for (int idx = lane; idx < total; idx += 32) {
+        const int r = idx / aosStride, e = idx - r * aosStride;
+        const long long rb = __shfl_sync(0xffffffffu, myRec, r);
+        const double x = (first + r < n) ? __ldcs(aos + rb + e) : 0.0;
+        tw[e * 33 + r] = x;
+    }
+    __syncwarp();
+    if (t >= n) return;
+    const long long p = base + t;
+    for (int k = 0; k < nDep + nJ + nNormal; ++k) {
+        const double val = tw[k * 33 + lane];
+        if (k < nDep) {
+            if (out.values) __stcs(out.values + k * out.ld + p, val);
+        } else if (k < nDep + nJ) {
+            if (out.jacobian) __stcs(out.jacobian + (k - nDep) * out.ld + p, val);
+        } else {
+            if (out.normal) __stcs(out.normal + (k - nDep - nJ) * out.ld + p, val);
+        }
+    }
+}
+
+constexpr long long BIN_REC_CHUNK = 1 << 22;   // points per chunk in sorted-record mode
 constexpr long long BIN_CHUNK_MAX = 1 << 20;  // workspace is sized for this many points per chunk
 
 // Points per chunk: the outputs of a chunk are scattered back to their original positions 8 bytes at a time, which
@@ -688,6 +799,23 @@ static long long binned_cells(const SplineDev &s)
     return cells;
 }
 
+static int bin_mode(long long N)
+{
+    // 0: scatter results 8 bytes at a time within L2-sized chunks; 1: sorted 32-byte point records, array-of-structs
+    // results and an un-permute pass over 4 Mi-point chunks (every scattered access is a whole sector)
+    const char *e = getenv("BSPY_BIN_MODE");
+    if (e) return atoi(e) ? 1 : 0;
+    return N >= (1 << 21) ? 1 : 0;
+}
+
+static int aos_stride(const SplineDev &s)
+{
+    const int D = (s.nInd - s.nDep == 1 || s.nDep - s.nInd == 1) ? (s.nInd > s.nDep ? s.nInd : s.nDep) : 0;
+    return (s.nDep + s.nDep * s.nInd + D + 3) & ~3;
+}
+
+static long long pad64(long long n) { return (n + 63) / 64 * 64; }
+
 // bytes of workspace for the binned path, 0 when binning does not apply to this spline
 long long binned_workspace(const SplineDev &s, long long N)
 {
@@ -699,19 +827,64 @@ long long binned_workspace(const SplineDev &s, long long N)
     const long long cells = binned_cells(s);
     if (!cells) return 0;
     if (!find_fixed(s, 0)) return 0;
+    if (bin_mode(N) == 1 && s.nInd <= 4) {
+        const long long chunk = N < BIN_REC_CHUNK ? N : BIN_REC_CHUNK;
+        return 4 * (3 * pad64(chunk) + pad64(cells + 1)) + 8 * (4 * pad64(chunk) + (long long)aos_stride(s) * pad64(chunk));
+    }
     const long long chunk = N < BIN_CHUNK_MAX ? N : BIN_CHUNK_MAX;
-    return 3 * 4 * ((chunk + 63) / 64 * 64) + 4 * ((cells + 1 + 63) / 64 * 64);
+    return 3 * 4 * pad64(chunk) + 4 * pad64(cells + 1);
+}
+
+static int eval_binned_records(const SplineDev &s, PointsDev in, long long N, const WrtDev &wrt, OutDev out, int jac,
+                               void *workspace, cudaStream_t stream)
+{
+    const long long cells = binned_cells(s);
+    const long long chunk = N < BIN_REC_CHUNK ? N : BIN_REC_CHUNK;
+    const long long cpad = pad64(chunk);
+    int *keys = (int *)workspace, *inv = keys + cpad, *recKey = inv + cpad, *hist = recKey + cpad;
+    double *records = (double *)(hist + pad64(cells + 1));
+    double *aos = records + 4 * cpad;
+    const int D = (s.nInd - s.nDep == 1 || s.nDep - s.nInd == 1) ? (s.nInd > s.nDep ? s.nInd : s.nDep) : 0;
+    const int nJ = jac ? s.nDep * s.nInd : 0;
+    const int nN = (jac && out.normal) ? D : 0;
+    const int stride = (s.nDep + nJ + nN + 3) & ~3;
+    FixedFn fn = find_fixed(s, jac);
+    for (long long base = 0; base < N; base += chunk) {
+        const int n = (int)(N - base < chunk ? N - base : chunk);
+        cudaError_t e = cudaMemsetAsync(hist, 0, sizeof(int) * (cells + 1), stream);
+        if (e != cudaSuccess) { set_error("cudaMemsetAsync: %s", cudaGetErrorString(e)); return (int)e; }
+        OutDev o1{};
+        o1.ld = out.ld; o1.spans = out.spans; o1.firstOutside = out.firstOutside;
+        bin_keys_kernel<<<(n + 255) / 256, 256, 0, stream>>>(s, in, base, n, keys, hist, o1);
+        bin_scan_kernel<<<1, 1024, 0, stream>>>(hist, (int)cells);
+        bin_scatter_records_kernel<<<(n + 255) / 256, 256, 0, stream>>>(s, in, base, n, keys, hist, records, recKey, inv);
+        PointsDev pin{};
+        pin.records = records; pin.recKey = recKey;
+        OutDev o2 = out;
+        o2.spans = nullptr; o2.firstOutside = nullptr;
+        o2.aos = aos; o2.aosStride = stride;
+        fn<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(s, pin, n, wrt, o2);
+        int uw = (int)(48 * 1024 / (sizeof(double) * stride * 33));     // warps per CTA that fit 48 KB of transpose tiles
+        uw = uw > UNPERM_WARPS ? UNPERM_WARPS : (uw < 1 ? 1 : uw);
+        bin_unpermute_kernel<<<(n + uw * 32 - 1) / (uw * 32), uw * 32, sizeof(double) * uw * stride * 33, stream>>>(
+            aos, stride, inv, base, n, s.nDep, nJ, nN, out);
+        count_launch(5);
+        int rc = check_launch("bspy_cuda_eval_points_binned");
+        if (rc) return rc;
+    }
+    return 0;
 }
 
 int eval_binned(const SplineDev &s, PointsDev in, long long N, const WrtDev &wrt, OutDev out, int jac, void *workspace,
                 cudaStream_t stream)
 {
+    if (bin_mode(N) == 1 && s.nInd <= 4) return eval_binned_records(s, in, N, wrt, out, jac, workspace, stream);
     const long long cells = binned_cells(s);
     const int D = s.nInd > s.nDep ? s.nInd : s.nDep;
     const long long outBytes = 8LL * ((out.values ? s.nDep : 0) + (out.jacobian ? s.nDep * s.nInd : 0) + (out.normal ? D : 0));
     const long long cap = N < BIN_CHUNK_MAX ? N : BIN_CHUNK_MAX;      // what the workspace was sized for
     const long long chunk = bin_chunk(outBytes) < cap ? bin_chunk(outBytes) : cap;
-    const long long cpad = (cap + 63) / 64 * 64;
+    const long long cpad = pad64(cap);
     int *keys = (int *)workspace, *perm = keys + cpad, *skey = perm + cpad, *hist = skey + cpad;
     FixedFn fn = find_fixed(s, jac);
     int32_t *spans = out.spans;

@@ -410,6 +410,17 @@ def test_binned_path_is_bit_identical_to_unbinned():
         flag = _cuda.new_flag(pts.device)
         _cuda.eval_points(ds, bad, s.nInd, 1, N, flag=flag, binned=True)
         assert int(flag.item()) == (1 << 19) + 5
+    # sorted-record mode (>= 2 Mi points): same bits again, unit normals included
+    s = bspy.Spline(2, 3, (4, 4), (70, 80), [K(4, 70), K(4, 80)], rng.standard_normal((3, 70, 80)))
+    ds = device_spline(s)
+    N = (1 << 22) + 4321
+    pts = torch.rand((N, 2), dtype=torch.float64, device="cuda", generator=torch.Generator(device="cuda").manual_seed(4))
+    for request in (dict(values=True, jacobian=True, normal=True, spans=True), dict(values=False, normal=True, normalize=False), dict(values=True)):
+        a = _cuda.eval_points(ds, pts, 2, 1, N, binned=True, **request)
+        b = _cuda.eval_points(ds, pts, 2, 1, N, binned=False, **request)
+        for key in a:
+            if a[key] is not None:
+                assert torch.equal(a[key], b[key]), key
     # curves / small splines / small N keep the direct kernel
     small = bspy.Spline(2, 3, (4, 4), (8, 8), [K(4, 8), K(4, 8)], rng.standard_normal((3, 8, 8)))
     assert _cuda.library().bspy_cuda_binned_workspace_bytes(device_spline(small).c, 1 << 20) == 0
