@@ -385,11 +385,12 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(cfg):
-    """dram bytes per launch of the dominant kernel from the committed ncu capture, if any."""
+def ncu_traffic(cfg, points_per_launch):
+    """DRAM bytes per launch of the dominant kernel, scaled from the committed `ncu --set full` capture
+    (profiles/traffic.json holds bytes per point and the capture it came from); None if there is none."""
     path = os.path.join(ROOT, "profiles", "traffic.json")
     try:
-        return json.load(open(path)).get(cfg)
+        return float(json.load(open(path))[cfg]["dram_bytes_per_point"]) * points_per_launch
     except Exception:
         return None
 
@@ -522,7 +523,7 @@ def run_ours(args):
     launch_s = float(np.mean(per_step)) / max(1, launches // args.steps)
     achieved = wl.bytes_per_point * wl.points / max(1, launches // args.steps) / launch_s / 1e9
     roofline = {"bound": wl.bound, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic(args.config), "kernel": wl.kernel, "peak_source": how,
+                "traffic": ncu_traffic(args.config, wl.points / max(1, launches // args.steps)), "kernel": wl.kernel, "peak_source": how,
                 "algorithmic_bytes_per_point": wl.bytes_per_point, "launch_ms": launch_s * 1e3}
     # FP64 context: flops/point x points/s against a live FMA probe
     try:
