@@ -328,6 +328,211 @@ __global__ void __launch_bounds__(GRID_WARPS * 32, 2) grid2_dmma_kernel(const Gr
     }
 }
 
+// ---- volumes (nInd == 3): rows of the MMA are (a, b) pairs, columns run along the third axis ------------------
+//     out[d,a,b,c] = sum_k ( sum_ij Bu[a][i] Bv[b][j] C[d][..i][..j][sw(c)-ow+k] ) * Bw[c][k]
+// A = T[(a,b)][k] for three kinds (value, d/du, d/dv), B = Bw^T and dBw^T; value, the three first partials and
+// nothing else (normals of a volume need nDep == 2 or 4 and go through the scattered kernels).  Same store
+// pattern as the surface kernel; dependent variables are processed one after the other to keep 16 accumulators.
+struct Grid3Params {
+    const double *knots[3], *coefs;
+    int o[3], nC[3];
+    long long depStride;
+    const double *axis[3];
+    long long n[3];
+    double *values, *jacobian;            // (nDep, nU, nV, nW), (nDep, 3, nU, nV, nW)
+    long long *firstOutside;
+    int vec, chunkCols, colChunks, tileRows;
+    long long rowBlocks;
+};
+
+template <int NDEP, int MAXO>
+__global__ void __launch_bounds__(GRID_WARPS * 32, 2) grid3_dmma_kernel(const Grid3Params P)
+{
+    constexpr int KS = MAXO / 4;
+    extern __shared__ double sm[];
+    const int VS = P.chunkCols + 2;
+    double *tabW = sm;                                          // [kind][k][col]: 2 * MAXO * VS
+    double *tabU = tabW + 2 * MAXO * VS;                        // [kind][i][row]: 2 * MAXO * GRID_TILE_ROWS
+    double *tabV = tabU + 2 * MAXO * GRID_TILE_ROWS;            // [kind][j][row]
+    int *spanW = reinterpret_cast<int *>(tabV + 2 * MAXO * GRID_TILE_ROWS);  // chunkCols
+    int *spanU = spanW + P.chunkCols;                           // GRID_TILE_ROWS
+    int *spanVr = spanU + GRID_TILE_ROWS;                       // GRID_TILE_ROWS
+
+    const long long tile = blockIdx.x;
+    const int cc = (int)(tile % P.colChunks);
+    const long long rb = tile / P.colChunks;
+    const long long nRows = P.n[0] * P.n[1];
+    const long long row0 = rb * P.tileRows;
+    const long long col0 = (long long)cc * P.chunkCols;
+    const long long nW = P.n[2];
+    const long long plane = nRows * nW;
+
+    for (int c = threadIdx.x; c < P.chunkCols; c += blockDim.x) {
+        const long long b = col0 + c;
+        const double *kw = P.knots[2];
+        int ix = P.o[2];
+        double w = __ldg(kw + P.o[2] - 1);
+        if (b < nW) {
+            w = __ldg(P.axis[2] + b);
+            ix = span_search_inner(kw, P.o[2] + P.nC[2], P.o[2], w);
+            if (((w < __ldg(kw + P.o[2] - 1)) | (w > __ldg(kw + P.nC[2]))) && rb == 0)
+                if (P.firstOutside) report_outside((int64_t *)P.firstOutside, b);
+        }
+        spanW[c] = ix;
+        double b0[MAXO], b1[MAXO];
+        axis_basis<MAXO>(kw, P.o[2], ix, w, b0, b1);
+#pragma unroll
+        for (int j = 0; j < MAXO; ++j) {
+            const int sl = j - (MAXO - P.o[2]);
+            const int row = sl >= 0 ? sl : P.o[2] + j;
+            tabW[row * VS + c] = sl >= 0 ? b0[j] : 0.0;
+            tabW[(MAXO + row) * VS + c] = sl >= 0 ? b1[j] : 0.0;
+        }
+    }
+    for (int t = threadIdx.x; t < 2 * P.tileRows; t += blockDim.x) {
+        const int which = t / P.tileRows, r = t - which * P.tileRows;      // 0: u of the row, 1: v of the row
+        const long long row = row0 + r;
+        const long long idx = which == 0 ? row / P.n[1] : row % P.n[1];
+        const double *kk = P.knots[which];
+        const int o = P.o[which], nC = P.nC[which];
+        int ix = o;
+        double x = __ldg(kk + o - 1);
+        if (row < nRows) {
+            x = __ldg(P.axis[which] + idx);
+            ix = span_search_inner(kk, o + nC, o, x);
+            if (((x < __ldg(kk + o - 1)) | (x > __ldg(kk + nC))) && cc == 0)
+                if (P.firstOutside) report_outside((int64_t *)P.firstOutside, (which == 0 ? idx * P.n[1] : idx) * nW);
+        }
+        (which == 0 ? spanU : spanVr)[r] = ix;
+        double b0[MAXO], b1[MAXO];
+        axis_basis<MAXO>(kk, o, ix, x, b0, b1);
+        double *tab = which == 0 ? tabU : tabV;
+#pragma unroll
+        for (int j = 0; j < MAXO; ++j) {
+            const int sl = j - (MAXO - o);
+            const int rowj = sl >= 0 ? sl : o + j;
+            tab[rowj * GRID_TILE_ROWS + r] = sl >= 0 ? b0[j] : 0.0;
+            tab[(MAXO + rowj) * GRID_TILE_ROWS + r] = sl >= 0 ? b1[j] : 0.0;
+        }
+    }
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = lane >> 2, r4 = lane & 3;
+    const int bcol = 4 * (q >> 1) + (q & 1);
+    const long long nColsHere = min((long long)P.chunkCols, nW - col0);
+    const int nStrips = (int)min((long long)(P.tileRows / 8), (nRows - row0 + 7) / 8);
+    const long long s0 = (long long)P.nC[1] * P.nC[2], s1 = P.nC[2];
+
+    for (int strip = 0; strip < nStrips; ++strip) {
+        const int myRow = strip * 8 + q;
+        const long long row = row0 + myRow;
+        const int su = spanU[myRow], sv = spanVr[myRow];
+        double tv[NDEP][KS], tdu[NDEP][KS], tdv[NDEP][KS];
+        int cached = -1;
+        for (int c0 = warp * 16; c0 < nColsHere; c0 += GRID_STEP) {
+            const int colA = c0 + bcol, colB = colA + 2;
+            const int swA = spanW[colA], swB = spanW[colB];
+            const long long b = col0 + c0 + 4 * r4;
+            const bool live = row < nRows && b < nW;
+            const int left = (int)min((long long)4, nW - b);
+            const long long at = row * nW + b;
+            auto put = [&](double *base, const double (&x)[4]) {
+                double *p = base + at;
+                if (P.vec == 4 && left == 4) {
+                    st_cs_v4(p, x[0], x[1], x[2], x[3]);
+                } else if (P.vec >= 2 && left == 4) {
+                    __stcs(reinterpret_cast<double2 *>(p), make_double2(x[0], x[1]));
+                    __stcs(reinterpret_cast<double2 *>(p + 2), make_double2(x[2], x[3]));
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (e < left) __stcs(p + e, x[e]);
+                }
+            };
+#pragma unroll
+            for (int d = 0; d < NDEP; ++d) {
+                double acc[4][4];                      // value, du, dv, dw
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) acc[k][e] = 0.0;
+                unsigned todoA = 0xffffffffu, todoB = 0xffffffffu;
+                while (todoA | todoB) {
+                    const int cur = todoA ? __shfl_sync(0xffffffffu, swA, __ffs(todoA) - 1)
+                                          : __shfl_sync(0xffffffffu, swB, __ffs(todoB) - 1);
+                    const bool mineA = swA == cur, mineB = swB == cur;
+                    if (cur != cached) {
+                        // T[(a,b)][k] = sum_ij Bu[a][i] Bv[b][j] C[dd][su-ou+i][sv-ov+j][cur-ow+k], all dd at once
+#pragma unroll
+                        for (int ks = 0; ks < KS; ++ks) {
+                            const int k = r4 + 4 * ks;
+#pragma unroll
+                            for (int dd = 0; dd < NDEP; ++dd) {
+                                double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+                                if (k < P.o[2]) {
+                                    const double *cp = P.coefs + dd * P.depStride + (long long)(su - P.o[0]) * s0 +
+                                                       (long long)(sv - P.o[1]) * s1 + (cur - P.o[2] + k);
+#pragma unroll
+                                    for (int i = 0; i < MAXO; ++i)
+                                        if (i < P.o[0]) {
+                                            double r0 = 0.0, r1 = 0.0;   // sum_j Bv, dBv
+#pragma unroll
+                                            for (int j = 0; j < MAXO; ++j)
+                                                if (j < P.o[1]) {
+                                                    const double x = __ldg(cp + i * s0 + j * s1);
+                                                    r0 = fma(x, tabV[j * GRID_TILE_ROWS + myRow], r0);
+                                                    r1 = fma(x, tabV[(MAXO + j) * GRID_TILE_ROWS + myRow], r1);
+                                                }
+                                            const double bu = tabU[i * GRID_TILE_ROWS + myRow];
+                                            t0 = fma(r0, bu, t0);
+                                            t1 = fma(r0, tabU[(MAXO + i) * GRID_TILE_ROWS + myRow], t1);
+                                            t2 = fma(r1, bu, t2);
+                                        }
+                                }
+                                tv[dd][ks] = t0;
+                                tdu[dd][ks] = t1;
+                                tdv[dd][ks] = t2;
+                            }
+                        }
+                        cached = cur;
+                    }
+#pragma unroll
+                    for (int ks = 0; ks < KS; ++ks) {
+                        const int k = r4 + 4 * ks;
+                        const double bwA = mineA ? tabW[k * VS + colA] : 0.0;
+                        const double dwA = mineA ? tabW[(MAXO + k) * VS + colA] : 0.0;
+                        const double bwB = mineB ? tabW[k * VS + colB] : 0.0;
+                        const double dwB = mineB ? tabW[(MAXO + k) * VS + colB] : 0.0;
+                        if (P.values) {
+                            dmma884(acc[0][0], acc[0][1], tv[d][ks], bwA);
+                            dmma884(acc[0][2], acc[0][3], tv[d][ks], bwB);
+                        }
+                        if (P.jacobian) {
+                            dmma884(acc[1][0], acc[1][1], tdu[d][ks], bwA);
+                            dmma884(acc[1][2], acc[1][3], tdu[d][ks], bwB);
+                            dmma884(acc[2][0], acc[2][1], tdv[d][ks], bwA);
+                            dmma884(acc[2][2], acc[2][3], tdv[d][ks], bwB);
+                            dmma884(acc[3][0], acc[3][1], tv[d][ks], dwA);
+                            dmma884(acc[3][2], acc[3][3], tv[d][ks], dwB);
+                        }
+                    }
+                    todoA &= ~__ballot_sync(0xffffffffu, mineA);
+                    todoB &= ~__ballot_sync(0xffffffffu, mineB);
+                }
+                if (live) {
+                    if (P.values) put(P.values + d * plane, acc[0]);
+                    if (P.jacobian) {
+                        put(P.jacobian + (d * 3 + 0) * plane, acc[1]);
+                        put(P.jacobian + (d * 3 + 1) * plane, acc[2]);
+                        put(P.jacobian + (d * 3 + 2) * plane, acc[3]);
+                    }
+                }
+            }
+        }
+    }
+}
+
 static bool aligned_to(const void *p, unsigned n) { return (reinterpret_cast<uintptr_t>(p) & (n - 1)) == 0; }
 
 template <int NDEP, int MAXO>
@@ -408,6 +613,66 @@ static int grid2_run(const bspy_spline *sp, long long nSplines, long long knotSt
     }
 }
 
+template <int NDEP, int MAXO>
+static int launch_grid3(const Grid3Params &P, cudaStream_t stream)
+{
+    const size_t smem = sizeof(double) * (2 * MAXO * (P.chunkCols + 2) + 4 * MAXO * GRID_TILE_ROWS) +
+                        sizeof(int) * (P.chunkCols + 2 * GRID_TILE_ROWS);
+    static size_t allowed = 48 * 1024;
+    if (smem > allowed) {
+        cudaError_t e = cudaFuncSetAttribute(grid3_dmma_kernel<NDEP, MAXO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+        allowed = smem;
+    }
+    const long long tiles = P.colChunks * P.rowBlocks;
+    if (tiles > 0x7fffffffLL) { set_error("grid too large for one launch"); return BSPY_E_UNSUPPORTED; }
+    grid3_dmma_kernel<NDEP, MAXO><<<(unsigned)tiles, GRID_WARPS * 32, smem, stream>>>(P);
+    count_launch();
+    return check_launch("bspy_cuda_eval_grid");
+}
+
+static bool grid3_supported(const bspy_spline *sp, const double *normal)
+{
+    if (sp->nInd != 3 || sp->nDep < 1 || sp->nDep > 4 || normal) return false;
+    for (int i = 0; i < 3; ++i)
+        if (sp->order[i] > GRID_MAX_ORDER) return false;
+    return true;
+}
+
+static int grid3_run(const bspy_spline *sp, const double *const *axes, const int64_t *nAxis, double *values, double *jacobian,
+                     int64_t *firstOutside, cudaStream_t stream)
+{
+    Grid3Params P{};
+    for (int i = 0; i < 3; ++i) {
+        P.knots[i] = sp->knots[i]; P.o[i] = sp->order[i]; P.nC[i] = sp->nCoef[i];
+        P.axis[i] = axes[i]; P.n[i] = nAxis[i];
+    }
+    P.coefs = sp->coefs;
+    P.depStride = (long long)sp->nCoef[0] * sp->nCoef[1] * sp->nCoef[2];
+    P.values = values; P.jacobian = jacobian;
+    P.firstOutside = (long long *)firstOutside;
+    if (P.n[0] == 0 || P.n[1] == 0 || P.n[2] == 0) return 0;
+    P.vec = 1;
+    if (P.n[2] % 2 == 0 && aligned_to(values, 16) && aligned_to(jacobian, 16)) P.vec = 2;
+    if (P.n[2] % 4 == 0 && aligned_to(values, 32) && aligned_to(jacobian, 32)) P.vec = 4;
+    const long long cap = 256;
+    const long long chunks = (P.n[2] + cap - 1) / cap;
+    long long per = (P.n[2] + chunks - 1) / chunks;
+    per = (per + GRID_STEP - 1) / GRID_STEP * GRID_STEP;
+    P.chunkCols = (int)per;
+    P.colChunks = (int)((P.n[2] + per - 1) / per);
+    const int doubles = (values ? sp->nDep : 0) + (jacobian ? 3 * sp->nDep : 0);
+    P.tileRows = doubles >= 6 ? 16 : GRID_TILE_ROWS;
+    P.rowBlocks = (P.n[0] * P.n[1] + P.tileRows - 1) / P.tileRows;
+    const bool small = P.o[0] <= 4 && P.o[1] <= 4 && P.o[2] <= 4;
+    switch (sp->nDep) {
+        case 1: return small ? launch_grid3<1, 4>(P, stream) : launch_grid3<1, 8>(P, stream);
+        case 2: return small ? launch_grid3<2, 4>(P, stream) : launch_grid3<2, 8>(P, stream);
+        case 3: return small ? launch_grid3<3, 4>(P, stream) : launch_grid3<3, 8>(P, stream);
+        default: return small ? launch_grid3<4, 4>(P, stream) : launch_grid3<4, 8>(P, stream);
+    }
+}
+
 }  // namespace bspy
 
 using namespace bspy;
@@ -436,6 +701,12 @@ extern "C" int bspy_cuda_eval_grid(const bspy_spline *spline, const double *cons
         if (rc) return rc;
         return grid2_run(spline, 1, 0, 0, 0, axes, nAxis, flags, normalMask, values, jacobian, normal, firstOutside,
                          (cudaStream_t)stream);
+    }
+    if (grid3_supported(spline, normal) && (values || jacobian)) {
+        SplineDev chk;
+        int rc = make_spline_dev(spline, chk, "bspy_cuda_eval_grid");
+        if (rc) return rc;
+        return grid3_run(spline, axes, nAxis, values, jacobian, firstOutside, (cudaStream_t)stream);
     }
     PointsDev in{};
     in.grid = 1;

@@ -275,6 +275,13 @@ def test_grid_vs_oracle(c):
     if want_normal:
         assert close_cond(r.normal.reshape(max(c.nInd, c.nDep), -1).T, O.normal_vec(so, uvw, False),
                           O.normal_abs_vec(so, uvw), k=64)
+    # without normals volumes take the tensor-pipe kernel too (with normals: the scattered kernels in grid mode)
+    r2 = s.evaluate_grid(*axes, jacobian=True)
+    assert close_cond(r2.values.reshape(c.nDep, -1).T, O.evaluate_vec(so, uvw), O.derivative_abs_vec(so, [0] * c.nInd, uvw))
+    assert close_cond(np.transpose(r2.jacobian.reshape(c.nDep, c.nInd, -1), (2, 0, 1)), O.jacobian_vec(so, uvw),
+                      O.jacobian_abs_vec(so, uvw))
+    r3 = s.evaluate_grid(*axes, values=True)
+    assert close_cond(r3.values.reshape(c.nDep, -1).T, O.evaluate_vec(so, uvw), O.derivative_abs_vec(so, [0] * c.nInd, uvw))
 
 
 def test_many_curves_vs_oracle():
@@ -345,6 +352,35 @@ def test_large_sample_vs_c_oracle_and_properties():
     s12 = bspy.Spline(3, 3, (4, 4, 4), (32, 32, 32), kn, 2.0 * c1 - 0.5 * c2)
     a, b, ab = (s.evaluate_points(pts).values for s in (s1, s2, s12))
     assert float((ab - (2.0 * a - 0.5 * b)).abs().max()) <= 1e-13 * 40
+
+
+def test_volume_grid_large_and_high_order():
+    """nInd == 3 grids on the tensor pipe: a 32^3-coefficient tricubic volume on a ragged 45 x 37 x 301 grid and an
+    order (5, 3, 6) volume (two K steps), against the oracle; out-of-domain axes raise."""
+    bspy, _, O, _ = _mods()
+    rng = np.random.default_rng(21)
+
+    def K(o, n):
+        w = rng.uniform(0.25, 1.75, n - o + 1)
+        inner = np.concatenate(([0.0], np.cumsum(w))); inner /= inner[-1]
+        return np.concatenate((np.zeros(o - 1), inner, np.ones(o - 1)))
+
+    for order, nCoef, nDep, shape in (((4, 4, 4), (32, 32, 32), 3, (45, 37, 301)), ((5, 3, 6), (7, 5, 9), 2, (9, 11, 130)),
+                                      ((2, 2, 2), (3, 4, 5), 4, (5, 4, 36))):
+        s = bspy.Spline(3, nDep, order, nCoef, [K(o, n) for o, n in zip(order, nCoef)], rng.standard_normal((nDep, *nCoef)))
+        axes = [np.sort(rng.uniform(0, 1, n)) for n in shape]
+        axes[2][0], axes[2][-1], axes[0][0] = 0.0, 1.0, 0.0
+        axes[1][3] = s.knots[1][order[1]] if nCoef[1] > order[1] else axes[1][3]
+        r = s.evaluate_grid(*axes, jacobian=True)
+        uvw = np.stack([m.reshape(-1) for m in np.meshgrid(*axes, indexing="ij")], axis=1)
+        so = O.OracleSpline.of(s)
+        assert r.values.shape == (nDep, *shape) and r.jacobian.shape == (nDep, 3, *shape)
+        assert close(r.values.reshape(nDep, -1).T, O.evaluate_vec(so, uvw))
+        assert close_cond(np.transpose(r.jacobian.reshape(nDep, 3, -1), (2, 0, 1)), O.jacobian_vec(so, uvw), O.jacobian_abs_vec(so, uvw))
+        bad = [a.copy() for a in axes]
+        bad[1][2] = 1.25
+        with pytest.raises(ValueError, match="outside domain"):
+            s.evaluate_grid(*bad)
 
 
 def test_strided_input_and_zero_points():
