@@ -21,7 +21,7 @@ E_ARG, E_UNSUPPORTED, E_NORMAL_DIMS = -1, -2, -3
 NORMALIZE = 1
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libbspy_cuda.so")
+LIB_PATH = os.environ.get("BSPY_CUDA_LIB") or os.path.join(HERE, "libbspy_cuda.so")   # override: kernel A/B experiments only
 
 # every symbol include/bspy_cuda.h declares (tests check the library exports exactly these)
 SYMBOLS = (

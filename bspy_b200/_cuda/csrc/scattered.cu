@@ -166,6 +166,17 @@ struct Contract {
     }
 };
 
+// CTAs per SM the fixed-shape kernel is compiled for: 4 (128 registers) unless the window is so large that the
+// accumulators spill (the 4-variate nDep-6 manifold: measured 1.83 vs 1.50 Gpts/s with 168 registers)
+constexpr int fixed_min_blocks(int nInd, int o0, int o1, int o2, int o3, int nDep, bool jac)
+{
+    int w = nDep * o0;
+    if (nInd > 1) w *= o1;
+    if (nInd > 2) w *= o2;
+    if (nInd > 3) w *= o3;
+    return (jac && w > 256) ? 3 : 4;
+}
+
 template <int IV, class Ord, int NDEP, bool JAC>
 __device__ __forceinline__ void setup_variable(const SplineDev &s, double u, int d, FixedCtx<Ord, NDEP, JAC> &c,
                                                int (&ix)[Ord::n], bool &outside, bool given)
@@ -191,7 +202,7 @@ __device__ __forceinline__ void setup_variable(const SplineDev &s, double u, int
 }
 
 template <int NIND, int O0, int O1, int O2, int O3, int NDEP, bool JAC>
-__global__ void __launch_bounds__(128) eval_fixed_kernel(const SplineDev s, const PointsDev in, const long long N,
+__global__ void __launch_bounds__(128, fixed_min_blocks(NIND, O0, O1, O2, O3, NDEP, JAC)) eval_fixed_kernel(const SplineDev s, const PointsDev in, const long long N,
                                                          const WrtDev wrt, const OutDev out)
 {
     using Ord = Orders<NIND, O0, O1, O2, O3>;
@@ -491,6 +502,7 @@ __global__ void __launch_bounds__(256) bin_keys_kernel(const SplineDev s, const 
                                                        int *__restrict__ keys, int *__restrict__ hist, const OutDev out)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned active = __ballot_sync(0xffffffffu, t < n);
     if (t >= n) return;
     const long long p = base + t;
     int key = 0;
@@ -506,7 +518,20 @@ __global__ void __launch_bounds__(256) bin_keys_kernel(const SplineDev s, const 
     }
     if (outside && out.firstOutside) report_outside((int64_t *)out.firstOutside, p);
     keys[t] = key;
-    atomicAdd(hist + key, 1);
+    // one atomic per distinct cell in the warp (coherent inputs would otherwise serialise on one counter)
+    const unsigned peers = __match_any_sync(active, key);
+    if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(hist + key, __popc(peers));
+}
+
+// warp-aggregated slot claim: the lanes of a warp that share a cell take consecutive slots with one atomic
+__device__ __forceinline__ int claim_slot(int *cursor, int key, unsigned active)
+{
+    const unsigned peers = __match_any_sync(active, key);
+    const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+    int first = 0;
+    if (lane == leader) first = atomicAdd(cursor + key, __popc(peers));
+    first = __shfl_sync(peers, first, leader);
+    return first + __popc(peers & ((1u << lane) - 1));
 }
 
 // exclusive scan of hist[0..cells) in place, one CTA
@@ -537,9 +562,10 @@ __global__ void __launch_bounds__(256) bin_scatter_kernel(const int *__restrict_
                                                           int *__restrict__ perm, int *__restrict__ sortedKey)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned active = __ballot_sync(0xffffffffu, t < n);
     if (t >= n) return;
     const int key = keys[t];
-    const int pos = atomicAdd(cursor + key, 1);
+    const int pos = claim_slot(cursor, key, active);
     perm[pos] = t;
     sortedKey[pos] = key;
 }
@@ -553,10 +579,11 @@ __global__ void __launch_bounds__(256) bin_scatter_records_kernel(const SplineDe
                                                                   int *__restrict__ recKey, int *__restrict__ inv)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned active = __ballot_sync(0xffffffffu, t < n);
     if (t >= n) return;
     const long long p = base + t;
     const int key = keys[t];
-    const int pos = atomicAdd(cursor + key, 1);
+    const int pos = claim_slot(cursor, key, active);
     double r[4] = {0.0, 0.0, 0.0, 0.0};
     for (int iv = 0; iv < s.nInd; ++iv) r[iv] = __ldg(in.uvw + p * in.pointStride + iv * in.varStride);
     if (s.nInd <= 3) r[3] = __longlong_as_double((long long)key);
@@ -829,10 +856,46 @@ long long binned_workspace(const SplineDev &s, long long N)
     if (!find_fixed(s, 0)) return 0;
     if (bin_mode(N) == 1 && s.nInd <= 4) {
         const long long chunk = N < BIN_REC_CHUNK ? N : BIN_REC_CHUNK;
-        return 4 * (3 * pad64(chunk) + pad64(cells + 1)) + 8 * (4 * pad64(chunk) + (long long)aos_stride(s) * pad64(chunk));
+        return 2 * (4 * (3 * pad64(chunk) + pad64(cells + 1)) + 8 * (4 * pad64(chunk) + (long long)aos_stride(s) * pad64(chunk)));
     }
     const long long chunk = N < BIN_CHUNK_MAX ? N : BIN_CHUNK_MAX;
     return 3 * 4 * pad64(chunk) + 4 * pad64(cells + 1);
+}
+
+// Two internal helper streams per device for the sorted-record pipeline: the sort / un-permute passes are
+// memory-bound, the evaluation FP64-bound, so chunk c+1 is sorted (high-priority stream) while chunk c is evaluated
+// (low-priority stream).  Fork from / join to the caller's stream with events; capturable in a CUDA graph.
+struct BinStreams {
+    cudaStream_t sort = nullptr, eval = nullptr;
+    cudaEvent_t fork = nullptr, sorted[2] = {nullptr, nullptr}, evaluated[2] = {nullptr, nullptr}, joinSort = nullptr,
+                joinEval = nullptr;
+    bool ok = false;
+};
+
+static BinStreams *bin_streams()
+{
+    static BinStreams per[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return nullptr;
+    BinStreams &b = per[dev];
+    if (!b.ok) {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);   // lo = lowest priority (numerically largest)
+        if (cudaStreamCreateWithPriority(&b.sort, cudaStreamNonBlocking, hi) != cudaSuccess) return nullptr;
+        if (cudaStreamCreateWithPriority(&b.eval, cudaStreamNonBlocking, lo) != cudaSuccess) return nullptr;
+        cudaEvent_t *evs[] = {&b.fork, &b.sorted[0], &b.sorted[1], &b.evaluated[0], &b.evaluated[1], &b.joinSort, &b.joinEval};
+        for (cudaEvent_t *e : evs)
+            if (cudaEventCreateWithFlags(e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        b.ok = true;
+    }
+    return &b;
+}
+
+static long long records_half_bytes(const SplineDev &s, long long chunk)
+{
+    const long long cells = binned_cells(s);
+    return 4 * (3 * pad64(chunk) + pad64(cells + 1)) + 8 * (4 * pad64(chunk) + (long long)aos_stride(s) * pad64(chunk));
 }
 
 static int eval_binned_records(const SplineDev &s, PointsDev in, long long N, const WrtDev &wrt, OutDev out, int jac,
@@ -841,38 +904,88 @@ static int eval_binned_records(const SplineDev &s, PointsDev in, long long N, co
     const long long cells = binned_cells(s);
     const long long chunk = N < BIN_REC_CHUNK ? N : BIN_REC_CHUNK;
     const long long cpad = pad64(chunk);
-    int *keys = (int *)workspace, *inv = keys + cpad, *recKey = inv + cpad, *hist = recKey + cpad;
-    double *records = (double *)(hist + pad64(cells + 1));
-    double *aos = records + 4 * cpad;
+    const long long half = records_half_bytes(s, chunk);
     const int D = (s.nInd - s.nDep == 1 || s.nDep - s.nInd == 1) ? (s.nInd > s.nDep ? s.nInd : s.nDep) : 0;
     const int nJ = jac ? s.nDep * s.nInd : 0;
     const int nN = (jac && out.normal) ? D : 0;
     const int stride = (s.nDep + nJ + nN + 3) & ~3;
     FixedFn fn = find_fixed(s, jac);
-    for (long long base = 0; base < N; base += chunk) {
+    // measured: no gain (the evaluation kernel already fills the register file, so the memory-bound passes only
+    // displace evaluation CTAs); off unless BSPY_BIN_OVERLAP=1
+    const char *env = getenv("BSPY_BIN_OVERLAP");
+    BinStreams *bs = (env && atoi(env)) ? bin_streams() : nullptr;
+    const long long nChunks = (N + chunk - 1) / chunk;
+    const bool overlap = bs != nullptr && nChunks > 1;
+    cudaStream_t sSort = overlap ? bs->sort : stream, sEval = overlap ? bs->eval : stream;
+    if (overlap) {
+        cudaEventRecord(bs->fork, stream);
+        cudaStreamWaitEvent(sSort, bs->fork, 0);
+        cudaStreamWaitEvent(sEval, bs->fork, 0);
+    }
+    struct Buf { int *keys, *inv, *recKey, *hist; double *records, *aos; } buf[2];
+    for (int h = 0; h < 2; ++h) {
+        char *base = (char *)workspace + h * half;
+        buf[h].keys = (int *)base; buf[h].inv = buf[h].keys + cpad; buf[h].recKey = buf[h].inv + cpad;
+        buf[h].hist = buf[h].recKey + cpad;
+        buf[h].records = (double *)(buf[h].hist + pad64(cells + 1));
+        buf[h].aos = buf[h].records + 4 * cpad;
+    }
+    auto sortChunk = [&](long long c) -> int {
+        const Buf &B = buf[c & 1];
+        const long long base = c * chunk;
         const int n = (int)(N - base < chunk ? N - base : chunk);
-        cudaError_t e = cudaMemsetAsync(hist, 0, sizeof(int) * (cells + 1), stream);
+        cudaError_t e = cudaMemsetAsync(B.hist, 0, sizeof(int) * (cells + 1), sSort);
         if (e != cudaSuccess) { set_error("cudaMemsetAsync: %s", cudaGetErrorString(e)); return (int)e; }
         OutDev o1{};
         o1.ld = out.ld; o1.spans = out.spans; o1.firstOutside = out.firstOutside;
-        bin_keys_kernel<<<(n + 255) / 256, 256, 0, stream>>>(s, in, base, n, keys, hist, o1);
-        bin_scan_kernel<<<1, 1024, 0, stream>>>(hist, (int)cells);
-        bin_scatter_records_kernel<<<(n + 255) / 256, 256, 0, stream>>>(s, in, base, n, keys, hist, records, recKey, inv);
+        bin_keys_kernel<<<(n + 255) / 256, 256, 0, sSort>>>(s, in, base, n, B.keys, B.hist, o1);
+        bin_scan_kernel<<<1, 1024, 0, sSort>>>(B.hist, (int)cells);
+        bin_scatter_records_kernel<<<(n + 255) / 256, 256, 0, sSort>>>(s, in, base, n, B.keys, B.hist, B.records, B.recKey, B.inv);
+        if (overlap) cudaEventRecord(bs->sorted[c & 1], sSort);
+        count_launch(3);
+        return check_launch("bspy_cuda_eval_points_binned(sort)");
+    };
+    auto evalChunk = [&](long long c) -> int {
+        const Buf &B = buf[c & 1];
+        const long long base = c * chunk;
+        const int n = (int)(N - base < chunk ? N - base : chunk);
+        if (overlap) cudaStreamWaitEvent(sEval, bs->sorted[c & 1], 0);
         PointsDev pin{};
-        pin.records = records; pin.recKey = recKey;
+        pin.records = B.records; pin.recKey = B.recKey;
         OutDev o2 = out;
         o2.spans = nullptr; o2.firstOutside = nullptr;
-        o2.aos = aos; o2.aosStride = stride;
-        fn<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(s, pin, n, wrt, o2);
+        o2.aos = B.aos; o2.aosStride = stride;
+        fn<<<(unsigned)((n + 127) / 128), 128, 0, sEval>>>(s, pin, n, wrt, o2);
+        if (overlap) cudaEventRecord(bs->evaluated[c & 1], sEval);
+        count_launch(1);
+        return check_launch("bspy_cuda_eval_points_binned(eval)");
+    };
+    auto unpermChunk = [&](long long c) -> int {
+        const Buf &B = buf[c & 1];
+        const long long base = c * chunk;
+        const int n = (int)(N - base < chunk ? N - base : chunk);
+        if (overlap) cudaStreamWaitEvent(sSort, bs->evaluated[c & 1], 0);
         int uw = (int)(48 * 1024 / (sizeof(double) * stride * 33));     // warps per CTA that fit 48 KB of transpose tiles
         uw = uw > UNPERM_WARPS ? UNPERM_WARPS : (uw < 1 ? 1 : uw);
-        bin_unpermute_kernel<<<(n + uw * 32 - 1) / (uw * 32), uw * 32, sizeof(double) * uw * stride * 33, stream>>>(
-            aos, stride, inv, base, n, s.nDep, nJ, nN, out);
-        count_launch(5);
-        int rc = check_launch("bspy_cuda_eval_points_binned");
-        if (rc) return rc;
+        bin_unpermute_kernel<<<(n + uw * 32 - 1) / (uw * 32), uw * 32, sizeof(double) * uw * stride * 33, sSort>>>(
+            B.aos, stride, B.inv, base, n, s.nDep, nJ, nN, out);
+        count_launch(1);
+        return check_launch("bspy_cuda_eval_points_binned(unpermute)");
+    };
+    // software pipeline: sort(c+1) is enqueued before unpermute(c) so that it runs under eval(c)
+    int rc = sortChunk(0);
+    for (long long c = 0; c < nChunks && !rc; ++c) {
+        rc = evalChunk(c);
+        if (!rc && c + 1 < nChunks) rc = sortChunk(c + 1);
+        if (!rc) rc = unpermChunk(c);
     }
-    return 0;
+    if (overlap) {
+        cudaEventRecord(bs->joinSort, sSort);
+        cudaEventRecord(bs->joinEval, sEval);
+        cudaStreamWaitEvent(stream, bs->joinSort, 0);
+        cudaStreamWaitEvent(stream, bs->joinEval, 0);
+    }
+    return rc;
 }
 
 int eval_binned(const SplineDev &s, PointsDev in, long long N, const WrtDev &wrt, OutDev out, int jac, void *workspace,

@@ -19,18 +19,21 @@ def run(cfg, N):
     order = torch.argsort(key)
     sorted_pts = pts[order].contiguous()
     block = pts.reshape(-1, 32, s.nInd)   # control: random
-    for name, p in (("random", pts), ("sorted-by-cell", sorted_pts)):
+    from bspy_b200 import _cuda
+    from bspy_b200._spline_evaluation import device_spline
+    ds = device_spline(s)
+    for name, p, binned in (("random direct", pts, False), ("sorted direct", sorted_pts, False), ("random binned", pts, True), ("sorted binned", sorted_pts, True)):
+        run1 = lambda: _cuda.eval_points(ds, p, s.nInd, 1, N, values=True, jacobian=True, binned=binned)
         for _ in range(2):
-            s.evaluate_points(p, jacobian=True, check_domain=False)
+            run1()
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         for _ in range(3):
-            s.evaluate_points(p, jacobian=True, check_domain=False)
+            run1()
         b.record(); torch.cuda.synchronize()
         ms = a.elapsed_time(b) / 3
         print(f"{cfg} N={N} {name:16s} {ms:8.3f} ms  {N/ms/1e6:7.2f} Gpts/s  fp64 {wl.flops_per_point*N/ms/1e9:6.2f} TF/s", flush=True)
 
 run("cfg4", 20_000_000)
 run("cfg5", 10_000_000)
-run("cfg1", 1_000_000)
