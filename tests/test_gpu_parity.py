@@ -460,3 +460,56 @@ def test_binned_path_is_bit_identical_to_unbinned():
     # curves / small splines / small N keep the direct kernel
     small = bspy.Spline(2, 3, (4, 4), (8, 8), [K(4, 8), K(4, 8)], rng.standard_normal((3, 8, 8)))
     assert _cuda.library().bspy_cuda_binned_workspace_bytes(device_spline(small).c, 1 << 20) == 0
+
+
+def test_batch_api_variants():
+    """SplineBatch: per-spline knots on the grid path, indices on normals, shard(), spline(i), host and device
+    inputs; bspline_values_batch; evaluate_grid for a curve."""
+    bspy, _, O, _ = _mods()
+    rng = np.random.default_rng(31)
+
+    def K(o, n):
+        w = rng.uniform(0.25, 1.75, n - o + 1)
+        inner = np.concatenate(([0.0], np.cumsum(w))); inner /= inner[-1]
+        return np.concatenate((np.zeros(o - 1), inner, np.ones(o - 1)))
+
+    S = 7
+    ku = np.stack([K(3, 6) for _ in range(S)])
+    kv = K(4, 9)                                            # shared in v, per-spline in u
+    coefs = rng.standard_normal((S, 3, 6, 9))
+    batch = bspy.SplineBatch(2, 3, (3, 4), (6, 9), [ku, kv], coefs)
+    ua, va = np.sort(rng.uniform(0, 1, 21)), np.sort(rng.uniform(0, 1, 150))
+    r = batch.evaluate_grid(ua, va, jacobian=True, normal=True, indices=(2, 0))
+    assert r.values.shape == (S, 3, 21, 150) and r.jacobian.shape == (S, 3, 2, 21, 150) and r.normal.shape == (S, 2, 21, 150)
+    uv = np.stack([m.reshape(-1) for m in np.meshgrid(ua, va, indexing="ij")], axis=1)
+    for i in (0, 3, 6):
+        si = batch.spline(i)
+        assert np.array_equal(si.knots[0], ku[i]) and np.array_equal(si.coefs, coefs[i])
+        so = O.OracleSpline.of(si)
+        assert close(r.values[i].reshape(3, -1).T, O.evaluate_vec(so, uv))
+        assert close(np.transpose(r.jacobian[i].reshape(3, 2, -1), (2, 0, 1)), O.jacobian_vec(so, uv), atol=1e-12)
+        assert close(r.normal[i].reshape(2, -1).T, O.normal_vec(so, uv, True, (2, 0)))
+    half = batch.shard(1, 2)
+    assert len(half) == 3 and torch.equal(half.coefs, batch.coefs[4:7])
+    rd = half.evaluate_grid(torch.from_numpy(ua).cuda(), torch.from_numpy(va).cuda())
+    assert rd.values.is_cuda and np.array_equal(rd.values.cpu().numpy(), r.values[4:7])
+    with pytest.raises(ValueError, match="outside domain: spline"):
+        batch.evaluate_grid(ua, np.append(va, 1.5))
+    # from_splines detects shared knots and refuses mixed shapes
+    b2 = bspy.SplineBatch.from_splines([batch.spline(0), batch.spline(1)])
+    assert b2.knots[0].dim() == 2 and b2.knots[1].dim() == 1
+    with pytest.raises(ValueError):
+        bspy.SplineBatch.from_splines([batch.spline(0), bspy.Spline(2, 3, (3, 3), (6, 9), [ku[0], K(3, 9)], coefs[0])])
+    # vectorised bspline_values: numpy in -> numpy out, CUDA in -> CUDA out, given spans
+    kn = K(5, 12)
+    u = rng.uniform(0, 1, 300)
+    ix, B = bspy.Spline.bspline_values_batch(None, kn, 5, u, 2, True)
+    ixo, Bo = O.basis_vec(kn, 5, u, 2, True)
+    assert np.array_equal(ix, ixo) and np.array_equal(B, Bo)
+    ix2, B2 = bspy.Spline.bspline_values_batch(ix, kn, 5, torch.from_numpy(u).cuda(), 2, True)
+    assert B2.is_cuda and np.array_equal(B2.cpu().numpy(), Bo)
+    # grid entry for a curve = the scattered path on the axis
+    c = CASES[3]
+    s = _spline(c)
+    g = s.evaluate_grid(c.uvw[:, 0], jacobian=True)
+    assert g.values.shape == (c.nDep, c.uvw.shape[0]) and close(g.values.T, c["values"]) and close(g.jacobian[:, 0].T, c["jacobian"][:, :, 0])
