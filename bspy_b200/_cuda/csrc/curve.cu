@@ -1,6 +1,8 @@
 // Scattered points on ONE curve (nInd == 1): the lean path of bspy_cuda_eval_points.
 // Every CTA stages the curve (knots, per-span records, interleaved coefficients; a few KB) in shared memory
 // once and then streams points: 8 B in, 8*nDep B out per point, no divisions and no global gathers in the loop.
+#include <stdlib.h>
+
 #include "curve.cuh"
 
 namespace bspy {
@@ -79,7 +81,9 @@ static int launch_curve3(const CurveParams &P, size_t smem, cudaStream_t stream)
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
     }
     const int threads = 256;
-    long long blocks = (P.N + threads * 8 - 1) / (threads * 8);      // ~8 points per thread amortise the table build
+    const char *e = getenv("BSPY_CURVE_PPT");
+    const int ppt = e ? atoi(e) : 8;
+    long long blocks = (P.N + threads * ppt - 1) / (threads * ppt);  // points per thread amortise the table build
     const long long cap = (long long)num_sms() * 8;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
