@@ -113,13 +113,6 @@ static int launch_many(const ManyParams &P, cudaStream_t stream)
 {
     const bool der = P.deriv1 != nullptr;
     switch (P.nDep) {
-                case 1: return der ? launch_many_warp<O, 1, true>(P, stream) : launch_many_warp<O, 1, false>(P, stream);
-                case 2: return der ? launch_many_warp<O, 2, true>(P, stream) : launch_many_warp<O, 2, false>(P, stream);
-                default: return der ? launch_many_warp<O, 3, true>(P, stream) : launch_many_warp<O, 3, false>(P, stream);
-            }
-        }
-    }
-    switch (P.nDep) {
         case 1: return der ? launch_many3<O, 1, true>(P, stream) : launch_many3<O, 1, false>(P, stream);
         case 2: return der ? launch_many3<O, 2, true>(P, stream) : launch_many3<O, 2, false>(P, stream);
         case 3: return der ? launch_many3<O, 3, true>(P, stream) : launch_many3<O, 3, false>(P, stream);
