@@ -29,7 +29,7 @@ SYMBOLS = (
     "bspy_cuda_spans", "bspy_cuda_basis", "bspy_cuda_eval_points", "bspy_cuda_eval_points_binned",
     "bspy_cuda_binned_workspace_bytes", "bspy_cuda_eval_grid",
     "bspy_cuda_eval_grid_batch", "bspy_cuda_eval_many", "bspy_cuda_probe_fp64", "bspy_cuda_probe_hbm",
-    "bspy_cuda_probe_tiles",
+    "bspy_cuda_probe_tiles", "bspy_cuda_curvature",
 )
 
 
@@ -84,6 +84,7 @@ def library():
             "bspy_cuda_probe_fp64": [i32, i32, vp, C.POINTER(C.c_double), vp],
             "bspy_cuda_probe_hbm": [i32, vp, vp, i64, C.POINTER(C.c_double), vp],
             "bspy_cuda_probe_tiles": [vp, i32, i64, i64, i32, i32, C.POINTER(C.c_double), vp],
+            "bspy_cuda_curvature": [i32, i32, i32, i64, vp, vp, vp, vp, vp],
         }
         for name, args in sig.items():
             fn = getattr(lib, name)
@@ -294,6 +295,18 @@ def eval_many(order, nCoef, nDep, knots, coefs, u, *, deriv1=False, flag=None, o
                                            _ptr(coefs), int(coefs.stride(0)), _ptr(u), nPts, _ptr(out["values"]),
                                            _ptr(out.get("derivative")), _ptr(flag), _stream(dev))
     _check(rc, "bspy_cuda_eval_many")
+    return out
+
+
+def curvature(nInd, nDep, graph, d1, d2, normal):
+    """Launch bspy_cuda_curvature on SoA derivative tensors (see include/bspy_cuda.h); returns (N,)."""
+    dev = d1.device
+    N = d1.shape[-1]
+    out = torch.empty(N, dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        rc = library().bspy_cuda_curvature(int(nInd), int(nDep), int(bool(graph)), int(N), _ptr(_f64(d1, dev)), _ptr(_f64(d2, dev)),
+                                           _ptr(normal), _ptr(out), _stream(dev))
+    _check(rc, "bspy_cuda_curvature")
     return out
 
 

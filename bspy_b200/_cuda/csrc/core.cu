@@ -86,9 +86,86 @@ __global__ void __launch_bounds__(128) basis_kernel(const double *__restrict__ k
     }
 }
 
+// ---- curvature ------------------------------------------------------------------------------
+// bspy/_spline_evaluation.py:80-107 from batched derivatives.  Curves: kappa = numerator / (f'.f')^1.5 with the
+// signed 2-D cross product for planar curves and sqrt(|f''|^2 |f'|^2 - (f'.f'')^2) otherwise.  Surfaces: Gaussian
+// curvature (L N - M^2) / (E G - F^2) from the first and second fundamental forms.  graph != 0: the spline is a
+// scalar function and the curve / surface is its graph (x(u) = u: first derivative 1, second 0).
+__global__ void __launch_bounds__(256) curvature_kernel(int nInd, int nDep, int graph, long long N, const double *__restrict__ d1,
+                                                        const double *__restrict__ d2, const double *__restrict__ normal,
+                                                        double *__restrict__ out)
+{
+    for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < N; p += (long long)gridDim.x * blockDim.x) {
+        if (nInd == 1) {
+            double pp = graph ? 1.0 : 0.0, pq = 0.0, qq = 0.0;     // f'.f', f'.f'', f''.f''
+            for (int d = 0; d < nDep; ++d) {
+                const double a = d1[d * N + p], b = d2[d * N + p];
+                pp = fma(a, a, pp);
+                pq = fma(a, b, pq);
+                qq = fma(b, b, qq);
+            }
+            double num;
+            if (graph)                       // (1, f') x (0, f'')
+                num = d2[p];
+            else if (nDep == 2)
+                num = d1[p] * d2[N + p] - d1[N + p] * d2[p];
+            else
+                num = sqrt(qq * pp - pq * pq);
+            out[p] = num / (pp * sqrt(pp));
+        } else {
+            double su[3], sv[3], suu[3], suv[3], svv[3], n[3];
+            if (graph) {
+                const double fu = d1[p], fv = d1[N + p];
+                su[0] = 1.0; su[1] = 0.0; su[2] = fu;
+                sv[0] = 0.0; sv[1] = 1.0; sv[2] = fv;
+                suu[0] = suu[1] = suv[0] = suv[1] = svv[0] = svv[1] = 0.0;
+                suu[2] = d2[p]; suv[2] = d2[N + p]; svv[2] = d2[2 * N + p];
+                const double len = sqrt(fu * fu + fv * fv + 1.0);
+                n[0] = -fu / len; n[1] = -fv / len; n[2] = 1.0 / len;
+            } else {
+                for (int d = 0; d < 3; ++d) {
+                    su[d] = d1[(d * 2 + 0) * N + p];
+                    sv[d] = d1[(d * 2 + 1) * N + p];
+                    suu[d] = d2[(0 * 3 + d) * N + p];
+                    suv[d] = d2[(1 * 3 + d) * N + p];
+                    svv[d] = d2[(2 * 3 + d) * N + p];
+                    n[d] = normal[d * N + p];
+                }
+            }
+            double E = 0, F = 0, G = 0, L = 0, M = 0, Nn = 0;
+            for (int d = 0; d < 3; ++d) {
+                E = fma(su[d], su[d], E); F = fma(su[d], sv[d], F); G = fma(sv[d], sv[d], G);
+                L = fma(suu[d], n[d], L); M = fma(suv[d], n[d], M); Nn = fma(svv[d], n[d], Nn);
+            }
+            out[p] = (L * Nn - M * M) / (E * G - F * F);
+        }
+    }
+}
+
 }  // namespace bspy
 
 using namespace bspy;
+
+extern "C" int bspy_cuda_curvature(int32_t nInd, int32_t nDep, int32_t graph, int64_t N, const double *d1, const double *d2,
+                                   const double *normal, double *out, void *stream)
+{
+    if (!d1 || !d2 || !out || N < 0 || nDep < 1 || (nInd != 1 && nInd != 2)) {
+        set_error("bspy_cuda_curvature: bad argument");
+        return BSPY_E_ARG;
+    }
+    if (graph && nDep != 1) { set_error("bspy_cuda_curvature: graph mode needs nDep == 1"); return BSPY_E_ARG; }
+    if (nInd == 2 && !graph && (nDep != 3 || !normal)) {
+        set_error("bspy_cuda_curvature: surfaces need nDep == 3 (or a scalar function) and their unit normals");
+        return BSPY_E_UNSUPPORTED;
+    }
+    if (N == 0) return 0;
+    long long blocks = (N + 255) / 256;
+    const long long cap = (long long)num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    curvature_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(nInd, nDep, graph, N, d1, d2, normal, out);
+    count_launch();
+    return check_launch("bspy_cuda_curvature");
+}
 
 extern "C" {
 

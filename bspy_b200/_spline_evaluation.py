@@ -17,7 +17,7 @@ import torch
 
 from bspy_b200 import _cuda
 
-__all__ = ["EvalResult", "bspline_values", "bspline_values_batch", "domain", "evaluate", "derivative", "jacobian",
+__all__ = ["curvature", "curvature_points", "EvalResult", "bspline_values", "bspline_values_batch", "domain", "evaluate", "derivative", "jacobian",
            "normal", "evaluate_points", "evaluate_grid", "device_spline", "freeze"]
 
 
@@ -338,3 +338,43 @@ def evaluate_grid(self, *axes, values=True, jacobian=False, normal=False, normal
                (lambda t: None if t is None else t.cpu())
         res = EvalResult(conv(res.values), None, conv(res.jacobian), conv(res.normal), None)
     return res
+
+
+# ----------------------------------------------------------------------------- curvature
+
+def curvature_points(self, uvw, check_domain=True, device=None):
+    """Curvature at N points (reference ``bspy/_spline_evaluation.py:80-107``, one point per call there):
+    curves (nInd == 1): signed curvature for planar curves, unsigned otherwise; surfaces (nInd == 2, nDep == 3):
+    Gaussian curvature; nDep == 1 is treated as the graph of the function, like the reference's ``self.graph()``.
+    ``uvw``: (N, nInd) numpy / CUDA tensor (flat (N,) for curves); returns (N,) of the same kind."""
+    if self.nInd not in (1, 2):
+        raise ValueError("curvature is defined for curves and surfaces (nInd 1 or 2)")
+    graph = self.nDep == 1
+    if self.nInd == 2 and not graph and self.nDep != 3:
+        raise ValueError("The number of independent variables must be one different than the number of dependent variables.")
+    on_device = isinstance(uvw, torch.Tensor) and uvw.is_cuda
+    if on_device:
+        pts = uvw.to(torch.float64)
+    else:
+        dev = _cuda.device(device)
+        pts = torch.from_numpy(np.ascontiguousarray(np.asarray(uvw, dtype=np.float64))).to(dev)
+    pts = pts.reshape(-1, self.nInd)
+    ev = lambda **kw: evaluate_points(self, pts, values=False, check_domain=kw.pop("check", False), **kw)
+    if self.nInd == 1:
+        d1 = ev(with_respect_to=[1], check=check_domain).derivative
+        d2 = ev(with_respect_to=[2]).derivative
+        k = _cuda.curvature(1, self.nDep, graph, d1.contiguous(), d2.contiguous(), None)
+    else:
+        first = ev(jacobian=True, normal=not graph, check=check_domain)
+        d2 = torch.stack([ev(with_respect_to=w).derivative for w in ([2, 0], [1, 1], [0, 2])])
+        d1 = first.jacobian.reshape(self.nDep * 2, -1) if not graph else first.jacobian.reshape(2, -1)
+        k = _cuda.curvature(2, self.nDep, graph, d1.contiguous(), d2.reshape(-1, d2.shape[-1]).contiguous(),
+                            None if graph else first.normal.contiguous())
+    return k if on_device else k.cpu().numpy()
+
+
+def curvature(self, uv):
+    """Curvature at one point (``float``), reference ``Spline.curvature``."""
+    uv = np.atleast_1d(np.asarray(uv, dtype=np.float64))
+    _single_point(self, uv)
+    return float(curvature_points(self, uv.reshape(1, -1), check_domain=False)[0])

@@ -134,6 +134,14 @@ class Spline(Manifold):
         """Normal at one point; needs ``|nInd - nDep| == 1``."""
         return _ev.normal(self, uvw, normalize, indices)
 
+    def curvature(self, uv):
+        """Curvature of a curve (signed if planar) or Gaussian curvature of a surface at one point."""
+        return _ev.curvature(self, uv)
+
+    def curvature_points(self, uvw, **kwargs):
+        return _ev.curvature_points(self, uvw, **kwargs)
+    curvature_points.__doc__ = _ev.curvature_points.__doc__
+
     def domain(self):
         """``(nInd, 2)`` array of lower / upper parameter bounds."""
         return _ev.domain(self)

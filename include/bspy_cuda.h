@@ -148,6 +148,15 @@ int bspy_cuda_eval_many(int32_t order, int32_t nCoef, int32_t nDep, int64_t nSpl
                         const double *u, int32_t nPts, double *values, double *deriv1,
                         int64_t *firstOutside, void *stream);
 
+/* ---- curvature: replaces curvature, bspy/_spline_evaluation.py:80-107, for N points
+ *      from batched derivatives produced by bspy_cuda_eval_points.
+ *      nInd == 1: d1 (nDep, N) first, d2 (nDep, N) second derivative; signed for planar curves.
+ *      nInd == 2: Gaussian curvature; d1 = jacobian (3, 2, N), d2 = (3 kinds uu|uv|vv, 3, N), normal (3, N) unit.
+ *      graph != 0: nDep == 1, the curve / surface is the graph of the scalar function (reference: self.graph());
+ *                  d1 (nInd, N), d2 (1 or 3 kinds, N), normal unused.                                  */
+int bspy_cuda_curvature(int32_t nInd, int32_t nDep, int32_t graph, int64_t N, const double *d1,
+                        const double *d2, const double *normal, double *out, void *stream);
+
 /* ---- measurement helpers used by bench.py (not part of the evaluation path) --------------
  *      bspy_cuda_probe_fp64: runs `iters` dependent-free FP64 FMA (kind 0) or DMMA m8n8k4
  *      (kind 1) chains on every SM and returns the flop count; time it with events on `stream`.

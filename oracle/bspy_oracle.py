@@ -39,7 +39,7 @@ import numpy as np
 __all__ = [
     "OracleSpline", "span_pt", "basis_pt", "domain", "derivative_pt", "evaluate_pt",
     "jacobian_pt", "normal_pt", "span_vec", "basis_vec", "derivative_vec", "evaluate_vec",
-    "jacobian_vec", "normal_vec", "check_domain_vec",
+    "jacobian_vec", "normal_vec", "check_domain_vec", "curvature_vec",
 ]
 
 
@@ -284,6 +284,39 @@ def normal_vec(s, uvw, normalize=True, indices=None):
         if normalize:
             n /= np.sqrt(np.sum(n * n, axis=1))[:, None]
     return n
+
+
+def curvature_vec(s, uvw):
+    """Curvature at N points, reference ``:80-107``: curves -> cross-product formula (signed for planar curves),
+    surfaces -> Gaussian curvature from the fundamental forms; nDep == 1 -> graph of the function (the reference
+    builds ``self.graph()``, whose extra coordinates are the parameters themselves: derivative 1, second derivative 0)."""
+    uvw = np.asarray(uvw, dtype=np.float64).reshape(-1, s.nInd)
+    N = uvw.shape[0]
+    graph = s.nDep == 1
+    with np.errstate(all="ignore"):
+        if s.nInd == 1:
+            fp, fpp = derivative_vec(s, [1], uvw), derivative_vec(s, [2], uvw)
+            if graph:
+                fp = np.concatenate([np.ones((N, 1)), fp], axis=1)
+                fpp = np.concatenate([np.zeros((N, 1)), fpp], axis=1)
+            pp, pq, qq = (fp * fp).sum(1), (fp * fpp).sum(1), (fpp * fpp).sum(1)
+            if fp.shape[1] == 2:
+                num = fp[:, 0] * fpp[:, 1] - fp[:, 1] * fpp[:, 0]
+            else:
+                num = np.sqrt(qq * pp - pq ** 2)
+            return num / pp ** 1.5
+        d = {w: derivative_vec(s, list(w), uvw) for w in ((1, 0), (0, 1), (2, 0), (1, 1), (0, 2))}
+        if graph:
+            z, o = np.zeros((N, 1)), np.ones((N, 1))
+            su, sv = np.hstack([o, z, d[1, 0]]), np.hstack([z, o, d[0, 1]])
+            suu, suv, svv = (np.hstack([z, z, d[w]]) for w in ((2, 0), (1, 1), (0, 2)))
+        else:
+            su, sv, suu, suv, svv = d[1, 0], d[0, 1], d[2, 0], d[1, 1], d[0, 2]
+        n = np.cross(su, sv)
+        n = n / np.sqrt((n * n).sum(1))[:, None]
+        E, F, G = (su * su).sum(1), (su * sv).sum(1), (sv * sv).sum(1)
+        L, M, Nn = (suu * n).sum(1), (suv * n).sum(1), (svv * n).sum(1)
+        return (L * Nn - M ** 2) / (E * G - F ** 2)
 
 
 # ------------------------------------------------------------- conditioning of the sums

@@ -95,8 +95,36 @@ def basis(knots, order, u, deriv=0, taylor=False, spans_in=None):
     return torch.from_numpy(ix), torch.from_numpy(b)
 
 
+def curvature(nInd, nDep, graph, d1, d2, normal):
+    """numpy restatement of curvature_kernel on the SoA derivative tensors (host-logic tests only)."""
+    launches[0] += 1
+    a, b = d1.numpy(), d2.numpy()
+    N = a.shape[-1]
+    with np.errstate(all="ignore"):
+        if nInd == 1:
+            if graph:
+                a, b = np.vstack([np.ones((1, N)), a]), np.vstack([np.zeros((1, N)), b])
+            pp, pq, qq = (a * a).sum(0), (a * b).sum(0), (b * b).sum(0)
+            num = a[0] * b[1] - a[1] * b[0] if a.shape[0] == 2 else np.sqrt(qq * pp - pq ** 2)
+            return torch.from_numpy(num / (pp * np.sqrt(pp)))
+        if graph:
+            z, o = np.zeros(N), np.ones(N)
+            su, sv = np.stack([o, z, a[0]]), np.stack([z, o, a[1]])
+            suu, suv, svv = (np.stack([z, z, b[i]]) for i in range(3))
+            n = np.cross(su.T, sv.T).T
+            n = n / np.sqrt((n * n).sum(0))
+        else:
+            J = a.reshape(3, 2, N)
+            su, sv = J[:, 0], J[:, 1]
+            suu, suv, svv = b.reshape(3, 3, N)
+            n = normal.numpy()
+        E, F, G = (su * su).sum(0), (su * sv).sum(0), (sv * sv).sum(0)
+        L, M, Nn = (suu * n).sum(0), (suv * n).sum(0), (svv * n).sum(0)
+        return torch.from_numpy((L * Nn - M ** 2) / (E * G - F ** 2))
+
+
 def install(monkeypatch):
     from bspy_b200 import _cuda
-    for name in ("device", "new_flag", "launch_count", "eval_points", "eval_points_host", "eval_grid", "spans", "basis"):
+    for name in ("device", "new_flag", "launch_count", "eval_points", "eval_points_host", "eval_grid", "spans", "basis", "curvature"):
         monkeypatch.setattr(_cuda, name, globals()[name])
     launches[0] = 0

@@ -22,6 +22,8 @@ Outputs (all small, committed):
                          float64 coefficient blocks (read by parsing the two tuple
                          literals; the module itself is never imported because it opens the
                          viewer) plus reference values / derivatives / normals on a 9x9 grid.
+* ``ref_curvature.npz`` – ``Spline.curvature`` (``bspy/_spline_evaluation.py:80-107``) at the sample points of ten of the
+                         cases above (curves with nDep 1/2/3, surfaces with nDep 3 and 1).
 * ``ref_dispatch.npz`` – results of the ufunc-style argument forms of ``Spline.evaluate`` /
                          ``Spline.derivative`` (``bspy/spline.py:757-770, 936-949``).
 """
@@ -223,6 +225,16 @@ def main():
         run_case(bspy, spline, uvw, arrays, meta, tag)
         print(tag, uvw.shape)
     np.savez_compressed(os.path.join(HERE, "ref_cases.npz"), **arrays)
+
+    # ---- 2b. curvature (bspy/_spline_evaluation.py:80-107) for curves (nDep 1, 2, 3) and surfaces (nDep 3, 1) ----
+    curv = {}
+    with np.errstate(all="ignore"):
+        for tag, spline, _ in cases:
+            if tag in ("curve_o3", "curve_o4", "curve_o5", "curve_cfg1", "planar_neg", "curve_doubleknot", "surf_34",
+                       "surf_44_neg", "surf_25_d1", "tomsnasty0"):
+                uvw = arrays[f"{tag}/uvw"]
+                curv[tag] = np.array([float(spline.curvature(uvw[p] if spline.nInd > 1 else uvw[p, 0])) for p in range(uvw.shape[0])])
+    np.savez_compressed(os.path.join(HERE, "ref_curvature.npz"), **curv)
     with open(os.path.join(HERE, "ref_cases.json"), "w") as f:
         json.dump(meta, f, indent=1)
 

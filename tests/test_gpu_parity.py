@@ -513,3 +513,21 @@ def test_batch_api_variants():
     s = _spline(c)
     g = s.evaluate_grid(c.uvw[:, 0], jacobian=True)
     assert g.values.shape == (c.nDep, c.uvw.shape[0]) and close(g.values.T, c["values"]) and close(g.jacobian[:, 0].T, c["jacobian"][:, :, 0])
+
+
+def test_curvature_vs_reference():
+    """batched curvature (curves nDep 1/2/3, surfaces nDep 3 and graph of a scalar function)
+    against Spline.curvature of the reference."""
+    ref = load_npz("ref_curvature.npz")
+    by_tag = {c.tag: c for c in CASES}
+    for tag, want in ref.items():
+        c = by_tag[tag]
+        s = _spline(c)
+        k = s.curvature_points(c.uvw)
+        ok = np.isfinite(want)
+        assert k.shape == want.shape
+        assert np.allclose(k[ok], want[ok], rtol=1e-8, atol=1e-8 * max(1.0, np.abs(want[ok]).max())), tag
+        kd = s.curvature_points(torch.from_numpy(c.uvw).cuda())
+        assert kd.is_cuda and np.array_equal(kd.cpu().numpy(), k, equal_nan=True)
+        p = int(np.flatnonzero(ok)[5])
+        assert np.isclose(s.curvature(c.uvw[p] if c.nInd > 1 else c.uvw[p, 0]), want[p], rtol=1e-8, atol=1e-8)

@@ -237,3 +237,22 @@ def test_float32_and_integer_inputs():
     assert np.allclose(v, ref, rtol=1e-6)
     i = bspy.Spline(1, 1, (2,), (3,), [[0, 0, 1, 2, 2]], [[0, 2, 4]])         # integer lists: computed in float64 here
     assert close(i(0.5), [1.0])
+
+
+def test_curvature_api():
+    ref = load_npz("ref_curvature.npz")
+    for tag in ("curve_o4", "curve_o5", "curve_o3", "surf_34", "surf_25_d1"):
+        c = CASES[tag]
+        s = _spline(c)
+        k = s.curvature_points(c.uvw)
+        want = ref[tag]
+        ok = np.isfinite(want)
+        assert isinstance(k, np.ndarray) and k.shape == want.shape
+        assert np.allclose(k[ok], want[ok], rtol=1e-8, atol=1e-8 * max(1.0, np.abs(want[ok]).max())), tag
+        p = int(np.flatnonzero(ok)[3])
+        one = s.curvature(c.uvw[p] if c.nInd > 1 else c.uvw[p, 0])
+        assert isinstance(one, float) and np.isclose(one, want[p], rtol=1e-8, atol=1e-8)
+    with pytest.raises(ValueError):
+        _spline(CASES["vol_444_d3"]).curvature([0.5, 0.5, 0.5])
+    with pytest.raises(ValueError, match="outside domain"):
+        _spline(CASES["curve_o4"]).curvature(1.5)

