@@ -531,3 +531,31 @@ def test_curvature_vs_reference():
         assert kd.is_cuda and np.array_equal(kd.cpu().numpy(), k, equal_nan=True)
         p = int(np.flatnonzero(ok)[5])
         assert np.isclose(s.curvature(c.uvw[p] if c.nInd > 1 else c.uvw[p, 0]), want[p], rtol=1e-8, atol=1e-8)
+
+
+def test_grid_edge_cases():
+    """Unsorted axes (a 16-column step may mix any knot spans), order-1 / order-8 variables, empty axes, odd sizes
+    that defeat the 32- and 16-byte store paths."""
+    bspy, _, O, _ = _mods()
+    rng = np.random.default_rng(41)
+
+    def K(o, n):
+        w = rng.uniform(0.25, 1.75, n - o + 1)
+        inner = np.concatenate(([0.0], np.cumsum(w))); inner /= inner[-1]
+        return np.concatenate((np.zeros(o - 1), inner, np.ones(o - 1)))
+
+    for order, nCoef, nDep, shape in (((4, 4), (12, 40), 3, (33, 301)), ((1, 8), (5, 11), 2, (17, 130)), ((8, 1), (9, 6), 1, (9, 18)),
+                                      ((3, 3, 4), (6, 5, 30), 3, (5, 6, 203)), ((1, 2, 8), (3, 4, 10), 2, (3, 5, 66)),
+                                      ((3, 2, 4), (4, 3, 90), 3, (4, 3, 300))):       # > 32 coefficient columns per chunk
+        nInd = len(order)
+        s = bspy.Spline(nInd, nDep, order, nCoef, [K(o, n) for o, n in zip(order, nCoef)], rng.standard_normal((nDep, *nCoef)))
+        axes = [rng.uniform(0, 1, n) for n in shape]           # NOT sorted
+        axes[-1][:3] = (1.0, 0.0, s.knots[-1][order[-1]] if nCoef[-1] > order[-1] else 0.5)
+        r = s.evaluate_grid(*axes, jacobian=True)
+        uvw = np.stack([m.reshape(-1) for m in np.meshgrid(*axes, indexing="ij")], axis=1)
+        so = O.OracleSpline.of(s)
+        assert close(r.values.reshape(nDep, -1).T, O.evaluate_vec(so, uvw)), (order, "values")
+        assert close_cond(np.transpose(r.jacobian.reshape(nDep, nInd, -1), (2, 0, 1)), O.jacobian_vec(so, uvw),
+                          O.jacobian_abs_vec(so, uvw)), (order, "jacobian")
+        empty = s.evaluate_grid(*([axes[0][:0]] + axes[1:]), jacobian=True)
+        assert empty.values.shape == (nDep, 0, *shape[1:]) and empty.jacobian.shape == (nDep, nInd, 0, *shape[1:])
