@@ -56,6 +56,9 @@ struct PointsDev {
     // span key is the int64 bit pattern of records[4t+3] for nInd <= 3, recKey[t] for nInd == 4
     const double *records;
     const int *recKey;
+    // per-span records of variable i (left knots | reciprocal knot gaps, SpanRec<order>::stride doubles per span), built
+    // once per call by span_records_kernel for the binned path; nullptr: gaps are divided per point
+    const double *spanRec[BSPY_MAX_IND];
 };
 
 struct OutDev {
@@ -146,20 +149,31 @@ __device__ __forceinline__ void basis_strict(const double *__restrict__ knots, i
     }
 }
 
-// Register-resident recurrence for a compile-time order.  kw[] is the knot window
-// kw[j] = knots[ix - (O-1) + j], j = 0 .. 2(O-1)-1, so knots[i] with i = ix-deg+t is
-// kw[O-1-deg+t] and knots[i+deg] is kw[O-1+t].
+// Register-resident recurrence for a compile-time order, written on reciprocal knot gaps so that the same code
+// serves the per-point path (gaps divided here) and the per-span records of the binned path (gaps divided once per
+// span by span_records_kernel): both give the same bits.
+//   dl[j] = u - knots[ix-(O-1)+j]            (j < O-1: the left knots)
+//   rc[at(deg)+t] = 1 / (knots[ix+t] - knots[ix-deg+t]),  at(deg) = deg(deg-1)/2, t < deg
 //   DER == false : b0 = basis of derivative order `d` (runtime, 0 = values)
 //   DER == true  : b0 = values, b1 = first derivatives; the O-2 lower stages are shared.
+template <int O>
+struct SpanRec {
+    static constexpr int left = O - 1;                       // left knots
+    static constexpr int recips = O * (O - 1) / 2;           // reciprocal gaps
+    static constexpr int used = left + recips;
+    static constexpr int stride = (used + 1) & ~1;           // doubles, even -> records are 16-byte aligned
+};
+
 template <int O, bool DER>
-__device__ __forceinline__ void basis_regs(const double (&kw)[2 * (O - 1) > 0 ? 2 * (O - 1) : 1], double u, int d,
-                                           double (&b0)[O], double (&b1)[O])
+__device__ __forceinline__ void basis_core(const double (&dl)[O > 1 ? O - 1 : 1], const double (&rc)[O > 1 ? O * (O - 1) / 2 : 1],
+                                           int d, double (&b0)[O], double (&b1)[O])
 {
 #pragma unroll
     for (int j = 0; j < O; ++j) { b0[j] = 0.0; b1[j] = 0.0; }
     if (!DER && d >= O) return;
     b0[O - 1] = 1.0;
     const int nValue = DER ? O - 1 : O - d;   // value stages: deg < nValue
+    int at = 0;
 #pragma unroll
     for (int deg = 1; deg < O; ++deg) {
         if (DER && deg == O - 1) {
@@ -169,35 +183,76 @@ __device__ __forceinline__ void basis_regs(const double (&kw)[2 * (O - 1) > 0 ? 
 #pragma unroll
             for (int t = 0; t < deg; ++t) {
                 const int slot = O - deg + t;
-                const double kl = kw[O - 1 - deg + t];
-                const double r = 1.0 / (kw[O - 1 + t] - kl);
-                const double a = (u - kl) * r;
-                b0[slot - 1] += (1.0 - a) * b0[slot];
+                const double r = rc[at + t];
+                const double a = dl[O - 1 - deg + t] * r;
+                b0[slot - 1] = fma(1.0 - a, b0[slot], b0[slot - 1]);
                 b0[slot] *= a;
                 const double g = (double)deg * r;
-                b1[slot - 1] -= g * b1[slot];
+                b1[slot - 1] = fma(-g, b1[slot], b1[slot - 1]);
                 b1[slot] *= g;
             }
         } else if (deg < nValue) {
 #pragma unroll
             for (int t = 0; t < deg; ++t) {
                 const int slot = O - deg + t;
-                const double kl = kw[O - 1 - deg + t];
-                const double a = (u - kl) / (kw[O - 1 + t] - kl);
-                b0[slot - 1] += (1.0 - a) * b0[slot];
+                const double a = dl[O - 1 - deg + t] * rc[at + t];
+                b0[slot - 1] = fma(1.0 - a, b0[slot], b0[slot - 1]);
                 b0[slot] *= a;
             }
         } else {
 #pragma unroll
             for (int t = 0; t < deg; ++t) {
                 const int slot = O - deg + t;
-                const double kl = kw[O - 1 - deg + t];
-                const double g = (double)deg / (kw[O - 1 + t] - kl);
-                b0[slot - 1] -= g * b0[slot];
+                const double g = (double)deg * rc[at + t];
+                b0[slot - 1] = fma(-g, b0[slot], b0[slot - 1]);
                 b0[slot] *= g;
             }
         }
+        at += deg;
     }
+}
+
+// from the knot window kw[j] = knots[ix - (O-1) + j], j = 0 .. 2(O-1)-1: knots[ix-deg+t] is kw[O-1-deg+t] and
+// knots[ix+t] is kw[O-1+t]
+template <int O, bool DER>
+__device__ __forceinline__ void basis_regs(const double (&kw)[2 * (O - 1) > 0 ? 2 * (O - 1) : 1], double u, int d,
+                                           double (&b0)[O], double (&b1)[O])
+{
+    double dl[O > 1 ? O - 1 : 1], rc[O > 1 ? O * (O - 1) / 2 : 1];
+#pragma unroll
+    for (int j = 0; j < O - 1; ++j) dl[j] = u - kw[j];
+    int at = 0;
+#pragma unroll
+    for (int deg = 1; deg < O; ++deg) {
+#pragma unroll
+        for (int t = 0; t < deg; ++t) rc[at + t] = 1.0 / (kw[O - 1 + t] - kw[O - 1 - deg + t]);
+        at += deg;
+    }
+    basis_core<O, DER>(dl, rc, d, b0, b1);
+}
+
+// from the per-span record rec = { left knots | reciprocal gaps } (SpanRec<O>::stride doubles, 16-byte aligned)
+template <int O, bool DER>
+__device__ __forceinline__ void basis_from_span_record(const double *__restrict__ rec, double u, int d, double (&b0)[O],
+                                                       double (&b1)[O])
+{
+    using R = SpanRec<O>;
+    double r[R::stride > 0 ? R::stride : 1];
+    if constexpr (R::stride > 0) {
+        const double2 *rp = reinterpret_cast<const double2 *>(rec);
+#pragma unroll
+        for (int j = 0; j < R::stride / 2; ++j) {
+            const double2 x = __ldg(rp + j);
+            r[2 * j] = x.x;
+            r[2 * j + 1] = x.y;
+        }
+    }
+    double dl[O > 1 ? O - 1 : 1], rc[O > 1 ? O * (O - 1) / 2 : 1];
+#pragma unroll
+    for (int j = 0; j < O - 1; ++j) dl[j] = u - r[j];
+#pragma unroll
+    for (int j = 0; j < O * (O - 1) / 2; ++j) rc[j] = r[O - 1 + j];
+    basis_core<O, DER>(dl, rc, d, b0, b1);
 }
 
 template <int O>

@@ -14,14 +14,6 @@
 
 namespace bspy {
 
-template <int O>
-struct SpanRec {
-    static constexpr int left = O - 1;                       // left knots
-    static constexpr int recips = O * (O - 1) / 2;           // reciprocal gaps
-    static constexpr int used = left + recips;
-    static constexpr int stride = (used + 1) & ~1;           // doubles, even -> records are 16-byte aligned
-};
-
 // cooperative build by `nthreads` threads (a warp or a CTA); kn may be shared or global memory
 template <int O>
 __device__ __forceinline__ void build_span_records(const double *kn, int nCoef, double *rec, int tid, int nthreads)

@@ -102,6 +102,70 @@ __device__ __forceinline__ void normal_from_jacobian(const double (&J)[NDEP * NI
     }
 }
 
+// ---- result records (sorted-record mode): [values | jacobian (d, iv) | normal], a multiple of 4 doubles ------
+template <int NIND, int NDEP, bool JAC>
+__device__ __forceinline__ void store_result_record(const SplineDev &s, const OutDev &out, double *__restrict__ recOut,
+                                                    const double (&v)[NDEP], const double (&g)[NIND][NDEP])
+{
+    constexpr int DN = (NIND - NDEP == 1 || NDEP - NIND == 1) ? (NIND > NDEP ? NIND : NDEP) : 0;
+    constexpr int R = JAC ? NDEP + NDEP * NIND + DN : NDEP;
+    constexpr int RP = (R + 3) & ~3;
+    double rec[RP];
+#pragma unroll
+    for (int j = 0; j < RP; ++j) rec[j] = 0.0;
+#pragma unroll
+    for (int d = 0; d < NDEP; ++d) rec[d] = v[d];
+    if constexpr (JAC) {
+#pragma unroll
+        for (int d = 0; d < NDEP; ++d)
+#pragma unroll
+            for (int iv = 0; iv < NIND; ++iv) rec[NDEP + d * NIND + iv] = g[iv][d];
+        if constexpr (DN > 0) {
+            if (out.normal) {
+                double J[NDEP * NIND];
+#pragma unroll
+                for (int d = 0; d < NDEP; ++d)
+#pragma unroll
+                    for (int iv = 0; iv < NIND; ++iv) J[d * NIND + iv] = g[iv][d];
+                double n[DN];
+                normal_from_jacobian<NIND, NDEP>(J, s.normalSign, out.normalize, out.normalMask, n);
+#pragma unroll
+                for (int i = 0; i < DN; ++i) rec[NDEP + NDEP * NIND + i] = n[i];
+            }
+        }
+    }
+    double2 *q = reinterpret_cast<double2 *>(recOut);
+#pragma unroll
+    for (int j = 0; j < RP / 2; ++j)
+        if (2 * j < out.aosStride) __stcs(q + j, make_double2(rec[2 * j], rec[2 * j + 1]));
+}
+
+// one tile of NDT dependent variables starting at d0 (no normals)
+template <int NIND, int NDEP, int NDT, bool JAC>
+__device__ __forceinline__ void store_result_tile(double *__restrict__ rec, const int d0, const double (&vt)[NDT],
+                                                  const double (&gt)[NIND][NDT])
+{
+#pragma unroll
+    for (int d = 0; d < NDT; ++d) __stcs(rec + d0 + d, vt[d]);
+    if constexpr (JAC) {
+        constexpr int run = NDT * NIND;
+        double jr[run];
+#pragma unroll
+        for (int d = 0; d < NDT; ++d)
+#pragma unroll
+            for (int iv = 0; iv < NIND; ++iv) jr[d * NIND + iv] = gt[iv][d];
+        const int start = NDEP + d0 * NIND;
+        if constexpr (NDEP % 2 == 0 && (NDT * NIND) % 2 == 0) {
+#pragma unroll
+            for (int j = 0; j < run / 2; ++j)
+                __stcs(reinterpret_cast<double2 *>(rec + start) + j, make_double2(jr[2 * j], jr[2 * j + 1]));
+        } else {
+#pragma unroll
+            for (int j = 0; j < run; ++j) __stcs(rec + start + j, jr[j]);
+        }
+    }
+}
+
 // ---- compile-time shape kernel ----------------------------------------------------------------
 template <int NIND, int O0, int O1, int O2, int O3>
 struct Orders {
@@ -179,7 +243,7 @@ constexpr int fixed_min_blocks(int nInd, int o0, int o1, int o2, int o3, int nDe
 
 template <int IV, class Ord, int NDEP, bool JAC>
 __device__ __forceinline__ void setup_variable(const SplineDev &s, double u, int d, FixedCtx<Ord, NDEP, JAC> &c,
-                                               int (&ix)[Ord::n], bool &outside, bool given)
+                                               int (&ix)[Ord::n], bool &outside, bool given, const double *__restrict__ rec)
 {
     constexpr int O = Ord::at(IV);
     const double *k = s.knots[IV];
@@ -190,10 +254,14 @@ __device__ __forceinline__ void setup_variable(const SplineDev &s, double u, int
         span = span_search_inner(k, nKnots, O, u);
         ix[IV] = span;
     }
-    double kw[2 * (O - 1) > 0 ? 2 * (O - 1) : 1];
-    load_knot_window<O>(k, span, kw);
     double b0[O], b1[O];
-    basis_regs<O, JAC>(kw, u, d, b0, b1);
+    if (rec) {
+        basis_from_span_record<O, JAC>(rec + (long long)(span - O) * SpanRec<O>::stride, u, d, b0, b1);
+    } else {
+        double kw[2 * (O - 1) > 0 ? 2 * (O - 1) : 1];
+        load_knot_window<O>(k, span, kw);
+        basis_regs<O, JAC>(kw, u, d, b0, b1);
+    }
 #pragma unroll
     for (int j = 0; j < O; ++j) {
         c.B[IV][j] = b0[j];
@@ -201,15 +269,18 @@ __device__ __forceinline__ void setup_variable(const SplineDev &s, double u, int
     }
 }
 
-template <int NIND, int O0, int O1, int O2, int O3, int NDEP, bool JAC>
-__global__ void __launch_bounds__(128, fixed_min_blocks(NIND, O0, O1, O2, O3, NDEP, JAC)) eval_fixed_kernel(const SplineDev s, const PointsDev in, const long long N,
+// NDT = dependent variables contracted per pass over the window (NDEP: one pass; fewer: smaller accumulator set,
+// more resident warps; the basis is computed once either way).  Normals need the whole jacobian: NDT == NDEP.
+template <int NIND, int O0, int O1, int O2, int O3, int NDEP, bool JAC, int NDT = NDEP, int MINB = 0>
+__global__ void __launch_bounds__(128, MINB ? MINB : fixed_min_blocks(NIND, O0, O1, O2, O3, NDT, JAC)) eval_fixed_kernel(const SplineDev s, const PointsDev in, const long long N,
                                                          const WrtDev wrt, const OutDev out)
 {
     using Ord = Orders<NIND, O0, O1, O2, O3>;
+    static_assert(NDEP % NDT == 0, "dependent-variable tile must divide nDep");
     const bool recs = in.records != nullptr;
     const bool binned = in.perm != nullptr || recs;
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < N; t += (long long)gridDim.x * blockDim.x) {
-        FixedCtx<Ord, NDEP, JAC> c;
+        FixedCtx<Ord, NDT, JAC> c;
         int ix[NIND];
         double u[NIND];
         bool outside = false;
@@ -240,10 +311,10 @@ __global__ void __launch_bounds__(128, fixed_min_blocks(NIND, O0, O1, O2, O3, ND
 #pragma unroll
             for (int iv = NIND - 1; iv >= 0; --iv) u[iv] = fetch_param(in, p, iv, rem);
         }
-        setup_variable<0, Ord, NDEP, JAC>(s, u[0], wrt.d[0], c, ix, outside, binned);
-        if constexpr (NIND > 1) setup_variable<1, Ord, NDEP, JAC>(s, u[1], wrt.d[1], c, ix, outside, binned);
-        if constexpr (NIND > 2) setup_variable<2, Ord, NDEP, JAC>(s, u[2], wrt.d[2], c, ix, outside, binned);
-        if constexpr (NIND > 3) setup_variable<3, Ord, NDEP, JAC>(s, u[3], wrt.d[3], c, ix, outside, binned);
+        setup_variable<0, Ord, NDT, JAC>(s, u[0], wrt.d[0], c, ix, outside, binned, in.spanRec[0]);
+        if constexpr (NIND > 1) setup_variable<1, Ord, NDT, JAC>(s, u[1], wrt.d[1], c, ix, outside, binned, in.spanRec[1]);
+        if constexpr (NIND > 2) setup_variable<2, Ord, NDT, JAC>(s, u[2], wrt.d[2], c, ix, outside, binned, in.spanRec[2]);
+        if constexpr (NIND > 3) setup_variable<3, Ord, NDT, JAC>(s, u[3], wrt.d[3], c, ix, outside, binned, in.spanRec[3]);
         if (outside && out.firstOutside) report_outside((int64_t *)out.firstOutside, p);
         long long off = 0;
 #pragma unroll
@@ -252,42 +323,41 @@ __global__ void __launch_bounds__(128, fixed_min_blocks(NIND, O0, O1, O2, O3, ND
             off += (long long)(ix[iv] - Ord::at(iv)) * s.stride[iv];
         }
         c.depStride = s.depStride;
+        if constexpr (NDT < NDEP) {
+            // one pass per tile of dependent variables, results stored as they come (no normals here)
+#pragma unroll
+            for (int d0 = 0; d0 < NDEP; d0 += NDT) {
+                double vt[NDT];
+                double gt[NIND][NDT];
+                Contract<0, Ord, NDT, JAC>::run(s.coefs + off + d0 * s.depStride, c, vt, gt);
+                if (out.aos) {
+                    store_result_tile<NIND, NDEP, NDT, JAC>(out.aos + t * out.aosStride, d0, vt, gt);
+                } else {
+                    if (out.values) {
+#pragma unroll
+                        for (int d = 0; d < NDT; ++d) __stcs(out.values + (d0 + d) * out.ld + p, vt[d]);
+                    }
+                    if constexpr (JAC) {
+                        if (out.jacobian) {
+#pragma unroll
+                            for (int d = 0; d < NDT; ++d)
+#pragma unroll
+                                for (int iv = 0; iv < NIND; ++iv) __stcs(out.jacobian + ((d0 + d) * NIND + iv) * out.ld + p, gt[iv][d]);
+                        }
+                    }
+                }
+            }
+            if (!out.aos && out.spans) {
+#pragma unroll
+                for (int iv = 0; iv < NIND; ++iv) __stcs(out.spans + iv * out.ld + p, ix[iv]);
+            }
+        } else {
         double v[NDEP];
         double g[NIND][NDEP];
         Contract<0, Ord, NDEP, JAC>::run(s.coefs + off, c, v, g);
         if (out.aos) {
             // sorted-record mode: one contiguous, sector-aligned result record per point
-            constexpr int DN = (NIND - NDEP == 1 || NDEP - NIND == 1) ? (NIND > NDEP ? NIND : NDEP) : 0;
-            constexpr int R = JAC ? NDEP + NDEP * NIND + DN : NDEP;
-            constexpr int RP = (R + 3) & ~3;
-            double rec[RP];
-#pragma unroll
-            for (int j = 0; j < RP; ++j) rec[j] = 0.0;
-#pragma unroll
-            for (int d = 0; d < NDEP; ++d) rec[d] = v[d];
-            if constexpr (JAC) {
-#pragma unroll
-                for (int d = 0; d < NDEP; ++d)
-#pragma unroll
-                    for (int iv = 0; iv < NIND; ++iv) rec[NDEP + d * NIND + iv] = g[iv][d];
-                if constexpr (DN > 0) {
-                    if (out.normal) {
-                        double J[NDEP * NIND];
-#pragma unroll
-                        for (int d = 0; d < NDEP; ++d)
-#pragma unroll
-                            for (int iv = 0; iv < NIND; ++iv) J[d * NIND + iv] = g[iv][d];
-                        double n[DN];
-                        normal_from_jacobian<NIND, NDEP>(J, s.normalSign, out.normalize, out.normalMask, n);
-#pragma unroll
-                        for (int i = 0; i < DN; ++i) rec[NDEP + NDEP * NIND + i] = n[i];
-                    }
-                }
-            }
-            double2 *q = reinterpret_cast<double2 *>(out.aos + t * out.aosStride);
-#pragma unroll
-            for (int j = 0; j < RP / 2; ++j)
-                if (2 * j < out.aosStride) __stcs(q + j, make_double2(rec[2 * j], rec[2 * j + 1]));
+            store_result_record<NIND, NDEP, JAC>(s, out, out.aos + t * out.aosStride, v, g);
             continue;
         }
         if (out.values) {
@@ -319,6 +389,241 @@ __global__ void __launch_bounds__(128, fixed_min_blocks(NIND, O0, O1, O2, O3, ND
                     for (int i = 0; i < D; ++i) __stcs(out.normal + i * out.ld + p, n[i]);
                 }
             }
+        }
+        }   // NDT == NDEP
+    }
+}
+
+// ---- warp-staged windows (sorted-record mode) -------------------------------------------------------------------
+// In cell order the 32 points of a warp share one coefficient window (two where the warp straddles a cell boundary),
+// yet the thread-per-point kernel above still walks it through L1 with run-time strides (~2 address instructions per
+// load, 212 to 540 loads per point) and every warp pays the whole latency chain record -> spans -> window once per
+// 32 points (ncu: 31 % of the warp time in long-scoreboard stalls, FP64 pipe 36-45 % active).  Here
+//   * warps are persistent and walk CONTIGUOUS runs of sorted tiles, so the window of the previous tile is normally
+//     the window of this one (110-170 points per cell): it stays in shared memory, two slots per warp;
+//   * a new window is copied once by the warp into a compact image with compile-time strides (cp.async, lanes along
+//     the elements), and the contraction reads it with immediate offsets and 16-byte broadcast loads: no address
+//     arithmetic, half the load instructions;
+//   * the next tile's point records are requested before the current tile is contracted.
+// Per-point arithmetic and summation order are those of Contract<> above: results are bit-identical.
+template <class Ord, int NDEP>
+struct WindowShape {
+    static constexpr int last = Ord::at(Ord::n - 1);                  // innermost variable: contiguous in the spline
+    __host__ __device__ static constexpr int stride(int iv)          // compact stride of variable iv (doubles)
+    {
+        int st = 1;
+        for (int m = Ord::n - 1; m > iv; --m) st *= Ord::at(m);
+        return st;
+    }
+    static constexpr int perDep = stride(0) * Ord::at(0);
+    static constexpr int perDepPad = (perDep + 1) & ~1;              // every dependent variable starts 16-byte aligned
+    static constexpr int size = perDepPad * NDEP;
+};
+
+// load n consecutive doubles at the compile-time-foldable offset `off` of a 16-byte aligned shared-memory image
+template <int N>
+__device__ __forceinline__ void load_run(const double *__restrict__ w, const int off, double (&x)[N])
+{
+    const int head = off & 1;                       // folds to a constant once the recursion is unrolled
+    if (head) x[0] = w[off];
+#pragma unroll
+    for (int j = 0; j < N / 2 + 1; ++j) {
+        const int idx = head + 2 * j;
+        if (idx + 1 < N) {
+            const double2 t = *reinterpret_cast<const double2 *>(w + off + idx);
+            x[idx] = t.x;
+            x[idx + 1] = t.y;
+        }
+    }
+    if ((N - head) & 1) x[N - 1] = w[off + N - 1];
+}
+
+// Contract variables L .. NIND-1 of the compact window image; same recursion and summation order as Contract<>.
+template <int L, class Ord, int NDEP, int NDT, bool JAC>
+struct ContractS {
+    using WS = WindowShape<Ord, NDEP>;
+    __device__ __forceinline__ static void run(const double *__restrict__ w, const int off, const FixedCtx<Ord, NDT, JAC> &c,
+                                               double (&v)[NDT], double (&g)[Ord::n][NDT])
+    {
+        constexpr int O = Ord::at(L);
+#pragma unroll
+        for (int d = 0; d < NDT; ++d) v[d] = 0.0;
+        if constexpr (JAC) {
+#pragma unroll
+            for (int m = L; m < Ord::n; ++m)
+#pragma unroll
+                for (int d = 0; d < NDT; ++d) g[m][d] = 0.0;
+        }
+        if constexpr (L == Ord::n - 1) {
+#pragma unroll
+            for (int d = 0; d < NDT; ++d) {
+                double x[O];
+                load_run<O>(w, off + d * WS::perDepPad, x);
+#pragma unroll
+                for (int i = 0; i < O; ++i) {
+                    v[d] = fma(x[i], c.B[L][i], v[d]);
+                    if constexpr (JAC) g[L][d] = fma(x[i], c.dB[L][i], g[L][d]);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < O; ++i) {
+                double cv[NDT];
+                double cg[Ord::n][NDT];
+                ContractS<L + 1, Ord, NDEP, NDT, JAC>::run(w, off + i * WS::stride(L), c, cv, cg);
+#pragma unroll
+                for (int d = 0; d < NDT; ++d) {
+                    v[d] = fma(cv[d], c.B[L][i], v[d]);
+                    if constexpr (JAC) {
+                        g[L][d] = fma(cv[d], c.dB[L][i], g[L][d]);
+#pragma unroll
+                        for (int m = L + 1; m < Ord::n; ++m) g[m][d] = fma(cg[m][d], c.B[L][i], g[m][d]);
+                    }
+                }
+            }
+        }
+    }
+};
+
+// the warp copies the window of cell `key` (packed spans, bin_keys_kernel) into the compact image `dst`;
+// lanes run along the elements: consecutive 8-byte words in shared memory, whole rows of the spline in global memory
+template <class Ord, int NDEP>
+__device__ __forceinline__ void stage_window(const SplineDev &s, int key, double *dst, const int lane)
+{
+    using WS = WindowShape<Ord, NDEP>;
+    long long base = 0;
+#pragma unroll
+    for (int iv = Ord::n - 1; iv >= 0; --iv) {
+        const int m = s.nCoef[iv] - Ord::at(iv) + 1;
+        base += (long long)(key % m) * s.stride[iv];
+        key /= m;
+    }
+    const unsigned dstAddr = (unsigned)__cvta_generic_to_shared(dst);
+    constexpr int total = WS::perDep * NDEP;
+#pragma unroll
+    for (int e0 = 0; e0 < total; e0 += 32) {
+        const int e = e0 + lane;
+        if (total % 32 == 0 || e < total) {
+            const int d = e / WS::perDep;
+            int q = e - d * WS::perDep;
+            long long src = base + (long long)d * s.depStride;
+#pragma unroll
+            for (int iv = Ord::n - 1; iv >= 0; --iv) {
+                src += (long long)(q % Ord::at(iv)) * s.stride[iv];
+                q /= Ord::at(iv);
+            }
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dstAddr + (unsigned)(d * WS::perDepPad + e - d * WS::perDep) * 8u), "l"(s.coefs + src) : "memory");
+        }
+    }
+}
+
+template <int NIND, int O0, int O1, int O2, int O3, int NDEP, bool JAC, int NDT, int MINB>
+__global__ void __launch_bounds__(128, MINB) eval_staged_kernel(const SplineDev s, const PointsDev in, const long long N,
+                                                                 const WrtDev wrt, const OutDev out)
+{
+    using Ord = Orders<NIND, O0, O1, O2, O3>;
+    using WS = WindowShape<Ord, NDEP>;
+    static_assert(NDEP % NDT == 0, "dependent-variable tile must divide nDep");
+    extern __shared__ __align__(16) double stagedWindows[];         // per warp: two window images
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *w0 = stagedWindows + warp * 2 * WS::size;
+    int slotKey0 = -1, slotKey1 = -1;                               // cells held by the two slots (warp-uniform)
+    // contiguous run of 32-point tiles for this warp
+    const long long tiles = (N + 31) >> 5, nWarps = gridDim.x * 4LL;
+    const long long per = (tiles + nWarps - 1) / nWarps;
+    const long long firstTile = (blockIdx.x * 4LL + warp) * per;
+    const long long endTile = firstTile + per < tiles ? firstTile + per : tiles;
+    double2 r0 = make_double2(0.0, 0.0), r1 = r0;
+    int k4 = -1;
+    auto fetch = [&](long long tile) {
+        const long long t = tile * 32 + lane;
+        if (tile < endTile && t < N) {
+            const double2 *rp = reinterpret_cast<const double2 *>(in.records + 4 * t);
+            r0 = __ldcs(rp);
+            r1 = __ldcs(rp + 1);
+            if constexpr (NIND > 3) k4 = __ldcs(in.recKey + t);
+        }
+    };
+    fetch(firstTile);
+    for (long long tile = firstTile; tile < endTile; ++tile) {
+        const long long t = tile * 32 + lane;
+        const bool live = t < N;
+        FixedCtx<Ord, NDT, JAC> c;
+        int ix[NIND];
+        double u[NIND];
+        u[0] = r0.x;
+        if constexpr (NIND > 1) u[1] = r0.y;
+        if constexpr (NIND > 2) u[2] = r1.x;
+        if constexpr (NIND > 3) u[3] = r1.y;
+        const int key = live ? (NIND > 3 ? k4 : (int)__double_as_longlong(r1.y)) : -1;
+        fetch(tile + 1);                                            // next tile's records arrive under this tile's arithmetic
+        {
+            int k = key < 0 ? 0 : key;
+#pragma unroll
+            for (int iv = NIND - 1; iv >= 0; --iv) {
+                const int m = s.nCoef[iv] - Ord::at(iv) + 1;
+                ix[iv] = Ord::at(iv) + k % m;
+                k /= m;
+            }
+        }
+        bool outside = false;
+        setup_variable<0, Ord, NDT, JAC>(s, u[0], wrt.d[0], c, ix, outside, true, in.spanRec[0]);
+        if constexpr (NIND > 1) setup_variable<1, Ord, NDT, JAC>(s, u[1], wrt.d[1], c, ix, outside, true, in.spanRec[1]);
+        if constexpr (NIND > 2) setup_variable<2, Ord, NDT, JAC>(s, u[2], wrt.d[2], c, ix, outside, true, in.spanRec[2]);
+        if constexpr (NIND > 3) setup_variable<3, Ord, NDT, JAC>(s, u[3], wrt.d[3], c, ix, outside, true, in.spanRec[3]);
+        bool done = !live;
+        while (true) {
+            const unsigned pending = __ballot_sync(0xffffffffu, !done);
+            if (!pending) break;
+            // up to two distinct cells per pass, each in the slot that already holds it or freshly staged
+            const int k0 = __shfl_sync(0xffffffffu, key, __ffs(pending) - 1);
+            const bool in0 = !done && key == k0;
+            const unsigned rest = __ballot_sync(0xffffffffu, !done && !in0);
+            const int k1 = rest ? __shfl_sync(0xffffffffu, key, __ffs(rest) - 1) : -1;
+            const bool in1 = !done && !in0 && key == k1;
+            int s0, s1 = -1;
+            bool staged = false;
+            if (k0 == slotKey0) s0 = 0;
+            else if (k0 == slotKey1) s0 = 1;
+            else {
+                s0 = (k1 >= 0 && k1 == slotKey0) ? 1 : 0;
+                stage_window<Ord, NDEP>(s, k0, w0 + s0 * WS::size, lane);
+                if (s0) slotKey1 = k0; else slotKey0 = k0;
+                staged = true;
+            }
+            if (k1 >= 0) {
+                s1 = 1 - s0;
+                if ((s1 ? slotKey1 : slotKey0) != k1) {
+                    stage_window<Ord, NDEP>(s, k1, w0 + s1 * WS::size, lane);
+                    if (s1) slotKey1 = k1; else slotKey0 = k1;
+                    staged = true;
+                }
+            }
+            if (staged) {
+                asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+                __syncwarp();
+            }
+            if (in0 || in1) {
+                const double *w = w0 + (in1 ? s1 : s0) * WS::size;
+                double *rec = out.aos + t * out.aosStride;
+                if constexpr (NDT == NDEP) {
+                    double v[NDEP];
+                    double g[NIND][NDEP];
+                    ContractS<0, Ord, NDEP, NDEP, JAC>::run(w, 0, c, v, g);
+                    store_result_record<NIND, NDEP, JAC>(s, out, rec, v, g);
+                } else {
+                    // one pass per tile of dependent variables; the loop stays rolled (instruction-cache footprint)
+#pragma unroll 1
+                    for (int d0 = 0; d0 < NDEP; d0 += NDT) {
+                        double vt[NDT];
+                        double gt[NIND][NDT];
+                        ContractS<0, Ord, NDEP, NDT, JAC>::run(w + d0 * WS::perDepPad, 0, c, vt, gt);
+                        store_result_tile<NIND, NDEP, NDT, JAC>(rec, d0, vt, gt);
+                    }
+                }
+                done = true;
+            }
+            __syncwarp();                                            // slots may be overwritten by the next pass / tile
         }
     }
 }
@@ -498,8 +803,27 @@ __global__ void __launch_bounds__(128) eval_generic_kernel(const SplineDev s, co
 // counting-sorted by knot-span cell, evaluated in cell order (window loads become L1 broadcasts) and written
 // straight back to their original positions.  Same arithmetic per point, so results are bit-identical to the
 // unbinned kernel.
+// per-span records of one variable (runtime order): rec[s] = { knots[ix-(o-1)..ix-1] | 1/(knots[ix+t]-knots[ix-deg+t]) }
+// with ix = o + s, the layout basis_from_span_record<O> reads; one thread per span
+__global__ void __launch_bounds__(128) span_records_kernel(const double *__restrict__ kn, const int o, const int nCoef,
+                                                           double *__restrict__ rec, const int stride)
+{
+    const int sp = blockIdx.x * blockDim.x + threadIdx.x;
+    if (sp > nCoef - o) return;
+    const int ix = o + sp;
+    double *r = rec + (long long)sp * stride;
+    for (int j = 0; j < o - 1; ++j) r[j] = kn[ix - (o - 1) + j];
+    int at = o - 1;
+    for (int deg = 1; deg < o; ++deg)
+        for (int t = 0; t < deg; ++t) r[at++] = 1.0 / (kn[ix + t] - kn[ix - deg + t]);
+    for (; at < stride; ++at) r[at] = 0.0;
+}
+
+static int span_rec_stride(int o) { return ((o - 1 + o * (o - 1) / 2) + 1) & ~1; }
+
 __global__ void __launch_bounds__(256) bin_keys_kernel(const SplineDev s, const PointsDev in, const long long base, const int n,
-                                                       int *__restrict__ keys, int *__restrict__ hist, const OutDev out)
+                                                       int *__restrict__ keys, int *__restrict__ hist, int *__restrict__ rank,
+                                                       const OutDev out)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned active = __ballot_sync(0xffffffffu, t < n);
@@ -520,7 +844,13 @@ __global__ void __launch_bounds__(256) bin_keys_kernel(const SplineDev s, const 
     keys[t] = key;
     // one atomic per distinct cell in the warp (coherent inputs would otherwise serialise on one counter)
     const unsigned peers = __match_any_sync(active, key);
-    if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(hist + key, __popc(peers));
+    const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+    int first = 0;
+    if (lane == leader) first = atomicAdd(hist + key, __popc(peers));
+    if (rank) {   // position inside the cell: the scatter pass then needs no second round of atomics
+        first = __shfl_sync(peers, first, leader);
+        rank[t] = first + __popc(peers & ((1u << lane) - 1));
+    }
 }
 
 // warp-aggregated slot claim: the lanes of a warp that share a cell take consecutive slots with one atomic
@@ -534,27 +864,55 @@ __device__ __forceinline__ int claim_slot(int *cursor, int key, unsigned active)
     return first + __popc(peers & ((1u << lane) - 1));
 }
 
-// exclusive scan of hist[0..cells) in place, one CTA
+// exclusive scan of hist[0..cells) in place, one CTA: 4096 counters per round (coalesced 16-byte loads, warp
+// shuffles, one shared-memory hop between the warps), running total carried from round to round
 __global__ void __launch_bounds__(1024) bin_scan_kernel(int *__restrict__ hist, const int cells)
 {
-    __shared__ int part[1024];
-    const int per = (cells + 1023) / 1024;
-    const int lo = threadIdx.x * per, hi = min(lo + per, cells);
-    int sum = 0;
-    for (int i = lo; i < hi; ++i) sum += hist[i];
-    part[threadIdx.x] = sum;
+    __shared__ int warpSum[32];
+    __shared__ int carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry = 0;
     __syncthreads();
-    for (int off = 1; off < 1024; off <<= 1) {
-        const int v = threadIdx.x >= off ? part[threadIdx.x - off] : 0;
+    for (int base = 0; base < cells; base += 4096) {
+        const int i = base + 4 * threadIdx.x;
+        int4 c = make_int4(0, 0, 0, 0);
+        if (i + 3 < cells) c = *reinterpret_cast<const int4 *>(hist + i);
+        else {
+            if (i < cells) c.x = hist[i];
+            if (i + 1 < cells) c.y = hist[i + 1];
+            if (i + 2 < cells) c.z = hist[i + 2];
+        }
+        const int mine = c.x + c.y + c.z + c.w;
+        int incl = mine;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) incl += v;
+        }
+        if (lane == 31) warpSum[warp] = incl;
         __syncthreads();
-        part[threadIdx.x] += v;
+        if (warp == 0) {
+            const int w = warpSum[lane];
+            int wi = w;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, wi, off);
+                if (lane >= off) wi += v;
+            }
+            warpSum[lane] = wi - w;                       // exclusive prefix of the warp totals
+        }
         __syncthreads();
-    }
-    int run = part[threadIdx.x] - sum;
-    for (int i = lo; i < hi; ++i) {
-        const int c = hist[i];
-        hist[i] = run;
-        run += c;
+        const int start = carry + warpSum[warp] + incl - mine;
+        const int4 o = make_int4(start, start + c.x, start + c.x + c.y, start + c.x + c.y + c.z);
+        if (i + 3 < cells) *reinterpret_cast<int4 *>(hist + i) = o;
+        else {
+            if (i < cells) hist[i] = o.x;
+            if (i + 1 < cells) hist[i + 1] = o.y;
+            if (i + 2 < cells) hist[i + 2] = o.z;
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = start + mine;
+        __syncthreads();
     }
 }
 
@@ -575,17 +933,16 @@ __global__ void __launch_bounds__(256) bin_scatter_kernel(const int *__restrict_
 // read-modify-write) + the inverse permutation (coalesced)
 __global__ void __launch_bounds__(256) bin_scatter_records_kernel(const SplineDev s, const PointsDev in, const long long base,
                                                                   const int n, const int *__restrict__ keys,
-                                                                  int *__restrict__ cursor, double *__restrict__ records,
+                                                                  const int *__restrict__ offset, double *__restrict__ records,
                                                                   int *__restrict__ recKey, int *__restrict__ inv)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    const unsigned active = __ballot_sync(0xffffffffu, t < n);
     if (t >= n) return;
     const long long p = base + t;
     const int key = keys[t];
-    const int pos = claim_slot(cursor, key, active);
+    const int pos = __ldg(offset + key) + inv[t];           // inv[t] holds the rank inside the cell (bin_keys_kernel)
     double r[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int iv = 0; iv < s.nInd; ++iv) r[iv] = __ldg(in.uvw + p * in.pointStride + iv * in.varStride);
+    for (int iv = 0; iv < s.nInd; ++iv) r[iv] = __ldcs(in.uvw + p * in.pointStride + iv * in.varStride);
     if (s.nInd <= 3) r[3] = __longlong_as_double((long long)key);
     else recKey[pos] = key;
     double2 *q = reinterpret_cast<double2 *>(records + 4LL * pos);
@@ -594,42 +951,67 @@ __global__ void __launch_bounds__(256) bin_scatter_records_kernel(const SplineDe
     inv[t] = pos;
 }
 
-// un-permute: a warp takes 32 consecutive points, reads their 32 result records with lanes running along each
-// record (every sector is requested once, 12 lanes per 96-byte record), transposes through shared memory and
-// writes the struct-of-arrays outputs coalesced.
+// un-permute: a warp takes 32 consecutive points and pulls their 32 result records (each a run of whole sectors
+// somewhere in the sorted array) into shared memory with 16-byte cp.async copies -- lanes run along the records,
+// every sector is requested once, and all of a warp's copies are in flight together -- then every lane reads its
+// own record and the warp writes the struct-of-arrays outputs coalesced (8 warps side by side: 2 KB per plane).
 constexpr int UNPERM_WARPS = 8;
+template <int S_>
 __global__ void __launch_bounds__(UNPERM_WARPS * 32) bin_unpermute_kernel(const double *__restrict__ aos, const int aosStride,
                                                                           const int *__restrict__ inv, const long long base,
                                                                           const int n, const int nDep, const int nJ,
                                                                           const int nNormal, const OutDev out)
 {
-    extern __shared__ double tile[];                       // per warp: aosStride x 33 doubles
+    extern __shared__ __align__(16) double tile[];         // per warp: 32 rows of (stride + 2) doubles
+    const int S = S_ ? S_ : aosStride;
+    const int pitch = S + 2, S2 = S >> 1;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double *tw = tile + (long long)warp * aosStride * 33;
-    const int first = (blockIdx.x * (blockDim.x >> 5) + warp) * 32;
+    double *tw = tile + (long long)warp * 32 * pitch;
+    const int first = (blockIdx.x * UNPERM_WARPS + warp) * 32;
     if (first >= n) return;
     const int t = first + lane;
-    const long long myRec = t < n ? (long long)__ldg(inv + t) * aosStride : 0;
-    const int total = 32 * aosStride;
+    const int myRec = t < n ? __ldg(inv + t) : -1;
+    const unsigned twAddr = (unsigned)__cvta_generic_to_shared(tw);
+    const int total = 32 * S2;
+#pragma unroll 8
     for (int idx = lane; idx < total; idx += 32) {
-        const int r = idx / aosStride, e = idx - r * aosStride;
-        const long long rb = __shfl_sync(0xffffffffu, myRec, r);
-        const double x = (first + r < n) ? __ldcs(aos + rb + e) : 0.0;
-        tw[e * 33 + r] = x;
+        const int r = idx / S2, c = idx - r * S2;
+        const int rec = __shfl_sync(0xffffffffu, myRec, r);
+        if (rec >= 0) {
+            const double *src = aos + (long long)rec * S + 2 * c;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(twAddr + (unsigned)(r * pitch + 2 * c) * 8u), "l"(src) : "memory");
+        }
     }
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
     __syncwarp();
     if (t >= n) return;
     const long long p = base + t;
-    for (int k = 0; k < nDep + nJ + nNormal; ++k) {
-        const double val = tw[k * 33 + lane];
-        if (k < nDep) {
-            if (out.values) __stcs(out.values + k * out.ld + p, val);
-        } else if (k < nDep + nJ) {
-            if (out.jacobian) __stcs(out.jacobian + (k - nDep) * out.ld + p, val);
-        } else {
-            if (out.normal) __stcs(out.normal + (k - nDep - nJ) * out.ld + p, val);
-        }
+    const double *mine = tw + lane * pitch;
+    if (out.values) {
+        for (int k = 0; k < nDep; ++k) __stcs(out.values + k * out.ld + p, mine[k]);
     }
+    if (out.jacobian) {
+        for (int k = 0; k < nJ; ++k) __stcs(out.jacobian + k * out.ld + p, mine[nDep + k]);
+    }
+    if (out.normal) {
+        for (int k = 0; k < nNormal; ++k) __stcs(out.normal + k * out.ld + p, mine[nDep + nJ + k]);
+    }
+}
+
+template <int S_>
+static int launch_unpermute(const double *aos, int stride, const int *inv, long long base, int n, int nDep, int nJ, int nN,
+                            const OutDev &out, cudaStream_t st)
+{
+    const size_t smem = sizeof(double) * UNPERM_WARPS * 32 * (stride + 2);
+    static size_t allowed = 48 * 1024;
+    if (smem > allowed) {
+        cudaError_t e = cudaFuncSetAttribute(bin_unpermute_kernel<S_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+        allowed = smem;
+    }
+    bin_unpermute_kernel<S_><<<(n + UNPERM_WARPS * 32 - 1) / (UNPERM_WARPS * 32), UNPERM_WARPS * 32, smem, st>>>(
+        aos, stride, inv, base, n, nDep, nJ, nN, out);
+    return 0;
 }
 
 constexpr long long BIN_REC_CHUNK = 1 << 22;   // points per chunk in sorted-record mode
@@ -684,6 +1066,52 @@ static const FixedEntry kFixed[] = {
     BSPY_FIXED(4, 2, 2, 2, 2, 3), BSPY_FIXED(4, 3, 3, 3, 3, 3), BSPY_FIXED(4, 3, 3, 3, 3, 5),
     BSPY_FIXED(4, 3, 3, 3, 3, 6),
 };
+
+// dependent-variable tiles for the two big-window shapes of the north-star configs (value + jacobian, no normals)
+static FixedFn find_fixed_tiled(const SplineDev &s, int jac, int code)
+{
+    // code = 10 * (dependent variables per pass) + (CTAs per SM the variant is compiled for).  Measured on the
+    // 4-variate nDep-6 manifold (config 5), sorted records: 14 -> 2.52 Gpts/s, 24 -> 2.42, one pass (168 registers,
+    // spills) -> 2.32, 33/34 -> 1.9; on the tricubic nDep-3 volume the single pass wins (5.8 vs 5.1-5.5).
+    if (!jac) return nullptr;
+    if (s.nInd == 4 && s.nDep == 6 && s.order[0] == 3 && s.order[1] == 3 && s.order[2] == 3 && s.order[3] == 3) {
+        switch (code) {
+            case 14: return eval_fixed_kernel<4, 3, 3, 3, 3, 6, true, 1, 4>;
+            case 24: return eval_fixed_kernel<4, 3, 3, 3, 3, 6, true, 2, 4>;
+        }
+    }
+    return nullptr;
+}
+
+// warp-staged variants (sorted-record mode).  code = 10 * (dependent variables per pass) + CTAs per SM; 0 = default
+struct StagedEntry {
+    int nInd, o[4], nDep, jac, code;
+    FixedFn fn;
+    int windowDoubles;
+};
+#define BSPY_STAGED(NI, A, B, C, D_, ND, J, NDT, MB)                                                          \
+    {NI, {A, B, C, D_}, ND, J, 10 * NDT + MB, eval_staged_kernel<NI, A, B, C, D_, ND, J != 0, NDT, MB>,       \
+     WindowShape<Orders<NI, A, B, C, D_>, ND>::size}
+static const StagedEntry kStaged[] = {
+    // volumes (measured: tricubic nDep 3, value + jacobian, 379 -> 326 us per 4 Mi points, FP64 pipe 37 -> 50 %);
+    // the 4-variate nDep-6 window gained nothing here (register spills once the pass over the dependent variables is
+    // rolled) and stays on eval_fixed_kernel with one dependent variable per pass
+    BSPY_STAGED(3, 3, 3, 3, 0, 3, 0, 3, 4), BSPY_STAGED(3, 3, 3, 3, 0, 3, 1, 3, 4),
+    BSPY_STAGED(3, 4, 4, 4, 0, 1, 0, 1, 4), BSPY_STAGED(3, 4, 4, 4, 0, 1, 1, 1, 4),
+    BSPY_STAGED(3, 4, 4, 4, 0, 3, 0, 3, 4), BSPY_STAGED(3, 4, 4, 4, 0, 3, 1, 3, 4),
+    BSPY_STAGED(3, 4, 4, 4, 0, 4, 0, 4, 4), BSPY_STAGED(3, 4, 4, 4, 0, 4, 1, 4, 4),
+};
+
+static const StagedEntry *find_staged(const SplineDev &s, int jac, int code)
+{
+    for (const StagedEntry &e : kStaged) {
+        if (e.nInd != s.nInd || e.nDep != s.nDep || e.jac != jac) continue;
+        bool same = true;
+        for (int i = 0; i < s.nInd; ++i) same &= e.o[i] == s.order[i];
+        if (same && (code == 0 || code == e.code)) return &e;
+    }
+    return nullptr;
+}
 
 static FixedFn find_fixed(const SplineDev &s, int jac)
 {
@@ -843,6 +1271,13 @@ static int aos_stride(const SplineDev &s)
 
 static long long pad64(long long n) { return (n + 63) / 64 * 64; }
 
+static long long span_records_bytes(const SplineDev &s)
+{
+    long long doubles = 0;
+    for (int i = 0; i < s.nInd; ++i) doubles += (long long)(s.nCoef[i] - s.order[i] + 1) * span_rec_stride(s.order[i]);
+    return 8 * pad64(doubles);
+}
+
 // bytes of workspace for the binned path, 0 when binning does not apply to this spline
 long long binned_workspace(const SplineDev &s, long long N)
 {
@@ -856,7 +1291,8 @@ long long binned_workspace(const SplineDev &s, long long N)
     if (!find_fixed(s, 0)) return 0;
     if (bin_mode(N) == 1 && s.nInd <= 4) {
         const long long chunk = N < BIN_REC_CHUNK ? N : BIN_REC_CHUNK;
-        return 2 * (4 * (3 * pad64(chunk) + pad64(cells + 1)) + 8 * (4 * pad64(chunk) + (long long)aos_stride(s) * pad64(chunk)));
+        return 2 * (4 * (3 * pad64(chunk) + pad64(cells + 1)) + 8 * (4 * pad64(chunk) + (long long)aos_stride(s) * pad64(chunk))) +
+               span_records_bytes(s);
     }
     const long long chunk = N < BIN_CHUNK_MAX ? N : BIN_CHUNK_MAX;
     return 3 * 4 * pad64(chunk) + 4 * pad64(cells + 1);
@@ -910,6 +1346,41 @@ static int eval_binned_records(const SplineDev &s, PointsDev in, long long N, co
     const int nN = (jac && out.normal) ? D : 0;
     const int stride = (s.nDep + nJ + nN + 3) & ~3;
     FixedFn fn = find_fixed(s, jac);
+    {
+        const char *te = getenv("BSPY_DEP_TILE");
+        const int ndt = te ? atoi(te) : 14;
+        FixedFn tiled = (ndt > 0 && !out.normal) ? find_fixed_tiled(s, jac, ndt) : nullptr;
+        if (tiled) fn = tiled;
+    }
+    // warp-staged windows where the shape is compiled (no normals there: they need the whole jacobian in one pass)
+    const StagedEntry *staged = nullptr;
+    {
+        const char *se = getenv("BSPY_STAGED");
+        const int code = se ? atoi(se) : 0;
+        if (code >= 0) staged = find_staged(s, jac, code);
+        if (staged) {
+            const size_t smem = sizeof(double) * 4 * 2 * staged->windowDoubles;
+            if (smem > 48 * 1024) {
+                cudaError_t e = cudaFuncSetAttribute(staged->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+            }
+        }
+    }
+    // per-span records (left knots | reciprocal gaps) for every variable: no divisions in the evaluation kernel
+    const double *spanRec[BSPY_MAX_IND] = {};
+    {
+        const char *re = getenv("BSPY_SPAN_RECORDS");
+        if (!re || atoi(re)) {
+            double *at = (double *)((char *)workspace + 2 * half);
+            for (int i = 0; i < s.nInd; ++i) {
+                const int spans = s.nCoef[i] - s.order[i] + 1, st = span_rec_stride(s.order[i]);
+                span_records_kernel<<<(spans + 127) / 128, 128, 0, stream>>>(s.knots[i], s.order[i], s.nCoef[i], at, st);
+                spanRec[i] = at;
+                at += (long long)spans * st;
+            }
+            count_launch(s.nInd);
+        }
+    }
     // measured: no gain (the evaluation kernel already fills the register file, so the memory-bound passes only
     // displace evaluation CTAs); off unless BSPY_BIN_OVERLAP=1
     const char *env = getenv("BSPY_BIN_OVERLAP");
@@ -938,7 +1409,7 @@ static int eval_binned_records(const SplineDev &s, PointsDev in, long long N, co
         if (e != cudaSuccess) { set_error("cudaMemsetAsync: %s", cudaGetErrorString(e)); return (int)e; }
         OutDev o1{};
         o1.ld = out.ld; o1.spans = out.spans; o1.firstOutside = out.firstOutside;
-        bin_keys_kernel<<<(n + 255) / 256, 256, 0, sSort>>>(s, in, base, n, B.keys, B.hist, o1);
+        bin_keys_kernel<<<(n + 255) / 256, 256, 0, sSort>>>(s, in, base, n, B.keys, B.hist, B.inv, o1);
         bin_scan_kernel<<<1, 1024, 0, sSort>>>(B.hist, (int)cells);
         bin_scatter_records_kernel<<<(n + 255) / 256, 256, 0, sSort>>>(s, in, base, n, B.keys, B.hist, B.records, B.recKey, B.inv);
         if (overlap) cudaEventRecord(bs->sorted[c & 1], sSort);
@@ -952,10 +1423,20 @@ static int eval_binned_records(const SplineDev &s, PointsDev in, long long N, co
         if (overlap) cudaStreamWaitEvent(sEval, bs->sorted[c & 1], 0);
         PointsDev pin{};
         pin.records = B.records; pin.recKey = B.recKey;
+        for (int i = 0; i < s.nInd; ++i) pin.spanRec[i] = spanRec[i];
         OutDev o2 = out;
         o2.spans = nullptr; o2.firstOutside = nullptr;
         o2.aos = B.aos; o2.aosStride = stride;
-        fn<<<(unsigned)((n + 127) / 128), 128, 0, sEval>>>(s, pin, n, wrt, o2);
+        // the staged kernel lives on window reuse: it needs cells that hold a few tiles' worth of points (a sparse
+        // tail chunk makes every tile straddle several cells); below that the L1-gather kernel is the faster one
+        if (staged && n >= 48 * cells) {
+            // persistent warps over contiguous runs of tiles (window reuse between consecutive tiles)
+            long long blocks = (long long)num_sms() * (staged->code % 10);
+            if (blocks > (n + 127) / 128) blocks = (n + 127) / 128;
+            staged->fn<<<(unsigned)blocks, 128, sizeof(double) * 4 * 2 * staged->windowDoubles, sEval>>>(s, pin, n, wrt, o2);
+        }
+        else
+            fn<<<(unsigned)((n + 127) / 128), 128, 0, sEval>>>(s, pin, n, wrt, o2);
         if (overlap) cudaEventRecord(bs->evaluated[c & 1], sEval);
         count_launch(1);
         return check_launch("bspy_cuda_eval_points_binned(eval)");
@@ -965,10 +1446,16 @@ static int eval_binned_records(const SplineDev &s, PointsDev in, long long N, co
         const long long base = c * chunk;
         const int n = (int)(N - base < chunk ? N - base : chunk);
         if (overlap) cudaStreamWaitEvent(sSort, bs->evaluated[c & 1], 0);
-        int uw = (int)(48 * 1024 / (sizeof(double) * stride * 33));     // warps per CTA that fit 48 KB of transpose tiles
-        uw = uw > UNPERM_WARPS ? UNPERM_WARPS : (uw < 1 ? 1 : uw);
-        bin_unpermute_kernel<<<(n + uw * 32 - 1) / (uw * 32), uw * 32, sizeof(double) * uw * stride * 33, sSort>>>(
-            B.aos, stride, B.inv, base, n, s.nDep, nJ, nN, out);
+        int urc;
+        switch (stride) {
+            case 4: urc = launch_unpermute<4>(B.aos, stride, B.inv, base, n, s.nDep, nJ, nN, out, sSort); break;
+            case 8: urc = launch_unpermute<8>(B.aos, stride, B.inv, base, n, s.nDep, nJ, nN, out, sSort); break;
+            case 12: urc = launch_unpermute<12>(B.aos, stride, B.inv, base, n, s.nDep, nJ, nN, out, sSort); break;
+            case 16: urc = launch_unpermute<16>(B.aos, stride, B.inv, base, n, s.nDep, nJ, nN, out, sSort); break;
+            case 32: urc = launch_unpermute<32>(B.aos, stride, B.inv, base, n, s.nDep, nJ, nN, out, sSort); break;
+            default: urc = launch_unpermute<0>(B.aos, stride, B.inv, base, n, s.nDep, nJ, nN, out, sSort); break;
+        }
+        if (urc) return urc;
         count_launch(1);
         return check_launch("bspy_cuda_eval_points_binned(unpermute)");
     };
@@ -1008,7 +1495,7 @@ int eval_binned(const SplineDev &s, PointsDev in, long long N, const WrtDev &wrt
         if (e != cudaSuccess) { set_error("cudaMemsetAsync: %s", cudaGetErrorString(e)); return (int)e; }
         OutDev o1{};
         o1.ld = out.ld; o1.spans = spans; o1.firstOutside = flag;
-        bin_keys_kernel<<<(n + 255) / 256, 256, 0, stream>>>(s, in, base, n, keys, hist, o1);
+        bin_keys_kernel<<<(n + 255) / 256, 256, 0, stream>>>(s, in, base, n, keys, hist, nullptr, o1);
         bin_scan_kernel<<<1, 1024, 0, stream>>>(hist, (int)cells);
         bin_scatter_kernel<<<(n + 255) / 256, 256, 0, stream>>>(keys, hist, n, perm, skey);
         PointsDev pin = in;

@@ -462,6 +462,49 @@ def test_binned_path_is_bit_identical_to_unbinned():
     assert _cuda.library().bspy_cuda_binned_workspace_bytes(device_spline(small).c, 1 << 20) == 0
 
 
+def test_record_mode_staged_windows_bit_identical(monkeypatch):
+    """Sorted-record mode (32-byte point records in cell order, per-span reciprocal records, warp-staged windows for
+    the volume shapes, one dependent variable per pass for the 4-variate nDep-6 shape, cp.async un-permute): same
+    bits as the direct thread-per-point kernel, for dense cells (staged kernel) and for a sparse tail."""
+    bspy, _cuda, O, _ = _mods()
+    from bspy_b200._spline_evaluation import device_spline
+    rng = np.random.default_rng(31)
+
+    def K(o, n):
+        w = rng.uniform(0.25, 1.75, n - o + 1)
+        inner = np.concatenate(([0.0], np.cumsum(w))); inner /= inner[-1]
+        return np.concatenate((np.zeros(o - 1), inner, np.ones(o - 1)))
+
+    monkeypatch.setenv("BSPY_BIN_MODE", "1")
+    shapes = [((4, 4, 4), 3, (18, 18, 18)), ((3, 3, 3), 3, (20, 19, 18)), ((4, 4, 4), 1, (28, 27, 26)), ((4, 4, 4), 4, (17, 16, 18)),
+              ((3, 3, 3, 3), 6, (10, 10, 9, 10))]
+    for order, nDep, nCoef in shapes:
+        nInd = len(order)
+        s = bspy.Spline(nInd, nDep, order, nCoef, [K(o, n) for o, n in zip(order, nCoef)], rng.standard_normal((nDep, *nCoef)))
+        ds = device_spline(s)
+        cells = int(np.prod([n - o + 1 for o, n in zip(order, nCoef)]))
+        for N in (64 * cells + 4321, 70_000):                       # dense cells (staged windows) / sparse cells
+            assert _cuda.library().bspy_cuda_binned_workspace_bytes(ds.c, N) > 0, (order, nDep, N)
+            g = torch.Generator(device="cuda").manual_seed(N)
+            pts = torch.rand((N, nInd), dtype=torch.float64, device="cuda", generator=g)
+            pts[7, 0], pts[N - 1, nInd - 1], pts[99, 1] = 0.0, 1.0, float(s.knots[1][order[1] + 2])
+            requests = [dict(values=True, jacobian=True, spans=True), dict(values=True)]
+            if abs(nInd - nDep) == 1:
+                requests.append(dict(values=True, jacobian=True, normal=True))
+            for request in requests:
+                a = _cuda.eval_points(ds, pts, nInd, 1, N, binned=True, **request)
+                b = _cuda.eval_points(ds, pts, nInd, 1, N, binned=False, **request)
+                for key in a:
+                    assert (a[key] is None) == (b[key] is None)
+                    if a[key] is not None:
+                        assert torch.equal(a[key], b[key]), (order, nDep, N, key)
+            # and the direct kernel itself against the oracle on a sample
+            idx = rng.integers(0, N, 3000)
+            so = O.OracleSpline.of(s)
+            ph = pts[idx].cpu().numpy()
+            assert close(a["values"][:, idx].cpu().numpy().T, O.evaluate_vec(so, ph))
+
+
 def test_batch_api_variants():
     """SplineBatch: per-spline knots on the grid path, indices on normals, shard(), spline(i), host and device
     inputs; bspline_values_batch; evaluate_grid for a curve."""
