@@ -17,6 +17,42 @@ struct CurveParams {
     int derivAsValue;   // derivative([1], u): write the first derivative into out.values
 };
 
+// results of one point: spans, values (or the first derivative when derivative([1], u) was asked for), jacobian,
+// normal of a planar curve
+template <int NDEP, bool DER>
+__device__ __forceinline__ void store_curve_point(const CurveParams &P, const long long p, const int ix, const double (&v)[NDEP],
+                                                  const double (&g)[NDEP])
+{
+    const OutDev &out = P.out;
+    if (out.spans) __stcs(out.spans + p, ix);
+    if (out.values) {
+#pragma unroll
+        for (int d = 0; d < NDEP; ++d) __stcs(out.values + d * out.ld + p, (DER && P.derivAsValue) ? g[d] : v[d]);
+    }
+    if constexpr (DER) {
+        if (out.jacobian) {
+#pragma unroll
+            for (int d = 0; d < NDEP; ++d) __stcs(out.jacobian + d * out.ld + p, g[d]);
+        }
+        if constexpr (NDEP == 2) {
+            if (out.normal) {
+                // planar curve: T = J is 2x1, n = sign * (t_y, -t_x)
+                double n0 = g[1] * P.normalSign, n1 = -g[0] * P.normalSign;
+                if (out.normalize) {
+                    double sq = 0.0;
+                    if (out.normalMask & 1u) sq = fma(n0, n0, sq);
+                    if (out.normalMask & 2u) sq = fma(n1, n1, sq);
+                    const double len = sqrt(sq);
+                    n0 = n0 / len;
+                    n1 = n1 / len;
+                }
+                __stcs(out.normal + p, n0);
+                __stcs(out.normal + out.ld + p, n1);
+            }
+        }
+    }
+}
+
 template <int O, int NDEP, bool DER>
 __global__ void __launch_bounds__(256) eval_curve_kernel(const CurveParams P)
 {
@@ -43,32 +79,188 @@ __global__ void __launch_bounds__(256) eval_curve_kernel(const CurveParams P)
         if (((u < lo) | (u > hi)) && out.firstOutside) report_outside((int64_t *)out.firstOutside, p);
         double v[NDEP], g[NDEP];
         const int ix = curve_point<O, NDEP, DER>(kn, rec, cf, P.nCoef, u, v, g);
-        if (out.spans) __stcs(out.spans + p, ix);
-        if (out.values) {
+        store_curve_point<NDEP, DER>(P, p, ix, v, g);
+    }
+}
+
+// ---- bank-replicated span rows (big batches) ------------------------------------------------------------------
+// The kernel above is bound by shared-memory wavefronts, not by HBM: per point it gathers 6 bisection probes, an
+// 80-byte span record and a 96-byte coefficient window (cubic, nDep 3) from random places; lanes collide on the banks
+// (~2.5 wavefronts where one would do), ~140 wavefronts per warp of 32 points = 68 Gpts/s on 148 SMs -- what is
+// measured -- against 204 Gpts/s at the HBM roofline.  For big batches each CTA therefore builds
+//   * one ROW per span holding everything a point of that span needs (left knots | reciprocal gaps | the O x nDep
+//     coefficient window), replicated once per lane position of a quarter warp: chunk j (16 bytes) of span s for
+//     copy q lives at 16-byte slot ((s * CH + j) * COPIES + q), so the 8 lanes that share a 128-byte wavefront of an
+//     LDS.128 always hit 8 different bank groups -- whatever their spans -- and a row costs CH * 4 wavefronts per warp;
+//   * a bucket table over the domain: tab[b] = first span whose knots may still be <= a parameter of bucket b
+//     (exactly: order + the number of interior knots whose own bucket is < b, with the same floating-point bucket
+//     function, which is monotone -- so the answer is bit-exact), followed by a short advance over the knots of the
+//     bucket itself (knots replicated per lane position of a half warp: LDS.64 conflict-free).
+// 44 + ~8 wavefronts per warp for the cubic nDep-3 curve instead of ~140.  Arithmetic per point is basis_core<> and the
+// same dot products as curve_point<>: bit-identical results.
+constexpr int REPL_COPIES = 8, REPL_KNOT_COPIES = 16;   // measured at 1e8 points: 8 / 4 / 2 row copies -> 132 / 87 / 77 Gpts/s
+constexpr int REPL_U = 2;
+constexpr int repl_threads(int O, int nDep) { return ((O - 1) + O * (O - 1) / 2 + O * nDep) <= 24 ? 512 : 256; }
+
+struct ReplLayout {
+    int buckets;         // power of two
+    size_t bytes;        // 0: the replicated tables do not fit
+};
+
+static ReplLayout repl_layout(int O, int nDep, int nCoef, size_t budget)
+{
+    ReplLayout L{};
+    const int rowDoubles = ((O - 1) + O * (O - 1) / 2 + O * nDep + 1) & ~1;
+    const int spans = nCoef - O + 1;
+    L.buckets = 64;
+    while (L.buckets < 4 * spans && L.buckets < 4096) L.buckets <<= 1;
+    L.bytes = sizeof(double) * ((size_t)spans * rowDoubles * REPL_COPIES + (size_t)(O + nCoef) * REPL_KNOT_COPIES) +
+              sizeof(int) * (L.buckets + 2) + sizeof(unsigned short) * L.buckets + 64;
+    if (L.bytes > budget) L.bytes = 0;
+    return L;
+}
+
+// Measured (ncu, config 1 at 2e7 points): the LSU data pipe is 97 % busy -- 51 shared-memory wavefronts per warp of
+// 32 points (44 for the rows, all conflict-free) plus ~22 for the 32 bytes/point of global traffic -- at 132 Gpts/s =
+// 65 % of the HBM roofline; 16-byte global accesses (two consecutive points per thread) change nothing, the pipe
+// charges global traffic by the byte.
+template <int O, int NDEP, bool DER>
+__global__ void __launch_bounds__(repl_threads(O, NDEP), 2) eval_curve_repl_kernel(const CurveParams P, const int buckets)
+{
+    using R = SpanRec<O>;
+    constexpr int ROW = ((O - 1) + O * (O - 1) / 2 + O * NDEP + 1) & ~1, CH = ROW / 2;
+    constexpr int CP = REPL_COPIES, KC = REPL_KNOT_COPIES;
+    extern __shared__ __align__(16) double sm[];
+    const int nKnots = O + P.nCoef, spans = P.nCoef - O + 1;
+    double *rows = sm;                                             // spans * ROW * CP
+    double *kn = rows + spans * ROW * CP;                          // nKnots * KC
+    int *cnt = reinterpret_cast<int *>(kn + nKnots * KC);          // buckets + 1 (scan scratch)
+    unsigned short *tab = reinterpret_cast<unsigned short *>(cnt + buckets + 2);
+    const int lane = threadIdx.x & 31;
+    // the first round of parameters travels from HBM while the tables are built
+    const long long stride = (long long)gridDim.x * blockDim.x;          // threads of the grid
+    const long long first = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    // point of (round, k) = first + (2 * round + k) * stride
+    const long long pstep = stride, rstep = 2 * stride;
+    const long long pfirst = first;
+    const double *up = P.in.uvw + pfirst * P.in.pointStride;
+    const long long ustep = pstep * P.in.pointStride, urstep = rstep * P.in.pointStride;
+    double un[REPL_U];
+    auto fetch = [&](const double *src, long long p0) {
 #pragma unroll
-            for (int d = 0; d < NDEP; ++d) __stcs(out.values + d * out.ld + p, (DER && P.derivAsValue) ? g[d] : v[d]);
+        for (int k = 0; k < REPL_U; ++k)
+            if (p0 + k * pstep < P.N) un[k] = __ldcs(src + k * ustep);
+    };
+    un[0] = un[1] = 0.0;
+    fetch(up, pfirst);
+    // knots, every copy
+    for (int i = threadIdx.x; i < nKnots * KC; i += blockDim.x) kn[i] = __ldg(P.knots + i / KC);
+    for (int i = threadIdx.x; i <= buckets; i += blockDim.x) cnt[i] = 0;
+    __syncthreads();
+    const double lo = kn[(O - 1) * KC], hi = kn[P.nCoef * KC];
+    const double scale = (double)buckets / (hi - lo);
+    const int lastBucket = buckets - 1;
+    // monotone in x (subtraction and multiplication by a positive constant are, so is the saturating conversion);
+    // NaN -> 0
+    auto bucket_of = [&](double x) -> int { return min(max(__double2int_rz((x - lo) * scale), 0), lastBucket); };
+    // rows (copy 0 is written first, then replicated) and the bucket histogram of the interior knots
+    for (int sp = threadIdx.x; sp < spans; sp += blockDim.x) {
+        const int ix = O + sp;
+        double r[ROW];
+#pragma unroll
+        for (int j = 0; j < O - 1; ++j) r[j] = kn[(ix - (O - 1) + j) * KC];
+        int at = O - 1;
+#pragma unroll
+        for (int deg = 1; deg < O; ++deg)
+#pragma unroll
+            for (int t = 0; t < deg; ++t) r[at++] = 1.0 / (kn[(ix + t) * KC] - kn[(ix - deg + t) * KC]);
+#pragma unroll
+        for (int j = 0; j < O; ++j)
+#pragma unroll
+            for (int d = 0; d < NDEP; ++d) r[R::used + j * NDEP + d] = __ldg(P.coefs + (size_t)d * P.nCoef + (sp + j));
+        if (ROW > R::used + O * NDEP) r[ROW - 1] = 0.0;
+#pragma unroll
+        for (int j = 0; j < CH; ++j)
+            *reinterpret_cast<double2 *>(rows + 2 * ((sp * CH + j) * CP)) = make_double2(r[2 * j], r[2 * j + 1]);
+    }
+    // interior knots O .. nCoef-1 (the candidates of the span search) into their buckets
+    for (int i = O + threadIdx.x; i < P.nCoef; i += blockDim.x) atomicAdd(cnt + bucket_of(kn[i * KC]) + 1, 1);
+    __syncthreads();
+    // replicate the rows
+    {
+        const int total = spans * CH * CP;
+        for (int i = threadIdx.x; i < total; i += blockDim.x) {
+            const int q = i & (CP - 1);
+            if (q) *reinterpret_cast<double2 *>(rows + 2 * i) = *reinterpret_cast<const double2 *>(rows + 2 * (i - q));
         }
-        if constexpr (DER) {
-            if (out.jacobian) {
+    }
+    // tab[b] = O + number of interior knots in buckets < b: inclusive scan of cnt (one warp)
+    if (threadIdx.x < 32) {
+        int run = 0;
+        for (int base = 0; base <= buckets; base += 32) {
+            const int i = base + lane;
+            const int c = i <= buckets ? cnt[i] : 0;
+            int incl = c;
 #pragma unroll
-                for (int d = 0; d < NDEP; ++d) __stcs(out.jacobian + d * out.ld + p, g[d]);
+            for (int off = 1; off < 32; off <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, off);
+                if (lane >= off) incl += v;
             }
-            if constexpr (NDEP == 2) {
-                if (out.normal) {
-                    // planar curve: T = J is 2x1, n = sign * (t_y, -t_x)
-                    double n0 = g[1] * P.normalSign, n1 = -g[0] * P.normalSign;
-                    if (out.normalize) {
-                        double sq = 0.0;
-                        if (out.normalMask & 1u) sq = fma(n0, n0, sq);
-                        if (out.normalMask & 2u) sq = fma(n1, n1, sq);
-                        const double len = sqrt(sq);
-                        n0 = n0 / len;
-                        n1 = n1 / len;
-                    }
-                    __stcs(out.normal + p, n0);
-                    __stcs(out.normal + out.ld + p, n1);
+            if (i < buckets) tab[i] = (unsigned short)(O + run + incl);
+            run += __shfl_sync(0xffffffffu, incl, 31);
+        }
+    }
+    __syncthreads();
+    // rows of this lane's copy start at myRows, O rows before span 0 so that the span index addresses them directly
+    const double2 *myRows = reinterpret_cast<const double2 *>(rows) + (lane & (CP - 1)) - O * CH * CP;
+    const double *myKnots = kn + (lane & (KC - 1));
+    const OutDev &out = P.out;
+    const bool report = out.firstOutside != nullptr;
+    const int nCoef = P.nCoef;
+    // REPL_U points per thread and round; the parameters of the next round are requested before this round's
+    // arithmetic (the loop is otherwise a chain DRAM load -> table -> row -> arithmetic -> store per point)
+    for (long long p0 = pfirst; p0 < P.N; p0 += rstep) {
+        double u[REPL_U];
+#pragma unroll
+        for (int k = 0; k < REPL_U; ++k) u[k] = un[k];
+        up += urstep;
+        fetch(up, p0 + rstep);
+#pragma unroll
+        for (int k = 0; k < REPL_U; ++k) {
+            const long long p = p0 + k * pstep;
+            if (p >= P.N) break;
+            const double uk = u[k];
+            if (report && ((uk < lo) | (uk > hi))) report_outside((int64_t *)out.firstOutside, p);
+            int ix = tab[bucket_of(uk)];
+            while (ix < nCoef && myKnots[ix * KC] <= uk) ++ix;
+            if (uk != uk) ix = nCoef;
+            double r[ROW];
+            const double2 *rp = myRows + ix * (CH * CP);
+#pragma unroll
+            for (int j = 0; j < CH; ++j) {
+                const double2 x = rp[j * CP];
+                r[2 * j] = x.x;
+                r[2 * j + 1] = x.y;
+            }
+            double dl[O > 1 ? O - 1 : 1], rc[O > 1 ? O * (O - 1) / 2 : 1];
+#pragma unroll
+            for (int j = 0; j < O - 1; ++j) dl[j] = uk - r[j];
+#pragma unroll
+            for (int j = 0; j < O * (O - 1) / 2; ++j) rc[j] = r[O - 1 + j];
+            double b0[O], b1[O];
+            basis_core<O, DER>(dl, rc, 0, b0, b1);
+            double v[NDEP], g[NDEP];
+#pragma unroll
+            for (int d = 0; d < NDEP; ++d) { v[d] = 0.0; g[d] = 0.0; }
+#pragma unroll
+            for (int j = 0; j < O; ++j)
+#pragma unroll
+                for (int d = 0; d < NDEP; ++d) {
+                    const double x = r[R::used + j * NDEP + d];
+                    v[d] = fma(x, b0[j], v[d]);
+                    if (DER) g[d] = fma(x, b1[j], g[d]);
                 }
-            }
+            store_curve_point<NDEP, DER>(P, p, ix, v, g);
         }
     }
 }
@@ -79,6 +271,27 @@ static int launch_curve3(const CurveParams &P, size_t smem, cudaStream_t stream)
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(eval_curve_kernel<O, NDEP, DER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+    }
+    {
+        // big batches: bank-replicated span rows (when 8 copies of the rows fit beside a second CTA)
+        const char *re = getenv("BSPY_CURVE_REPL");
+        const long long minN = re ? (atoi(re) ? 0 : (1LL << 62)) : 131072;
+        const ReplLayout L = repl_layout(O, NDEP, P.nCoef, 100 * 1024);
+        if (P.N >= minN && L.bytes && !P.in.grid && P.nCoef < 65535) {
+            static size_t allowed = 48 * 1024;
+            if (L.bytes > allowed) {
+                cudaError_t e2 = cudaFuncSetAttribute(eval_curve_repl_kernel<O, NDEP, DER>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+                if (e2 != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e2)); return (int)e2; }
+                allowed = 100 * 1024;
+            }
+            const int threads = repl_threads(O, NDEP);
+            long long blocks = (P.N + threads * 4 - 1) / (threads * 4);
+            const long long cap = (long long)num_sms() * 2;
+            if (blocks > cap) blocks = cap;
+            eval_curve_repl_kernel<O, NDEP, DER><<<(unsigned)blocks, threads, L.bytes, stream>>>(P, L.buckets);
+            count_launch();
+            return check_launch("bspy_cuda_eval_points(curve, replicated rows)");
+        }
     }
     const int threads = 256;
     const char *e = getenv("BSPY_CURVE_PPT");

@@ -505,6 +505,76 @@ def test_record_mode_staged_windows_bit_identical(monkeypatch):
             assert close(a["values"][:, idx].cpu().numpy().T, O.evaluate_vec(so, ph))
 
 
+def test_curve_replicated_rows_bit_identical(monkeypatch):
+    """Big batches on one curve go through eval_curve_repl_kernel (bank-replicated span rows, bucket table + short
+    advance instead of a bisection): spans bit-exact, values and derivatives bit-identical to the plain curve kernel,
+    and both within tolerance of the oracle."""
+    bspy, _cuda, O, _ = _mods()
+    from bspy_b200._spline_evaluation import device_spline
+    rng = np.random.default_rng(21)
+
+    def K(o, n, clamp=True, cluster=False):
+        w = rng.uniform(0.25, 1.75, n - o + 1)
+        if cluster and n - o + 1 > 6:
+            w[2:5] = 1e-7                                         # several knots inside one bucket
+        inner = np.concatenate(([0.0], np.cumsum(w))); inner /= inner[-1]
+        if clamp:
+            return np.concatenate((np.zeros(o - 1), inner, np.ones(o - 1)))
+        return np.concatenate((-np.cumsum(rng.uniform(0.1, 0.3, o - 1))[::-1], inner, 1.0 + np.cumsum(rng.uniform(0.1, 0.3, o - 1))))
+
+    shapes = [(4, 3, 64, True, False), (4, 3, 64, False, True), (2, 1, 5, True, False), (3, 2, 300, True, True), (6, 4, 17, True, False),
+              (1, 2, 9, True, False), (5, 2, 40, False, False), (4, 3, 2000, True, False)]
+    for order, nDep, nCoef, clamp, cluster in shapes:
+        s = bspy.Spline(1, nDep, (order,), (nCoef,), [K(order, nCoef, clamp, cluster)], rng.standard_normal((nDep, nCoef)))
+        ds = device_spline(s)
+        lo, hi = s.knots[0][order - 1], s.knots[0][nCoef]
+        N = 140_000 + 1234
+        g = torch.Generator(device="cuda").manual_seed(order * 100 + nCoef)
+        u = lo + (hi - lo) * torch.rand((N, 1), dtype=torch.float64, device="cuda", generator=g)
+        u.clamp_(lo, hi)
+        kn = torch.from_numpy(np.asarray(s.knots[0][order - 1:nCoef + 1], dtype=np.float64)).cuda()
+        m = kn.numel()
+        u[:m, 0] = kn                                             # every knot, both ends ...
+        u[m:2 * m, 0] = torch.from_numpy(np.clip(np.nextafter(kn.cpu().numpy(), -np.inf), lo, hi)).cuda()   # ... and their neighbours
+        u[2 * m:3 * m, 0] = torch.from_numpy(np.clip(np.nextafter(kn.cpu().numpy(), np.inf), lo, hi)).cuda()
+        u[N - 1, 0] = float("nan")
+        requests = [dict(values=True, spans=True), dict(values=True, jacobian=True), dict(values=False, wrt=[1])]
+        if nDep == 2:
+            requests.append(dict(values=True, jacobian=True, normal=True))
+            requests.append(dict(values=False, normal=True, normalize=False))
+        for request in requests:
+            monkeypatch.setenv("BSPY_CURVE_REPL", "1")
+            a = _cuda.eval_points(ds, u, 1, 1, N, **request)
+            monkeypatch.setenv("BSPY_CURVE_REPL", "0")
+            b = _cuda.eval_points(ds, u, 1, 1, N, **request)
+            for key in a:
+                assert (a[key] is None) == (b[key] is None)
+                if a[key] is not None:
+                    x, y = a[key], b[key]
+                    if x.dtype.is_floating_point:
+                        x, y = torch.nan_to_num(x, nan=-7.0), torch.nan_to_num(y, nan=-7.0)
+                    assert torch.equal(x, y), (order, nDep, nCoef, key)
+        # default dispatch (replicated rows for this N) against the oracle: spans bit-exact, values within tolerance
+        monkeypatch.delenv("BSPY_CURVE_REPL")
+        r = _cuda.eval_points(ds, u, 1, 1, N, values=True, jacobian=True, spans=True)
+        idx = np.concatenate((np.arange(0, min(3 * m, 6000)), rng.integers(0, N - 1, 4000)))
+        so = O.OracleSpline.of(s)
+        uh = u[idx].cpu().numpy()
+        ref, sp = O.evaluate_vec(so, uh, return_spans=True)
+        assert np.array_equal(r["spans"][0, idx].cpu().numpy(), sp[:, 0]), (order, nDep, nCoef)
+        if not cluster:                                            # 1e-7 gaps make the derivative scale 1e7: condition-aware bar elsewhere
+            assert close(r["values"][:, idx].cpu().numpy().T, ref)
+            assert close(r["jacobian"][:, 0, idx].cpu().numpy().T, O.jacobian_vec(so, uh)[:, :, 0])
+        # outside the domain: first offender reported, like the direct kernel
+        bad = u.clone()
+        bad[N - 1, 0] = lo
+        bad[136_000, 0] = hi + 1.0
+        bad[138_000, 0] = lo - 1.0
+        flag = _cuda.new_flag(u.device)
+        _cuda.eval_points(ds, bad, 1, 1, N, flag=flag)
+        assert int(flag.item()) == 136_000
+
+
 def test_batch_api_variants():
     """SplineBatch: per-spline knots on the grid path, indices on normals, shard(), spline(i), host and device
     inputs; bspline_values_batch; evaluate_grid for a curve."""
