@@ -10,6 +10,7 @@ impossible, or no CUDA device is present when a computation is requested, the ca
 from __future__ import annotations
 
 import ctypes as C
+import math
 import os
 import threading
 
@@ -29,7 +30,8 @@ SYMBOLS = (
     "bspy_cuda_spans", "bspy_cuda_basis", "bspy_cuda_eval_points", "bspy_cuda_eval_points_binned",
     "bspy_cuda_binned_workspace_bytes", "bspy_cuda_eval_grid",
     "bspy_cuda_eval_grid_batch", "bspy_cuda_eval_many", "bspy_cuda_probe_fp64", "bspy_cuda_probe_hbm",
-    "bspy_cuda_probe_tiles", "bspy_cuda_curvature",
+    "bspy_cuda_probe_tiles", "bspy_cuda_curvature", "bspy_cuda_contract_axis", "bspy_cuda_block_accumulate",
+    "bspy_cuda_normal_from_jacobian",
 )
 
 
@@ -85,6 +87,9 @@ def library():
             "bspy_cuda_probe_hbm": [i32, vp, vp, i64, C.POINTER(C.c_double), vp],
             "bspy_cuda_probe_tiles": [vp, i32, i64, i64, i32, i32, C.POINTER(C.c_double), vp],
             "bspy_cuda_curvature": [i32, i32, i32, i64, vp, vp, vp, vp, vp],
+            "bspy_cuda_contract_axis": [vp, i64, i64, i64, i32, i32, vp, vp, vp],
+            "bspy_cuda_block_accumulate": [vp, i64, vp, i64, i32, C.POINTER(i32), i64, vp],
+            "bspy_cuda_normal_from_jacobian": [vp, i32, i32, i64, i32, u32, u32, vp, vp],
         }
         for name, args in sig.items():
             fn = getattr(lib, name)
@@ -307,6 +312,44 @@ def curvature(nInd, nDep, graph, d1, d2, normal):
         rc = library().bspy_cuda_curvature(int(nInd), int(nDep), int(bool(graph)), int(N), _ptr(_f64(d1, dev)), _ptr(_f64(d2, dev)),
                                            _ptr(normal), _ptr(out), _stream(dev))
     _check(rc, "bspy_cuda_curvature")
+    return out
+
+
+def contract_axis(coefs, axis, first, order, basis):
+    """Launch bspy_cuda_contract_axis: ``coefs`` (contiguous device tensor) with dimension ``axis`` contracted against
+    ``basis`` (device tensor of ``order`` doubles) over indices first .. first+order-1; returns the tensor without
+    that dimension."""
+    dev = coefs.device
+    shape = list(coefs.shape)
+    outer = math.prod(shape[:axis])
+    inner = math.prod(shape[axis + 1:])
+    out = torch.empty(shape[:axis] + shape[axis + 1:], dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        rc = library().bspy_cuda_contract_axis(_ptr(coefs), outer, int(shape[axis]), inner, int(first), int(order), _ptr(basis),
+                                               _ptr(out), _stream(dev))
+    _check(rc, "bspy_cuda_contract_axis")
+    return out
+
+
+def block_accumulate(dst, src, dst_rows):
+    """dst[dst_rows[r], :] += src[r, :] for 2-D views (rows, N) of device tensors (bspy_cuda_block_accumulate)."""
+    dev = dst.device
+    rows = (C.c_int32 * max(len(dst_rows), 1))(*[int(r) for r in dst_rows])
+    with torch.cuda.device(dev):
+        rc = library().bspy_cuda_block_accumulate(_ptr(dst), int(dst.stride(0)), _ptr(src), int(src.stride(0)), len(dst_rows), rows,
+                                                  int(dst.shape[1]), _stream(dev))
+    _check(rc, "bspy_cuda_block_accumulate")
+
+
+def normal_from_jacobian(jac, nDep, nInd, sign, normalize, mask):
+    """Cofactor normals (D, N) of the jacobians ``jac`` (nDep, nInd, N) (bspy_cuda_normal_from_jacobian)."""
+    dev = jac.device
+    N = jac.shape[-1]
+    out = torch.empty((max(nDep, nInd), N), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        rc = library().bspy_cuda_normal_from_jacobian(_ptr(jac), int(nDep), int(nInd), int(N), int(sign), NORMALIZE if normalize else 0,
+                                                      int(mask), _ptr(out), _stream(dev))
+    _check(rc, "bspy_cuda_normal_from_jacobian")
     return out
 
 

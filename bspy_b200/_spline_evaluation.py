@@ -17,7 +17,7 @@ import torch
 
 from bspy_b200 import _cuda
 
-__all__ = ["curvature", "curvature_points", "EvalResult", "bspline_values", "bspline_values_batch", "domain", "evaluate", "derivative", "jacobian",
+__all__ = ["contract", "curvature", "curvature_points", "EvalResult", "bspline_values", "bspline_values_batch", "domain", "evaluate", "derivative", "jacobian",
            "normal", "evaluate_points", "evaluate_grid", "device_spline", "freeze"]
 
 
@@ -218,6 +218,36 @@ def normal(self, uvw, normalize=True, indices=None):
         n = n[idx]
     dt = np.asarray(self.coefs).dtype if hasattr(self, "coefs") else getattr(self, "coefsDtype", np.float64)
     return n.astype(dt if np.issubdtype(dt, np.floating) else np.float64, copy=False)
+
+
+def contract(self, uvw):
+    """``Spline.contract`` (reference ``bspy/_spline_operations.py:184-223``): fix the independent variables whose entry
+    of ``uvw`` is not ``None``; returns a spline in the remaining variables (``self`` when nothing is fixed).  The basis
+    values come from ``bspy_cuda_basis`` (bit-identical to the reference), every fixed variable is one
+    ``bspy_cuda_contract_axis`` launch over the coefficient array."""
+    box = domain(self)
+    fixed = []
+    for iv in range(self.nInd):
+        if uvw[iv] is not None:
+            if uvw[iv] < box[iv][0] or uvw[iv] > box[iv][1]:
+                raise ValueError(f"Spline evaluation outside domain: {uvw}")
+            fixed.append(iv)
+    if not fixed:
+        return self
+    ds = device_spline(self)
+    dev = ds.device
+    coefs = ds.coefs                                            # (nDep, *nCoef) contiguous float64 on the device
+    removed = 0
+    for iv in fixed:
+        u = torch.tensor([float(uvw[iv])], dtype=torch.float64, device=dev)
+        sp, b = _cuda.basis(ds.knots[iv], int(self.order[iv]), u, 0, False, None)
+        ix = int(sp[0].item())
+        coefs = _cuda.contract_axis(coefs, 1 + iv - removed, ix - self.order[iv], self.order[iv], b.reshape(-1))
+        removed += 1
+    keep = [iv for iv in range(self.nInd) if uvw[iv] is None]
+    out = coefs.cpu().numpy().astype(np.asarray(self.coefs).dtype, copy=False)
+    return type(self)(len(keep), self.nDep, [self.order[i] for i in keep], [self.nCoef[i] for i in keep],
+                      [self.knots[i] for i in keep], out, self.metadata)
 
 
 # ----------------------------------------------------------------------------- vectorised entries

@@ -134,6 +134,10 @@ class Spline(Manifold):
         """Normal at one point; needs ``|nInd - nDep| == 1``."""
         return _ev.normal(self, uvw, normalize, indices)
 
+    def contract(self, uvw):
+        return _ev.contract(self, uvw)
+    contract.__doc__ = _ev.contract.__doc__
+
     def curvature(self, uv):
         """Curvature of a curve (signed if planar) or Gaussian curvature of a surface at one point."""
         return _ev.curvature(self, uv)

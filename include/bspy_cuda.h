@@ -157,6 +157,25 @@ int bspy_cuda_eval_many(int32_t order, int32_t nCoef, int32_t nDep, int64_t nSpl
 int bspy_cuda_curvature(int32_t nInd, int32_t nDep, int32_t graph, int64_t N, const double *d1,
                         const double *d2, const double *normal, double *out, void *stream);
 
+/* ---- Spline.contract and SplineBlock -------------------------------------------------
+ *      bspy_cuda_contract_axis: out[a, b] = sum_j coefs[a, first + j, b] * basis[j], a < outer, b < inner, j < order:
+ *      one variable of a C-contiguous coefficient array (outer, n, inner) contracted against the `order` non-zero
+ *      basis values of one parameter (basis: device pointer, e.g. the output of bspy_cuda_basis); replaces
+ *      `coefs[..., ix-order:ix, ...] @ bValues` of bspy/_spline_operations.py:184-223 (Spline.contract).
+ *      bspy_cuda_block_accumulate: dst[dstRows[r] * dstLd + p] += src[r * srcLd + p], r < nRows, p < N: the row sums
+ *      of SplineBlock._block_evaluation / SplineBlock.jacobian (bspy/spline_block.py:37-44, 231-245); dstRows is a
+ *      HOST array.
+ *      bspy_cuda_normal_from_jacobian: cofactor normals (D = max(nInd, nDep) components, SoA (D, N)) of N jacobians
+ *      stored SoA as (nDep, nInd, N): bspy/_spline_evaluation.py:215-246 applied to a block's jacobian
+ *      (bspy/spline_block.py:282).  flags: BSPY_NORMALIZE; normalMask as in bspy_cuda_eval_points.          */
+int bspy_cuda_contract_axis(const double *coefs, int64_t outer, int64_t n, int64_t inner, int32_t first,
+                            int32_t order, const double *basis, double *out, void *stream);
+int bspy_cuda_block_accumulate(double *dst, int64_t dstLd, const double *src, int64_t srcLd, int32_t nRows,
+                               const int32_t *dstRows_host, int64_t N, void *stream);
+int bspy_cuda_normal_from_jacobian(const double *jacobian, int32_t nDep, int32_t nInd, int64_t N,
+                                   int32_t normalSign, uint32_t flags, uint32_t normalMask, double *normal,
+                                   void *stream);
+
 /* ---- measurement helpers used by bench.py (not part of the evaluation path) --------------
  *      bspy_cuda_probe_fp64: runs `iters` dependent-free FP64 FMA (kind 0) or DMMA m8n8k4
  *      (kind 1) chains on every SM and returns the flop count; time it with events on `stream`.

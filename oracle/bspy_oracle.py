@@ -22,6 +22,8 @@ Reference lines followed (all in ``bspy/_spline_evaluation.py`` unless noted):
 * jacobian ............... ``:205-213``
 * normal ................. ``:215-246``  (cofactors via ``np.linalg.det``)
 * ufunc-style dispatch ... ``bspy/spline.py:757-770, 936-949``
+* contract ............... ``bspy/_spline_operations.py:184-223``
+* SplineBlock sums ....... ``bspy/spline_block.py:37-44, 179-282``
 
 Two tiers live here:
 
@@ -39,7 +41,7 @@ import numpy as np
 __all__ = [
     "OracleSpline", "span_pt", "basis_pt", "domain", "derivative_pt", "evaluate_pt",
     "jacobian_pt", "normal_pt", "span_vec", "basis_vec", "derivative_vec", "evaluate_vec",
-    "jacobian_vec", "normal_vec", "check_domain_vec", "curvature_vec",
+    "jacobian_vec", "normal_vec", "check_domain_vec", "curvature_vec", "contract", "OracleBlock",
 ]
 
 
@@ -379,3 +381,90 @@ def normal_abs_vec(s, uvw):
                 term = term * M[:, r, c]
             out[:, i] += term
     return out
+
+
+# --------------------------------------------------------------------------- callers of the path
+
+def contract(s, uvw):
+    """``Spline.contract`` (``bspy/_spline_operations.py:184-223``): variables whose entry of ``uvw`` is not None are
+    fixed; the coefficient window of each is contracted against its basis values, variable by variable, with the
+    contracted axis moved last and ``coefs @ bValues`` like the reference."""
+    box = domain(s)
+    section = [slice(None)]
+    bValues = []
+    contracting = False
+    for iv in range(s.nInd):
+        if uvw[iv] is not None:
+            if uvw[iv] < box[iv][0] or uvw[iv] > box[iv][1]:
+                raise ValueError(f"Spline evaluation outside domain: {uvw}")
+            ix, b = basis_pt(None, s.knots[iv], s.order[iv], uvw[iv])
+            bValues.append(b)
+            section.append(slice(ix - s.order[iv], ix))
+            contracting = True
+        else:
+            bValues.append([])
+            section.append(slice(None))
+    if not contracting:
+        return s
+    order, nCoef, knots = list(s.order), list(s.nCoef), list(s.knots)
+    coefs = s.coefs[tuple(section)]
+    ix = 0
+    for iv in range(s.nInd):
+        if uvw[iv] is not None:
+            del order[ix], nCoef[ix], knots[ix]
+            coefs = np.moveaxis(coefs, ix + 1, -1) @ bValues[iv]
+        else:
+            ix += 1
+    return OracleSpline(len(order), s.nDep, order, nCoef, knots, coefs, s.metadata)
+
+
+class OracleBlock:
+    """Rows of ``(map, OracleSpline)``: the sums of ``bspy/spline_block.py:37-44`` (values, derivatives), ``:231-245``
+    (jacobian) and the cofactor normal of ``bspy/_spline_evaluation.py:215-246`` applied to the block jacobian."""
+
+    def __init__(self, rows):
+        self.rows = [[(list(m), sp) for m, sp in row] for row in rows]
+        self.nDep = sum(row[0][1].nDep for row in self.rows)
+        self.nInd = 1 + max(i for row in self.rows for m, _ in row for i in m)
+        self.metadata = {}
+
+    def derivative_vec(self, wrt, uvw):
+        uvw = np.asarray(uvw, dtype=np.float64).reshape(-1, self.nInd)
+        out = np.zeros((uvw.shape[0], self.nDep))
+        at = 0
+        for row in self.rows:
+            n = row[0][1].nDep
+            for m, sp in row:
+                out[:, at:at + n] += derivative_vec(sp, [wrt[i] for i in m], uvw[:, m])
+            at += n
+        return out
+
+    def evaluate_vec(self, uvw):
+        return self.derivative_vec([0] * self.nInd, uvw)
+
+    def jacobian_vec(self, uvw):
+        uvw = np.asarray(uvw, dtype=np.float64).reshape(-1, self.nInd)
+        J = np.zeros((uvw.shape[0], self.nDep, self.nInd))
+        at = 0
+        for row in self.rows:
+            n = row[0][1].nDep
+            for m, sp in row:
+                J[:, at:at + n, m] += jacobian_vec(sp, uvw[:, m])
+            at += n
+        return J
+
+    def normal_vec(self, uvw, normalize=True, indices=None):
+        if abs(self.nInd - self.nDep) != 1:
+            raise ValueError("The number of independent variables must be one different than the number of dependent variables.")
+        T = self.jacobian_vec(uvw)
+        if self.nInd > self.nDep:
+            T = np.swapaxes(T, 1, 2)
+        D = T.shape[1]
+        which = list(range(D)) if indices is None else list(indices)
+        n = np.empty((T.shape[0], len(which)))
+        with np.errstate(all="ignore"):
+            for slot, i in enumerate(which):
+                n[:, slot] = ((-1) ** i) * np.linalg.det(T[:, [j for j in range(D) if j != i], :])
+            if normalize:
+                n /= np.sqrt(np.sum(n * n, axis=1))[:, None]
+        return n

@@ -102,3 +102,23 @@ def nondegenerate_normal(normal_raw, scale, floor=1e-9):
     with np.errstate(all="ignore"):
         n = np.sqrt((normal_raw ** 2).sum(axis=-1))
         return n > floor * np.asarray(scale).max(axis=-1)
+
+
+def _spline_from(arrays, tag):
+    """(nInd, nDep, order, nCoef, knots, coefs) of a spline stored by tests/golden/make_golden_block.py"""
+    shape = [int(x) for x in arrays[f"{tag}/shape"]]
+    nInd, nDep = shape[0], shape[1]
+    order, nCoef = shape[2:2 + nInd], shape[2 + nInd:2 + 2 * nInd]
+    return nInd, nDep, tuple(order), tuple(nCoef), [arrays[f"{tag}/knots{i}"] for i in range(nInd)], arrays[f"{tag}/coefs"]
+
+
+def block_members(arrays, tag):
+    """rows of (map, spline-tuple) of block ``tag`` in ref_block.npz"""
+    rows, j = [], 0
+    for n in arrays[f"block/{tag}/rows"]:
+        row = []
+        for _ in range(int(n)):
+            row.append(([int(i) for i in arrays[f"block/{tag}/member{j}/map"]], _spline_from(arrays, f"block/{tag}/member{j}")))
+            j += 1
+        rows.append(row)
+    return rows

@@ -672,3 +672,89 @@ def test_grid_edge_cases():
                           O.jacobian_abs_vec(so, uvw)), (order, "jacobian")
         empty = s.evaluate_grid(*([axes[0][:0]] + axes[1:]), jacobian=True)
         assert empty.values.shape == (nDep, 0, *shape[1:]) and empty.jacobian.shape == (nDep, nInd, 0, *shape[1:])
+
+
+def test_contract_vs_reference():
+    """Spline.contract against the unmodified reference's results, and the reference's own test
+    (tests/bspy_test.py:639-652: surface(.25, u) == contracted(u) to 2.5 eps) on its golden surface."""
+    bspy, _, O, _ = _mods()
+    from golden_io import _spline_from
+    a = load_npz("ref_block.npz")
+    for name in a["contract/names"]:
+        tag, j = str(name).split("/")
+        s = bspy.Spline(*_spline_from(a, f"contract/{tag}"))
+        uvw = [None if np.isnan(v) else float(v) for v in a[f"contract/{tag}/{j}/uvw"]]
+        c = s.contract(uvw)
+        nInd, nDep, order, nCoef, knots, coefs = _spline_from(a, f"contract/{tag}/{j}/result")
+        assert (c.nInd, c.nDep, tuple(c.order), tuple(c.nCoef)) == (nInd, nDep, order, nCoef)
+        assert all(np.array_equal(x, y) for x, y in zip(c.knots, knots))
+        assert close(np.asarray(c.coefs), coefs.reshape(np.asarray(c.coefs).shape)), name
+    t = load_npz("ref_tables.npz")
+    surf = bspy.Spline(2, 3, t["surface/order"], t["surface/coefs"].shape[1:], [t["surface/knots0"], t["surface/knots1"]], t["surface/coefs"])
+    assert surf.contract([None, None]) is surf
+    for fixed, at in (([.25, None], 0), ([None, .75], 1)):
+        c = surf.contract(fixed)
+        worst_err = 0.0
+        for u in np.linspace(0, 1, 21):
+            full = [.25, u] if at == 0 else [u, .75]
+            d = surf(full) - c([u])
+            worst_err = max(worst_err, float(np.sqrt(d @ d)))
+        assert worst_err <= 2.5 * EPS
+    with pytest.raises(ValueError, match="outside domain"):
+        surf.contract([1.5, None])
+
+
+def test_spline_block_vs_reference():
+    """SplineBlock.evaluate / derivative / jacobian / normal / contract: single-point API and the
+    batched evaluate_points against outputs of the unmodified reference (maps, row sums, nInd > nDep normal)."""
+    bspy, _cuda, O, _ = _mods()
+    from golden_io import block_members
+    a = load_npz("ref_block.npz")
+    for tag in ("A", "B", "C"):
+        rows = [[(m, bspy.Spline(*sp)) for m, sp in row] for row in block_members(a, tag)]
+        b = bspy.SplineBlock(rows)
+        assert [b.nInd, b.nDep] == list(a[f"block/{tag}/nIndnDep"])
+        assert np.array_equal(b.domain(), a[f"block/{tag}/domain"])
+        uvw = a[f"block/{tag}/uvw"]
+        has_normal = f"block/{tag}/normal_unit" in a
+        r = b.evaluate_points(uvw, jacobian=True, normal=has_normal, with_respect_to=list(a[f"block/{tag}/wrt"][0]))
+        assert close(r.values.T, a[f"block/{tag}/values"])
+        assert close(np.transpose(r.jacobian, (2, 0, 1)), a[f"block/{tag}/jacobian"])
+        assert close(r.derivative.T, a[f"block/{tag}/deriv0"])
+        r2 = b.evaluate_points(torch.from_numpy(uvw).cuda(), values=False, with_respect_to=list(a[f"block/{tag}/wrt"][1]))
+        assert r2.derivative.is_cuda and close(r2.derivative.cpu().numpy().T, a[f"block/{tag}/deriv1"])
+        if has_normal:
+            assert close(r.normal.T, a[f"block/{tag}/normal_unit"])
+            assert close(b.evaluate_points(uvw, values=False, normal=True, normalize=False).normal.T, a[f"block/{tag}/normal_raw"])
+            assert close(b.evaluate_points(uvw, values=False, normal=True, indices=(0, 2)).normal.T, a[f"block/{tag}/normal_idx"])
+        for p in (0, 1, 7):
+            assert close(b(uvw[p]), a[f"block/{tag}/values"][p])
+            assert close(b.jacobian(uvw[p]), a[f"block/{tag}/jacobian"][p])
+            assert close(b.derivative(list(a[f"block/{tag}/wrt"][0]), uvw[p]), a[f"block/{tag}/deriv0"][p])
+            if has_normal:
+                assert close(b.normal(uvw[p]), a[f"block/{tag}/normal_unit"][p])
+                assert close(b.normal(uvw[p], False, (0, 2)), a[f"block/{tag}/normal_raw"][p][[0, 2]])
+            else:
+                with pytest.raises(ValueError, match="one different"):
+                    b.normal(uvw[p])
+        bad = uvw.copy(); bad[5, 0] = a[f"block/{tag}/domain"][0, 1] + 1.0
+        with pytest.raises(ValueError, match="outside domain"):
+            b.evaluate_points(bad)
+    # contracted block
+    rows = [[(m, bspy.Spline(*sp)) for m, sp in row] for row in block_members(a, "A")]
+    cb = bspy.SplineBlock(rows).contract([None if np.isnan(v) else float(v) for v in a["block/A/contract_uvw"]])
+    assert [cb.nInd, cb.nDep] == list(a["block/A/contract_nIndnDep"])
+    assert close(cb.evaluate_points(a["block/A/contract_pts"]).values.T, a["block/A/contract_values"])
+    # constructor errors of the reference (bspy/spline_block.py:83, 91, 96)
+    F, G = rows[0][0][1], rows[0][1][1]
+    with pytest.raises(ValueError, match="same nDep"):
+        bspy.SplineBlock([[F, rows[1][0][1]]])
+    with pytest.raises(ValueError, match="Multiple splines in the same row"):
+        bspy.SplineBlock([[([0, 1, 2], F), ([2, 3], G)]])
+    # a bigger batch against the oracle
+    rng = np.random.default_rng(9)
+    ob = O.OracleBlock([[(m, O.OracleSpline.of(sp)) for m, sp in row] for row in rows])
+    dom = a["block/A/domain"]
+    big = dom[:, 0] + (dom[:, 1] - dom[:, 0]) * rng.uniform(0, 1, (20_000, 5))
+    r = bspy.SplineBlock(rows).evaluate_points(big, jacobian=True)
+    assert close(r.values.T, ob.evaluate_vec(big)) and close(np.transpose(r.jacobian, (2, 0, 1)), ob.jacobian_vec(big))

@@ -125,3 +125,32 @@ def test_curvature_vs_reference():
         assert np.array_equal(np.isnan(got), np.isnan(want)) or tag == "tomsnasty0"
         # curvature divides by |f'|^3 or EG-F^2 and subtracts nearly equal products: compare on a relative scale
         assert np.allclose(got[ok], want[ok], rtol=1e-8, atol=1e-8 * max(1.0, np.nanmax(np.abs(want[ok])))), tag
+
+
+def test_contract_and_block_oracle_vs_reference():
+    """the oracle's contract / SplineBlock restatements against outputs of the unmodified reference
+    (tests/golden/make_golden_block.py)."""
+    from golden_io import _spline_from, block_members
+    a = load_npz("ref_block.npz")
+    for name in a["contract/names"]:
+        tag, j = str(name).split("/")
+        s = O.OracleSpline(*_spline_from(a, f"contract/{tag}"))
+        uvw = [None if np.isnan(v) else float(v) for v in a[f"contract/{tag}/{j}/uvw"]]
+        c = O.contract(s, uvw)
+        nInd, nDep, order, nCoef, knots, coefs = _spline_from(a, f"contract/{tag}/{j}/result")
+        assert (c.nInd, c.nDep, tuple(c.order), tuple(c.nCoef)) == (nInd, nDep, order, nCoef)
+        assert all(np.array_equal(x, y) for x, y in zip(c.knots, knots))
+        assert close(c.coefs, coefs.reshape(c.coefs.shape))
+    for tag in ("A", "B", "C"):
+        rows = [[(m, O.OracleSpline(*sp)) for m, sp in row] for row in block_members(a, tag)]
+        b = O.OracleBlock(rows)
+        assert [b.nInd, b.nDep] == list(a[f"block/{tag}/nIndnDep"])
+        uvw = a[f"block/{tag}/uvw"]
+        assert close(b.evaluate_vec(uvw), a[f"block/{tag}/values"])
+        assert close(b.jacobian_vec(uvw), a[f"block/{tag}/jacobian"])
+        for k in (0, 1):
+            assert close(b.derivative_vec(list(a[f"block/{tag}/wrt"][k]), uvw), a[f"block/{tag}/deriv{k}"])
+        if f"block/{tag}/normal_unit" in a:
+            assert close(b.normal_vec(uvw), a[f"block/{tag}/normal_unit"])
+            assert close(b.normal_vec(uvw, False), a[f"block/{tag}/normal_raw"])
+            assert close(b.normal_vec(uvw, True, (0, 2)), a[f"block/{tag}/normal_idx"])
