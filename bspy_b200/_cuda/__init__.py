@@ -31,7 +31,7 @@ SYMBOLS = (
     "bspy_cuda_binned_workspace_bytes", "bspy_cuda_eval_grid",
     "bspy_cuda_eval_grid_batch", "bspy_cuda_eval_many", "bspy_cuda_probe_fp64", "bspy_cuda_probe_hbm",
     "bspy_cuda_probe_tiles", "bspy_cuda_curvature", "bspy_cuda_contract_axis", "bspy_cuda_block_accumulate",
-    "bspy_cuda_normal_from_jacobian",
+    "bspy_cuda_normal_from_jacobian", "bspy_cuda_collocation",
 )
 
 
@@ -90,6 +90,7 @@ def library():
             "bspy_cuda_contract_axis": [vp, i64, i64, i64, i32, i32, vp, vp, vp],
             "bspy_cuda_block_accumulate": [vp, i64, vp, i64, i32, C.POINTER(i32), i64, vp],
             "bspy_cuda_normal_from_jacobian": [vp, i32, i32, i64, i32, u32, u32, vp, vp],
+            "bspy_cuda_collocation": [vp, i32, i32, vp, vp, i64, vp, vp, i64, vp],
         }
         for name, args in sig.items():
             fn = getattr(lib, name)
@@ -351,6 +352,22 @@ def normal_from_jacobian(jac, nDep, nInd, sign, normalize, mask):
                                                       int(mask), _ptr(out), _stream(dev))
     _check(rc, "bspy_cuda_normal_from_jacobian")
     return out
+
+
+def collocation(knots, order, u, deriv_orders=None):
+    """(spans int32[N], A float64[N, nCoef]) -- dense collocation rows (bspy_cuda_collocation)."""
+    dev = u.device
+    N = u.numel()
+    nCoef = knots.numel() - int(order)
+    sp = torch.empty(N, dtype=torch.int32, device=dev)
+    A = torch.empty((N, nCoef), dtype=torch.float64, device=dev)
+    if deriv_orders is not None:
+        assert deriv_orders.dtype == torch.int32 and deriv_orders.device == dev and deriv_orders.is_contiguous()
+    with torch.cuda.device(dev):
+        rc = library().bspy_cuda_collocation(_ptr(_f64(knots, dev)), knots.numel(), int(order), _ptr(_f64(u, dev)), _ptr(deriv_orders),
+                                             N, _ptr(sp), _ptr(A), nCoef, _stream(dev))
+    _check(rc, "bspy_cuda_collocation")
+    return sp, A
 
 
 def probe_fp64(kind, iters, dev):

@@ -6,6 +6,9 @@
 //                                  (reference bspy/spline_block.py:37-44, 231-245)
 //   bspy_cuda_normal_from_jacobian cofactor normals of N jacobians (reference bspy/_spline_evaluation.py:215-246 with a
 //                                  SplineBlock as `self`, bspy/spline_block.py:282)
+// and of row 3:
+//   bspy_cuda_collocation          rows of the collocation matrix of least_squares / contour (reference
+//                                  bspy/_spline_fitting.py:736-750, 190-219): A[r, ix-order:ix] = bspline_values(...)
 #include "common.cuh"
 
 namespace bspy {
@@ -22,6 +25,29 @@ __global__ void __launch_bounds__(256) contract_axis_kernel(const double *__rest
         double acc = 0.0;
         for (int j = 0; j < order; ++j) acc = fma(__ldg(src + j * inner), __ldg(basis + j), acc);
         out[t] = acc;
+    }
+}
+
+// one thread per row: bit-exact basis (basis_strict, the reference's operation order) of derivative order deriv[r]
+// scattered into the zeroed row r of the dense matrix A (N x nCoef, leading dimension ldA)
+struct GlobalColumn {
+    double *base;
+    __device__ __forceinline__ double &operator()(int j) const { return base[j]; }
+};
+
+__global__ void __launch_bounds__(128) collocation_kernel(const double *__restrict__ knots, const int nKnots, const int order,
+                                                          const double *__restrict__ u, const int32_t *__restrict__ deriv,
+                                                          const long long N, int32_t *__restrict__ spansOut, double *__restrict__ A,
+                                                          const long long ldA)
+{
+    const int nCoef = nKnots - order;
+    for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < N; r += (long long)gridDim.x * blockDim.x) {
+        const double x = u[r];
+        const int ix = span_search(knots, nKnots, order, x);
+        if (spansOut) spansOut[r] = ix;
+        double *row = A + r * ldA;
+        for (int c = 0; c < nCoef; ++c) row[c] = 0.0;
+        basis_strict(knots, order, ix, x, deriv ? deriv[r] : 0, false, GlobalColumn{row + ix - order});
     }
 }
 
@@ -170,4 +196,20 @@ extern "C" int bspy_cuda_normal_from_jacobian(const double *jacobian, int32_t nD
                                                                                   (flags & BSPY_NORMALIZE) ? 1u : 0u, normalMask, normal);
     count_launch();
     return check_launch("bspy_cuda_normal_from_jacobian");
+}
+
+extern "C" int bspy_cuda_collocation(const double *knots, int32_t nKnots, int32_t order, const double *u, const int32_t *derivOrders,
+                                     int64_t N, int32_t *spansOut, double *A, int64_t ldA, void *stream)
+{
+    if (!knots || !u || !A || N < 0 || order < 1 || nKnots < 2 * order || ldA < nKnots - order) {
+        set_error("bspy_cuda_collocation: bad argument");
+        return BSPY_E_ARG;
+    }
+    if (N == 0) return 0;
+    long long blocks = (N + 127) / 128;
+    const long long cap = (long long)num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    collocation_kernel<<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(knots, nKnots, order, u, derivOrders, N, spansOut, A, ldA);
+    count_launch();
+    return check_launch("bspy_cuda_collocation");
 }

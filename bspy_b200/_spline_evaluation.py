@@ -17,7 +17,7 @@ import torch
 
 from bspy_b200 import _cuda
 
-__all__ = ["contract", "curvature", "curvature_points", "EvalResult", "bspline_values", "bspline_values_batch", "domain", "evaluate", "derivative", "jacobian",
+__all__ = ["collocation_matrix", "contract", "curvature", "curvature_points", "EvalResult", "bspline_values", "bspline_values_batch", "domain", "evaluate", "derivative", "jacobian",
            "normal", "evaluate_points", "evaluate_grid", "device_spline", "freeze"]
 
 
@@ -218,6 +218,33 @@ def normal(self, uvw, normalize=True, indices=None):
         n = n[idx]
     dt = np.asarray(self.coefs).dtype if hasattr(self, "coefs") else getattr(self, "coefsDtype", np.float64)
     return n.astype(dt if np.issubdtype(dt, np.floating) else np.float64, copy=False)
+
+
+def collocation_matrix(knots, splineOrder, uValues, derivativeOrders=None, dev=None):
+    """Dense collocation matrix ``A`` (N, nCoef) with ``A[r, ix-order:ix] = bspline_values(None, knots, order, u[r], d[r])``
+    -- the rows ``Spline.least_squares`` assembles one Python call at a time (reference ``bspy/_spline_fitting.py:736-750``;
+    also ``contour``, ``:190-219``).  ``derivativeOrders=None`` follows ``least_squares``: a parameter equal to its
+    predecessor raises the derivative order by one (Hermite rows), otherwise values.  Returns ``(spans, A)`` as numpy
+    arrays, or as CUDA tensors when ``uValues`` is a CUDA tensor.  Basis values are bit-identical to the reference."""
+    on_device = isinstance(uValues, torch.Tensor) and uValues.is_cuda
+    dev = uValues.device if on_device else _cuda.device(dev)
+    kt = knots if (isinstance(knots, torch.Tensor) and knots.is_cuda) else \
+        torch.from_numpy(np.ascontiguousarray(knots, dtype=np.float64)).to(dev)
+    ut = uValues.contiguous().to(torch.float64) if on_device else \
+        torch.from_numpy(np.ascontiguousarray(uValues, dtype=np.float64).reshape(-1)).to(dev)
+    if derivativeOrders is None:
+        uh = ut.cpu().numpy() if on_device else np.ascontiguousarray(uValues, dtype=np.float64).reshape(-1)
+        d = np.zeros(uh.shape[0], np.int32)                      # run lengths of equal parameters (index logic only)
+        for r in range(1, uh.shape[0]):
+            if uh[r] == uh[r - 1]:
+                d[r] = d[r - 1] + 1
+    else:
+        d = np.ascontiguousarray(derivativeOrders.cpu().numpy() if isinstance(derivativeOrders, torch.Tensor) else derivativeOrders,
+                                 dtype=np.int32).reshape(-1)
+    sp, A = _cuda.collocation(kt, int(splineOrder), ut, torch.from_numpy(d).to(dev) if d.any() else None)
+    if on_device:
+        return sp, A
+    return sp.cpu().numpy(), A.cpu().numpy()
 
 
 def contract(self, uvw):

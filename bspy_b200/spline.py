@@ -176,6 +176,11 @@ class Spline(Manifold):
         return _ev.bspline_values_batch(knot, knots, splineOrder, u, derivativeOrder, taylorCoefs)
     bspline_values_batch.__doc__ = _ev.bspline_values_batch.__doc__
 
+    @staticmethod
+    def collocation_matrix(knots, splineOrder, uValues, derivativeOrders=None):
+        return _ev.collocation_matrix(knots, splineOrder, uValues, derivativeOrders)
+    collocation_matrix.__doc__ = _ev.collocation_matrix.__doc__
+
     def freeze(self, device=None):
         return _ev.freeze(self, device)
     freeze.__doc__ = _ev.freeze.__doc__

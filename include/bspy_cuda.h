@@ -176,6 +176,16 @@ int bspy_cuda_normal_from_jacobian(const double *jacobian, int32_t nDep, int32_t
                                    int32_t normalSign, uint32_t flags, uint32_t normalMask, double *normal,
                                    void *stream);
 
+/* ---- collocation rows ------------------------------------------------------------------
+ *      A[r, ix_r - order : ix_r] = bspline_values(None, knots, order, u[r], derivOrders[r]) (bit-identical to the
+ *      reference), every other entry of row r zero: the matrix assembled row by row in Spline.least_squares
+ *      (bspy/_spline_fitting.py:736-750; consecutive equal parameters raise the derivative order) and in contour
+ *      (bspy/_spline_fitting.py:190-219).  A: dense (N, nKnots - order), row-major with leading dimension ldA;
+ *      derivOrders NULL = values; spansOut optional.                                                          */
+int bspy_cuda_collocation(const double *knots, int32_t nKnots, int32_t order, const double *u,
+                          const int32_t *derivOrders, int64_t N, int32_t *spansOut, double *A, int64_t ldA,
+                          void *stream);
+
 /* ---- measurement helpers used by bench.py (not part of the evaluation path) --------------
  *      bspy_cuda_probe_fp64: runs `iters` dependent-free FP64 FMA (kind 0) or DMMA m8n8k4
  *      (kind 1) chains on every SM and returns the flop count; time it with events on `stream`.

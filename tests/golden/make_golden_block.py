@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Golden fixtures for SURVEY 8(f) row 1 from the UNMODIFIED reference: ``Spline.contract``
 (``bspy/_spline_operations.py:184-223``) and ``SplineBlock.evaluate / derivative / jacobian / normal / contract``
-(``bspy/spline_block.py``).  Run in the build container only:
+(``bspy/spline_block.py``), plus row 3: the collocation rows of ``Spline.least_squares`` and the normal sampling of
+``normal_spline``.  Run in the build container only:
 
     python tests/golden/make_golden_block.py [--ref /root/reference]
 
@@ -110,6 +111,38 @@ def main():
     out["block/A/contract_pts"] = pts
     out["block/A/contract_values"] = np.array([cb.evaluate(p) for p in pts])
     out["block/A/contract_nIndnDep"] = np.array([cb.nInd, cb.nDep])
+    # ---- collocation rows: the assembly loop of Spline.least_squares, bspy/_spline_fitting.py:736-750,
+    #      driven by the reference's own bspline_values; repeated parameters raise the derivative order ----------
+    for tag, order, nCoef in (("o4", 4, 12), ("o3", 3, 7), ("o6", 6, 9)):
+        knots = knots_nonuniform(order, nCoef, rng)
+        uu = np.sort(rng.uniform(0, 1, 40))
+        uu = np.concatenate(([0.0, 0.0], uu[:10], [uu[10]] * 3, uu[11:], [knots[order + 1]] * 2, [1.0, 1.0]))
+        uu = np.sort(uu)
+        A = np.zeros((len(uu), nCoef))
+        derivs = np.zeros(len(uu), np.int32)
+        u = -np.finfo(float).max
+        for iRow in range(len(uu)):
+            uNew = uu[iRow]
+            if uNew != u:
+                iDerivative = 0
+                u = uNew
+                ix = None
+            else:
+                iDerivative += 1
+            ix, row = Spline.bspline_values(ix, knots, order, u, iDerivative)
+            A[iRow, ix - order:ix] = row
+            derivs[iRow] = iDerivative
+        out[f"colloc/{tag}/knots"] = knots
+        out[f"colloc/{tag}/order"] = np.array(order)
+        out[f"colloc/{tag}/u"] = uu
+        out[f"colloc/{tag}/derivs"] = derivs
+        out[f"colloc/{tag}/A"] = A
+    # ---- normal_spline sampling (bspy/_spline_operations.py:735-751): un-normalised normals on a tensor grid --------
+    surf = synth(2, 3, (3, 4), (6, 7))
+    put_spline("nsample/surf", surf)
+    gu, gv = np.linspace(0, 1, 9), np.sort(rng.uniform(0, 1, 7))
+    out["nsample/gu"], out["nsample/gv"] = gu, gv
+    out["nsample/normals"] = np.array([[surf.normal([a, b], False) for b in gv] for a in gu])      # (9, 7, 3)
     np.savez_compressed(os.path.join(HERE, "ref_block.npz"), **out)
     print("ref_block.npz:", len(out), "arrays")
 

@@ -758,3 +758,25 @@ def test_spline_block_vs_reference():
     big = dom[:, 0] + (dom[:, 1] - dom[:, 0]) * rng.uniform(0, 1, (20_000, 5))
     r = bspy.SplineBlock(rows).evaluate_points(big, jacobian=True)
     assert close(r.values.T, ob.evaluate_vec(big)) and close(np.transpose(r.jacobian, (2, 0, 1)), ob.jacobian_vec(big))
+
+
+def test_collocation_rows_and_normal_sampling_vs_reference():
+    """the collocation matrix of Spline.least_squares (rows assembled from the reference's own
+    bspline_values, repeated parameters raising the derivative order) bit-for-bit, and the un-normalised normal
+    sampling of normal_spline through the grid kernels."""
+    bspy, _cuda, O, _ = _mods()
+    a = load_npz("ref_block.npz")
+    for tag in ("o4", "o3", "o6"):
+        knots, order, u = a[f"colloc/{tag}/knots"], int(a[f"colloc/{tag}/order"]), a[f"colloc/{tag}/u"]
+        sp, A = bspy.Spline.collocation_matrix(knots, order, u)                     # derivative orders from the runs of equal u
+        assert np.array_equal(A, a[f"colloc/{tag}/A"]), tag
+        sp2, A2 = bspy.Spline.collocation_matrix(torch.from_numpy(knots).cuda(), order, torch.from_numpy(u).cuda(),
+                                                 derivativeOrders=a[f"colloc/{tag}/derivs"])
+        assert A2.is_cuda and np.array_equal(A2.cpu().numpy(), a[f"colloc/{tag}/A"])
+        assert np.array_equal(sp, sp2.cpu().numpy())
+        rows = np.arange(len(u))
+        assert all(np.all(A[r, :sp[r] - order] == 0) and np.all(A[r, sp[r]:] == 0) for r in rows)
+    from golden_io import _spline_from
+    surf = bspy.Spline(*_spline_from(a, "nsample/surf"))
+    g = surf.evaluate_grid(a["nsample/gu"], a["nsample/gv"], values=False, normal=True, normalize=False)
+    assert close(np.transpose(g.normal, (1, 2, 0)), a["nsample/normals"])
