@@ -780,3 +780,57 @@ def test_collocation_rows_and_normal_sampling_vs_reference():
     surf = bspy.Spline(*_spline_from(a, "nsample/surf"))
     g = surf.evaluate_grid(a["nsample/gu"], a["nsample/gv"], values=False, normal=True, normalize=False)
     assert close(np.transpose(g.normal, (1, 2, 0)), a["nsample/normals"])
+
+
+def test_random_shapes_vs_oracle():
+    """Seeded sweep over random shapes (nInd 1-4, orders 1-6, nDep 1-6, clamped / unclamped / repeated interior knots):
+    spans bit-exact, values / jacobians / one mixed partial / normals against the oracle -- exercises the fixed-shape
+    kernels where a shape is compiled and the any-shape kernel elsewhere, scattered and grid entry points."""
+    bspy, _cuda, O, _ = _mods()
+    rng = np.random.default_rng(4242)
+
+    def knots(o, n, style):
+        w = rng.uniform(0.25, 1.75, n - o + 1)
+        inner = np.concatenate(([0.0], np.cumsum(w))); inner /= inner[-1]
+        if style == 2 and n - o + 1 >= 3 and o >= 3:
+            inner[2] = inner[1]                                    # double interior knot (legal for order >= 3)
+        if style == 1:
+            left = -np.cumsum(rng.uniform(0.05, 0.3, o - 1))[::-1]
+            right = 1.0 + np.cumsum(rng.uniform(0.05, 0.3, o - 1))
+            return np.concatenate((left, inner, right))
+        return np.concatenate((np.zeros(o - 1), inner, np.ones(o - 1)))
+
+    for trial in range(48):
+        nInd = int(rng.integers(1, 5))
+        nDep = int(rng.integers(1, 7))
+        order = tuple(int(rng.integers(1, 7 if nInd < 3 else 5)) for _ in range(nInd))
+        nCoef = tuple(int(o + rng.integers(0, 6)) for o in order)
+        kk = [knots(o, n, int(rng.integers(0, 3))) for o, n in zip(order, nCoef)]
+        coefs = rng.standard_normal((nDep, *nCoef))
+        s = bspy.Spline(nInd, nDep, order, nCoef, kk, coefs, {"negateNormal": bool(trial % 2)})
+        so = O.OracleSpline.of(s)
+        dom = s.domain()
+        N = 700
+        pts = dom[:, 0] + (dom[:, 1] - dom[:, 0]) * rng.uniform(0, 1, (N, nInd))
+        pts[0], pts[1] = dom[:, 0], dom[:, 1]
+        for i in range(nInd):                                      # knots of every variable as parameters
+            inside = np.unique(kk[i][(kk[i] >= dom[i, 0]) & (kk[i] <= dom[i, 1])])
+            pts[2:2 + len(inside), i] = inside
+        wrt = [int(rng.integers(0, 3)) for _ in range(nInd)]
+        want_normal = abs(nInd - nDep) == 1
+        r = s.evaluate_points(pts, jacobian=True, spans=True, with_respect_to=wrt, normal=want_normal, normalize=False)
+        ref, sp = O.evaluate_vec(so, pts, return_spans=True)
+        tag = (trial, nInd, nDep, order, nCoef)
+        assert np.array_equal(r.spans.T, sp), tag
+        assert close(r.values.T, ref), tag
+        assert close_cond(np.transpose(r.jacobian, (2, 0, 1)), O.jacobian_vec(so, pts), O.jacobian_abs_vec(so, pts)), tag
+        assert close_cond(r.derivative.T, O.derivative_vec(so, wrt, pts), O.derivative_abs_vec(so, wrt, pts)), tag
+        if want_normal:
+            assert close_cond(r.normal.T, O.normal_vec(so, pts, False), O.normal_abs_vec(so, pts)), tag
+        if nInd in (2, 3):                                         # tensor-grid entry (DMMA kernels for these shapes)
+            axes = [np.sort(pts[:17 + 3 * i, i]) for i in range(nInd)]
+            g = s.evaluate_grid(*axes, jacobian=True)
+            mesh = np.stack([m.reshape(-1) for m in np.meshgrid(*axes, indexing="ij")], axis=1)
+            assert close(g.values.reshape(nDep, -1).T, O.evaluate_vec(so, mesh)), tag
+            assert close_cond(np.transpose(g.jacobian.reshape(nDep, nInd, -1), (2, 0, 1)), O.jacobian_vec(so, mesh),
+                              O.jacobian_abs_vec(so, mesh)), tag
