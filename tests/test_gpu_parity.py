@@ -575,6 +575,39 @@ def test_curve_replicated_rows_bit_identical(monkeypatch):
         assert int(flag.item()) == 136_000
 
 
+def test_record_mode_multi_chunk_overlap_bit_identical(monkeypatch):
+    """More than one 4 Mi-point chunk: the sort / un-permute passes of neighbouring chunks run on a second stream under
+    the evaluation (double-buffered workspace halves, event fork / join).  Same bits with and without the overlap and
+    as the direct kernel; the first out-of-domain index survives the chunking."""
+    bspy, _cuda, O, _ = _mods()
+    from bspy_b200._spline_evaluation import device_spline
+    rng = np.random.default_rng(41)
+
+    def K(o, n):
+        w = rng.uniform(0.25, 1.75, n - o + 1)
+        inner = np.concatenate(([0.0], np.cumsum(w))); inner /= inner[-1]
+        return np.concatenate((np.zeros(o - 1), inner, np.ones(o - 1)))
+
+    s = bspy.Spline(3, 3, (4, 4, 4), (18, 18, 18), [K(4, 18) for _ in range(3)], rng.standard_normal((3, 18, 18, 18)))
+    ds = device_spline(s)
+    N = 2 * (1 << 22) + 70_001                                     # three chunks, ragged sparse tail
+    pts = torch.rand((N, 3), dtype=torch.float64, device="cuda", generator=torch.Generator(device="cuda").manual_seed(5))
+    ref = _cuda.eval_points(ds, pts, 3, 1, N, binned=False, values=True, jacobian=True)
+    for flag in ("1", "0"):
+        monkeypatch.setenv("BSPY_BIN_OVERLAP", flag)
+        a = _cuda.eval_points(ds, pts, 3, 1, N, binned=True, values=True, jacobian=True)
+        torch.cuda.synchronize()
+        assert torch.equal(a["values"], ref["values"]) and torch.equal(a["jacobian"], ref["jacobian"]), flag
+        del a
+    monkeypatch.delenv("BSPY_BIN_OVERLAP")
+    bad = pts.clone()
+    bad[(1 << 22) + 17, 2] = 1.25
+    bad[2 * (1 << 22) + 5, 0] = -0.5
+    f = _cuda.new_flag(pts.device)
+    _cuda.eval_points(ds, bad, 3, 1, N, flag=f, binned=True)
+    assert int(f.item()) == (1 << 22) + 17
+
+
 def test_batch_api_variants():
     """SplineBatch: per-spline knots on the grid path, indices on normals, shard(), spline(i), host and device
     inputs; bspline_values_batch; evaluate_grid for a curve."""
