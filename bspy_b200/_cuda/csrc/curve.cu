@@ -114,7 +114,8 @@ static ReplLayout repl_layout(int O, int nDep, int nCoef, size_t budget)
     const int spans = nCoef - O + 1;
     L.buckets = 64;
     while (L.buckets < 4 * spans && L.buckets < 4096) L.buckets <<= 1;
-    L.bytes = sizeof(double) * ((size_t)spans * rowDoubles * REPL_COPIES + (size_t)(O + nCoef) * REPL_KNOT_COPIES) +
+    L.bytes = sizeof(double) * ((size_t)spans * rowDoubles * REPL_COPIES + (size_t)(O + nCoef) * REPL_KNOT_COPIES +
+                               (size_t)nDep * nCoef) +
               sizeof(int) * (L.buckets + 2) + sizeof(unsigned short) * L.buckets + 64;
     if (L.bytes > budget) L.bytes = 0;
     return L;
@@ -134,7 +135,8 @@ __global__ void __launch_bounds__(repl_threads(O, NDEP), 2) eval_curve_repl_kern
     const int nKnots = O + P.nCoef, spans = P.nCoef - O + 1;
     double *rows = sm;                                             // spans * ROW * CP
     double *kn = rows + spans * ROW * CP;                          // nKnots * KC
-    int *cnt = reinterpret_cast<int *>(kn + nKnots * KC);          // buckets + 1 (scan scratch)
+    double *raw = kn + nKnots * KC;                                // NDEP * nCoef: the coefficients as they come
+    int *cnt = reinterpret_cast<int *>(raw + NDEP * P.nCoef);      // buckets + 1 (scan scratch)
     unsigned short *tab = reinterpret_cast<unsigned short *>(cnt + buckets + 2);
     const int lane = threadIdx.x & 31;
     // the first round of parameters travels from HBM while the tables are built
@@ -153,8 +155,9 @@ __global__ void __launch_bounds__(repl_threads(O, NDEP), 2) eval_curve_repl_kern
     };
     un[0] = un[1] = 0.0;
     fetch(up, pfirst);
-    // knots, every copy
+    // knots (every copy) and coefficients in one DRAM round trip
     for (int i = threadIdx.x; i < nKnots * KC; i += blockDim.x) kn[i] = __ldg(P.knots + i / KC);
+    for (int i = threadIdx.x; i < NDEP * P.nCoef; i += blockDim.x) raw[i] = __ldg(P.coefs + i);
     for (int i = threadIdx.x; i <= buckets; i += blockDim.x) cnt[i] = 0;
     __syncthreads();
     const double lo = kn[(O - 1) * KC], hi = kn[P.nCoef * KC];
@@ -177,7 +180,7 @@ __global__ void __launch_bounds__(repl_threads(O, NDEP), 2) eval_curve_repl_kern
 #pragma unroll
         for (int j = 0; j < O; ++j)
 #pragma unroll
-            for (int d = 0; d < NDEP; ++d) r[R::used + j * NDEP + d] = __ldg(P.coefs + (size_t)d * P.nCoef + (sp + j));
+            for (int d = 0; d < NDEP; ++d) r[R::used + j * NDEP + d] = raw[d * P.nCoef + (sp + j)];
         if (ROW > R::used + O * NDEP) r[ROW - 1] = 0.0;
 #pragma unroll
         for (int j = 0; j < CH; ++j)
