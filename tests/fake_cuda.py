@@ -123,8 +123,50 @@ def curvature(nInd, nDep, graph, d1, d2, normal):
         return torch.from_numpy((L * Nn - M ** 2) / (E * G - F ** 2))
 
 
+def contract_axis(coefs, axis, first, order, basis):
+    launches[0] += 1
+    c = np.moveaxis(coefs.numpy(), axis, -1)[..., first:first + order]
+    return torch.from_numpy(np.ascontiguousarray(c @ basis.numpy()))
+
+
+def block_accumulate(dst, src, dst_rows):
+    launches[0] += 1
+    for r, row in enumerate(dst_rows):
+        dst[row] += src[r]
+
+
+def normal_from_jacobian(jac, nDep, nInd, sign, normalize, mask):
+    launches[0] += 1
+    T = np.transpose(jac.numpy(), (2, 0, 1))                  # (N, nDep, nInd)
+    if nInd > nDep:
+        T = np.swapaxes(T, 1, 2)
+    D = T.shape[1]
+    n = np.empty((T.shape[0], D))
+    with np.errstate(all="ignore"):
+        for i in range(D):
+            n[:, i] = sign * ((-1) ** i) * np.linalg.det(T[:, [j for j in range(D) if j != i], :])
+        if normalize:
+            sel = _mask_indices(mask, D)
+            n = n / np.sqrt((n[:, sel] ** 2).sum(axis=1))[:, None]
+    return torch.from_numpy(np.ascontiguousarray(n.T))
+
+
+def collocation(knots, order, u, deriv_orders=None):
+    launches[0] += 1
+    kn, uu = knots.numpy(), u.numpy()
+    nCoef = kn.shape[0] - order
+    A = np.zeros((uu.shape[0], nCoef))
+    sp = np.empty(uu.shape[0], np.int32)
+    for r in range(uu.shape[0]):
+        ix, b = O.basis_pt(None, kn, order, uu[r], 0 if deriv_orders is None else int(deriv_orders[r]))
+        A[r, ix - order:ix] = b
+        sp[r] = ix
+    return torch.from_numpy(sp), torch.from_numpy(A)
+
+
 def install(monkeypatch):
     from bspy_b200 import _cuda
-    for name in ("device", "new_flag", "launch_count", "eval_points", "eval_points_host", "eval_grid", "spans", "basis", "curvature"):
+    for name in ("device", "new_flag", "launch_count", "eval_points", "eval_points_host", "eval_grid", "spans", "basis", "curvature",
+                 "contract_axis", "block_accumulate", "normal_from_jacobian", "collocation"):
         monkeypatch.setattr(_cuda, name, globals()[name])
     launches[0] = 0

@@ -256,3 +256,38 @@ def test_curvature_api():
         _spline(CASES["vol_444_d3"]).curvature([0.5, 0.5, 0.5])
     with pytest.raises(ValueError, match="outside domain"):
         _spline(CASES["curve_o4"]).curvature(1.5)
+
+
+def test_contract_block_and_collocation_host_logic():
+    """Host side of SURVEY 8(f) rows 1 and 3 (maps, row sums, remapping after contract, run lengths of equal parameters)
+    against the reference's golden outputs, with the oracle-backed fake binding."""
+    from golden_io import _spline_from, block_members, load_npz
+    a = load_npz("ref_block.npz")
+    for name in a["contract/names"]:
+        tag, j = str(name).split("/")
+        s = bspy.Spline(*_spline_from(a, f"contract/{tag}"))
+        uvw = [None if np.isnan(v) else float(v) for v in a[f"contract/{tag}/{j}/uvw"]]
+        c = s.contract(uvw)
+        nInd, nDep, order, nCoef, knots, coefs = _spline_from(a, f"contract/{tag}/{j}/result")
+        assert (c.nInd, c.nDep, tuple(c.order), tuple(c.nCoef)) == (nInd, nDep, order, nCoef)
+        assert close(np.asarray(c.coefs), coefs.reshape(np.asarray(c.coefs).shape))
+    for tag in ("A", "B", "C"):
+        rows = [[(m, bspy.Spline(*sp)) for m, sp in row] for row in block_members(a, tag)]
+        b = bspy.SplineBlock(rows)
+        assert [b.nInd, b.nDep] == list(a[f"block/{tag}/nIndnDep"])
+        uvw = a[f"block/{tag}/uvw"]
+        r = b.evaluate_points(uvw, jacobian=True, with_respect_to=list(a[f"block/{tag}/wrt"][1]))
+        assert close(r.values.T, a[f"block/{tag}/values"])
+        assert close(np.transpose(r.jacobian, (2, 0, 1)), a[f"block/{tag}/jacobian"])
+        assert close(r.derivative.T, a[f"block/{tag}/deriv1"])
+        assert close(b(uvw[3]), a[f"block/{tag}/values"][3]) and close(b.jacobian(uvw[3]), a[f"block/{tag}/jacobian"][3])
+        if f"block/{tag}/normal_unit" in a:
+            assert close(b.normal(uvw[3]), a[f"block/{tag}/normal_unit"][3])
+            assert close(b.normal(uvw[3], False, (0, 2)), a[f"block/{tag}/normal_raw"][3][[0, 2]])
+    rows = [[(m, bspy.Spline(*sp)) for m, sp in row] for row in block_members(a, "A")]
+    cb = bspy.SplineBlock(rows).contract([None if np.isnan(v) else float(v) for v in a["block/A/contract_uvw"]])
+    assert [cb.nInd, cb.nDep] == list(a["block/A/contract_nIndnDep"])
+    assert close(cb.evaluate_points(a["block/A/contract_pts"]).values.T, a["block/A/contract_values"])
+    for tag in ("o4", "o3", "o6"):
+        sp, A = bspy.Spline.collocation_matrix(a[f"colloc/{tag}/knots"], int(a[f"colloc/{tag}/order"]), a[f"colloc/{tag}/u"])
+        assert np.array_equal(A, a[f"colloc/{tag}/A"])
