@@ -1109,7 +1109,18 @@ static int launch_unpermute(const double *aos, int stride, const int *inv, long 
     return 0;
 }
 
-constexpr long long BIN_REC_CHUNK = 1 << 22;   // points per chunk in sorted-record mode
+// points per chunk in sorted-record mode (BSPY_BIN_REC_CHUNK_LOG2 overrides for experiments)
+static long long bin_rec_chunk()
+{
+    static long long v = 0;
+    if (!v) {
+        const char *e = getenv("BSPY_BIN_REC_CHUNK_LOG2");
+        const int lg = e ? atoi(e) : 22;
+        v = 1LL << (lg < 16 ? 16 : (lg > 26 ? 26 : lg));
+    }
+    return v;
+}
+#define BIN_REC_CHUNK bin_rec_chunk()
 constexpr long long BIN_CHUNK_MAX = 1 << 20;  // workspace is sized for this many points per chunk
 
 // Points per chunk: the outputs of a chunk are scattered back to their original positions 8 bytes at a time, which

@@ -488,7 +488,8 @@ def test_record_mode_staged_windows_bit_identical(monkeypatch):
             g = torch.Generator(device="cuda").manual_seed(N)
             pts = torch.rand((N, nInd), dtype=torch.float64, device="cuda", generator=g)
             pts[7, 0], pts[N - 1, nInd - 1], pts[99, 1] = 0.0, 1.0, float(s.knots[1][order[1] + 2])
-            requests = [dict(values=True, jacobian=True, spans=True), dict(values=True)]
+            requests = [dict(values=True, jacobian=True, spans=True), dict(values=True),
+                        dict(values=False, wrt=[1] + [0] * (nInd - 2) + [2]), dict(values=True, wrt=[0] * (nInd - 1) + [1])]
             if abs(nInd - nDep) == 1:
                 requests.append(dict(values=True, jacobian=True, normal=True))
             for request in requests:
