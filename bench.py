@@ -588,6 +588,17 @@ def run_ours(args):
                 ts.append(a.elapsed_time(b) * 1e-3)
             probes["copy_of_step_bytes_us"] = min(ts[1:]) * 1e6
             probes["copy_of_step_bytes_gbs"] = nbytes / min(ts[1:]) / 1e9
+            # ... and of 8 KB: what one launch costs between two events after the flush, with nothing to do
+            ts = []
+            for _ in range(6):
+                flush.fill_(1.0)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                _cuda.probe_hbm(0, src[:512], dst[:512])
+                b.record()
+                torch.cuda.synchronize()
+                ts.append(a.elapsed_time(b) * 1e-3)
+            probes["launch_floor_us"] = min(ts[1:]) * 1e6
         roofline["hbm_probe"] = probes
         del src, dst
     except Exception as exc:  # pragma: no cover
