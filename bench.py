@@ -343,9 +343,9 @@ class ClockSampler:
                     mask = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
                 except Exception:
                     mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
-                # the power query is the slow one (milliseconds): every 16th round only, so that a 20 ms timed
+                # the power query is the slow one (milliseconds): every 8th round only, so that a 20 ms timed
                 # region still collects clock samples
-                pw = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0 if it % 16 == 15 else None
+                pw = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0 if it % 8 == 0 else None
                 self.rows.append((time.perf_counter(), clk, pw, [k for k, b in bits.items() if mask & b]))
             except Exception:
                 pass
