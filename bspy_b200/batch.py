@@ -74,6 +74,43 @@ class SplineBatch:
         return cls(first.nInd, first.nDep, first.order, first.nCoef, knots, coefs,
                    {"negateNormal": True} if negate == {True} else {}, device)
 
+    @classmethod
+    def load(cls, fileName, device=None):
+        """Bulk loader: every spline stored in a BSpy json file -- a single ``Spline`` dict, a list of
+        them (``Spline.save`` / ``Spline.load``, reference ``bspy/spline.py:1542-1583, 1998-2026``), or splines nested as
+        the ``manifold`` of a ``Solid``'s boundaries (``tests/teapots.json``) -- packed straight into device batches, one
+        per shape ``(nInd, nDep, order, nCoef, negateNormal)``.  Returns a list of batches in order of first appearance;
+        ``batch.indices`` holds the positions (file order) of its splines."""
+        import json
+
+        from bspy_b200.spline import Spline
+        with open(fileName, "r", encoding="utf-8") as f:
+            data = json.load(f)
+        found = []
+
+        def walk(node):
+            if isinstance(node, dict):
+                if node.get("type") == "Spline" and "coefs" in node and "knots" in node:
+                    found.append(Spline.from_dict(node))
+                    return
+                for v in node.values():
+                    walk(v)
+            elif isinstance(node, list):
+                for v in node:
+                    walk(v)
+
+        walk(data)
+        groups = {}
+        for i, s in enumerate(found):
+            key = (s.nInd, s.nDep, tuple(s.order), tuple(s.nCoef), bool(s.metadata.get("negateNormal", False)))
+            groups.setdefault(key, []).append(i)
+        batches = []
+        for idx in groups.values():
+            b = cls.from_splines([found[i] for i in idx], device)
+            b.indices = list(idx)
+            batches.append(b)
+        return batches
+
     def __len__(self):
         return self.nSplines
 

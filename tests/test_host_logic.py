@@ -291,3 +291,33 @@ def test_contract_block_and_collocation_host_logic():
     for tag in ("o4", "o3", "o6"):
         sp, A = bspy.Spline.collocation_matrix(a[f"colloc/{tag}/knots"], int(a[f"colloc/{tag}/order"]), a[f"colloc/{tag}/u"])
         assert np.array_equal(A, a[f"colloc/{tag}/A"])
+
+
+def test_spline_batch_bulk_loader(tmp_path):
+    """SplineBatch.load: lists written by Spline.save, and splines nested as the manifolds of a Solid's boundaries
+    (the layout of the reference's tests/teapots.json), grouped by shape in file order."""
+    rng = np.random.default_rng(3)
+    a = [_spline(CASES["surf_34"]), _spline(CASES["curve_o4"]), _spline(CASES["surf_34"]), _spline(CASES["surf_44_neg"])]
+    a[2].coefs = a[2].coefs + 1.0
+    path = tmp_path / "list.json"
+    a[0].save(str(path), *a[1:])
+    batches = bspy.SplineBatch.load(str(path))
+    assert [b.indices for b in batches] == [[0, 2], [1], [3]]
+    assert batches[0].nSplines == 2 and batches[0].order == (3, 4) and batches[2].metadata.get("negateNormal") is True
+    assert np.array_equal(batches[0].coefs[1].numpy(), np.asarray(a[2].coefs)) and np.array_equal(batches[0].spline(0).knots[1], a[0].knots[1])
+    solid = [{"type": "Solid", "dimension": 3, "containsInfinity": False, "metadata": {},
+              "boundaries": [{"type": "Boundary", "manifold": s.to_dict(), "trim": {"type": "Solid", "boundaries": []}} for s in (a[0], a[2])]}]
+
+    class Enc(json.JSONEncoder):
+        def default(self, obj):
+            return obj.tolist() if isinstance(obj, np.ndarray) else super().default(obj)
+    nested = tmp_path / "solid.json"
+    nested.write_text(json.dumps(solid, cls=Enc))
+    (b,) = bspy.SplineBatch.load(str(nested))
+    assert b.nSplines == 2 and np.array_equal(b.coefs[0].numpy(), np.asarray(a[0].coefs))
+    import os
+    ref = "/root/reference/tests/teapots.json"
+    if os.path.exists(ref):                                       # build container only: teapot patches + their trim curves
+        loaded = bspy.SplineBatch.load(ref)
+        shapes = {(t.nInd, t.nDep, t.order, t.nCoef): t.nSplines for t in loaded}
+        assert shapes == {(2, 3, (4, 4), (4, 4)): 82, (1, 2, (4,), (4,)): 24, (1, 2, (4,), (6,)): 4, (1, 2, (4,), (8,)): 4}
