@@ -24,60 +24,54 @@ class SplineBlock:
     rules and error messages as the reference (``bspy/spline_block.py:46-109``)."""
 
     def __init__(self, block):
-        if isinstance(block, Spline):
-            block = [[block]]
-        elif isinstance(block[0], Spline) or (len(block) > 1 and isinstance(block[1], Spline)):
-            block = [block]
-        self.block = []
-        self.nInd = 0
-        self.nDep = 0
-        self.knotsDtype = None
-        self.coefsDtype = None
-        self.size = 0
-        domain = {}
-        for row in block:
-            rowInd = 0
-            rowDep = 0
-            indSet = set()
-            newRow = []
-            for entry in row:
-                if isinstance(entry, Spline):
-                    spline = entry
-                    map = list(range(rowInd, rowInd + spline.nInd))
+        rows = self._as_rows(block)
+        self.block, self.nInd, self.nDep, self.size = [], 0, 0, 0
+        self.knotsDtype = self.coefsDtype = None
+        bounds = {}                                   # block variable -> (lower, upper), first spline that uses it wins
+        for entries in rows:
+            members, used, depRow, nextDefault = [], set(), 0, 0
+            for entry in entries:
+                if isinstance(entry, Spline):         # no map given: the row's variables are numbered consecutively
+                    spline, varMap = entry, list(range(nextDefault, nextDefault + entry.nInd))
                 else:
-                    (map, spline) = entry
-                    map = list(map)
-                rowInd += spline.nInd
-                if rowDep == 0:
-                    rowDep = spline.nDep
-                    if self.nDep == 0:
+                    varMap, spline = list(entry[0]), entry[1]
+                nextDefault += spline.nInd
+                if not members:
+                    depRow = spline.nDep
+                    if self.coefsDtype is None:
                         self.knotsDtype = np.asarray(spline.knots[0]).dtype
                         self.coefsDtype = np.asarray(spline.coefs).dtype
-                elif rowDep != spline.nDep:
+                elif spline.nDep != depRow:
                     raise ValueError("All splines in the same row must have the same nDep")
-                d = spline.domain()
-                for ind, i in enumerate(map):
-                    if i in indSet:
-                        raise ValueError(f"Multiple splines in the same row map to independent variable {i}")
-                    indSet.add(i)
-                    if i in domain:
-                        if domain[i][0] != d[ind, 0] or domain[i][1] != d[ind, 1]:
-                            raise ValueError("Domains of independent variables must match")
-                    else:
-                        domain[i] = d[ind]
-                newRow.append((map, spline))
-            if rowDep > 0:
-                self.nDep += rowDep
-                self.size += len(row)
-                self.block.append(newRow)
-        self.nInd = len(domain)
-        self._domain = []
-        for i in range(self.nInd):
-            if i in domain:
-                self._domain.append(domain[i])
-            else:
-                raise ValueError(f"Block is missing independent variable {i}")
-        self._domain = np.array(self._domain, self.knotsDtype)
+                box = spline.domain()
+                for own, var in enumerate(varMap):
+                    if var in used:
+                        raise ValueError(f"Multiple splines in the same row map to independent variable {var}")
+                    used.add(var)
+                    known = bounds.get(var)
+                    if known is None:
+                        bounds[var] = box[own]
+                    elif known[0] != box[own, 0] or known[1] != box[own, 1]:
+                        raise ValueError("Domains of independent variables must match")
+                members.append((varMap, spline))
+            if depRow > 0:
+                self.block.append(members)
+                self.nDep += depRow
+                self.size += len(entries)
+        self.nInd = len(bounds)
+        missing = [var for var in range(self.nInd) if var not in bounds]
+        if missing:
+            raise ValueError(f"Block is missing independent variable {missing[0]}")
+        self._domain = np.array([bounds[var] for var in range(self.nInd)], self.knotsDtype)
+
+    @staticmethod
+    def _as_rows(block):
+        """The accepted spellings (reference ``:56-59``): one spline, one row of splines, or a list of rows."""
+        if isinstance(block, Spline):
+            return [[block]]
+        if isinstance(block[0], Spline) or (len(block) > 1 and isinstance(block[1], Spline)):
+            return [block]
+        return block
 
     def __call__(self, uvw):
         return self.evaluate(uvw)
@@ -174,19 +168,8 @@ class SplineBlock:
     def contract(self, uvw):
         """Block of the member splines contracted at the given parameter values (``None`` keeps a variable), reference
         ``:143-177``; the remaining variables are renumbered consecutively."""
-        remap = []
-        newIndex = 0
-        for value in uvw:
-            if value is None:
-                remap.append(newIndex)
-                newIndex += 1
-            else:
-                remap.append(None)
-        newBlock = []
-        for row in self.block:
-            newRow = []
-            for map, spline in row:
-                contracted = spline.contract([uvw[index] for index in map])
-                newRow.append(([remap[ind] for ind in map if uvw[ind] is None], contracted))
-            newBlock.append(newRow)
-        return SplineBlock(newBlock)
+        kept = [var for var, value in enumerate(uvw) if value is None]
+        renumber = {var: position for position, var in enumerate(kept)}
+        rows = [[([renumber[var] for var in varMap if var in renumber], spline.contract([uvw[var] for var in varMap]))
+                 for varMap, spline in members] for members in self.block]
+        return SplineBlock(rows)
