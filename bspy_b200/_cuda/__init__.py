@@ -20,6 +20,7 @@ MAX_IND = 8
 MAX_ORDER = 32
 E_ARG, E_UNSUPPORTED, E_NORMAL_DIMS = -1, -2, -3
 NORMALIZE = 1
+OUT_F32 = 2
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BSPY_CUDA_LIB") or os.path.join(HERE, "libbspy_cuda.so")   # override: kernel A/B experiments only
@@ -242,14 +243,16 @@ def eval_points(ds: DeviceSpline, uvw, point_stride, var_stride, N, *, wrt=None,
 
 
 def eval_grid(ds: DeviceSpline, axes, *, values=True, jacobian=False, normal=False, normalize=True, normal_mask=0,
-              flag=None):
-    """Launch bspy_cuda_eval_grid; outputs (nDep, *nAxis), (nDep, nInd, *nAxis), (D, *nAxis)."""
+              flag=None, out_f32=False):
+    """Launch bspy_cuda_eval_grid; outputs (nDep, *nAxis), (nDep, nInd, *nAxis), (D, *nAxis); ``out_f32``: float32
+    outputs (surfaces only: BSPY_OUT_F32)."""
     dev = ds.device
     shape = tuple(int(a.numel()) for a in axes)
+    odt = torch.float32 if out_f32 else torch.float64
     out = {
-        "values": torch.empty((ds.nDep, *shape), dtype=torch.float64, device=dev) if values else None,
-        "jacobian": torch.empty((ds.nDep, ds.nInd, *shape), dtype=torch.float64, device=dev) if jacobian else None,
-        "normal": torch.empty((ds.normal_dim, *shape), dtype=torch.float64, device=dev) if normal else None,
+        "values": torch.empty((ds.nDep, *shape), dtype=odt, device=dev) if values else None,
+        "jacobian": torch.empty((ds.nDep, ds.nInd, *shape), dtype=odt, device=dev) if jacobian else None,
+        "normal": torch.empty((ds.normal_dim, *shape), dtype=odt, device=dev) if normal else None,
     }
     n = max(ds.nInd, 1)
     ax = (C.c_void_p * n)(*[a.data_ptr() for a in axes])
@@ -257,7 +260,7 @@ def eval_grid(ds: DeviceSpline, axes, *, values=True, jacobian=False, normal=Fal
     for a in axes:
         _f64(a, dev)
     with torch.cuda.device(dev):
-        rc = library().bspy_cuda_eval_grid(C.byref(ds.c), ax, na, NORMALIZE if normalize else 0, int(normal_mask),
+        rc = library().bspy_cuda_eval_grid(C.byref(ds.c), ax, na, (NORMALIZE if normalize else 0) | (OUT_F32 if out_f32 else 0), int(normal_mask),
                                            _ptr(out["values"]), _ptr(out["jacobian"]), _ptr(out["normal"]), _ptr(flag),
                                            _stream(dev))
     _check(rc, "bspy_cuda_eval_grid")
@@ -265,23 +268,28 @@ def eval_grid(ds: DeviceSpline, axes, *, values=True, jacobian=False, normal=Fal
 
 
 def eval_grid_batch(ds: DeviceSpline, n_splines, knot_strides, coef_stride, axes, *, values=True, jacobian=False,
-                    normal=False, normalize=True, normal_mask=0, flag=None, out=None):
-    """Launch bspy_cuda_eval_grid_batch for ``n_splines`` surfaces; ``ds`` describes element 0."""
+                    normal=False, normalize=True, normal_mask=0, flag=None, out=None, out_f32=False):
+    """Launch bspy_cuda_eval_grid_batch for ``n_splines`` surfaces; ``ds`` describes element 0; ``out_f32``: float32
+    outputs (BSPY_OUT_F32)."""
     dev = ds.device
     shape = tuple(int(a.numel()) for a in axes)
     S = int(n_splines)
+    odt = torch.float32 if out_f32 else torch.float64
     if out is None:
         out = {
-            "values": torch.empty((S, ds.nDep, *shape), dtype=torch.float64, device=dev) if values else None,
-            "jacobian": torch.empty((S, ds.nDep, 2, *shape), dtype=torch.float64, device=dev) if jacobian else None,
-            "normal": torch.empty((S, ds.normal_dim, *shape), dtype=torch.float64, device=dev) if normal else None,
+            "values": torch.empty((S, ds.nDep, *shape), dtype=odt, device=dev) if values else None,
+            "jacobian": torch.empty((S, ds.nDep, 2, *shape), dtype=odt, device=dev) if jacobian else None,
+            "normal": torch.empty((S, ds.normal_dim, *shape), dtype=odt, device=dev) if normal else None,
         }
+    for t in out.values():
+        if t is not None and (t.dtype != odt or not t.is_contiguous()):
+            raise ValueError(f"eval_grid_batch: output buffers must be contiguous {odt} tensors")
     ax = (C.c_void_p * 2)(*[a.data_ptr() for a in axes])
     na = (C.c_int64 * 2)(*shape)
     ks = (C.c_int64 * 2)(*[int(k) for k in knot_strides])
     with torch.cuda.device(dev):
         rc = library().bspy_cuda_eval_grid_batch(C.byref(ds.c), S, ks, int(coef_stride), ax, na,
-                                                 NORMALIZE if normalize else 0, int(normal_mask), _ptr(out.get("values")),
+                                                 (NORMALIZE if normalize else 0) | (OUT_F32 if out_f32 else 0), int(normal_mask), _ptr(out.get("values")),
                                                  _ptr(out.get("jacobian")), _ptr(out.get("normal")), _ptr(flag), _stream(dev))
     _check(rc, "bspy_cuda_eval_grid_batch")
     return out

@@ -109,7 +109,10 @@ __device__ __forceinline__ void axis_basis(const double *__restrict__ knots, int
 // Measured with a pure store-pattern probe (tools/pattern_probe*.py): HBM sustains the most when the set of
 // rows being written at any moment is small and each row receives long contiguous runs; one warp per strip
 // sweeping along the row (the previous layout) topped out at 5.0 TB/s of the 6.5 TB/s a linear fill reaches.
-template <int NDEP, int MAXO>
+// F32: the outputs are float arrays of the same shapes (computed in float64, rounded to nearest on the store): the
+// tessellation path of the reference's viewer, which hands float32 buffers to OpenGL (bspy/splineOpenGLFrame.py:1461-1513);
+// half the bytes on a kernel that is bound by its store stream.
+template <int NDEP, int MAXO, bool F32 = false>
 __global__ void __launch_bounds__(GRID_WARPS * 32, 2) grid2_dmma_kernel(const Grid2Params P)
 {
     constexpr int D = NDEP > 2 ? NDEP : 2;
@@ -268,28 +271,40 @@ __global__ void __launch_bounds__(GRID_WARPS * 32, 2) grid2_dmma_kernel(const Gr
             if (a < P.nU && b < P.nV) {
                 const int left = (int)min((long long)4, P.nV - b);
                 const long long at = a * P.nV + b;
-                auto put = [&](double *base, const double (&x)[4]) {
-                    double *p = base + at;
-                    if (P.vec == 4 && left == 4) {
-                        st_cs_v4(p, x[0], x[1], x[2], x[3]);
-                    } else if (P.vec >= 2 && left == 4) {
-                        __stcs(reinterpret_cast<double2 *>(p), make_double2(x[0], x[1]));
-                        __stcs(reinterpret_cast<double2 *>(p + 2), make_double2(x[2], x[3]));
-                    } else {
+                auto put = [&](double *base, const long long planeIdx, const double (&x)[4]) {
+                    if constexpr (F32) {
+                        float *p = reinterpret_cast<float *>(base) + planeIdx * plane + at;
+                        if (P.vec == 4 && left == 4) {
+                            __stcs(reinterpret_cast<float4 *>(p), make_float4(__double2float_rn(x[0]), __double2float_rn(x[1]),
+                                                                              __double2float_rn(x[2]), __double2float_rn(x[3])));
+                        } else {
 #pragma unroll
-                        for (int e = 0; e < 4; ++e)
-                            if (e < left) __stcs(p + e, x[e]);
+                            for (int e = 0; e < 4; ++e)
+                                if (e < left) __stcs(p + e, __double2float_rn(x[e]));
+                        }
+                    } else {
+                        double *p = base + planeIdx * plane + at;
+                        if (P.vec == 4 && left == 4) {
+                            st_cs_v4(p, x[0], x[1], x[2], x[3]);
+                        } else if (P.vec >= 2 && left == 4) {
+                            __stcs(reinterpret_cast<double2 *>(p), make_double2(x[0], x[1]));
+                            __stcs(reinterpret_cast<double2 *>(p + 2), make_double2(x[2], x[3]));
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                if (e < left) __stcs(p + e, x[e]);
+                        }
                     }
                 };
                 if (P.values) {
 #pragma unroll
-                    for (int d = 0; d < NDEP; ++d) put(P.values + (sIdx * NDEP + d) * plane, acc[d][0]);
+                    for (int d = 0; d < NDEP; ++d) put(P.values, sIdx * NDEP + d, acc[d][0]);
                 }
                 if (P.jacobian) {
 #pragma unroll
                     for (int d = 0; d < NDEP; ++d) {
-                        put(P.jacobian + ((sIdx * NDEP + d) * 2 + 0) * plane, acc[d][1]);
-                        put(P.jacobian + ((sIdx * NDEP + d) * 2 + 1) * plane, acc[d][2]);
+                        put(P.jacobian, (sIdx * NDEP + d) * 2 + 0, acc[d][1]);
+                        put(P.jacobian, (sIdx * NDEP + d) * 2 + 1, acc[d][2]);
                     }
                 }
                 if constexpr (NDEP == 3 || NDEP == 1) {
@@ -320,7 +335,7 @@ __global__ void __launch_bounds__(GRID_WARPS * 32, 2) grid2_dmma_kernel(const Gr
                             }
                         }
 #pragma unroll
-                        for (int i = 0; i < D; ++i) put(P.normal + (sIdx * D + i) * plane, n[i]);
+                        for (int i = 0; i < D; ++i) put(P.normal, sIdx * D + i, n[i]);
                     }
                 }
             }
@@ -657,21 +672,21 @@ __global__ void __launch_bounds__(GRID_WARPS * 32, 2) grid3_dmma_kernel(const Gr
 
 static bool aligned_to(const void *p, unsigned n) { return (reinterpret_cast<uintptr_t>(p) & (n - 1)) == 0; }
 
-template <int NDEP, int MAXO>
+template <int NDEP, int MAXO, bool F32 = false>
 static int launch_grid2(const Grid2Params &P, cudaStream_t stream)
 {
     const size_t smem = sizeof(double) * (2 * MAXO * (P.chunkCols + 2) + 2 * MAXO * GRID_TILE_ROWS) +
                         sizeof(int) * (P.chunkCols + GRID_TILE_ROWS);
     static size_t allowed = 48 * 1024;
     if (smem > allowed) {
-        cudaError_t e = cudaFuncSetAttribute(grid2_dmma_kernel<NDEP, MAXO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(grid2_dmma_kernel<NDEP, MAXO, F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
         allowed = smem;
     }
     const long long groups = (P.nSplines + P.group - 1) / P.group;
     const long long tiles = groups * P.colChunks * P.rowBlocks;
     if (tiles > 0x7fffffffLL) { set_error("grid too large for one launch"); return BSPY_E_UNSUPPORTED; }
-    grid2_dmma_kernel<NDEP, MAXO><<<(unsigned)tiles, GRID_WARPS * 32, smem, stream>>>(P);
+    grid2_dmma_kernel<NDEP, MAXO, F32><<<(unsigned)tiles, GRID_WARPS * 32, smem, stream>>>(P);
     count_launch();
     return check_launch("bspy_cuda_eval_grid");
 }
@@ -699,9 +714,14 @@ static int grid2_run(const bspy_spline *sp, long long nSplines, long long knotSt
     P.normalSign = sp->normalSign < 0 ? -1 : 1;
     P.normalize = (flags & BSPY_NORMALIZE) ? 1u : 0u;
     P.normalMask = normalMask ? normalMask : 0xffffffffu;
+    const bool f32 = (flags & BSPY_OUT_F32) != 0;
     P.vec = 1;
-    if (P.nV % 2 == 0 && aligned_to(values, 16) && aligned_to(jacobian, 16) && aligned_to(normal, 16)) P.vec = 2;
-    if (P.nV % 4 == 0 && aligned_to(values, 32) && aligned_to(jacobian, 32) && aligned_to(normal, 32)) P.vec = 4;
+    if (f32) {
+        if (P.nV % 4 == 0 && aligned_to(values, 16) && aligned_to(jacobian, 16) && aligned_to(normal, 16)) P.vec = 4;
+    } else {
+        if (P.nV % 2 == 0 && aligned_to(values, 16) && aligned_to(jacobian, 16) && aligned_to(normal, 16)) P.vec = 2;
+        if (P.nV % 4 == 0 && aligned_to(values, 32) && aligned_to(jacobian, 32) && aligned_to(normal, 32)) P.vec = 4;
+    }
     {
         // Tile shape.  Write-heavy requests (>= 6 doubles per point, e.g. value + jacobian + normal = 12) are bound
         // by the HBM store stream, which is fastest when CTAs are short-lived and close together: 16 rows x 256
@@ -727,6 +747,14 @@ static int grid2_run(const bspy_spline *sp, long long nSplines, long long knotSt
     }
     if (P.nU == 0 || P.nV == 0 || nSplines == 0) return 0;
     const bool small = P.ou <= 4 && P.ov <= 4;
+    if (f32) {
+        switch (sp->nDep) {
+            case 1: return small ? launch_grid2<1, 4, true>(P, stream) : launch_grid2<1, 8, true>(P, stream);
+            case 2: return small ? launch_grid2<2, 4, true>(P, stream) : launch_grid2<2, 8, true>(P, stream);
+            case 3: return small ? launch_grid2<3, 4, true>(P, stream) : launch_grid2<3, 8, true>(P, stream);
+            default: return small ? launch_grid2<4, 4, true>(P, stream) : launch_grid2<4, 8, true>(P, stream);
+        }
+    }
     switch (sp->nDep) {
         case 1: return small ? launch_grid2<1, 4>(P, stream) : launch_grid2<1, 8>(P, stream);
         case 2: return small ? launch_grid2<2, 4>(P, stream) : launch_grid2<2, 8>(P, stream);
@@ -823,6 +851,10 @@ extern "C" int bspy_cuda_eval_grid(const bspy_spline *spline, const double *cons
         if (rc) return rc;
         return grid2_run(spline, 1, 0, 0, 0, axes, nAxis, flags, normalMask, values, jacobian, normal, firstOutside,
                          (cudaStream_t)stream);
+    }
+    if (flags & BSPY_OUT_F32) {
+        set_error("bspy_cuda_eval_grid: float32 outputs are available for surfaces (nInd == 2, nDep <= 4, orders <= 8) only");
+        return BSPY_E_UNSUPPORTED;
     }
     if (grid3_supported(spline, normal) && (values || jacobian)) {
         SplineDev chk;

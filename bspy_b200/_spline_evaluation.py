@@ -353,12 +353,18 @@ def evaluate_points(self, uvw, *, with_respect_to=None, values=True, jacobian=Fa
 
 
 def evaluate_grid(self, *axes, values=True, jacobian=False, normal=False, normalize=True, indices=None,
-                  check_domain=True, device=None) -> EvalResult:
+                  check_domain=True, device=None, dtype=None) -> EvalResult:
     """Evaluate on the tensor grid ``axes[0] x axes[1] x ...`` (one 1-D axis per independent
     variable).  Outputs have the grid shape in place of N, last variable fastest: values
     ``(nDep, n_0, .., n_last)``, jacobian ``(nDep, nInd, n_0, ..)``, normal ``(D, n_0, ..)`` -- the same
     numbers as ``spline(*np.meshgrid(*axes, indexing="ij"))`` in the reference.  Surfaces run on the
-    FP64 tensor pipe."""
+    FP64 tensor pipe.  ``dtype=np.float32`` (surfaces only): float32 outputs, computed in float64 and rounded on the
+    store -- the tessellation buffers of the reference's viewer (``bspy/splineOpenGLFrame.py:1461-1513``)."""
+    f32 = dtype is not None and np.dtype(dtype) == np.float32
+    if dtype is not None and not f32 and np.dtype(dtype) != np.float64:
+        raise ValueError("dtype must be float64 (default) or float32")
+    if f32 and self.nInd != 2:
+        raise NotImplementedError("float32 grid outputs are available for surfaces (nInd == 2)")
     if len(axes) == 1 and self.nInd != 1 and not np.isscalar(axes[0]) and len(axes[0]) == self.nInd \
             and not isinstance(axes[0], (np.ndarray, torch.Tensor)):
         axes = tuple(axes[0])
@@ -379,7 +385,7 @@ def evaluate_grid(self, *axes, values=True, jacobian=False, normal=False, normal
             d_axes.append(torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64).reshape(-1)).to(dev))
     flag = _cuda.new_flag(dev) if check_domain else None
     out = _cuda.eval_grid(ds, d_axes, values=bool(values), jacobian=bool(jacobian), normal=bool(normal),
-                          normalize=bool(normalize), normal_mask=mask, flag=flag)
+                          normalize=bool(normalize), normal_mask=mask, flag=flag, **({"out_f32": True} if f32 else {}))
     if check_domain:
         off = int(flag.item())
         if off >= 0:

@@ -161,11 +161,15 @@ class SplineBatch:
 
     # ---- surfaces ----------------------------------------------------------------------------
     def evaluate_grid(self, uAxis, vAxis, values=True, jacobian=False, normal=False, normalize=True, indices=None,
-                      check_domain=True, out=None) -> EvalResult:
+                      check_domain=True, out=None, dtype=None) -> EvalResult:
         """Surfaces only: every spline of the batch on the grid ``uAxis x vAxis``; outputs
-        ``(S, nDep, nU, nV)``, ``(S, nDep, 2, nU, nV)``, ``(S, D, nU, nV)`` (v fastest)."""
+        ``(S, nDep, nU, nV)``, ``(S, nDep, 2, nU, nV)``, ``(S, D, nU, nV)`` (v fastest).  ``dtype=np.float32``: float32
+        outputs (device tensors, or ``out`` buffers of that type), computed in float64 and rounded on the store."""
         if self.nInd != 2:
             raise NotImplementedError("SplineBatch.evaluate_grid handles surfaces (nInd == 2)")
+        f32 = dtype is not None and np.dtype(dtype) == np.float32
+        if dtype is not None and not f32 and np.dtype(dtype) != np.float64:
+            raise ValueError("dtype must be float64 (default) or float32")
         idx, mask = (None, 0)
         if normal:
             idx, mask = _normal_request(self, indices)
@@ -173,10 +177,10 @@ class SplineBatch:
         axes = [_to_device(uAxis, self.device).reshape(-1), _to_device(vAxis, self.device).reshape(-1)]
         strides = [0 if k.dim() == 1 else int(k.stride(0)) for k in self.knots]
         request = dict(values=values, jacobian=jacobian, normal=normal, normalize=normalize, normal_mask=mask)
-        if on_device or out is not None:
+        if on_device or out is not None or f32:
             flag = _cuda.new_flag(self.device) if check_domain else None
             res = _cuda.eval_grid_batch(self._descriptor(), self.nSplines, strides, int(self.coefs.stride(0)), axes,
-                                        flag=flag, out=out, **request)
+                                        flag=flag, out=out, **request, **({"out_f32": True} if f32 else {}))
             off = int(flag.item()) if check_domain else -1
         else:
             res, off = _cuda.eval_grid_batch_host(self._descriptor(), self.nSplines, strides, int(self.coefs.stride(0)),

@@ -57,6 +57,7 @@ typedef struct bspy_spline {
 
 /* what bspy_cuda_eval_* computes */
 #define BSPY_NORMALIZE 1u /* divide the normal by its 2-norm over the selected components */
+#define BSPY_OUT_F32 2u   /* grid entry points, surfaces only: values / jacobian / normal point to float arrays */
 
 /* ---- library ------------------------------------------------------------------------- */
 int bspy_cuda_abi_version(void);

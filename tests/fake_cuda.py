@@ -74,14 +74,15 @@ def eval_points_host(ds, host, layout, *, check=True, chunk=None, **request):
     return out, (int(flag[0]) if check else -1)
 
 
-def eval_grid(ds, axes, *, values=True, jacobian=False, normal=False, normalize=True, normal_mask=0, flag=None):
+def eval_grid(ds, axes, *, values=True, jacobian=False, normal=False, normalize=True, normal_mask=0, flag=None, out_f32=False):
     shape = tuple(int(a.numel()) for a in axes)
     mesh = np.meshgrid(*[a.numpy() for a in axes], indexing="ij") if axes else []
     pts = np.stack([m.reshape(-1) for m in mesh], axis=1) if axes else np.empty((1, 0))
     r = _evaluate(ds, pts, values=values, jacobian=jacobian, normal=normal, normalize=normalize, normal_mask=normal_mask, flag=flag)
-    return {"values": None if r["values"] is None else r["values"].reshape(ds.nDep, *shape),
-            "jacobian": None if r["jacobian"] is None else r["jacobian"].reshape(ds.nDep, ds.nInd, *shape),
-            "normal": None if r["normal"] is None else r["normal"].reshape(-1, *shape)}
+    cast = (lambda t: t.to(torch.float32)) if out_f32 else (lambda t: t)
+    return {"values": None if r["values"] is None else cast(r["values"].reshape(ds.nDep, *shape)),
+            "jacobian": None if r["jacobian"] is None else cast(r["jacobian"].reshape(ds.nDep, ds.nInd, *shape)),
+            "normal": None if r["normal"] is None else cast(r["normal"].reshape(-1, *shape))}
 
 
 def spans(knots, order, u):

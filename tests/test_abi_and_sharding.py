@@ -39,7 +39,7 @@ def test_library_is_sm100a_with_dmma_and_lineinfo():
     from bspy_b200 import _cuda
     out = subprocess.run(["cuobjdump", "-lelf", _cuda.LIB_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in out
-    sass = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN4bspy17grid2_dmma_kernelILi3ELi4EEEvNS_11Grid2ParamsE", _cuda.LIB_PATH],
+    sass = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN4bspy17grid2_dmma_kernelILi3ELi4ELb0EEEvNS_11Grid2ParamsE", _cuda.LIB_PATH],
                           capture_output=True, text=True).stdout
     assert "DMMA" in sass, "the grid kernel must run on the FP64 tensor pipe"
 

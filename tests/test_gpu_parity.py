@@ -868,3 +868,33 @@ def test_random_shapes_vs_oracle():
             assert close(g.values.reshape(nDep, -1).T, O.evaluate_vec(so, mesh)), tag
             assert close_cond(np.transpose(g.jacobian.reshape(nDep, nInd, -1), (2, 0, 1)), O.jacobian_vec(so, mesh),
                               O.jacobian_abs_vec(so, mesh)), tag
+
+
+def test_grid_float32_outputs():
+    """float32 outputs of the surface grid kernels (the viewer's tessellation buffers) are the float64
+    results rounded to nearest, element for element -- single surfaces and batches, ragged and unaligned sizes, orders
+    above 4, all three output kinds; other shapes refuse the flag."""
+    bspy, _cuda, O, _ = _mods()
+    a = load_npz("teapot.npz")
+    kn = a["knots"]
+    patches = [bspy.Spline(2, 3, (4, 4), (4, 4), (kn, kn), a["coefs"][p]) for p in range(6)]
+    batch = bspy.SplineBatch.from_splines(patches)
+    for nU, nV in ((64, 256), (33, 77), (8, 4)):
+        u = torch.linspace(0, 1, nU, dtype=torch.float64, device="cuda")
+        v = torch.linspace(0, 1, nV, dtype=torch.float64, device="cuda")
+        r64 = batch.evaluate_grid(u, v, jacobian=True, normal=True)
+        r32 = batch.evaluate_grid(u, v, jacobian=True, normal=True, dtype=np.float32)
+        for x64, x32 in ((r64.values, r32.values), (r64.jacobian, r32.jacobian), (r64.normal, r32.normal)):
+            assert x32.dtype == torch.float32 and x32.shape == x64.shape
+            assert torch.equal(torch.nan_to_num(x32, nan=-7.0), torch.nan_to_num(x64.to(torch.float32), nan=-7.0)), (nU, nV)
+    c = [c for c in CASES if c.tag == "surf_25_d1"][0]                      # orders (2, 5), nDep 1 (nInd > nDep normal)
+    s = _spline(c)
+    g = [np.linspace(*s.domain()[i], 19 + 6 * i) for i in range(2)]
+    r64 = s.evaluate_grid(*g, jacobian=True, normal=True)
+    r32 = s.evaluate_grid(*g, jacobian=True, normal=True, dtype=np.float32)
+    assert r32.values.dtype == np.float32
+    assert np.array_equal(r32.values, r64.values.astype(np.float32)) and np.array_equal(r32.jacobian, r64.jacobian.astype(np.float32))
+    assert np.array_equal(r32.normal, r64.normal.astype(np.float32), equal_nan=True)
+    vol = _spline([c for c in CASES if c.tag == "vol_444_d3"][0])
+    with pytest.raises(NotImplementedError):
+        vol.evaluate_grid(*[np.linspace(0, 1, 5)] * 3, dtype=np.float32)
