@@ -731,18 +731,21 @@ static int grid2_run(const bspy_spline *sp, long long nSplines, long long knotSt
         const int doubles = (values ? sp->nDep : 0) + (jacobian ? 2 * sp->nDep : 0) + (normal ? D : 0);
         const bool heavy = doubles >= 6;
         const char *e = getenv("BSPY_GRID_CHUNK");
-        const long long cap = e ? atoi(e) : 256;
+        // float32 outputs halve the store stream: the kernel is then bound by the per-CTA tables and the arithmetic, and
+        // larger tiles win (measured, 32 patches x 2048^2, 12 floats per point: 16 x 256 x 1 -> 81.6 Gpts/s,
+        // 32 x 512 x 4 -> 103.8 Gpts/s = 5.0 TB/s written)
+        const long long cap = e ? atoi(e) : (f32 ? 512 : 256);
         const long long chunks = (P.nV + cap - 1) / cap;
         long long per = (P.nV + chunks - 1) / chunks;
         per = (per + GRID_STEP - 1) / GRID_STEP * GRID_STEP;
         P.chunkCols = (int)per;
         P.colChunks = (int)((P.nV + per - 1) / per);
         e = getenv("BSPY_GRID_ROWS");
-        P.tileRows = e ? atoi(e) : (heavy ? 16 : GRID_TILE_ROWS);
+        P.tileRows = e ? atoi(e) : (f32 ? 32 : (heavy ? 16 : GRID_TILE_ROWS));
         if (P.tileRows < 8 || P.tileRows > GRID_TILE_ROWS || P.tileRows % 8) P.tileRows = GRID_TILE_ROWS;
         P.rowBlocks = (P.nU + P.tileRows - 1) / P.tileRows;
         e = getenv("BSPY_GRID_GROUP");
-        const int g = e ? atoi(e) : (heavy ? 1 : GRID_GROUP);
+        const int g = e ? atoi(e) : ((heavy && !f32) ? 1 : GRID_GROUP);
         P.group = (knotStride0 == 0 && knotStride1 == 0) ? (int)(nSplines < g ? nSplines : g) : 1;
     }
     if (P.nU == 0 || P.nV == 0 || nSplines == 0) return 0;
