@@ -84,7 +84,7 @@ def _spline_payload(s):
 
 class Cfg2Teapot(Workload):
     name = "cfg2: 32 bicubic Utah-teapot patches, value+du+dv+unit normal on a 2048x2048 grid per patch"
-    kernel = "grid2_dmma_kernel<3,4>"
+    kernel = "grid2_dmma_kernel<3,4,false>"
     bytes_per_point = 96.0
     flops_per_point = 92.0
     bound = "hbm"
