@@ -324,3 +324,19 @@ def test_spline_batch_bulk_loader(tmp_path):
             key = (t.nInd, t.nDep, t.order, t.nCoef)
             shapes[key] = shapes.get(key, 0) + t.nSplines
         assert shapes == {(2, 3, (4, 4), (4, 4)): 82, (1, 2, (4,), (4,)): 24, (1, 2, (4,), (6,)): 4, (1, 2, (4,), (8,)): 4}
+
+
+def test_grid_dtype_option_host_logic():
+    """evaluate_grid(dtype=...): float32 for surfaces only, float64 default, anything else refused (fake binding)."""
+    s = _spline(CASES["surf_34"])
+    g = [np.linspace(*s.domain()[i], 5 + i) for i in range(2)]
+    r64 = s.evaluate_grid(*g, jacobian=True)
+    r32 = s.evaluate_grid(*g, jacobian=True, dtype=np.float32)
+    assert r64.values.dtype == np.float64 and r32.values.dtype == np.float32 and r32.jacobian.dtype == np.float32
+    assert np.array_equal(r32.values, r64.values.astype(np.float32))
+    assert s.evaluate_grid(*g, dtype=np.float64).values.dtype == np.float64
+    with pytest.raises(ValueError, match="dtype"):
+        s.evaluate_grid(*g, dtype=np.int32)
+    c = _spline(CASES["curve_o4"])
+    with pytest.raises(NotImplementedError):
+        c.evaluate_grid(np.linspace(*c.domain()[0], 7), dtype=np.float32)
