@@ -18,6 +18,7 @@ import torch
 
 MAX_IND = 8
 MAX_ORDER = 32
+MANY_MAX_ORDER = 8     # bspy_cuda_eval_many (warp per curve)
 E_ARG, E_UNSUPPORTED, E_NORMAL_DIMS = -1, -2, -3
 NORMALIZE = 1
 OUT_F32 = 2
@@ -27,7 +28,7 @@ LIB_PATH = os.environ.get("BSPY_CUDA_LIB") or os.path.join(HERE, "libbspy_cuda.s
 
 # every symbol include/bspy_cuda.h declares (tests check the library exports exactly these)
 SYMBOLS = (
-    "bspy_cuda_abi_version", "bspy_cuda_last_error_string", "bspy_cuda_launch_count",
+    "bspy_cuda_abi_version", "bspy_cuda_last_error_string", "bspy_cuda_launch_count", "bspy_cuda_set_option",
     "bspy_cuda_spans", "bspy_cuda_basis", "bspy_cuda_eval_points", "bspy_cuda_eval_points_binned",
     "bspy_cuda_binned_workspace_bytes", "bspy_cuda_eval_grid",
     "bspy_cuda_eval_grid_batch", "bspy_cuda_eval_many", "bspy_cuda_probe_fp64", "bspy_cuda_probe_hbm",
@@ -62,12 +63,14 @@ def library():
     with _lock:
         if _lib is not None:
             return _lib
-        if not os.path.exists(LIB_PATH):
+        if "BSPY_CUDA_LIB" not in os.environ:
             try:
                 from . import build as _build
-                _build.build()
+                _build.build()          # no-op unless the .so is missing or older than its sources; inter-process lock
             except Exception as exc:  # no nvcc, compile error
-                raise CudaPathError(f"libbspy_cuda.so is missing and could not be built: {exc}") from exc
+                if not os.path.exists(LIB_PATH):
+                    raise CudaPathError(f"libbspy_cuda.so is missing and could not be built: {exc}") from exc
+                raise CudaPathError(f"libbspy_cuda.so is older than its sources and could not be rebuilt: {exc}") from exc
         try:
             lib = C.CDLL(LIB_PATH)
         except OSError as exc:
@@ -77,6 +80,7 @@ def library():
         lib.bspy_cuda_launch_count.restype = C.c_int64
         vp, i32, i64, u32 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint32
         sig = {
+            "bspy_cuda_set_option": [C.c_char_p, i64, i32],
             "bspy_cuda_spans": [vp, i32, i32, vp, i64, vp, vp],
             "bspy_cuda_basis": [vp, i32, i32, vp, vp, i64, i32, i32, vp, vp, vp],
             "bspy_cuda_eval_points": [C.POINTER(CSpline), vp, i64, i64, i64, C.POINTER(i32), u32, u32, vp, vp, vp, vp, vp, vp, vp],
@@ -107,6 +111,13 @@ def library():
 
 def launch_count() -> int:
     return int(library().bspy_cuda_launch_count())
+
+
+def set_option(name: str, value=None):
+    """Experiment switch of the library (``bspy_cuda_set_option``): ``value=None`` returns it to its default.
+    Names as in the environment variables without the ``BSPY_`` prefix (``BIN_MODE``, ``CURVE_REPL``, ...)."""
+    _check(library().bspy_cuda_set_option(name.encode(), 0 if value is None else int(value), 0 if value is None else 1),
+           "bspy_cuda_set_option")
 
 
 def device(index=None) -> torch.device:

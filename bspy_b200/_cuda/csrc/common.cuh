@@ -16,17 +16,40 @@ void set_error(const char *fmt, ...);
 void count_launch(int n = 1);
 int check_launch(const char *what);   // cudaGetLastError -> status code (+ error string)
 
+// SM count of the CURRENT device (cached per device ordinal; benign race: every writer stores the same value)
 static inline int num_sms()
 {
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (sms <= 0) sms = 148;
+    static int sms[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (!sms[dev]) {
+        int n = 0;
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        sms[dev] = n > 0 ? n : 148;
     }
-    return sms;
+    return sms[dev];
 }
+
+// Opt a kernel in to more than 48 KB of dynamic shared memory.  The attribute is per function AND per device, so it is
+// set on every launch that needs it (a driver call of well under a microsecond) instead of being cached per process.
+template <class K>
+static inline int allow_dynamic_smem(K kernel, size_t smem)
+{
+    if (smem <= 48 * 1024) return 0;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(%zu bytes of shared memory): %s", smem, cudaGetErrorString(e)); return (int)e; }
+    return 0;
+}
+
+// Experiment switches (bspy_cuda_set_option / environment BSPY_<NAME> read ONCE when the library is first used; the
+// launch path never calls getenv).  option() returns `unset` when the switch was neither set nor in the environment.
+enum Option {
+    OPT_CURVE_REPL, OPT_CURVE_PPT, OPT_BIN_MODE, OPT_BIN_OVERLAP, OPT_STAGED, OPT_DEP_TILE, OPT_SPAN_RECORDS, OPT_BIN_CHUNK,
+    OPT_BIN_REC_CHUNK_LOG2, OPT_GRID_CHUNK, OPT_GRID_ROWS, OPT_GRID_GROUP, OPT_CELL_KERNEL, OPT_CURVE_TMA, OPT_MANY_MODE,
+    OPT_GRID3_ROWS, OPT_GRID3_CHUNK, OPT_EXP_A, OPT_EXP_B, OPT_COUNT
+};
+long long option(Option o, long long unset);
 
 // ---- kernel parameter blocks shared by scattered.cu and grid.cu ------------------------------------
 struct SplineDev {

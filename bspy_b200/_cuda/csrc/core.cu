@@ -1,7 +1,11 @@
 // libbspy_cuda.so: error handling, launch accounting, spans and (bit-exact) basis kernels.
 #include <stdarg.h>
 
+#include <stdlib.h>
+#include <string.h>
+
 #include <atomic>
+#include <mutex>
 
 #include "common.cuh"
 
@@ -19,6 +23,33 @@ void set_error(const char *fmt, ...)
 }
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// ---- experiment switches --------------------------------------------------------------------------
+static const char *const kOptionNames[OPT_COUNT] = {
+    "CURVE_REPL", "CURVE_PPT", "BIN_MODE", "BIN_OVERLAP", "STAGED", "DEP_TILE", "SPAN_RECORDS", "BIN_CHUNK",
+    "BIN_REC_CHUNK_LOG2", "GRID_CHUNK", "GRID_ROWS", "GRID_GROUP", "CELL_KERNEL", "CURVE_TMA", "MANY_MODE",
+    "GRID3_ROWS", "GRID3_CHUNK", "EXP_A", "EXP_B",
+};
+constexpr long long kOptionUnset = INT64_MIN;
+static std::atomic<long long> g_options[OPT_COUNT];
+static std::once_flag g_optionsOnce;
+
+static void options_from_environment()
+{
+    for (int i = 0; i < OPT_COUNT; ++i) {
+        char name[64];
+        snprintf(name, sizeof name, "BSPY_%s", kOptionNames[i]);
+        const char *e = getenv(name);
+        g_options[i].store(e && *e ? atoll(e) : kOptionUnset, std::memory_order_relaxed);
+    }
+}
+
+long long option(Option o, long long unset)
+{
+    std::call_once(g_optionsOnce, options_from_environment);
+    const long long v = g_options[o].load(std::memory_order_relaxed);
+    return v == kOptionUnset ? unset : v;
+}
 
 int check_launch(const char *what)
 {
@@ -81,6 +112,12 @@ __global__ void __launch_bounds__(128) basis_kernel(const double *__restrict__ k
         const double x = u[p];
         const int ix = spansIn ? spansIn[p] : span_search(knots, nKnots, order, x);
         if (spansOut) spansOut[p] = ix;
+        // a caller-supplied span whose knot window knots[ix-order+1 .. ix+order-2] leaves the array is not evaluated
+        // (the host wrapper raises IndexError for it, like numpy indexing would): NaN row, no out-of-bounds read
+        if (ix < order - 1 || ix > nKnots - order + 1) {
+            for (int j = 0; j < order; ++j) basis[p * order + j] = __longlong_as_double(0x7ff8000000000000LL);
+            continue;
+        }
         basis_strict(knots, order, ix, x, deriv, taylor != 0, col);
         for (int j = 0; j < order; ++j) basis[p * order + j] = col(j);
     }
@@ -174,6 +211,20 @@ int bspy_cuda_abi_version(void) { return BSPY_ABI_VERSION; }
 const char *bspy_cuda_last_error_string(void) { return g_err; }
 
 int64_t bspy_cuda_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int bspy_cuda_set_option(const char *name, int64_t value, int32_t isSet)
+{
+    if (!name) { set_error("bspy_cuda_set_option: name is NULL"); return BSPY_E_ARG; }
+    option(OPT_COUNT == 0 ? OPT_CURVE_REPL : OPT_CURVE_REPL, 0);   // environment defaults are read first
+    for (int i = 0; i < OPT_COUNT; ++i) {
+        if (strcmp(name, kOptionNames[i]) == 0) {
+            g_options[i].store(isSet ? (long long)value : kOptionUnset, std::memory_order_relaxed);
+            return 0;
+        }
+    }
+    set_error("bspy_cuda_set_option: unknown option %s", name);
+    return BSPY_E_ARG;
+}
 
 int bspy_cuda_spans(const double *knots, int32_t nKnots, int32_t order, const double *u, int64_t N,
                     int32_t *spans, void *stream)

@@ -271,22 +271,14 @@ __global__ void __launch_bounds__(repl_threads(O, NDEP), 2) eval_curve_repl_kern
 template <int O, int NDEP, bool DER>
 static int launch_curve3(const CurveParams &P, size_t smem, cudaStream_t stream)
 {
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(eval_curve_kernel<O, NDEP, DER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-    }
+    if (int rc = allow_dynamic_smem(eval_curve_kernel<O, NDEP, DER>, smem)) return rc;
     {
         // big batches: bank-replicated span rows (when 8 copies of the rows fit beside a second CTA)
-        const char *re = getenv("BSPY_CURVE_REPL");
-        const long long minN = re ? (atoi(re) ? 0 : (1LL << 62)) : 131072;
+        const long long re = option(OPT_CURVE_REPL, -1);
+        const long long minN = re >= 0 ? (re ? 0 : (1LL << 62)) : 131072;
         const ReplLayout L = repl_layout(O, NDEP, P.nCoef, 100 * 1024);
         if (P.N >= minN && L.bytes && !P.in.grid && P.nCoef < 65535) {
-            static size_t allowed = 48 * 1024;
-            if (L.bytes > allowed) {
-                cudaError_t e2 = cudaFuncSetAttribute(eval_curve_repl_kernel<O, NDEP, DER>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-                if (e2 != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e2)); return (int)e2; }
-                allowed = 100 * 1024;
-            }
+            if (int rc = allow_dynamic_smem(eval_curve_repl_kernel<O, NDEP, DER>, L.bytes)) return rc;
             const int threads = repl_threads(O, NDEP);
             long long blocks = (P.N + threads * 4 - 1) / (threads * 4);
             const long long cap = (long long)num_sms() * 2;
@@ -297,8 +289,7 @@ static int launch_curve3(const CurveParams &P, size_t smem, cudaStream_t stream)
         }
     }
     const int threads = 256;
-    const char *e = getenv("BSPY_CURVE_PPT");
-    const int ppt = e ? atoi(e) : 8;
+    const int ppt = (int)option(OPT_CURVE_PPT, 8);
     long long blocks = (P.N + threads * ppt - 1) / (threads * ppt);  // points per thread amortise the table build
     const long long cap = (long long)num_sms() * 8;
     if (blocks > cap) blocks = cap;

@@ -677,12 +677,7 @@ static int launch_grid2(const Grid2Params &P, cudaStream_t stream)
 {
     const size_t smem = sizeof(double) * (2 * MAXO * (P.chunkCols + 2) + 2 * MAXO * GRID_TILE_ROWS) +
                         sizeof(int) * (P.chunkCols + GRID_TILE_ROWS);
-    static size_t allowed = 48 * 1024;
-    if (smem > allowed) {
-        cudaError_t e = cudaFuncSetAttribute(grid2_dmma_kernel<NDEP, MAXO, F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-        allowed = smem;
-    }
+    if (int rc = allow_dynamic_smem(grid2_dmma_kernel<NDEP, MAXO, F32>, smem)) return rc;
     const long long groups = (P.nSplines + P.group - 1) / P.group;
     const long long tiles = groups * P.colChunks * P.rowBlocks;
     if (tiles > 0x7fffffffLL) { set_error("grid too large for one launch"); return BSPY_E_UNSUPPORTED; }
@@ -730,22 +725,19 @@ static int grid2_run(const bspy_spline *sp, long long nSplines, long long knotSt
         const int D = sp->nDep > 2 ? sp->nDep : 2;
         const int doubles = (values ? sp->nDep : 0) + (jacobian ? 2 * sp->nDep : 0) + (normal ? D : 0);
         const bool heavy = doubles >= 6;
-        const char *e = getenv("BSPY_GRID_CHUNK");
         // float32 outputs halve the store stream: the kernel is then bound by the per-CTA tables and the arithmetic, and
         // larger tiles win (measured, 32 patches x 2048^2, 12 floats per point: 16 x 256 x 1 -> 81.6 Gpts/s,
         // 32 x 512 x 4 -> 103.8 Gpts/s = 5.0 TB/s written)
-        const long long cap = e ? atoi(e) : (f32 ? 512 : 256);
+        const long long cap = option(OPT_GRID_CHUNK, f32 ? 512 : 256);
         const long long chunks = (P.nV + cap - 1) / cap;
         long long per = (P.nV + chunks - 1) / chunks;
         per = (per + GRID_STEP - 1) / GRID_STEP * GRID_STEP;
         P.chunkCols = (int)per;
         P.colChunks = (int)((P.nV + per - 1) / per);
-        e = getenv("BSPY_GRID_ROWS");
-        P.tileRows = e ? atoi(e) : (f32 ? 32 : (heavy ? 16 : GRID_TILE_ROWS));
+        P.tileRows = (int)option(OPT_GRID_ROWS, f32 ? 32 : (heavy ? 16 : GRID_TILE_ROWS));
         if (P.tileRows < 8 || P.tileRows > GRID_TILE_ROWS || P.tileRows % 8) P.tileRows = GRID_TILE_ROWS;
         P.rowBlocks = (P.nU + P.tileRows - 1) / P.tileRows;
-        e = getenv("BSPY_GRID_GROUP");
-        const int g = e ? atoi(e) : ((heavy && !f32) ? 1 : GRID_GROUP);
+        const int g = (int)option(OPT_GRID_GROUP, (heavy && !f32) ? 1 : GRID_GROUP);
         P.group = (knotStride0 == 0 && knotStride1 == 0) ? (int)(nSplines < g ? nSplines : g) : 1;
     }
     if (P.nU == 0 || P.nV == 0 || nSplines == 0) return 0;
@@ -772,12 +764,7 @@ static int launch_grid3(const Grid3Params &P, cudaStream_t stream)
     const size_t smem = sizeof(double) * (2 * MAXO * (P.chunkCols + 2) + 4 * MAXO * GRID_TILE_ROWS) +
                         sizeof(int) * (P.chunkCols + 2 * GRID_TILE_ROWS + 2) +
                         sizeof(double) * (3 * NDEP * GRID3_BAND_ROWS * GRID3_TS);
-    static size_t allowed = 48 * 1024;
-    if (smem > allowed) {
-        cudaError_t e = cudaFuncSetAttribute(grid3_dmma_kernel<NDEP, MAXO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-        allowed = smem;
-    }
+    if (int rc = allow_dynamic_smem(grid3_dmma_kernel<NDEP, MAXO>, smem)) return rc;
     const long long tiles = P.colChunks * P.rowBlocks;
     if (tiles > 0x7fffffffLL) { set_error("grid too large for one launch"); return BSPY_E_UNSUPPORTED; }
     grid3_dmma_kernel<NDEP, MAXO><<<(unsigned)tiles, GRID_WARPS * 32, smem, stream>>>(P);

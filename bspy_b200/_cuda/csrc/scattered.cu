@@ -15,6 +15,8 @@
 // the common shapes, eval_generic for any nInd <= 8, order <= 32 and any nDep.
 #include <stdlib.h>
 
+#include <mutex>
+
 #include "common.cuh"
 
 namespace bspy {
@@ -1098,12 +1100,7 @@ static int launch_unpermute(const double *aos, int stride, const int *inv, long 
                             const OutDev &out, cudaStream_t st)
 {
     const size_t smem = sizeof(double) * UNPERM_WARPS * 32 * (stride + 2);
-    static size_t allowed = 48 * 1024;
-    if (smem > allowed) {
-        cudaError_t e = cudaFuncSetAttribute(bin_unpermute_kernel<S_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-        allowed = smem;
-    }
+    if (int rc = allow_dynamic_smem(bin_unpermute_kernel<S_>, smem)) return rc;
     bin_unpermute_kernel<S_><<<(n + UNPERM_WARPS * 32 - 1) / (UNPERM_WARPS * 32), UNPERM_WARPS * 32, smem, st>>>(
         aos, stride, inv, base, n, nDep, nJ, nN, out);
     return 0;
@@ -1112,13 +1109,8 @@ static int launch_unpermute(const double *aos, int stride, const int *inv, long 
 // points per chunk in sorted-record mode (BSPY_BIN_REC_CHUNK_LOG2 overrides for experiments)
 static long long bin_rec_chunk()
 {
-    static long long v = 0;
-    if (!v) {
-        const char *e = getenv("BSPY_BIN_REC_CHUNK_LOG2");
-        const int lg = e ? atoi(e) : 22;
-        v = 1LL << (lg < 16 ? 16 : (lg > 26 ? 26 : lg));
-    }
-    return v;
+    const long long lg = option(OPT_BIN_REC_CHUNK_LOG2, 22);
+    return 1LL << (lg < 16 ? 16 : (lg > 26 ? 26 : lg));
 }
 #define BIN_REC_CHUNK bin_rec_chunk()
 constexpr long long BIN_CHUNK_MAX = 1 << 20;  // workspace is sized for this many points per chunk
@@ -1128,8 +1120,7 @@ constexpr long long BIN_CHUNK_MAX = 1 << 20;  // workspace is sized for this man
 // chunks give more points per cell but turn the scatter into DRAM read-modify-writes and are 2x slower).
 static long long bin_chunk(long long outBytesPerPoint)
 {
-    const char *e = getenv("BSPY_BIN_CHUNK");
-    long long v = e ? atoll(e) : (56LL << 20) / (outBytesPerPoint > 0 ? outBytesPerPoint : 8);
+    long long v = option(OPT_BIN_CHUNK, (56LL << 20) / (outBytesPerPoint > 0 ? outBytesPerPoint : 8));
     v = v / 1024 * 1024;
     if (v < 65536) v = 65536;
     if (v > BIN_CHUNK_MAX) v = BIN_CHUNK_MAX;
@@ -1283,10 +1274,7 @@ int launch_eval(const SplineDev &s, const PointsDev &in, long long N, const WrtD
         size_t smem = (size_t)rowLen * (jac ? 2 : 1) * t * sizeof(double);
         while (smem > 160 * 1024 && t > 32) { t >>= 1; smem >>= 1; }
         if (smem > 200 * 1024) { set_error("eval_generic: basis scratch too large"); return BSPY_E_UNSUPPORTED; }
-        if (smem > 48 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(eval_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-        }
+        if (int rc = allow_dynamic_smem(eval_generic_kernel, smem)) return rc;
         blocks = (N + t - 1) / t;
         const long long cap = (long long)num_sms() * 16;
         if (blocks > cap) blocks = cap;
@@ -1364,9 +1352,7 @@ static int bin_mode(long long N)
 {
     // 0: scatter results 8 bytes at a time within L2-sized chunks; 1: sorted 32-byte point records, array-of-structs
     // results and an un-permute pass over 4 Mi-point chunks (every scattered access is a whole sector)
-    const char *e = getenv("BSPY_BIN_MODE");
-    if (e) return atoi(e) ? 1 : 0;
-    return N >= (1 << 21) ? 1 : 0;
+    return option(OPT_BIN_MODE, N >= (1 << 21) ? 1 : 0) ? 1 : 0;
 }
 
 static int aos_stride(const SplineDev &s)
@@ -1404,34 +1390,57 @@ long long binned_workspace(const SplineDev &s, long long N)
     return 3 * 4 * pad64(chunk) + 4 * pad64(cells + 1);
 }
 
-// Two internal helper streams per device for the sorted-record pipeline: the sort / un-permute passes are
-// memory-bound, the evaluation FP64-bound, so chunk c+1 is sorted (high-priority stream) while chunk c is evaluated
-// (low-priority stream).  Fork from / join to the caller's stream with events; capturable in a CUDA graph.
+// Two internal helper streams (+ the events that fork from / join to the caller's stream) for the sorted-record
+// pipeline: the sort / un-permute passes are memory-bound, the evaluation FP64-bound, so chunk c+1 is sorted
+// (high-priority stream) while chunk c is evaluated (low-priority stream).  Capturable in a CUDA graph.
+// Sets are pooled per device behind a mutex: a call owns its set exclusively while it ENQUEUES (event record / wait
+// pairs of two host threads can therefore never interleave) and returns it when it is done enqueueing; work already
+// enqueued keeps the dependencies it captured, so the next owner may reuse streams and events right away.
 struct BinStreams {
     cudaStream_t sort = nullptr, eval = nullptr;
     cudaEvent_t fork = nullptr, sorted[2] = {nullptr, nullptr}, evaluated[2] = {nullptr, nullptr}, joinSort = nullptr,
                 joinEval = nullptr;
-    bool ok = false;
+    int device = -1;
+    BinStreams *next = nullptr;
 };
 
-static BinStreams *bin_streams()
+static std::mutex g_binStreamsMutex;
+static BinStreams *g_binStreamsFree[64] = {};
+
+static BinStreams *acquire_bin_streams()
 {
-    static BinStreams per[64];
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64) return nullptr;
-    BinStreams &b = per[dev];
-    if (!b.ok) {
-        int lo = 0, hi = 0;
-        cudaDeviceGetStreamPriorityRange(&lo, &hi);   // lo = lowest priority (numerically largest)
-        if (cudaStreamCreateWithPriority(&b.sort, cudaStreamNonBlocking, hi) != cudaSuccess) return nullptr;
-        if (cudaStreamCreateWithPriority(&b.eval, cudaStreamNonBlocking, lo) != cudaSuccess) return nullptr;
-        cudaEvent_t *evs[] = {&b.fork, &b.sorted[0], &b.sorted[1], &b.evaluated[0], &b.evaluated[1], &b.joinSort, &b.joinEval};
-        for (cudaEvent_t *e : evs)
-            if (cudaEventCreateWithFlags(e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-        b.ok = true;
+    {
+        std::lock_guard<std::mutex> lock(g_binStreamsMutex);
+        if (BinStreams *b = g_binStreamsFree[dev]) {
+            g_binStreamsFree[dev] = b->next;
+            b->next = nullptr;
+            return b;
+        }
     }
-    return &b;
+    BinStreams *b = new BinStreams();
+    b->device = dev;
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);   // lo = lowest priority (numerically largest)
+    bool ok = cudaStreamCreateWithPriority(&b->sort, cudaStreamNonBlocking, hi) == cudaSuccess &&
+              cudaStreamCreateWithPriority(&b->eval, cudaStreamNonBlocking, lo) == cudaSuccess;
+    cudaEvent_t *evs[] = {&b->fork, &b->sorted[0], &b->sorted[1], &b->evaluated[0], &b->evaluated[1], &b->joinSort, &b->joinEval};
+    for (cudaEvent_t *e : evs) ok = ok && cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {   // leave the partially built set to the process; the caller runs without overlap
+        cudaGetLastError();
+        delete b;
+        return nullptr;
+    }
+    return b;
+}
+
+static void release_bin_streams(BinStreams *b)
+{
+    std::lock_guard<std::mutex> lock(g_binStreamsMutex);
+    b->next = g_binStreamsFree[b->device];
+    g_binStreamsFree[b->device] = b;
 }
 
 static long long records_half_bytes(const SplineDev &s, long long chunk)
@@ -1453,30 +1462,23 @@ static int eval_binned_records(const SplineDev &s, PointsDev in, long long N, co
     const int stride = (s.nDep + nJ + nN + 3) & ~3;
     FixedFn fn = find_fixed(s, jac);
     {
-        const char *te = getenv("BSPY_DEP_TILE");
-        const int ndt = te ? atoi(te) : 14;
+        const int ndt = (int)option(OPT_DEP_TILE, 14);
         FixedFn tiled = (ndt > 0 && !out.normal) ? find_fixed_tiled(s, jac, ndt) : nullptr;
         if (tiled) fn = tiled;
     }
     // warp-staged windows where the shape is compiled (no normals there: they need the whole jacobian in one pass)
     const StagedEntry *staged = nullptr;
     {
-        const char *se = getenv("BSPY_STAGED");
-        const int code = se ? atoi(se) : 0;
+        const int code = (int)option(OPT_STAGED, 0);
         if (code >= 0) staged = find_staged(s, jac, code);
         if (staged) {
-            const size_t smem = sizeof(double) * 4 * 2 * staged->windowDoubles;
-            if (smem > 48 * 1024) {
-                cudaError_t e = cudaFuncSetAttribute(staged->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-            }
+            if (int rc = allow_dynamic_smem(staged->fn, sizeof(double) * 4 * 2 * staged->windowDoubles)) return rc;
         }
     }
     // per-span records (left knots | reciprocal gaps) for every variable: no divisions in the evaluation kernel
     const double *spanRec[BSPY_MAX_IND] = {};
     {
-        const char *re = getenv("BSPY_SPAN_RECORDS");
-        if (!re || atoi(re)) {
+        if (option(OPT_SPAN_RECORDS, 1)) {
             double *at = (double *)((char *)workspace + 2 * half);
             for (int i = 0; i < s.nInd; ++i) {
                 const int spans = s.nCoef[i] - s.order[i] + 1, st = span_rec_stride(s.order[i]);
@@ -1492,9 +1494,9 @@ static int eval_binned_records(const SplineDev &s, PointsDev in, long long N, co
     // each other's gaps), nothing with the one-tile-per-CTA gather kernel (config 5: 2.47 -> 2.46), and a loss when
     // the evaluation is launched with fewer CTAs per SM to make room (3 CTAs: 6.6, 2 CTAs: 5.9).  BSPY_BIN_OVERLAP=0/1
     // overrides.
-    const char *env = getenv("BSPY_BIN_OVERLAP");
-    const bool wantOverlap = env ? atoi(env) != 0 : staged != nullptr;
-    BinStreams *bs = wantOverlap ? bin_streams() : nullptr;
+    const bool wantOverlap = option(OPT_BIN_OVERLAP, staged != nullptr ? 1 : 0) != 0;
+    BinStreams *bs = wantOverlap ? acquire_bin_streams() : nullptr;
+    struct Release { BinStreams *b; ~Release() { if (b) release_bin_streams(b); } } releaseOnExit{bs};
     const long long nChunks = (N + chunk - 1) / chunk;
     const bool overlap = bs != nullptr && nChunks > 1;
     cudaStream_t sSort = overlap ? bs->sort : stream, sEval = overlap ? bs->eval : stream;

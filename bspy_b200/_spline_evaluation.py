@@ -128,6 +128,13 @@ def bspline_values_batch(knot, knots, splineOrder, u, derivativeOrder=0, taylorC
             spans_in = knot.to(device=dev, dtype=torch.int32).contiguous()
         else:
             spans_in = torch.from_numpy(np.ascontiguousarray(knot, dtype=np.int32)).to(dev)
+        # a supplied span must keep its knot window knots[ix-order+1 .. ix+order-2] inside the array: the reference
+        # would raise IndexError (or wrap a negative index) there; the kernel refuses such rows (NaN) and we raise
+        if spans_in.numel():
+            lo, hi = int(spans_in.min().item()), int(spans_in.max().item())
+            if lo < int(splineOrder) - 1 or hi > kt.numel() - int(splineOrder) + 1:
+                raise IndexError(f"knot index {lo if lo < int(splineOrder) - 1 else hi} is out of bounds for "
+                                 f"{kt.numel()} knots of order {int(splineOrder)}")
     sp, b = _cuda.basis(kt, int(splineOrder), ut, int(derivativeOrder), bool(taylorCoefs), spans_in)
     if on_device:
         return sp, b

@@ -141,13 +141,24 @@ class SplineBatch:
         ut = _to_device(u, self.device)
         if ut.dim() != 2 or ut.shape[0] != self.nSplines:
             raise ValueError(f"u must have shape (nSplines, nPts) = ({self.nSplines}, nPts)")
+        nPts = int(ut.shape[1])
+        if self.nSplines == 0 or nPts == 0:                    # a rank whose shard is empty: empty outputs, no launch
+            shape = (self.nSplines, self.nDep, nPts)
+            vals = torch.empty(shape, dtype=torch.float64, device=self.device)
+            der = torch.empty(shape, dtype=torch.float64, device=self.device) if derivative else None
+            if not on_device:
+                vals, der = vals.cpu().numpy(), None if der is None else der.cpu().numpy()
+            return EvalResult(values=vals, derivative=der)
         k = self.knots[0]
         if k.dim() == 1:
             k = k.unsqueeze(0).expand(self.nSplines, -1)       # stride 0: every warp stages the same knots
         flag = _cuda.new_flag(self.device) if check_domain else None
         coefs = self.coefs.reshape(self.nSplines, self.nDep, self.nCoef[0])
-        res = _cuda.eval_many(self.order[0], self.nCoef[0], self.nDep, _ExpandedKnots(k), coefs, ut, deriv1=derivative,
-                              flag=flag, out=out)
+        if self.order[0] > _cuda.MANY_MAX_ORDER:
+            res = self._evaluate_per_spline(k, coefs, ut, derivative, flag, out)
+        else:
+            res = _cuda.eval_many(self.order[0], self.nCoef[0], self.nDep, _ExpandedKnots(k), coefs, ut, deriv1=derivative,
+                                  flag=flag, out=out)
         if check_domain:
             off = int(flag.item())
             if off >= 0:
@@ -158,6 +169,24 @@ class SplineBatch:
             vals = vals.cpu().numpy()
             der = None if der is None else der.cpu().numpy()
         return EvalResult(values=vals, derivative=der)
+
+    def _evaluate_per_spline(self, k, coefs, ut, derivative, flag, out):
+        """Curves whose order exceeds the warp-per-curve kernel's limit: one scattered-point launch per curve
+        (any order up to 32), same outputs and the same flat first-outside index."""
+        S, nPts = self.nSplines, int(ut.shape[1])
+        if out is None:
+            out = {"values": torch.empty((S, self.nDep, nPts), dtype=torch.float64, device=self.device),
+                   "derivative": torch.empty((S, self.nDep, nPts), dtype=torch.float64, device=self.device) if derivative else None}
+        for s in range(S):
+            ds = _cuda.DeviceSpline(1, self.nDep, self.order, self.nCoef, [k[s].contiguous()], coefs[s].contiguous())
+            one = _cuda.new_flag(self.device) if flag is not None else None
+            r = _cuda.eval_points(ds, ut[s], 1, 1, nPts, wrt=[1] if derivative else None, values=True, flag=one)
+            out["values"][s].copy_(r["values"])
+            if derivative:
+                out["derivative"][s].copy_(r["derivative"])
+            if flag is not None and int(flag.item()) < 0 and int(one.item()) >= 0:
+                flag.fill_(s * nPts + int(one.item()))
+        return out
 
     # ---- surfaces ----------------------------------------------------------------------------
     def evaluate_grid(self, uAxis, vAxis, values=True, jacobian=False, normal=False, normalize=True, indices=None,
@@ -177,6 +206,18 @@ class SplineBatch:
         axes = [_to_device(uAxis, self.device).reshape(-1), _to_device(vAxis, self.device).reshape(-1)]
         strides = [0 if k.dim() == 1 else int(k.stride(0)) for k in self.knots]
         request = dict(values=values, jacobian=jacobian, normal=normal, normalize=normalize, normal_mask=mask)
+        if self.nSplines == 0 or axes[0].numel() == 0 or axes[1].numel() == 0:
+            # a rank whose shard is empty (world > nSplines): empty outputs of the right shape, no launch
+            nU, nV = int(axes[0].numel()), int(axes[1].numel())
+            odt, S, D = (torch.float32 if f32 else torch.float64), self.nSplines, max(self.nInd, self.nDep)
+            mk = lambda *shape: torch.empty(shape, dtype=odt, device=self.device)
+            r = EvalResult(values=mk(S, self.nDep, nU, nV) if values else None,
+                           jacobian=mk(S, self.nDep, 2, nU, nV) if jacobian else None,
+                           normal=mk(S, D if idx is None else len(idx), nU, nV) if normal else None)
+            if not on_device and out is None and not f32:
+                conv = lambda t: None if t is None else t.cpu().numpy()
+                r = EvalResult(values=conv(r.values), jacobian=conv(r.jacobian), normal=conv(r.normal))
+            return r
         if on_device or out is not None or f32:
             flag = _cuda.new_flag(self.device) if check_domain else None
             res = _cuda.eval_grid_batch(self._descriptor(), self.nSplines, strides, int(self.coefs.stride(0)), axes,

@@ -64,6 +64,10 @@ int bspy_cuda_abi_version(void);
 const char *bspy_cuda_last_error_string(void);
 /* number of kernels launched by this library in this process so far (bench.py reports it) */
 int64_t bspy_cuda_launch_count(void);
+/* Experiment switches (kernel variants, tile shapes, chunk sizes; names listed in DESIGN.md section 7).  Defaults are
+ * the measured best; the environment variable BSPY_<NAME> is read ONCE when the library is first used and this call
+ * overrides it (isSet == 0 returns the switch to "unset" = built-in default).  Process-wide; not an evaluation entry. */
+int bspy_cuda_set_option(const char *name, int64_t value, int32_t isSet);
 
 /* ---- knot spans: replaces the search in bspline_values
  *      (bspy/_spline_evaluation.py:7-8: np.searchsorted(knots, u, 'right') clamped to

@@ -30,3 +30,19 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture
+def option():
+    """Set experiment switches of libbspy_cuda.so (bspy_cuda_set_option) for one test; every switch the test touched
+    returns to its default afterwards."""
+    from bspy_b200 import _cuda
+    touched = set()
+
+    def set_(name, value):
+        touched.add(name)
+        _cuda.set_option(name, value)
+
+    yield set_
+    for name in touched:
+        _cuda.set_option(name, None)

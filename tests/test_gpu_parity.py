@@ -462,7 +462,7 @@ def test_binned_path_is_bit_identical_to_unbinned():
     assert _cuda.library().bspy_cuda_binned_workspace_bytes(device_spline(small).c, 1 << 20) == 0
 
 
-def test_record_mode_staged_windows_bit_identical(monkeypatch):
+def test_record_mode_staged_windows_bit_identical(option):
     """Sorted-record mode (32-byte point records in cell order, per-span reciprocal records, warp-staged windows for
     the volume shapes, one dependent variable per pass for the 4-variate nDep-6 shape, cp.async un-permute): same
     bits as the direct thread-per-point kernel, for dense cells (staged kernel) and for a sparse tail."""
@@ -475,7 +475,7 @@ def test_record_mode_staged_windows_bit_identical(monkeypatch):
         inner = np.concatenate(([0.0], np.cumsum(w))); inner /= inner[-1]
         return np.concatenate((np.zeros(o - 1), inner, np.ones(o - 1)))
 
-    monkeypatch.setenv("BSPY_BIN_MODE", "1")
+    option("BIN_MODE", 1)
     shapes = [((4, 4, 4), 3, (18, 18, 18)), ((3, 3, 3), 3, (20, 19, 18)), ((4, 4, 4), 1, (28, 27, 26)), ((4, 4, 4), 4, (17, 16, 18)),
               ((3, 3, 3, 3), 6, (10, 10, 9, 10))]
     for order, nDep, nCoef in shapes:
@@ -506,7 +506,7 @@ def test_record_mode_staged_windows_bit_identical(monkeypatch):
             assert close(a["values"][:, idx].cpu().numpy().T, O.evaluate_vec(so, ph))
 
 
-def test_curve_replicated_rows_bit_identical(monkeypatch):
+def test_curve_replicated_rows_bit_identical(option):
     """Big batches on one curve go through eval_curve_repl_kernel (bank-replicated span rows, bucket table + short
     advance instead of a bisection): spans bit-exact, values and derivatives bit-identical to the plain curve kernel,
     and both within tolerance of the oracle."""
@@ -544,9 +544,9 @@ def test_curve_replicated_rows_bit_identical(monkeypatch):
             requests.append(dict(values=True, jacobian=True, normal=True))
             requests.append(dict(values=False, normal=True, normalize=False))
         for request in requests:
-            monkeypatch.setenv("BSPY_CURVE_REPL", "1")
+            option("CURVE_REPL", 1)
             a = _cuda.eval_points(ds, u, 1, 1, N, **request)
-            monkeypatch.setenv("BSPY_CURVE_REPL", "0")
+            option("CURVE_REPL", 0)
             b = _cuda.eval_points(ds, u, 1, 1, N, **request)
             for key in a:
                 assert (a[key] is None) == (b[key] is None)
@@ -556,7 +556,7 @@ def test_curve_replicated_rows_bit_identical(monkeypatch):
                         x, y = torch.nan_to_num(x, nan=-7.0), torch.nan_to_num(y, nan=-7.0)
                     assert torch.equal(x, y), (order, nDep, nCoef, key)
         # default dispatch (replicated rows for this N) against the oracle: spans bit-exact, values within tolerance
-        monkeypatch.delenv("BSPY_CURVE_REPL")
+        option("CURVE_REPL", None)
         r = _cuda.eval_points(ds, u, 1, 1, N, values=True, jacobian=True, spans=True)
         idx = np.concatenate((np.arange(0, min(3 * m, 6000)), rng.integers(0, N - 1, 4000)))
         so = O.OracleSpline.of(s)
@@ -576,7 +576,7 @@ def test_curve_replicated_rows_bit_identical(monkeypatch):
         assert int(flag.item()) == 136_000
 
 
-def test_record_mode_multi_chunk_overlap_bit_identical(monkeypatch):
+def test_record_mode_multi_chunk_overlap_bit_identical(option):
     """More than one 4 Mi-point chunk: the sort / un-permute passes of neighbouring chunks run on a second stream under
     the evaluation (double-buffered workspace halves, event fork / join).  Same bits with and without the overlap and
     as the direct kernel; the first out-of-domain index survives the chunking."""
@@ -595,12 +595,12 @@ def test_record_mode_multi_chunk_overlap_bit_identical(monkeypatch):
     pts = torch.rand((N, 3), dtype=torch.float64, device="cuda", generator=torch.Generator(device="cuda").manual_seed(5))
     ref = _cuda.eval_points(ds, pts, 3, 1, N, binned=False, values=True, jacobian=True)
     for flag in ("1", "0"):
-        monkeypatch.setenv("BSPY_BIN_OVERLAP", flag)
+        option("BIN_OVERLAP", int(flag))
         a = _cuda.eval_points(ds, pts, 3, 1, N, binned=True, values=True, jacobian=True)
         torch.cuda.synchronize()
         assert torch.equal(a["values"], ref["values"]) and torch.equal(a["jacobian"], ref["jacobian"]), flag
         del a
-    monkeypatch.delenv("BSPY_BIN_OVERLAP")
+    option("BIN_OVERLAP", None)
     bad = pts.clone()
     bad[(1 << 22) + 17, 2] = 1.25
     bad[2 * (1 << 22) + 5, 0] = -0.5
