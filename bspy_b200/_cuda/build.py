@@ -13,8 +13,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libbspy_cuda.so")
 STAMP = LIB + ".stamp"
-SOURCES = ["core.cu", "scattered.cu", "curve.cu", "grid.cu", "many.cu", "block.cu", "probe.cu"]
-HEADERS = ["common.cuh", "curve.cuh", os.path.join("..", "..", "..", "include", "bspy_cuda.h")]
+SOURCES = ["core.cu", "scattered.cu", "cells.cu", "curve.cu", "grid.cu", "many.cu", "block.cu", "probe.cu"]
+HEADERS = ["common.cuh", "curve.cuh", "scattered.cuh", os.path.join("..", "..", "..", "include", "bspy_cuda.h")]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 

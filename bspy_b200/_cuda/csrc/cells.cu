@@ -1,0 +1,688 @@
+// Cell-sorted evaluation of big scattered batches: bspy_cuda_eval_points_binned (struct-of-arrays outputs) and
+// bspy_cuda_eval_points_aos (one result record per point).
+//
+// Replaces evaluate / derivative / jacobian / normal of bspy/_spline_evaluation.py:109-246 for N scattered points on a
+// spline whose coefficients do not fit in L1: the points of a chunk are counting-sorted by knot-span cell so that the
+// points a warp works on share their coefficient window.
+#include <stdlib.h>
+
+#include <mutex>
+
+#include "scattered.cuh"
+
+namespace bspy {
+
+// ---- cell binning --------------------------------------------------------------------------------
+// Scattered points on a spline whose coefficients do not fit in L1 gather a window of prod(order)*nDep doubles
+// per point from L2 (1.5 KB for a tricubic volume, 3.9 KB for the 4-variate manifold): measured, the
+// thread-per-point kernel is then bound by L2->SM traffic (~7 TB/s) at 10% of the FP64 roofline.  Binning makes
+// the lanes of a warp share their window: the points of a chunk (small enough that its outputs stay in L2) are
+// counting-sorted by knot-span cell, evaluated in cell order (window loads become L1 broadcasts) and written
+// straight back to their original positions.  Same arithmetic per point, so results are bit-identical to the
+// unbinned kernel.
+// per-span records of one variable (runtime order): rec[s] = { knots[ix-(o-1)..ix-1] | 1/(knots[ix+t]-knots[ix-deg+t]) }
+// with ix = o + s, the layout basis_from_span_record<O> reads; one thread per span
+__global__ void __launch_bounds__(128) span_records_kernel(const double *__restrict__ kn, const int o, const int nCoef,
+                                                           double *__restrict__ rec, const int stride)
+{
+    const int sp = blockIdx.x * blockDim.x + threadIdx.x;
+    if (sp > nCoef - o) return;
+    const int ix = o + sp;
+    double *r = rec + (long long)sp * stride;
+    for (int j = 0; j < o - 1; ++j) r[j] = kn[ix - (o - 1) + j];
+    int at = o - 1;
+    for (int deg = 1; deg < o; ++deg)
+        for (int t = 0; t < deg; ++t) r[at++] = 1.0 / (kn[ix + t] - kn[ix - deg + t]);
+    for (; at < stride; ++at) r[at] = 0.0;
+}
+
+static int span_rec_stride(int o) { return ((o - 1 + o * (o - 1) / 2) + 1) & ~1; }
+
+__global__ void __launch_bounds__(256) bin_keys_kernel(const SplineDev s, const PointsDev in, const long long base, const int n,
+                                                       int *__restrict__ keys, int *__restrict__ hist, int *__restrict__ rank,
+                                                       const OutDev out)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned active = __ballot_sync(0xffffffffu, t < n);
+    if (t >= n) return;
+    const long long p = base + t;
+    int key = 0;
+    bool outside = false;
+    for (int iv = 0; iv < s.nInd; ++iv) {
+        const double *k = s.knots[iv];
+        const int o = s.order[iv];
+        const double u = __ldg(in.uvw + p * in.pointStride + iv * in.varStride);
+        outside |= (u < __ldg(k + o - 1)) | (u > __ldg(k + s.nCoef[iv]));
+        const int ix = span_search_inner(k, o + s.nCoef[iv], o, u);
+        if (out.spans) __stcs(out.spans + iv * out.ld + p, ix);
+        key = key * (s.nCoef[iv] - o + 1) + (ix - o);
+    }
+    if (outside && out.firstOutside) report_outside((int64_t *)out.firstOutside, p);
+    keys[t] = key;
+    // one atomic per distinct cell in the warp (coherent inputs would otherwise serialise on one counter)
+    const unsigned peers = __match_any_sync(active, key);
+    const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+    int first = 0;
+    if (lane == leader) first = atomicAdd(hist + key, __popc(peers));
+    if (rank) {   // position inside the cell: the scatter pass then needs no second round of atomics
+        first = __shfl_sync(peers, first, leader);
+        rank[t] = first + __popc(peers & ((1u << lane) - 1));
+    }
+}
+
+// The same pass with P points per thread in flight (coordinates of all P points requested first, the P bisections
+// advance together, P atomics outstanding), plus the rank of every point inside its cell; used by the sorted-record
+// pipeline.  The pass is latency-bound (halving its occupancy doubles its time), and a quarter of the threads with
+// four points each keeps more in flight than one point per thread.
+template <int P>
+__global__ void __launch_bounds__(128) bin_keys_batched_kernel(const SplineDev s, const PointsDev in, const long long base,
+                                                               const int n, int *__restrict__ keys, int *__restrict__ hist,
+                                                               int *__restrict__ rank, const OutDev out)
+{
+    const int t0 = blockIdx.x * (blockDim.x * P) + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    int key[P];
+    bool outside[P];
+#pragma unroll
+    for (int j = 0; j < P; ++j) { key[j] = 0; outside[j] = false; }
+    for (int iv = 0; iv < s.nInd; ++iv) {
+        const double *k = s.knots[iv];
+        const int o = s.order[iv], nKnots = o + s.nCoef[iv];
+        const double lo = __ldg(k + o - 1), hi = __ldg(k + s.nCoef[iv]);
+        double u[P];
+#pragma unroll
+        for (int j = 0; j < P; ++j) {
+            const int t = t0 + j * blockDim.x;
+            u[j] = t < n ? __ldcs(in.uvw + (base + t) * in.pointStride + iv * in.varStride) : lo;
+        }
+        int at[P], cnt[P];
+#pragma unroll
+        for (int j = 0; j < P; ++j) {
+            outside[j] |= (u[j] < lo) | (u[j] > hi);
+            at[j] = o;
+            cnt[j] = (u[j] != u[j]) ? 0 : nKnots - 2 * o;
+        }
+        bool more = true;
+        while (more) {                                    // P upper-bound bisections side by side (span_search_inner)
+            more = false;
+#pragma unroll
+            for (int j = 0; j < P; ++j) {
+                if (cnt[j] > 0) {
+                    const int half = cnt[j] >> 1, mid = at[j] + half;
+                    const bool le = __ldg(k + mid) <= u[j];
+                    at[j] = le ? mid + 1 : at[j];
+                    cnt[j] = le ? cnt[j] - half - 1 : half;
+                    more |= cnt[j] > 0;
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < P; ++j) {
+            const int ix = (u[j] != u[j]) ? nKnots - o : at[j];
+            const int t = t0 + j * blockDim.x;
+            if (out.spans && t < n) __stcs(out.spans + iv * out.ld + base + t, ix);
+            key[j] = key[j] * (s.nCoef[iv] - o + 1) + (ix - o);
+        }
+    }
+    int first[P];
+    unsigned peers[P];
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+        const int t = t0 + j * blockDim.x;
+        const unsigned active = __ballot_sync(0xffffffffu, t < n);
+        first[j] = 0;
+        peers[j] = 0;
+        if (t < n) {
+            if (outside[j] && out.firstOutside) report_outside((int64_t *)out.firstOutside, base + t);
+            keys[t] = key[j];
+            peers[j] = __match_any_sync(active, key[j]);
+            if (lane == __ffs(peers[j]) - 1) first[j] = atomicAdd(hist + key[j], __popc(peers[j]));
+        }
+    }
+    if (rank) {
+#pragma unroll
+        for (int j = 0; j < P; ++j) {
+            const int t = t0 + j * blockDim.x;
+            if (t < n) {
+                const int f = __shfl_sync(peers[j], first[j], __ffs(peers[j]) - 1);
+                rank[t] = f + __popc(peers[j] & ((1u << lane) - 1));
+            }
+        }
+    }
+}
+
+// ---- sorted-record variant (large chunks; no L2-residency assumption) --------------------------------------
+// scatter: 32-byte point records in cell order (a full sector per point, so the scattered write needs no
+// read-modify-write) at offset[cell] + rank (no atomics) + the inverse permutation (coalesced); P points per thread
+template <int P>
+__global__ void __launch_bounds__(128) bin_scatter_records_batched_kernel(const SplineDev s, const PointsDev in, const long long base,
+                                                                          const int n, const int *__restrict__ keys,
+                                                                          const int *__restrict__ offset, double *__restrict__ records,
+                                                                          int *__restrict__ recKey, int *__restrict__ inv)
+{
+    const int t0 = blockIdx.x * (blockDim.x * P) + threadIdx.x;
+    int key[P], pos[P];
+    double r[P][4];
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+        const int t = t0 + j * blockDim.x;
+        key[j] = t < n ? keys[t] : 0;
+        pos[j] = t < n ? inv[t] : 0;
+#pragma unroll
+        for (int iv = 0; iv < 4; ++iv)
+            r[j][iv] = (t < n && iv < s.nInd) ? __ldcs(in.uvw + (base + t) * in.pointStride + iv * in.varStride) : 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < P; ++j) pos[j] += __ldg(offset + key[j]);
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+        const int t = t0 + j * blockDim.x;
+        if (t < n) {
+            if (s.nInd <= 3) r[j][3] = __longlong_as_double((long long)key[j]);
+            else recKey[pos[j]] = key[j];
+            double2 *q = reinterpret_cast<double2 *>(records + 4LL * pos[j]);
+            q[0] = make_double2(r[j][0], r[j][1]);
+            q[1] = make_double2(r[j][2], r[j][3]);
+            inv[t] = pos[j];
+        }
+    }
+}
+
+// warp-aggregated slot claim: the lanes of a warp that share a cell take consecutive slots with one atomic
+__device__ __forceinline__ int claim_slot(int *cursor, int key, unsigned active)
+{
+    const unsigned peers = __match_any_sync(active, key);
+    const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+    int first = 0;
+    if (lane == leader) first = atomicAdd(cursor + key, __popc(peers));
+    first = __shfl_sync(peers, first, leader);
+    return first + __popc(peers & ((1u << lane) - 1));
+}
+
+// exclusive scan of hist[0..cells) in place, one CTA: 4096 counters per round (coalesced 16-byte loads, warp
+// shuffles, one shared-memory hop between the warps), running total carried from round to round
+__global__ void __launch_bounds__(1024) bin_scan_kernel(int *__restrict__ hist, const int cells)
+{
+    __shared__ int warpSum[32];
+    __shared__ int carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < cells; base += 4096) {
+        const int i = base + 4 * threadIdx.x;
+        int4 c = make_int4(0, 0, 0, 0);
+        if (i + 3 < cells) c = *reinterpret_cast<const int4 *>(hist + i);
+        else {
+            if (i < cells) c.x = hist[i];
+            if (i + 1 < cells) c.y = hist[i + 1];
+            if (i + 2 < cells) c.z = hist[i + 2];
+        }
+        const int mine = c.x + c.y + c.z + c.w;
+        int incl = mine;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) incl += v;
+        }
+        if (lane == 31) warpSum[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const int w = warpSum[lane];
+            int wi = w;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, wi, off);
+                if (lane >= off) wi += v;
+            }
+            warpSum[lane] = wi - w;                       // exclusive prefix of the warp totals
+        }
+        __syncthreads();
+        const int start = carry + warpSum[warp] + incl - mine;
+        const int4 o = make_int4(start, start + c.x, start + c.x + c.y, start + c.x + c.y + c.z);
+        if (i + 3 < cells) *reinterpret_cast<int4 *>(hist + i) = o;
+        else {
+            if (i < cells) hist[i] = o.x;
+            if (i + 1 < cells) hist[i + 1] = o.y;
+            if (i + 2 < cells) hist[i + 2] = o.z;
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = start + mine;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256) bin_scatter_kernel(const int *__restrict__ keys, int *__restrict__ cursor, const int n,
+                                                          int *__restrict__ perm, int *__restrict__ sortedKey)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned active = __ballot_sync(0xffffffffu, t < n);
+    if (t >= n) return;
+    const int key = keys[t];
+    const int pos = claim_slot(cursor, key, active);
+    perm[pos] = t;
+    sortedKey[pos] = key;
+}
+
+// un-permute: a warp takes 32 consecutive points and pulls their 32 result records (each a run of whole sectors
+// somewhere in the sorted array) into shared memory with 16-byte cp.async copies -- lanes run along the records,
+// every sector is requested once, and all of a warp's copies are in flight together -- then every lane reads its
+// own record and the warp writes the struct-of-arrays outputs coalesced (8 warps side by side: 2 KB per plane).
+constexpr int UNPERM_WARPS = 8;
+template <int S_>
+__global__ void __launch_bounds__(UNPERM_WARPS * 32) bin_unpermute_kernel(const double *__restrict__ aos, const int aosStride,
+                                                                          const int *__restrict__ inv, const long long base,
+                                                                          const int n, const int nDep, const int nJ,
+                                                                          const int nNormal, const OutDev out)
+{
+    extern __shared__ __align__(16) double tile[];         // per warp: 32 rows of (stride + 2) doubles
+    const int S = S_ ? S_ : aosStride;
+    const int pitch = S + 2, S2 = S >> 1;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *tw = tile + (long long)warp * 32 * pitch;
+    const int first = (blockIdx.x * UNPERM_WARPS + warp) * 32;
+    if (first >= n) return;
+    const int t = first + lane;
+    const int myRec = t < n ? __ldg(inv + t) : -1;
+    const unsigned twAddr = (unsigned)__cvta_generic_to_shared(tw);
+    const int total = 32 * S2;
+#pragma unroll 8
+    for (int idx = lane; idx < total; idx += 32) {
+        const int r = idx / S2, c = idx - r * S2;
+        const int rec = __shfl_sync(0xffffffffu, myRec, r);
+        if (rec >= 0) {
+            const double *src = aos + (long long)rec * S + 2 * c;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(twAddr + (unsigned)(r * pitch + 2 * c) * 8u), "l"(src) : "memory");
+        }
+    }
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    if (t >= n) return;
+    const long long p = base + t;
+    const double *mine = tw + lane * pitch;
+    if (out.values) {
+        for (int k = 0; k < nDep; ++k) __stcs(out.values + k * out.ld + p, mine[k]);
+    }
+    if (out.jacobian) {
+        for (int k = 0; k < nJ; ++k) __stcs(out.jacobian + k * out.ld + p, mine[nDep + k]);
+    }
+    if (out.normal) {
+        for (int k = 0; k < nNormal; ++k) __stcs(out.normal + k * out.ld + p, mine[nDep + nJ + k]);
+    }
+}
+
+template <int S_>
+static int launch_unpermute(const double *aos, int stride, const int *inv, long long base, int n, int nDep, int nJ, int nN,
+                            const OutDev &out, cudaStream_t st)
+{
+    const size_t smem = sizeof(double) * UNPERM_WARPS * 32 * (stride + 2);
+    if (int rc = allow_dynamic_smem(bin_unpermute_kernel<S_>, smem)) return rc;
+    bin_unpermute_kernel<S_><<<(n + UNPERM_WARPS * 32 - 1) / (UNPERM_WARPS * 32), UNPERM_WARPS * 32, smem, st>>>(
+        aos, stride, inv, base, n, nDep, nJ, nN, out);
+    return 0;
+}
+
+// points per chunk in sorted-record mode (BSPY_BIN_REC_CHUNK_LOG2 overrides for experiments)
+static long long bin_rec_chunk()
+{
+    const long long lg = option(OPT_BIN_REC_CHUNK_LOG2, 22);
+    return 1LL << (lg < 16 ? 16 : (lg > 26 ? 26 : lg));
+}
+#define BIN_REC_CHUNK bin_rec_chunk()
+constexpr long long BIN_CHUNK_MAX = 1 << 20;  // workspace is sized for this many points per chunk
+
+// Points per chunk: the outputs of a chunk are scattered back to their original positions 8 bytes at a time, which
+// is only cheap while the chunk's output region stays in L2 (measured optimum: ~56 MB of outputs per chunk; larger
+// chunks give more points per cell but turn the scatter into DRAM read-modify-writes and are 2x slower).
+static long long bin_chunk(long long outBytesPerPoint)
+{
+    long long v = option(OPT_BIN_CHUNK, (56LL << 20) / (outBytesPerPoint > 0 ? outBytesPerPoint : 8));
+    v = v / 1024 * 1024;
+    if (v < 65536) v = 65536;
+    if (v > BIN_CHUNK_MAX) v = BIN_CHUNK_MAX;
+    return v;
+}
+constexpr long long BIN_MAX_CELLS = 1 << 18;  // histogram / scan size limit
+
+static long long binned_cells(const SplineDev &s)
+{
+    long long cells = 1;
+    for (int i = 0; i < s.nInd; ++i) {
+        cells *= (s.nCoef[i] - s.order[i] + 1);
+        if (cells > BIN_MAX_CELLS) return 0;
+    }
+    return cells;
+}
+
+static int bin_mode(long long N)
+{
+    // 0: scatter results 8 bytes at a time within L2-sized chunks; 1: sorted 32-byte point records, array-of-structs
+    // results and an un-permute pass over 4 Mi-point chunks (every scattered access is a whole sector)
+    return option(OPT_BIN_MODE, N >= (1 << 21) ? 1 : 0) ? 1 : 0;
+}
+
+static int aos_stride(const SplineDev &s)
+{
+    const int D = (s.nInd - s.nDep == 1 || s.nDep - s.nInd == 1) ? (s.nInd > s.nDep ? s.nInd : s.nDep) : 0;
+    return (s.nDep + s.nDep * s.nInd + D + 3) & ~3;
+}
+
+static long long pad64(long long n) { return (n + 63) / 64 * 64; }
+
+static long long span_records_bytes(const SplineDev &s)
+{
+    long long doubles = 0;
+    for (int i = 0; i < s.nInd; ++i) doubles += (long long)(s.nCoef[i] - s.order[i] + 1) * span_rec_stride(s.order[i]);
+    return 8 * pad64(doubles);
+}
+
+// bytes of workspace for the binned path, 0 when binning does not apply to this spline
+long long binned_workspace(const SplineDev &s, long long N)
+{
+    if (s.nInd < 2 || N < 65536) return 0;
+    long long window = s.nDep;
+    for (int i = 0; i < s.nInd; ++i) window *= s.order[i];
+    if (window * 8 < 512) return 0;                         // small windows: the gather is cheap anyway
+    if (s.depStride * s.nDep * 8 < 128 * 1024) return 0;    // the whole spline fits in L1
+    const long long cells = binned_cells(s);
+    if (!cells) return 0;
+    if (!find_fixed(s, 0)) return 0;
+    if (bin_mode(N) == 1 && s.nInd <= 4) {
+        const long long chunk = N < BIN_REC_CHUNK ? N : BIN_REC_CHUNK;
+        return 2 * (4 * (3 * pad64(chunk) + pad64(cells + 1)) + 8 * (4 * pad64(chunk) + (long long)aos_stride(s) * pad64(chunk))) +
+               span_records_bytes(s);
+    }
+    const long long chunk = N < BIN_CHUNK_MAX ? N : BIN_CHUNK_MAX;
+    return 3 * 4 * pad64(chunk) + 4 * pad64(cells + 1);
+}
+
+// Two internal helper streams (+ the events that fork from / join to the caller's stream) for the sorted-record
+// pipeline: the sort / un-permute passes are memory-bound, the evaluation FP64-bound, so chunk c+1 is sorted
+// (high-priority stream) while chunk c is evaluated (low-priority stream).  Capturable in a CUDA graph.
+// Sets are pooled per device behind a mutex: a call owns its set exclusively while it ENQUEUES (event record / wait
+// pairs of two host threads can therefore never interleave) and returns it when it is done enqueueing; work already
+// enqueued keeps the dependencies it captured, so the next owner may reuse streams and events right away.
+struct BinStreams {
+    cudaStream_t sort = nullptr, eval = nullptr;
+    cudaEvent_t fork = nullptr, sorted[2] = {nullptr, nullptr}, evaluated[2] = {nullptr, nullptr}, joinSort = nullptr,
+                joinEval = nullptr;
+    int device = -1;
+    BinStreams *next = nullptr;
+};
+
+static std::mutex g_binStreamsMutex;
+static BinStreams *g_binStreamsFree[64] = {};
+
+static BinStreams *acquire_bin_streams()
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return nullptr;
+    {
+        std::lock_guard<std::mutex> lock(g_binStreamsMutex);
+        if (BinStreams *b = g_binStreamsFree[dev]) {
+            g_binStreamsFree[dev] = b->next;
+            b->next = nullptr;
+            return b;
+        }
+    }
+    BinStreams *b = new BinStreams();
+    b->device = dev;
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);   // lo = lowest priority (numerically largest)
+    bool ok = cudaStreamCreateWithPriority(&b->sort, cudaStreamNonBlocking, hi) == cudaSuccess &&
+              cudaStreamCreateWithPriority(&b->eval, cudaStreamNonBlocking, lo) == cudaSuccess;
+    cudaEvent_t *evs[] = {&b->fork, &b->sorted[0], &b->sorted[1], &b->evaluated[0], &b->evaluated[1], &b->joinSort, &b->joinEval};
+    for (cudaEvent_t *e : evs) ok = ok && cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {   // leave the partially built set to the process; the caller runs without overlap
+        cudaGetLastError();
+        delete b;
+        return nullptr;
+    }
+    return b;
+}
+
+static void release_bin_streams(BinStreams *b)
+{
+    std::lock_guard<std::mutex> lock(g_binStreamsMutex);
+    b->next = g_binStreamsFree[b->device];
+    g_binStreamsFree[b->device] = b;
+}
+
+static long long records_half_bytes(const SplineDev &s, long long chunk)
+{
+    const long long cells = binned_cells(s);
+    return 4 * (3 * pad64(chunk) + pad64(cells + 1)) + 8 * (4 * pad64(chunk) + (long long)aos_stride(s) * pad64(chunk));
+}
+
+static int eval_binned_records(const SplineDev &s, PointsDev in, long long N, const WrtDev &wrt, OutDev out, int jac,
+                               void *workspace, cudaStream_t stream)
+{
+    const long long cells = binned_cells(s);
+    const long long chunk = N < BIN_REC_CHUNK ? N : BIN_REC_CHUNK;
+    const long long cpad = pad64(chunk);
+    const long long half = records_half_bytes(s, chunk);
+    const int D = (s.nInd - s.nDep == 1 || s.nDep - s.nInd == 1) ? (s.nInd > s.nDep ? s.nInd : s.nDep) : 0;
+    const int nJ = jac ? s.nDep * s.nInd : 0;
+    const int nN = (jac && out.normal) ? D : 0;
+    const int stride = (s.nDep + nJ + nN + 3) & ~3;
+    FixedFn fn = find_fixed(s, jac);
+    {
+        const int ndt = (int)option(OPT_DEP_TILE, 14);
+        FixedFn tiled = (ndt > 0 && !out.normal) ? find_fixed_tiled(s, jac, ndt) : nullptr;
+        if (tiled) fn = tiled;
+    }
+    // warp-staged windows where the shape is compiled (no normals there: they need the whole jacobian in one pass)
+    const StagedEntry *staged = nullptr;
+    {
+        const int code = (int)option(OPT_STAGED, 0);
+        if (code >= 0) staged = find_staged(s, jac, code);
+        if (staged) {
+            if (int rc = allow_dynamic_smem(staged->fn, sizeof(double) * 4 * 2 * staged->windowDoubles)) return rc;
+        }
+    }
+    // per-span records (left knots | reciprocal gaps) for every variable: no divisions in the evaluation kernel
+    const double *spanRec[BSPY_MAX_IND] = {};
+    {
+        if (option(OPT_SPAN_RECORDS, 1)) {
+            double *at = (double *)((char *)workspace + 2 * half);
+            for (int i = 0; i < s.nInd; ++i) {
+                const int spans = s.nCoef[i] - s.order[i] + 1, st = span_rec_stride(s.order[i]);
+                span_records_kernel<<<(spans + 127) / 128, 128, 0, stream>>>(s.knots[i], s.order[i], s.nCoef[i], at, st);
+                spanRec[i] = at;
+                at += (long long)spans * st;
+            }
+            count_launch(s.nInd);
+        }
+    }
+    // Sort / un-permute of the neighbouring chunks on a second stream under the evaluation of this one.  Measured: +9 %
+    // on config 4 with the persistent staged kernel (6.40 -> 7.00 Gpts/s; its tail and the memory-bound passes fill
+    // each other's gaps), nothing with the one-tile-per-CTA gather kernel (config 5: 2.47 -> 2.46), and a loss when
+    // the evaluation is launched with fewer CTAs per SM to make room (3 CTAs: 6.6, 2 CTAs: 5.9).  BSPY_BIN_OVERLAP=0/1
+    // overrides.
+    const bool wantOverlap = option(OPT_BIN_OVERLAP, staged != nullptr ? 1 : 0) != 0;
+    BinStreams *bs = wantOverlap ? acquire_bin_streams() : nullptr;
+    struct Release { BinStreams *b; ~Release() { if (b) release_bin_streams(b); } } releaseOnExit{bs};
+    const long long nChunks = (N + chunk - 1) / chunk;
+    const bool overlap = bs != nullptr && nChunks > 1;
+    cudaStream_t sSort = overlap ? bs->sort : stream, sEval = overlap ? bs->eval : stream;
+    if (overlap) {
+        cudaEventRecord(bs->fork, stream);
+        cudaStreamWaitEvent(sSort, bs->fork, 0);
+        cudaStreamWaitEvent(sEval, bs->fork, 0);
+    }
+    struct Buf { int *keys, *inv, *recKey, *hist; double *records, *aos; } buf[2];
+    for (int h = 0; h < 2; ++h) {
+        char *base = (char *)workspace + h * half;
+        buf[h].keys = (int *)base; buf[h].inv = buf[h].keys + cpad; buf[h].recKey = buf[h].inv + cpad;
+        buf[h].hist = buf[h].recKey + cpad;
+        buf[h].records = (double *)(buf[h].hist + pad64(cells + 1));
+        buf[h].aos = buf[h].records + 4 * cpad;
+    }
+    auto sortChunk = [&](long long c) -> int {
+        const Buf &B = buf[c & 1];
+        const long long base = c * chunk;
+        const int n = (int)(N - base < chunk ? N - base : chunk);
+        cudaError_t e = cudaMemsetAsync(B.hist, 0, sizeof(int) * (cells + 1), sSort);
+        if (e != cudaSuccess) { set_error("cudaMemsetAsync: %s", cudaGetErrorString(e)); return (int)e; }
+        OutDev o1{};
+        o1.ld = out.ld; o1.spans = out.spans; o1.firstOutside = out.firstOutside;
+        // four points per thread in flight (measured against one point per thread at full occupancy: keys 106 -> 95 us,
+        // scatter 88 -> 71 us per 4 Mi points)
+        bin_keys_batched_kernel<4><<<(n + 511) / 512, 128, 0, sSort>>>(s, in, base, n, B.keys, B.hist, B.inv, o1);
+        bin_scan_kernel<<<1, 1024, 0, sSort>>>(B.hist, (int)cells);
+        bin_scatter_records_batched_kernel<4><<<(n + 511) / 512, 128, 0, sSort>>>(s, in, base, n, B.keys, B.hist, B.records, B.recKey, B.inv);
+        if (overlap) cudaEventRecord(bs->sorted[c & 1], sSort);
+        count_launch(3);
+        return check_launch("bspy_cuda_eval_points_binned(sort)");
+    };
+    auto evalChunk = [&](long long c) -> int {
+        const Buf &B = buf[c & 1];
+        const long long base = c * chunk;
+        const int n = (int)(N - base < chunk ? N - base : chunk);
+        if (overlap) cudaStreamWaitEvent(sEval, bs->sorted[c & 1], 0);
+        PointsDev pin{};
+        pin.records = B.records; pin.recKey = B.recKey;
+        for (int i = 0; i < s.nInd; ++i) pin.spanRec[i] = spanRec[i];
+        OutDev o2 = out;
+        o2.spans = nullptr; o2.firstOutside = nullptr;
+        o2.aos = B.aos; o2.aosStride = stride;
+        // the staged kernel lives on window reuse: it needs cells that hold a few tiles' worth of points (a sparse
+        // tail chunk makes every tile straddle several cells); below that the L1-gather kernel is the faster one
+        if (staged && n >= 48 * cells) {
+            // persistent warps over contiguous runs of tiles (window reuse between consecutive tiles)
+            long long blocks = (long long)num_sms() * (staged->code % 10);
+            if (blocks > (n + 127) / 128) blocks = (n + 127) / 128;
+            staged->fn<<<(unsigned)blocks, 128, sizeof(double) * 4 * 2 * staged->windowDoubles, sEval>>>(s, pin, n, wrt, o2);
+        }
+        else
+            fn<<<(unsigned)((n + 127) / 128), 128, 0, sEval>>>(s, pin, n, wrt, o2);
+        if (overlap) cudaEventRecord(bs->evaluated[c & 1], sEval);
+        count_launch(1);
+        return check_launch("bspy_cuda_eval_points_binned(eval)");
+    };
+    auto unpermChunk = [&](long long c) -> int {
+        const Buf &B = buf[c & 1];
+        const long long base = c * chunk;
+        const int n = (int)(N - base < chunk ? N - base : chunk);
+        if (overlap) cudaStreamWaitEvent(sSort, bs->evaluated[c & 1], 0);
+        int urc;
+        switch (stride) {
+            case 4: urc = launch_unpermute<4>(B.aos, stride, B.inv, base, n, s.nDep, nJ, nN, out, sSort); break;
+            case 8: urc = launch_unpermute<8>(B.aos, stride, B.inv, base, n, s.nDep, nJ, nN, out, sSort); break;
+            case 12: urc = launch_unpermute<12>(B.aos, stride, B.inv, base, n, s.nDep, nJ, nN, out, sSort); break;
+            case 16: urc = launch_unpermute<16>(B.aos, stride, B.inv, base, n, s.nDep, nJ, nN, out, sSort); break;
+            case 32: urc = launch_unpermute<32>(B.aos, stride, B.inv, base, n, s.nDep, nJ, nN, out, sSort); break;
+            default: urc = launch_unpermute<0>(B.aos, stride, B.inv, base, n, s.nDep, nJ, nN, out, sSort); break;
+        }
+        if (urc) return urc;
+        count_launch(1);
+        return check_launch("bspy_cuda_eval_points_binned(unpermute)");
+    };
+    // software pipeline: sort(c+1) is enqueued before unpermute(c) so that it runs under eval(c)
+    int rc = sortChunk(0);
+    for (long long c = 0; c < nChunks && !rc; ++c) {
+        rc = evalChunk(c);
+        if (!rc && c + 1 < nChunks) rc = sortChunk(c + 1);
+        if (!rc) rc = unpermChunk(c);
+    }
+    if (overlap) {
+        cudaEventRecord(bs->joinSort, sSort);
+        cudaEventRecord(bs->joinEval, sEval);
+        cudaStreamWaitEvent(stream, bs->joinSort, 0);
+        cudaStreamWaitEvent(stream, bs->joinEval, 0);
+    }
+    return rc;
+}
+
+int eval_binned(const SplineDev &s, PointsDev in, long long N, const WrtDev &wrt, OutDev out, int jac, void *workspace,
+                cudaStream_t stream)
+{
+    if (bin_mode(N) == 1 && s.nInd <= 4) return eval_binned_records(s, in, N, wrt, out, jac, workspace, stream);
+    const long long cells = binned_cells(s);
+    const int D = s.nInd > s.nDep ? s.nInd : s.nDep;
+    const long long outBytes = 8LL * ((out.values ? s.nDep : 0) + (out.jacobian ? s.nDep * s.nInd : 0) + (out.normal ? D : 0));
+    const long long cap = N < BIN_CHUNK_MAX ? N : BIN_CHUNK_MAX;      // what the workspace was sized for
+    const long long chunk = bin_chunk(outBytes) < cap ? bin_chunk(outBytes) : cap;
+    const long long cpad = pad64(cap);
+    int *keys = (int *)workspace, *perm = keys + cpad, *skey = perm + cpad, *hist = skey + cpad;
+    FixedFn fn = find_fixed(s, jac);
+    int32_t *spans = out.spans;
+    long long *flag = out.firstOutside;
+    for (long long base = 0; base < N; base += chunk) {
+        const int n = (int)(N - base < chunk ? N - base : chunk);
+        cudaError_t e = cudaMemsetAsync(hist, 0, sizeof(int) * (cells + 1), stream);
+        if (e != cudaSuccess) { set_error("cudaMemsetAsync: %s", cudaGetErrorString(e)); return (int)e; }
+        OutDev o1{};
+        o1.ld = out.ld; o1.spans = spans; o1.firstOutside = flag;
+        bin_keys_kernel<<<(n + 255) / 256, 256, 0, stream>>>(s, in, base, n, keys, hist, nullptr, o1);
+        bin_scan_kernel<<<1, 1024, 0, stream>>>(hist, (int)cells);
+        bin_scatter_kernel<<<(n + 255) / 256, 256, 0, stream>>>(keys, hist, n, perm, skey);
+        PointsDev pin = in;
+        pin.perm = perm; pin.cellKey = skey; pin.base = base;
+        OutDev o2 = out;
+        o2.spans = nullptr; o2.firstOutside = nullptr;
+        long long blocks = (n + 127) / 128;
+        fn<<<(unsigned)blocks, 128, 0, stream>>>(s, pin, n, wrt, o2);
+        count_launch(4);
+        int rc = check_launch("bspy_cuda_eval_points_binned");
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+}  // namespace bspy
+
+using namespace bspy;
+
+extern "C" int64_t bspy_cuda_binned_workspace_bytes(const bspy_spline *spline, int64_t N)
+{
+    SplineDev s;
+    if (make_spline_dev(spline, s, "bspy_cuda_binned_workspace_bytes")) return 0;
+    return binned_workspace(s, N);
+}
+
+extern "C" int bspy_cuda_eval_points_binned(const bspy_spline *spline, const double *uvw, int64_t pointStride, int64_t varStride,
+                                            int64_t N, const int32_t *wrt, uint32_t flags, uint32_t normalMask, double *values,
+                                            double *deriv, double *jacobian, double *normal, int32_t *spans,
+                                            int64_t *firstOutside, void *workspace, int64_t workspaceBytes, void *stream)
+{
+    const char *who = "bspy_cuda_eval_points_binned";
+    SplineDev s;
+    int rc = make_spline_dev(spline, s, who);
+    if (rc) return rc;
+    const long long need = binned_workspace(s, N);
+    const bool onePass = !(deriv && (values || jacobian || normal));
+    if (!need || !workspace || workspaceBytes < need || !onePass || !uvw)
+        return bspy_cuda_eval_points(spline, uvw, pointStride, varStride, N, wrt, flags, normalMask, values, deriv, jacobian,
+                                     normal, spans, firstOutside, stream);
+    if ((deriv != nullptr) != (wrt != nullptr)) { set_error("%s: wrt and deriv must be given together", who); return BSPY_E_ARG; }
+    const int D = s.nInd > s.nDep ? s.nInd : s.nDep;
+    if (normal && (s.nInd - s.nDep != 1 && s.nDep - s.nInd != 1)) {
+        set_error("The number of independent variables must be one different than the number of dependent variables.");
+        return BSPY_E_NORMAL_DIMS;
+    }
+    if (normalMask == 0 || D >= 32) normalMask = 0xffffffffu;
+    PointsDev in{};
+    in.uvw = uvw; in.pointStride = pointStride; in.varStride = varStride;
+    OutDev out{};
+    out.ld = N;
+    out.firstOutside = (long long *)firstOutside;
+    out.spans = spans;
+    out.normalize = (flags & BSPY_NORMALIZE) ? 1u : 0u;
+    out.normalMask = normalMask;
+    WrtDev w{};
+    int jac = 0;
+    if (jacobian || normal) {
+        jac = 1;
+        out.values = values; out.jacobian = jacobian; out.normal = normal;
+    } else if (deriv) {
+        for (int i = 0; i < s.nInd; ++i) {
+            if (wrt[i] < 0) { set_error("%s: negative derivative order", who); return BSPY_E_ARG; }
+            w.d[i] = wrt[i];
+        }
+        out.values = deriv;
+    } else {
+        out.values = values;
+    }
+    return eval_binned(s, in, N, w, out, jac, workspace, (cudaStream_t)stream);
+}

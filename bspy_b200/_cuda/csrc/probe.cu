@@ -32,6 +32,35 @@ __global__ void __launch_bounds__(256) probe_dmma_kernel(int iters, double *sink
     if (r == 123.456) sink[0] = r;
 }
 
+// Are DFMA and DMMA one pipe or two?  kind 2: every warp interleaves 4 DMMA with 32 DFMA per iteration (equal pipe time if one pipe); kind 3: even
+// warps run the DMMA loop, odd warps the DFMA loop.  If the sum of the two rates exceeds either alone, the pipes overlap.
+__global__ void __launch_bounds__(256) probe_mixed_kernel(int iters, double *sink, int split)
+{
+    double c[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+    const double a = 1.0 + threadIdx.x * 1e-6, b = 1.0 - threadIdx.x * 1e-6;
+    double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 1.0000001, cc = 1e-9;
+    const bool doMma = !split || ((threadIdx.x >> 5) & 1) == 0, doFma = !split || ((threadIdx.x >> 5) & 1) == 1;
+    for (int i = 0; i < iters; ++i) {
+        if (doMma) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                             : "+d"(c[k][0]), "+d"(c[k][1])
+                             : "d"(a), "d"(b));
+        }
+        if (doFma) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                a0 = fma(a0, m, cc); a1 = fma(a1, m, cc); a2 = fma(a2, m, cc); a3 = fma(a3, m, cc);
+                a4 = fma(a4, m, cc); a5 = fma(a5, m, cc); a6 = fma(a6, m, cc); a7 = fma(a7, m, cc);
+            }
+        }
+    }
+    const double r = c[0][0] + c[1][1] + c[2][0] + c[3][1] + a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (r == 123.456) sink[0] = r;
+}
+
 __global__ void __launch_bounds__(256) probe_copy_kernel(const double2 *__restrict__ src, double2 *__restrict__ dst, long long n2)
 {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x)
@@ -104,9 +133,15 @@ extern "C" int bspy_cuda_probe_fp64(int32_t kind, int32_t iters, double *sink, d
     if (kind == 0) {
         probe_dfma_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(iters, sink);
         if (flopsOut_host) *flopsOut_host = (double)blocks * threads * (double)iters * 8.0 * 2.0;
-    } else {
+    } else if (kind == 1) {
         probe_dmma_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(iters, sink);
         if (flopsOut_host) *flopsOut_host = (double)blocks * (threads / 32) * (double)iters * 4.0 * 512.0;
+    } else {
+        // kind 2: DMMA and DFMA interleaved in every warp; kind 3: alternate warps
+        probe_mixed_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(iters, sink, kind == 3);
+        const double warps = (double)blocks * (threads / 32);
+        const double perWarp = 4.0 * 512.0 + 32.0 * 32.0 * 2.0;
+        if (flopsOut_host) *flopsOut_host = (kind == 3 ? 0.5 : 1.0) * warps * (double)iters * perWarp;
     }
     count_launch();
     return check_launch("bspy_cuda_probe_fp64");

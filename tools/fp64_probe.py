@@ -5,7 +5,7 @@ import torch
 from bspy_b200 import _cuda
 
 dev = torch.device("cuda:0")
-for kind, name in ((0, "dfma"), (1, "dmma")):
+for kind, name in ((0, "dfma"), (1, "dmma"), (2, "dmma+dfma interleaved per warp"), (3, "dmma / dfma on alternate warps")):
     _cuda.probe_fp64(kind, 2000, dev)
     torch.cuda.synchronize()
     best = 0.0
