@@ -22,15 +22,17 @@ MANY_MAX_ORDER = 8     # bspy_cuda_eval_many (warp per curve)
 E_ARG, E_UNSUPPORTED, E_NORMAL_DIMS = -1, -2, -3
 NORMALIZE = 1
 OUT_F32 = 2
+WANT_JACOBIAN = 4
+WANT_NORMAL = 8
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BSPY_CUDA_LIB") or os.path.join(HERE, "libbspy_cuda.so")   # override: kernel A/B experiments only
 
 # every symbol include/bspy_cuda.h declares (tests check the library exports exactly these)
 SYMBOLS = (
-    "bspy_cuda_abi_version", "bspy_cuda_last_error_string", "bspy_cuda_launch_count", "bspy_cuda_set_option",
+    "bspy_cuda_abi_version", "bspy_cuda_last_error_string", "bspy_cuda_launch_count", "bspy_cuda_set_option", "bspy_cuda_copy_2d",
     "bspy_cuda_spans", "bspy_cuda_basis", "bspy_cuda_eval_points", "bspy_cuda_eval_points_binned",
-    "bspy_cuda_binned_workspace_bytes", "bspy_cuda_eval_grid",
+    "bspy_cuda_binned_workspace_bytes", "bspy_cuda_eval_points_aos", "bspy_cuda_aos_workspace_bytes", "bspy_cuda_eval_grid",
     "bspy_cuda_eval_grid_batch", "bspy_cuda_eval_many", "bspy_cuda_probe_fp64", "bspy_cuda_probe_hbm",
     "bspy_cuda_probe_tiles", "bspy_cuda_curvature", "bspy_cuda_contract_axis", "bspy_cuda_block_accumulate",
     "bspy_cuda_normal_from_jacobian", "bspy_cuda_collocation",
@@ -81,10 +83,12 @@ def library():
         vp, i32, i64, u32 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint32
         sig = {
             "bspy_cuda_set_option": [C.c_char_p, i64, i32],
+            "bspy_cuda_copy_2d": [vp, i64, vp, i64, i64, i64, vp],
             "bspy_cuda_spans": [vp, i32, i32, vp, i64, vp, vp],
             "bspy_cuda_basis": [vp, i32, i32, vp, vp, i64, i32, i32, vp, vp, vp],
             "bspy_cuda_eval_points": [C.POINTER(CSpline), vp, i64, i64, i64, C.POINTER(i32), u32, u32, vp, vp, vp, vp, vp, vp, vp],
             "bspy_cuda_eval_points_binned": [C.POINTER(CSpline), vp, i64, i64, i64, C.POINTER(i32), u32, u32, vp, vp, vp, vp, vp, vp, vp, i64, vp],
+            "bspy_cuda_eval_points_aos": [C.POINTER(CSpline), vp, i64, i64, i64, u32, u32, vp, i64, vp, vp, vp, i64, vp],
             "bspy_cuda_eval_grid": [C.POINTER(CSpline), C.POINTER(vp), C.POINTER(i64), u32, u32, vp, vp, vp, vp, vp],
             "bspy_cuda_eval_grid_batch": [C.POINTER(CSpline), i64, C.POINTER(i64), i64, C.POINTER(vp), C.POINTER(i64), u32, u32, vp, vp, vp, vp, vp],
             "bspy_cuda_eval_many": [i32, i32, i32, i64, vp, i64, vp, i64, vp, i32, vp, vp, vp, vp],
@@ -103,6 +107,8 @@ def library():
             fn.restype = C.c_int
         lib.bspy_cuda_binned_workspace_bytes.argtypes = [C.POINTER(CSpline), i64]
         lib.bspy_cuda_binned_workspace_bytes.restype = C.c_int64
+        lib.bspy_cuda_aos_workspace_bytes.argtypes = [C.POINTER(CSpline), i64]
+        lib.bspy_cuda_aos_workspace_bytes.restype = C.c_int64
         if lib.bspy_cuda_abi_version() != 1:
             raise CudaPathError("libbspy_cuda.so ABI version mismatch; rebuild with python -m bspy_b200._cuda.build --force")
         _lib = lib
@@ -251,6 +257,35 @@ def eval_points(ds: DeviceSpline, uvw, point_stride, var_stride, N, *, wrt=None,
                                            _ptr(out["spans"]), _ptr(flag), _stream(dev))
     _check(rc, "bspy_cuda_eval_points")
     return out
+
+
+def record_layout(ds: DeviceSpline, jacobian, normal):
+    """(length, stride) in doubles of an array-of-structs record [values | jacobian | normal]; the stride is the length
+    rounded up to whole 32-byte sectors."""
+    length = ds.nDep + (ds.nDep * ds.nInd if (jacobian or normal) else 0) + (ds.normal_dim if normal else 0)
+    return length, (length + 3) // 4 * 4
+
+
+def eval_points_aos(ds: DeviceSpline, uvw, point_stride, var_stride, N, *, jacobian=False, normal=False, normalize=True,
+                    normal_mask=0, spans=False, flag=None, records=None):
+    """Launch bspy_cuda_eval_points_aos: one record [values | jacobian (d, i) | normal] per point, ``records`` is
+    (N, stride) float64 on the device (allocated here unless given).  Returns (records, spans or None)."""
+    dev = ds.device
+    length, stride = record_layout(ds, jacobian, normal)
+    if records is None:
+        records = torch.empty((N, stride), dtype=torch.float64, device=dev)
+    assert records.dtype == torch.float64 and records.device == dev and records.stride(1) == 1 and records.shape[0] >= N
+    sp = torch.empty((ds.nInd, N), dtype=torch.int32, device=dev) if spans else None
+    flags = (NORMALIZE if normalize else 0) | (WANT_JACOBIAN if (jacobian or normal) else 0) | (WANT_NORMAL if normal else 0)
+    lib = library()
+    ws_bytes = int(lib.bspy_cuda_aos_workspace_bytes(C.byref(ds.c), int(N)))
+    with torch.cuda.device(dev):
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes > 0 else None
+        rc = lib.bspy_cuda_eval_points_aos(C.byref(ds.c), _ptr(uvw), int(point_stride), int(var_stride), int(N), flags,
+                                           int(normal_mask), _ptr(records), int(records.stride(0)), _ptr(sp), _ptr(flag),
+                                           _ptr(ws), ws_bytes, _stream(dev))
+    _check(rc, "bspy_cuda_eval_points_aos")
+    return records, sp
 
 
 def eval_grid(ds: DeviceSpline, axes, *, values=True, jacobian=False, normal=False, normalize=True, normal_mask=0,
@@ -426,9 +461,20 @@ HOST_CHUNK = 1 << 22      # points per chunk
 _RING = 3
 
 
-def eval_points_host(ds: DeviceSpline, host, layout, *, check=True, chunk=None, **request):
+def copy_rows(dst, src, stream):
+    """dst[r, :] <- src[r, :] for 2-D views with unit inner stride (device <-> pinned host), ONE cudaMemcpy2DAsync."""
+    assert dst.dim() == 2 and src.dim() == 2 and dst.shape == src.shape and dst.stride(1) == 1 and src.stride(1) == 1
+    es = dst.element_size()
+    rc = library().bspy_cuda_copy_2d(C.c_void_p(dst.data_ptr()), int(dst.stride(0)) * es, C.c_void_p(src.data_ptr()),
+                                     int(src.stride(0)) * es, int(dst.shape[1]) * es, int(dst.shape[0]),
+                                     C.c_void_p(stream.cuda_stream))
+    _check(rc, "bspy_cuda_copy_2d")
+
+
+def eval_points_host(ds: DeviceSpline, host, layout, *, check=True, chunk=None, aos=False, **request):
     """``host``: CPU float64 tensor, (N, nInd) for layout "points" or (nInd, N) for "variables".
-    Returns (dict of pinned CPU tensors in SoA layout, index of the first out-of-domain point or -1)."""
+    Returns (dict of pinned CPU tensors in SoA layout -- or {"records": (N, stride)} with ``aos`` --, index of the first
+    out-of-domain point or -1).  Per chunk: one H2D copy, the kernels, one D2H copy per output array."""
     dev = ds.device
     chunk = int(chunk or HOST_CHUNK)
     N = host.shape[0] if layout == "points" else host.shape[1]
@@ -437,13 +483,17 @@ def eval_points_host(ds: DeviceSpline, host, layout, *, check=True, chunk=None, 
     def pinned(shape, dtype=torch.float64):
         return torch.empty(shape, dtype=dtype, pin_memory=True)
 
-    res = {
-        "values": pinned((ds.nDep, N)) if request.get("values") else None,
-        "derivative": pinned((ds.nDep, N)) if request.get("wrt") is not None else None,
-        "jacobian": pinned((ds.nDep, ds.nInd, N)) if request.get("jacobian") else None,
-        "normal": pinned((D, N)) if request.get("normal") else None,
-        "spans": pinned((ds.nInd, N), torch.int32) if request.get("spans") else None,
-    }
+    if aos:
+        _, rstride = record_layout(ds, request.get("jacobian"), request.get("normal"))
+        res = {"records": pinned((N, rstride)), "spans": pinned((ds.nInd, N), torch.int32) if request.get("spans") else None}
+    else:
+        res = {
+            "values": pinned((ds.nDep, N)) if request.get("values") else None,
+            "derivative": pinned((ds.nDep, N)) if request.get("wrt") is not None else None,
+            "jacobian": pinned((ds.nDep, ds.nInd, N)) if request.get("jacobian") else None,
+            "normal": pinned((D, N)) if request.get("normal") else None,
+            "spans": pinned((ds.nInd, N), torch.int32) if request.get("spans") else None,
+        }
     starts = list(range(0, N, chunk))
     flags = torch.full((max(len(starts), 1),), -1, dtype=torch.int64, device=dev) if check else None
     streams = [torch.cuda.Stream(dev) for _ in range(min(_RING, max(1, len(starts))))]
@@ -459,16 +509,21 @@ def eval_points_host(ds: DeviceSpline, host, layout, *, check=True, chunk=None, 
                 ps, vs = ds.nInd, 1
             else:
                 d_pts = torch.empty((ds.nInd, n), dtype=torch.float64, device=dev)
-                for i in range(ds.nInd):
-                    d_pts[i].copy_(host[i, start:start + n], non_blocking=True)
+                copy_rows(d_pts, host[:, start:start + n], st)
                 ps, vs = 1, n
-            out = eval_points(ds, d_pts, ps, vs, n, flag=None if flags is None else flags[c:c + 1], **request)
+            fl = None if flags is None else flags[c:c + 1]
+            if aos:
+                rec, sp = eval_points_aos(ds, d_pts, ps, vs, n, jacobian=bool(request.get("jacobian")), normal=bool(request.get("normal")),
+                                          normalize=request.get("normalize", True), normal_mask=request.get("normal_mask", 0),
+                                          spans=bool(request.get("spans")), flag=fl)
+                res["records"][start:start + n].copy_(rec, non_blocking=True)
+                out = {"spans": sp}
+            else:
+                out = eval_points(ds, d_pts, ps, vs, n, flag=fl, **request)
             for key, full in res.items():
-                if full is None:
+                if full is None or key == "records":
                     continue
-                dst, src = full.reshape(-1, N), out[key].reshape(-1, n)
-                for r in range(dst.shape[0]):
-                    dst[r, start:start + n].copy_(src[r], non_blocking=True)
+                copy_rows(full.reshape(-1, N)[:, start:start + n], out[key].reshape(-1, n), st)
     for st in streams:
         st.synchronize()
     first = -1

@@ -158,7 +158,8 @@ template <int P>
 __global__ void __launch_bounds__(128) bin_scatter_records_batched_kernel(const SplineDev s, const PointsDev in, const long long base,
                                                                           const int n, const int *__restrict__ keys,
                                                                           const int *__restrict__ offset, double *__restrict__ records,
-                                                                          int *__restrict__ recKey, int *__restrict__ inv)
+                                                                          int2 *__restrict__ recKI, int *__restrict__ inv,
+                                                                          const int writeInv)
 {
     const int t0 = blockIdx.x * (blockDim.x * P) + threadIdx.x;
     int key[P], pos[P];
@@ -178,12 +179,13 @@ __global__ void __launch_bounds__(128) bin_scatter_records_batched_kernel(const 
     for (int j = 0; j < P; ++j) {
         const int t = t0 + j * blockDim.x;
         if (t < n) {
-            if (s.nInd <= 3) r[j][3] = __longlong_as_double((long long)key[j]);
-            else recKey[pos[j]] = key[j];
+            // cell key in the low, index inside the chunk in the high 32 bits
+            if (s.nInd <= 3) r[j][3] = __longlong_as_double(((long long)t << 32) | (unsigned)key[j]);
+            else recKI[pos[j]] = make_int2(key[j], t);
             double2 *q = reinterpret_cast<double2 *>(records + 4LL * pos[j]);
             q[0] = make_double2(r[j][0], r[j][1]);
             q[1] = make_double2(r[j][2], r[j][3]);
-            inv[t] = pos[j];
+            if (writeInv) inv[t] = pos[j];   // inverse permutation for the un-permute pass (rank before, position after)
         }
     }
 }
@@ -375,25 +377,34 @@ static long long span_records_bytes(const SplineDev &s)
     return 8 * pad64(doubles);
 }
 
-// bytes of workspace for the binned path, 0 when binning does not apply to this spline
-long long binned_workspace(const SplineDev &s, long long N)
+// bytes of workspace for the binned path, 0 when binning does not apply to this spline; aosOut: results go to
+// caller-visible records (always the sorted-record pipeline, no private result records)
+static long long records_half_bytes(const SplineDev &s, long long chunk, bool ownAos);
+
+static bool binning_applies(const SplineDev &s, long long N)
 {
-    if (s.nInd < 2 || N < 65536) return 0;
+    if (s.nInd < 2 || s.nInd > 4 || N < 65536) return false;
     long long window = s.nDep;
     for (int i = 0; i < s.nInd; ++i) window *= s.order[i];
-    if (window * 8 < 512) return 0;                         // small windows: the gather is cheap anyway
-    if (s.depStride * s.nDep * 8 < 128 * 1024) return 0;    // the whole spline fits in L1
+    if (window * 8 < 512) return false;                         // small windows: the gather is cheap anyway
+    if (s.depStride * s.nDep * 8 < 128 * 1024) return false;    // the whole spline fits in L1
+    if (!binned_cells(s)) return false;
+    return find_fixed(s, 0) != nullptr;
+}
+
+long long binned_workspace(const SplineDev &s, long long N, bool aosOut)
+{
+    if (!binning_applies(s, N)) return 0;
     const long long cells = binned_cells(s);
-    if (!cells) return 0;
-    if (!find_fixed(s, 0)) return 0;
-    if (bin_mode(N) == 1 && s.nInd <= 4) {
+    if (aosOut || bin_mode(N) == 1) {
         const long long chunk = N < BIN_REC_CHUNK ? N : BIN_REC_CHUNK;
-        return 2 * (4 * (3 * pad64(chunk) + pad64(cells + 1)) + 8 * (4 * pad64(chunk) + (long long)aos_stride(s) * pad64(chunk))) +
-               span_records_bytes(s);
+        return 2 * records_half_bytes(s, chunk, !aosOut) + span_records_bytes(s);
     }
     const long long chunk = N < BIN_CHUNK_MAX ? N : BIN_CHUNK_MAX;
     return 3 * 4 * pad64(chunk) + 4 * pad64(cells + 1);
 }
+
+long long binned_workspace(const SplineDev &s, long long N) { return binned_workspace(s, N, false); }
 
 // Two internal helper streams (+ the events that fork from / join to the caller's stream) for the sorted-record
 // pipeline: the sort / un-permute passes are memory-bound, the evaluation FP64-bound, so chunk c+1 is sorted
@@ -448,37 +459,342 @@ static void release_bin_streams(BinStreams *b)
     g_binStreamsFree[b->device] = b;
 }
 
-static long long records_half_bytes(const SplineDev &s, long long chunk)
+// ---- cell evaluation with the first contraction stage on the FP64 tensor pipe ---------------------------------------
+// In cell order the points of an 8-row group share their coefficient window, so the contraction of the LAST variable
+// (contiguous in the spline, order OL <= 4 = K of DMMA.8x8x4) is a small dense product per dependent variable d:
+//     T[p][q] = sum_k Bw[p][k] * C[d][q][k],   Tw[p][q] = sum_k dBw[p][k] * C[d][q][k]
+// with p = 8 points (rows of A), q = the prod(outer orders) window positions of the other variables (columns, 8 per
+// tile) -- (cubic volume: 2 tiles x 2 kinds per group and dependent variable).  The D fragments go to a per-warp tile
+// in shared memory, T[point][kind][q], and every lane then finishes ITS point with the register-resident
+// sum-factorised contraction over the outer variables (ContractT, same recursion as Contract<>): value, derivatives with
+// respect to the outer variables from T, derivative with respect to the last variable from Tw.
+//   * warps are persistent and walk contiguous runs of sorted 32-point tiles; the window image of a cell ([d][q][k], k
+//     padded to 4) is staged once per cell with cp.async into one of two slots per warp; a tile that straddles cells
+//     runs the MMAs of the straddling group once per cell with the other rows' A operand zeroed;
+//   * B fragments are one conflict-free LDS.64 per tile (lane l reads element 32 t + l of the image);
+//   * ~450 warp instructions per tile instead of ~1060 for the all-DFMA staged kernel, the same FP64-pipe work.
+// Summation order differs from Contract<> in the last variable only (the MMA's k order): results agree with the
+// other kernels to rounding, not bit for bit.
+template <class Ord, int NDEP>
+struct CellShape {
+    static constexpr int n = Ord::n;
+    static constexpr int OL = Ord::at(n - 1);
+    __host__ __device__ static constexpr int qstride(int iv)          // stride of outer variable iv in q (iv < n-1)
+    {
+        int st = 1;
+        for (int m = n - 2; m > iv; --m) st *= Ord::at(m);
+        return st;
+    }
+    static constexpr int Q = n > 1 ? qstride(0) * Ord::at(0) : 1;     // window positions of the outer variables
+    static constexpr int NT = (Q + 7) / 8;                            // MMA column tiles per dependent variable
+    static constexpr int QP = NT * 8;
+    static constexpr int winDoubles = NDEP * QP * 4;                  // image [d][QP][4]
+    static constexpr int TS = 2 * QP + 2;                             // T row [kind][QP] + 2: odd number of 16-byte units
+    static constexpr int ES = 12;                                     // A-operand exchange row: Bw[4] | dBw[4] | pad
+    static constexpr int perWarp = 2 * winDoubles + 32 * TS + 32 * ES;
+    static_assert(OL <= 4, "the last variable's order is the K of DMMA.8x8x4");
+};
+
+template <class Ord, int NDEP>
+__device__ __forceinline__ void stage_window_k4(const SplineDev &s, int key, double *dst, const int lane)
+{
+    using CS = CellShape<Ord, NDEP>;
+    long long base = 0;
+#pragma unroll
+    for (int iv = Ord::n - 1; iv >= 0; --iv) {
+        const int m = s.nCoef[iv] - Ord::at(iv) + 1;
+        base += (long long)(key % m) * s.stride[iv];
+        key /= m;
+    }
+    const unsigned dstAddr = (unsigned)__cvta_generic_to_shared(dst);
+    constexpr int perDep = CS::Q * CS::OL, total = perDep * NDEP;
+#pragma unroll
+    for (int e0 = 0; e0 < total; e0 += 32) {
+        const int e = e0 + lane;
+        if (total % 32 == 0 || e < total) {
+            const int d = e / perDep;
+            const int rem = e - d * perDep;
+            const int q = rem / CS::OL, k = rem - q * CS::OL;
+            long long src = base + (long long)d * s.depStride + k;
+#pragma unroll
+            for (int iv = 0; iv < Ord::n - 1; ++iv) src += (long long)((q / CS::qstride(iv)) % Ord::at(iv)) * s.stride[iv];
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dstAddr + (unsigned)((d * CS::QP + q) * 4 + k) * 8u), "l"(s.coefs + src) : "memory");
+        }
+    }
+}
+
+// Contract the outer variables L .. n-2 of one dependent variable's T row (Tv: value kind, Tw: last-variable-derivative
+// kind) starting at window position off: v value, gw derivative w.r.t. the last variable, g[m] w.r.t. outer variable m.
+template <int L, class Ord>
+struct ContractT {
+    static constexpr int n = Ord::n;
+    __device__ __forceinline__ static void run(const double *__restrict__ Tv, const double *__restrict__ Tw, const int off,
+                                               const FixedCtx<Ord, 1, true> &c, double &v, double &gw, double (&g)[n])
+    {
+        constexpr int O = Ord::at(L);
+        v = 0.0;
+        gw = 0.0;
+#pragma unroll
+        for (int m = L; m < n - 1; ++m) g[m] = 0.0;
+        if constexpr (L == n - 2) {
+            double x[O], y[O];
+            load_run<O>(Tv, off, x);
+            load_run<O>(Tw, off, y);
+#pragma unroll
+            for (int i = 0; i < O; ++i) {
+                v = fma(x[i], c.B[L][i], v);
+                g[L] = fma(x[i], c.dB[L][i], g[L]);
+                gw = fma(y[i], c.B[L][i], gw);
+            }
+        } else {
+            using CS = CellShape<Ord, 1>;
+#pragma unroll
+            for (int i = 0; i < O; ++i) {
+                double cv, cgw, cg[n];
+                ContractT<L + 1, Ord>::run(Tv, Tw, off + i * CS::qstride(L), c, cv, cgw, cg);
+                v = fma(cv, c.B[L][i], v);
+                g[L] = fma(cv, c.dB[L][i], g[L]);
+                gw = fma(cgw, c.B[L][i], gw);
+#pragma unroll
+                for (int m = L + 1; m < n - 1; ++m) g[m] = fma(cg[m], c.B[L][i], g[m]);
+            }
+        }
+    }
+};
+
+__device__ __forceinline__ void dmma_8x8x4(double &d0, double &d1, const double a, const double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};"
+                 : "=d"(d0), "=d"(d1)
+                 : "d"(a), "d"(b), "d"(0.0), "d"(0.0));
+}
+
+constexpr int CELL_WARPS = 2;   // warps per CTA (small CTAs: the per-warp shared-memory slice decides the occupancy)
+
+template <int NIND, int O0, int O1, int O2, int O3, int NDEP, int MINB>
+__global__ void __launch_bounds__(CELL_WARPS * 32, MINB) eval_cell_mma_kernel(const SplineDev s, const PointsDev in, const long long N,
+                                                                               const WrtDev wrt, const OutDev out)
+{
+    using Ord = Orders<NIND, O0, O1, O2, O3>;
+    using CS = CellShape<Ord, NDEP>;
+    static_assert(NIND >= 2, "curves have no outer variables");
+    extern __shared__ __align__(16) double cellSmem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, row = lane >> 2, c2 = lane & 3;
+    double *win = cellSmem + warp * CS::perWarp;                      // two window slots
+    double *T = win + 2 * CS::winDoubles;
+    double *exch = T + 32 * CS::TS;
+    for (int i = lane; i < 2 * CS::winDoubles; i += 32) win[i] = 0.0;  // K / column padding stays zero for good
+    __syncwarp();
+    int slotKey0 = -1, slotKey1 = -1;
+    const long long tiles = (N + 31) >> 5, nWarps = gridDim.x * (long long)CELL_WARPS;
+    const long long per = (tiles + nWarps - 1) / nWarps;
+    const long long firstTile = (blockIdx.x * (long long)CELL_WARPS + warp) * per;
+    const long long endTile = firstTile + per < tiles ? firstTile + per : tiles;
+    double2 r0 = make_double2(0.0, 0.0), r1 = r0;
+    long long k4 = -1;
+    auto fetch = [&](long long tile) {
+        const long long t = tile * 32 + lane;
+        if (tile < endTile && t < N) {
+            const double2 *rp = reinterpret_cast<const double2 *>(in.records + 4 * t);
+            r0 = __ldcs(rp);
+            r1 = __ldcs(rp + 1);
+            if constexpr (NIND > 3) k4 = __ldcs(reinterpret_cast<const long long *>(in.recKI) + t);
+        }
+    };
+    fetch(firstTile);
+    for (long long tile = firstTile; tile < endTile; ++tile) {
+        const long long t = tile * 32 + lane;
+        const bool live = t < N;
+        FixedCtx<Ord, 1, true> c;
+        int ix[NIND];
+        double u[NIND];
+        u[0] = r0.x;
+        if constexpr (NIND > 1) u[1] = r0.y;
+        if constexpr (NIND > 2) u[2] = r1.x;
+        if constexpr (NIND > 3) u[3] = r1.y;
+        const long long ki = NIND > 3 ? k4 : __double_as_longlong(r1.y);
+        const int key = live ? (int)ki : -1;
+        const long long dest = out.aosScatter ? out.aosBase + (ki >> 32) : t;
+        fetch(tile + 1);                                            // next tile's records arrive under this tile's arithmetic
+        {
+            int k = key < 0 ? 0 : key;
+#pragma unroll
+            for (int iv = NIND - 1; iv >= 0; --iv) {
+                const int m = s.nCoef[iv] - Ord::at(iv) + 1;
+                ix[iv] = Ord::at(iv) + k % m;
+                k /= m;
+            }
+        }
+        bool outside = false;
+        setup_variable<0, Ord, 1, true>(s, u[0], 0, c, ix, outside, true, in.spanRec[0]);
+        if constexpr (NIND > 1) setup_variable<1, Ord, 1, true>(s, u[1], 0, c, ix, outside, true, in.spanRec[1]);
+        if constexpr (NIND > 2) setup_variable<2, Ord, 1, true>(s, u[2], 0, c, ix, outside, true, in.spanRec[2]);
+        if constexpr (NIND > 3) setup_variable<3, Ord, 1, true>(s, u[3], 0, c, ix, outside, true, in.spanRec[3]);
+        __syncwarp();                                               // the previous tile is done with exch / T
+        {
+            // A operand of this lane's point: basis values and first derivatives of the last variable, K padded to 4
+            double2 *e = reinterpret_cast<double2 *>(exch + lane * CS::ES);
+            double a[8];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                a[k] = (k < CS::OL && live) ? c.B[NIND - 1][k < CS::OL ? k : 0] : 0.0;
+                a[4 + k] = (k < CS::OL && live) ? c.dB[NIND - 1][k < CS::OL ? k : 0] : 0.0;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) e[k] = make_double2(a[2 * k], a[2 * k + 1]);
+        }
+        double v[NDEP];
+        double g[NIND][NDEP];
+        bool done = !live;
+        while (true) {
+            const unsigned pending = __ballot_sync(0xffffffffu, !done);
+            if (!pending) break;
+            // up to two distinct cells per round, each in the slot that already holds it or freshly staged
+            const int k0 = __shfl_sync(0xffffffffu, key, __ffs(pending) - 1);
+            const bool in0 = !done && key == k0;
+            const unsigned rest = __ballot_sync(0xffffffffu, !done && !in0);
+            const int k1 = rest ? __shfl_sync(0xffffffffu, key, __ffs(rest) - 1) : -1;
+            const bool in1 = !done && !in0 && key == k1;
+            int s0, s1 = -1;
+            bool staged = false;
+            if (k0 == slotKey0) s0 = 0;
+            else if (k0 == slotKey1) s0 = 1;
+            else {
+                s0 = (k1 >= 0 && k1 == slotKey0) ? 1 : 0;
+                stage_window_k4<Ord, NDEP>(s, k0, win + s0 * CS::winDoubles, lane);
+                if (s0) slotKey1 = k0; else slotKey0 = k0;
+                staged = true;
+            }
+            if (k1 >= 0) {
+                s1 = 1 - s0;
+                if ((s1 ? slotKey1 : slotKey0) != k1) {
+                    stage_window_k4<Ord, NDEP>(s, k1, win + s1 * CS::winDoubles, lane);
+                    if (s1) slotKey1 = k1; else slotKey0 = k1;
+                    staged = true;
+                }
+            }
+            if (staged) asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+            __syncwarp();                                            // windows and the A exchange are visible
+            const unsigned m0 = __ballot_sync(0xffffffffu, in0), m1 = __ballot_sync(0xffffffffu, in1);
+            const bool member = in0 || in1;
+#pragma unroll
+            for (int d = 0; d < NDEP; ++d) {
+                // stage 1: DMMA per cell of the round, group of 8 rows and column tile
+#pragma unroll
+                for (int cc = 0; cc < 2; ++cc) {
+                    const unsigned mask = cc ? m1 : m0;
+                    if (!mask) continue;
+                    const double *w = win + (cc ? s1 : s0) * CS::winDoubles + d * CS::QP * 4;
+                    double bf[CS::NT];
+#pragma unroll
+                    for (int tt = 0; tt < CS::NT; ++tt) bf[tt] = w[32 * tt + lane];
+#pragma unroll
+                    for (int gq = 0; gq < 4; ++gq) {
+                        const unsigned gm = (mask >> (8 * gq)) & 0xffu;
+                        if (!gm) continue;
+                        const bool rowIn = (gm >> row) & 1u;
+                        const double *e = exch + (8 * gq + row) * CS::ES;
+                        const double av = rowIn ? e[c2] : 0.0, ad = rowIn ? e[4 + c2] : 0.0;
+                        double *trow = T + (8 * gq + row) * CS::TS + 2 * c2;
+#pragma unroll
+                        for (int tt = 0; tt < CS::NT; ++tt) {
+                            double x0, x1, y0, y1;
+                            dmma_8x8x4(x0, x1, av, bf[tt]);
+                            dmma_8x8x4(y0, y1, ad, bf[tt]);
+                            if (rowIn) {
+                                *reinterpret_cast<double2 *>(trow + 8 * tt) = make_double2(x0, x1);
+                                *reinterpret_cast<double2 *>(trow + CS::QP + 8 * tt) = make_double2(y0, y1);
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+                // stage 2: this lane's point, outer variables
+                if (member) {
+                    double vd, gw, gd[NIND];
+                    ContractT<0, Ord>::run(T + lane * CS::TS, T + lane * CS::TS + CS::QP, 0, c, vd, gw, gd);
+                    v[d] = vd;
+                    g[NIND - 1][d] = gw;
+#pragma unroll
+                    for (int m = 0; m < NIND - 1; ++m) g[m][d] = gd[m];
+                }
+                __syncwarp();                                        // T is rewritten by the next dependent variable
+            }
+            if (member) {
+                store_result_record<NIND, NDEP, true>(s, out, out.aos + dest * out.aosStride, v, g);
+                done = true;
+            }
+        }
+    }
+}
+
+struct CellEntry {
+    int nInd, o[4], nDep;
+    FixedFn fn;
+    int warpDoubles, minBlocks;
+};
+#define BSPY_CELL(NI, A, B, C, D_, ND, MB)                                                     \
+    {NI, {A, B, C, D_}, ND, eval_cell_mma_kernel<NI, A, B, C, D_, ND, MB>, CellShape<Orders<NI, A, B, C, D_>, ND>::perWarp, MB}
+static const CellEntry kCell[] = {
+    BSPY_CELL(3, 4, 4, 4, 0, 3, 7),      // config 4: 14.8 KB per warp -> 7 CTAs of 2 warps
+    BSPY_CELL(3, 4, 4, 4, 0, 1, 8),
+    BSPY_CELL(3, 3, 3, 3, 0, 3, 7),
+    BSPY_CELL(4, 3, 3, 3, 3, 6, 3),      // config 5: 32 KB per warp -> 3 CTAs of 2 warps
+};
+
+static const CellEntry *find_cell(const SplineDev &s)
+{
+    for (const CellEntry &e : kCell) {
+        if (e.nInd != s.nInd || e.nDep != s.nDep) continue;
+        bool same = true;
+        for (int i = 0; i < s.nInd; ++i) same &= e.o[i] == s.order[i];
+        if (same) return &e;
+    }
+    return nullptr;
+}
+
+// ---- sorted-record pipeline ------------------------------------------------------------------------------------------
+// per workspace half: keys | rank -> inverse permutation | (key, index) pairs (nInd == 4) | histogram | point records |
+// result records (struct-of-arrays outputs only: with caller-visible records the evaluation writes them in place)
+static long long records_half_bytes(const SplineDev &s, long long chunk, bool ownAos)
 {
     const long long cells = binned_cells(s);
-    return 4 * (3 * pad64(chunk) + pad64(cells + 1)) + 8 * (4 * pad64(chunk) + (long long)aos_stride(s) * pad64(chunk));
+    return 4 * (2 * pad64(chunk) + pad64(cells + 1)) + 8 * pad64(chunk) +
+           8 * (4 * pad64(chunk) + (ownAos ? (long long)aos_stride(s) * pad64(chunk) : 0));
 }
 
 static int eval_binned_records(const SplineDev &s, PointsDev in, long long N, const WrtDev &wrt, OutDev out, int jac,
                                void *workspace, cudaStream_t stream)
 {
+    const bool userAos = out.aos != nullptr;                     // caller-visible records: written in place, no un-permute
     const long long cells = binned_cells(s);
     const long long chunk = N < BIN_REC_CHUNK ? N : BIN_REC_CHUNK;
     const long long cpad = pad64(chunk);
-    const long long half = records_half_bytes(s, chunk);
+    const long long half = records_half_bytes(s, chunk, !userAos);
     const int D = (s.nInd - s.nDep == 1 || s.nDep - s.nInd == 1) ? (s.nInd > s.nDep ? s.nInd : s.nDep) : 0;
     const int nJ = jac ? s.nDep * s.nInd : 0;
-    const int nN = (jac && out.normal) ? D : 0;
-    const int stride = (s.nDep + nJ + nN + 3) & ~3;
+    const int nN = (jac && (out.normal || out.aosNormal)) ? D : 0;
+    const int stride = userAos ? out.aosStride : (s.nDep + nJ + nN + 3) & ~3;
+    const bool plainWrt = wrt.d[0] == 0 && wrt.d[1] == 0 && wrt.d[2] == 0 && wrt.d[3] == 0;
     FixedFn fn = find_fixed(s, jac);
     {
         const int ndt = (int)option(OPT_DEP_TILE, 14);
-        FixedFn tiled = (ndt > 0 && !out.normal) ? find_fixed_tiled(s, jac, ndt) : nullptr;
+        // one dependent variable per pass stores partial records: only where the records are private (workspace)
+        FixedFn tiled = (ndt > 0 && !nN && !userAos) ? find_fixed_tiled(s, jac, ndt) : nullptr;
         if (tiled) fn = tiled;
     }
-    // warp-staged windows where the shape is compiled (no normals there: they need the whole jacobian in one pass)
+    // evaluation kernel for dense chunks: tensor-pipe cell kernel (value + jacobian requests), else warp-staged
+    // windows, else the L1-gather kernel.  CELL_KERNEL: 0 = never the tensor-pipe kernel, 1 = default
+    const CellEntry *cell = (jac && plainWrt && option(OPT_CELL_KERNEL, 1)) ? find_cell(s) : nullptr;
+    const size_t cellSmem = cell ? sizeof(double) * CELL_WARPS * cell->warpDoubles : 0;
+    if (cell)
+        if (int rc = allow_dynamic_smem(cell->fn, cellSmem)) return rc;
     const StagedEntry *staged = nullptr;
     {
         const int code = (int)option(OPT_STAGED, 0);
-        if (code >= 0) staged = find_staged(s, jac, code);
-        if (staged) {
+        if (code >= 0 && !nN) staged = find_staged(s, jac, code);
+        if (staged)
             if (int rc = allow_dynamic_smem(staged->fn, sizeof(double) * 4 * 2 * staged->windowDoubles)) return rc;
-        }
     }
     // per-span records (left knots | reciprocal gaps) for every variable: no divisions in the evaluation kernel
     const double *spanRec[BSPY_MAX_IND] = {};
@@ -494,12 +810,9 @@ static int eval_binned_records(const SplineDev &s, PointsDev in, long long N, co
             count_launch(s.nInd);
         }
     }
-    // Sort / un-permute of the neighbouring chunks on a second stream under the evaluation of this one.  Measured: +9 %
-    // on config 4 with the persistent staged kernel (6.40 -> 7.00 Gpts/s; its tail and the memory-bound passes fill
-    // each other's gaps), nothing with the one-tile-per-CTA gather kernel (config 5: 2.47 -> 2.46), and a loss when
-    // the evaluation is launched with fewer CTAs per SM to make room (3 CTAs: 6.6, 2 CTAs: 5.9).  BSPY_BIN_OVERLAP=0/1
-    // overrides.
-    const bool wantOverlap = option(OPT_BIN_OVERLAP, staged != nullptr ? 1 : 0) != 0;
+    // Sort (and un-permute) of the neighbouring chunks on a second stream under the evaluation of this one: the sort
+    // passes are memory / latency bound, the evaluation FP64 bound.  BIN_OVERLAP=0/1 overrides.
+    const bool wantOverlap = option(OPT_BIN_OVERLAP, (staged != nullptr || cell != nullptr) ? 1 : 0) != 0;
     BinStreams *bs = wantOverlap ? acquire_bin_streams() : nullptr;
     struct Release { BinStreams *b; ~Release() { if (b) release_bin_streams(b); } } releaseOnExit{bs};
     const long long nChunks = (N + chunk - 1) / chunk;
@@ -510,18 +823,21 @@ static int eval_binned_records(const SplineDev &s, PointsDev in, long long N, co
         cudaStreamWaitEvent(sSort, bs->fork, 0);
         cudaStreamWaitEvent(sEval, bs->fork, 0);
     }
-    struct Buf { int *keys, *inv, *recKey, *hist; double *records, *aos; } buf[2];
+    struct Buf { int *keys, *inv, *hist; int2 *recKI; double *records, *aos; } buf[2];
     for (int h = 0; h < 2; ++h) {
         char *base = (char *)workspace + h * half;
-        buf[h].keys = (int *)base; buf[h].inv = buf[h].keys + cpad; buf[h].recKey = buf[h].inv + cpad;
-        buf[h].hist = buf[h].recKey + cpad;
-        buf[h].records = (double *)(buf[h].hist + pad64(cells + 1));
+        buf[h].keys = (int *)base; buf[h].inv = buf[h].keys + cpad;
+        buf[h].hist = buf[h].inv + cpad;
+        buf[h].recKI = (int2 *)(buf[h].hist + pad64(cells + 1));
+        buf[h].records = (double *)(buf[h].recKI + cpad);
         buf[h].aos = buf[h].records + 4 * cpad;
     }
     auto sortChunk = [&](long long c) -> int {
         const Buf &B = buf[c & 1];
         const long long base = c * chunk;
         const int n = (int)(N - base < chunk ? N - base : chunk);
+        // the evaluation of chunk c-2 (same half) must be done with the records before they are overwritten
+        if (overlap && c >= 2) cudaStreamWaitEvent(sSort, bs->evaluated[c & 1], 0);
         cudaError_t e = cudaMemsetAsync(B.hist, 0, sizeof(int) * (cells + 1), sSort);
         if (e != cudaSuccess) { set_error("cudaMemsetAsync: %s", cudaGetErrorString(e)); return (int)e; }
         OutDev o1{};
@@ -530,7 +846,8 @@ static int eval_binned_records(const SplineDev &s, PointsDev in, long long N, co
         // scatter 88 -> 71 us per 4 Mi points)
         bin_keys_batched_kernel<4><<<(n + 511) / 512, 128, 0, sSort>>>(s, in, base, n, B.keys, B.hist, B.inv, o1);
         bin_scan_kernel<<<1, 1024, 0, sSort>>>(B.hist, (int)cells);
-        bin_scatter_records_batched_kernel<4><<<(n + 511) / 512, 128, 0, sSort>>>(s, in, base, n, B.keys, B.hist, B.records, B.recKey, B.inv);
+        bin_scatter_records_batched_kernel<4><<<(n + 511) / 512, 128, 0, sSort>>>(s, in, base, n, B.keys, B.hist, B.records, B.recKI,
+                                                                                 B.inv, userAos ? 0 : 1);
         if (overlap) cudaEventRecord(bs->sorted[c & 1], sSort);
         count_launch(3);
         return check_launch("bspy_cuda_eval_points_binned(sort)");
@@ -541,14 +858,21 @@ static int eval_binned_records(const SplineDev &s, PointsDev in, long long N, co
         const int n = (int)(N - base < chunk ? N - base : chunk);
         if (overlap) cudaStreamWaitEvent(sEval, bs->sorted[c & 1], 0);
         PointsDev pin{};
-        pin.records = B.records; pin.recKey = B.recKey;
+        pin.records = B.records; pin.recKI = B.recKI;
         for (int i = 0; i < s.nInd; ++i) pin.spanRec[i] = spanRec[i];
         OutDev o2 = out;
         o2.spans = nullptr; o2.firstOutside = nullptr;
-        o2.aos = B.aos; o2.aosStride = stride;
-        // the staged kernel lives on window reuse: it needs cells that hold a few tiles' worth of points (a sparse
+        o2.aosStride = stride;
+        if (userAos) { o2.aosScatter = 1; o2.aosBase = base; }
+        else { o2.aos = B.aos; o2.aosScatter = 0; o2.aosBase = 0; }
+        // the window-sharing kernels live on reuse: they need cells that hold a few tiles' worth of points (a sparse
         // tail chunk makes every tile straddle several cells); below that the L1-gather kernel is the faster one
-        if (staged && n >= 48 * cells) {
+        if (cell && n >= 48 * cells) {
+            long long blocks = (long long)num_sms() * cell->minBlocks;
+            const long long most = (n + 32 * CELL_WARPS - 1) / (32 * CELL_WARPS);
+            if (blocks > most) blocks = most;
+            cell->fn<<<(unsigned)blocks, CELL_WARPS * 32, cellSmem, sEval>>>(s, pin, n, wrt, o2);
+        } else if (staged && n >= 48 * cells) {
             // persistent warps over contiguous runs of tiles (window reuse between consecutive tiles)
             long long blocks = (long long)num_sms() * (staged->code % 10);
             if (blocks > (n + 127) / 128) blocks = (n + 127) / 128;
@@ -561,6 +885,7 @@ static int eval_binned_records(const SplineDev &s, PointsDev in, long long N, co
         return check_launch("bspy_cuda_eval_points_binned(eval)");
     };
     auto unpermChunk = [&](long long c) -> int {
+        if (userAos) return 0;
         const Buf &B = buf[c & 1];
         const long long base = c * chunk;
         const int n = (int)(N - base < chunk ? N - base : chunk);
@@ -597,7 +922,7 @@ static int eval_binned_records(const SplineDev &s, PointsDev in, long long N, co
 int eval_binned(const SplineDev &s, PointsDev in, long long N, const WrtDev &wrt, OutDev out, int jac, void *workspace,
                 cudaStream_t stream)
 {
-    if (bin_mode(N) == 1 && s.nInd <= 4) return eval_binned_records(s, in, N, wrt, out, jac, workspace, stream);
+    if (out.aos || (bin_mode(N) == 1 && s.nInd <= 4)) return eval_binned_records(s, in, N, wrt, out, jac, workspace, stream);
     const long long cells = binned_cells(s);
     const int D = s.nInd > s.nDep ? s.nInd : s.nDep;
     const long long outBytes = 8LL * ((out.values ? s.nDep : 0) + (out.jacobian ? s.nDep * s.nInd : 0) + (out.normal ? D : 0));
@@ -685,4 +1010,52 @@ extern "C" int bspy_cuda_eval_points_binned(const bspy_spline *spline, const dou
         out.values = values;
     }
     return eval_binned(s, in, N, w, out, jac, workspace, (cudaStream_t)stream);
+}
+
+extern "C" int64_t bspy_cuda_aos_workspace_bytes(const bspy_spline *spline, int64_t N)
+{
+    SplineDev s;
+    if (make_spline_dev(spline, s, "bspy_cuda_aos_workspace_bytes")) return 0;
+    return binned_workspace(s, N, true);
+}
+
+extern "C" int bspy_cuda_eval_points_aos(const bspy_spline *spline, const double *uvw, int64_t pointStride, int64_t varStride,
+                                         int64_t N, uint32_t flags, uint32_t normalMask, double *records, int64_t recordStride,
+                                         int32_t *spans, int64_t *firstOutside, void *workspace, int64_t workspaceBytes,
+                                         void *stream)
+{
+    const char *who = "bspy_cuda_eval_points_aos";
+    SplineDev s;
+    int rc = make_spline_dev(spline, s, who);
+    if (rc) return rc;
+    if (N < 0 || (!uvw && N > 0 && s.nInd > 0) || (!records && N > 0)) { set_error("%s: bad argument", who); return BSPY_E_ARG; }
+    const bool wantNormal = (flags & BSPY_WANT_NORMAL) != 0;
+    const int jac = (flags & (BSPY_WANT_JACOBIAN | BSPY_WANT_NORMAL)) ? 1 : 0;
+    const int D = s.nInd > s.nDep ? s.nInd : s.nDep;
+    if (wantNormal && (s.nInd - s.nDep != 1 && s.nDep - s.nInd != 1)) {
+        set_error("The number of independent variables must be one different than the number of dependent variables.");
+        return BSPY_E_NORMAL_DIMS;
+    }
+    const long long length = s.nDep + (jac ? (long long)s.nDep * s.nInd : 0) + (wantNormal ? D : 0);
+    if (recordStride < length || recordStride > 0x7fffffff || (recordStride & 1) || (reinterpret_cast<uintptr_t>(records) & 15)) {
+        set_error("%s: recordStride must be even and >= %lld doubles, records 16-byte aligned", who, length);
+        return BSPY_E_ARG;
+    }
+    if (N == 0) return 0;
+    if (normalMask == 0 || D >= 32) normalMask = 0xffffffffu;
+    PointsDev in{};
+    in.uvw = uvw; in.pointStride = pointStride; in.varStride = varStride;
+    OutDev out{};
+    out.ld = N;
+    out.firstOutside = (long long *)firstOutside;
+    out.spans = spans;
+    out.normalize = (flags & BSPY_NORMALIZE) ? 1u : 0u;
+    out.normalMask = normalMask;
+    out.aos = records;
+    out.aosStride = (int)recordStride;
+    out.aosNormal = wantNormal ? 1 : 0;
+    WrtDev w{};
+    const long long need = binned_workspace(s, N, true);
+    if (need && workspace && workspaceBytes >= need) return eval_binned(s, in, N, w, out, jac, workspace, (cudaStream_t)stream);
+    return launch_eval(s, in, N, w, out, jac, (cudaStream_t)stream);
 }

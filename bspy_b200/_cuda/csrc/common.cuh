@@ -76,9 +76,10 @@ struct PointsDev {
     long long base;
     // sorted-record mode (records != nullptr): thread t evaluates the point whose parameters are
     // records[4t .. 4t+nInd) (32-byte records written in cell order by bin_scatter_records_kernel); the packed
-    // span key is the int64 bit pattern of records[4t+3] for nInd <= 3, recKey[t] for nInd == 4
+    // span key (cell) and the point's index inside its chunk are the low / high 32 bits of the bit pattern of
+    // records[4t+3] for nInd <= 3, recKI[t] = (key, index) for nInd == 4
     const double *records;
-    const int *recKey;
+    const int2 *recKI;
     // per-span records of variable i (left knots | reciprocal knot gaps, SpanRec<order>::stride doubles per span), built
     // once per call by span_records_kernel for the binned path; nullptr: gaps are divided per point
     const double *spanRec[BSPY_MAX_IND];
@@ -94,8 +95,13 @@ struct OutDev {
     unsigned normalize, normalMask;
     // array-of-structs results (sorted-record mode): point t writes [values | jacobian (d, iv) | normal] to
     // aos[t * aosStride ..]; aosStride is a multiple of 4 doubles so that records are whole 32-byte sectors
+    // aosScatter != 0: the record of sorted point t goes to aos[(aosBase + index inside the chunk) * aosStride ..], i.e.
+    // straight to the point's ORIGINAL position in a caller-visible array of records (no un-permute pass)
     double *aos;
     int aosStride;
+    int aosScatter;
+    int aosNormal;      // array-of-structs records carry the normal after the jacobian (out.normal itself stays NULL)
+    long long aosBase;
 };
 
 struct WrtDev {

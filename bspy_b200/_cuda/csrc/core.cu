@@ -212,6 +212,20 @@ const char *bspy_cuda_last_error_string(void) { return g_err; }
 
 int64_t bspy_cuda_launch_count(void) { return (int64_t)g_launches.load(); }
 
+int bspy_cuda_copy_2d(void *dst, int64_t dstPitchBytes, const void *src, int64_t srcPitchBytes, int64_t widthBytes,
+                      int64_t rows, void *stream)
+{
+    if (!dst || !src || widthBytes < 0 || rows < 0 || dstPitchBytes < widthBytes || srcPitchBytes < widthBytes) {
+        set_error("bspy_cuda_copy_2d: bad argument");
+        return BSPY_E_ARG;
+    }
+    if (widthBytes == 0 || rows == 0) return 0;
+    cudaError_t e = cudaMemcpy2DAsync(dst, (size_t)dstPitchBytes, src, (size_t)srcPitchBytes, (size_t)widthBytes, (size_t)rows,
+                                      cudaMemcpyDefault, (cudaStream_t)stream);
+    if (e != cudaSuccess) { set_error("cudaMemcpy2DAsync: %s", cudaGetErrorString(e)); return (int)e; }
+    return 0;
+}
+
 int bspy_cuda_set_option(const char *name, int64_t value, int32_t isSet)
 {
     if (!name) { set_error("bspy_cuda_set_option: name is NULL"); return BSPY_E_ARG; }

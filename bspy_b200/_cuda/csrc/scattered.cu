@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(128, MINB ? MINB : fixed_min_blocks(NIND, O0, 
         int ix[NIND];
         double u[NIND];
         bool outside = false;
-        long long p = t;
+        long long p = t, dest = t;                        // dest: where the result record goes (array-of-structs modes)
         if (binned) {
             int key;
             if (recs) {
@@ -42,7 +42,9 @@ __global__ void __launch_bounds__(128, MINB ? MINB : fixed_min_blocks(NIND, O0, 
                 if constexpr (NIND > 1) u[1] = r0.y;
                 if constexpr (NIND > 2) u[2] = r1.x;
                 if constexpr (NIND > 3) u[3] = r1.y;
-                key = NIND > 3 ? __ldcs(in.recKey + t) : (int)__double_as_longlong(r1.y);
+                const long long ki = NIND > 3 ? __ldcs(reinterpret_cast<const long long *>(in.recKI) + t) : __double_as_longlong(r1.y);
+                key = (int)ki;
+                dest = out.aosScatter ? out.aosBase + (ki >> 32) : t;
             } else {
                 p = in.base + __ldg(in.perm + t);
                 key = __ldg(in.cellKey + t);
@@ -79,7 +81,7 @@ __global__ void __launch_bounds__(128, MINB ? MINB : fixed_min_blocks(NIND, O0, 
                 double gt[NIND][NDT];
                 Contract<0, Ord, NDT, JAC>::run(s.coefs + off + d0 * s.depStride, c, vt, gt);
                 if (out.aos) {
-                    store_result_tile<NIND, NDEP, NDT, JAC>(out.aos + t * out.aosStride, d0, vt, gt);
+                    store_result_tile<NIND, NDEP, NDT, JAC>(out.aos + dest * out.aosStride, d0, vt, gt);
                 } else {
                     if (out.values) {
 #pragma unroll
@@ -95,7 +97,7 @@ __global__ void __launch_bounds__(128, MINB ? MINB : fixed_min_blocks(NIND, O0, 
                     }
                 }
             }
-            if (!out.aos && out.spans) {
+            if (!binned && out.spans) {
 #pragma unroll
                 for (int iv = 0; iv < NIND; ++iv) __stcs(out.spans + iv * out.ld + p, ix[iv]);
             }
@@ -105,7 +107,11 @@ __global__ void __launch_bounds__(128, MINB ? MINB : fixed_min_blocks(NIND, O0, 
         Contract<0, Ord, NDEP, JAC>::run(s.coefs + off, c, v, g);
         if (out.aos) {
             // sorted-record mode: one contiguous, sector-aligned result record per point
-            store_result_record<NIND, NDEP, JAC>(s, out, out.aos + t * out.aosStride, v, g);
+            store_result_record<NIND, NDEP, JAC>(s, out, out.aos + dest * out.aosStride, v, g);
+            if (!binned && out.spans) {
+#pragma unroll
+                for (int iv = 0; iv < NIND; ++iv) __stcs(out.spans + iv * out.ld + p, ix[iv]);
+            }
             continue;
         }
         if (out.values) {
@@ -159,14 +165,14 @@ __global__ void __launch_bounds__(128, MINB) eval_staged_kernel(const SplineDev 
     const long long firstTile = (blockIdx.x * 4LL + warp) * per;
     const long long endTile = firstTile + per < tiles ? firstTile + per : tiles;
     double2 r0 = make_double2(0.0, 0.0), r1 = r0;
-    int k4 = -1;
+    long long k4 = -1;
     auto fetch = [&](long long tile) {
         const long long t = tile * 32 + lane;
         if (tile < endTile && t < N) {
             const double2 *rp = reinterpret_cast<const double2 *>(in.records + 4 * t);
             r0 = __ldcs(rp);
             r1 = __ldcs(rp + 1);
-            if constexpr (NIND > 3) k4 = __ldcs(in.recKey + t);
+            if constexpr (NIND > 3) k4 = __ldcs(reinterpret_cast<const long long *>(in.recKI) + t);
         }
     };
     fetch(firstTile);
@@ -180,7 +186,9 @@ __global__ void __launch_bounds__(128, MINB) eval_staged_kernel(const SplineDev 
         if constexpr (NIND > 1) u[1] = r0.y;
         if constexpr (NIND > 2) u[2] = r1.x;
         if constexpr (NIND > 3) u[3] = r1.y;
-        const int key = live ? (NIND > 3 ? k4 : (int)__double_as_longlong(r1.y)) : -1;
+        const long long ki = NIND > 3 ? k4 : __double_as_longlong(r1.y);
+        const int key = live ? (int)ki : -1;
+        const long long dest = out.aosScatter ? out.aosBase + (ki >> 32) : t;
         fetch(tile + 1);                                            // next tile's records arrive under this tile's arithmetic
         {
             int k = key < 0 ? 0 : key;
@@ -230,7 +238,7 @@ __global__ void __launch_bounds__(128, MINB) eval_staged_kernel(const SplineDev 
             }
             if (in0 || in1) {
                 const double *w = w0 + (in1 ? s1 : s0) * WS::size;
-                double *rec = out.aos + t * out.aosStride;
+                double *rec = out.aos + dest * out.aosStride;
                 if constexpr (NDT == NDEP) {
                     double v[NDEP];
                     double g[NIND][NDEP];
@@ -390,15 +398,21 @@ __global__ void __launch_bounds__(128) eval_generic_kernel(const SplineDev s, co
                     more = iv >= 0;
                 }
             }
+            if (out.aos) {                                  // array-of-structs record [values | jacobian (d, iv) | normal]
+                double *rec = out.aos + p * out.aosStride;
+                rec[d] = val;
+                if (jac)
+                    for (int iv = 0; iv < nInd; ++iv) rec[nDep + d * nInd + iv] = der[iv];
+            }
             if (out.values) out.values[d * out.ld + p] = val;
             if (jac) {
                 if (out.jacobian)
                     for (int iv = 0; iv < nInd; ++iv) out.jacobian[((long long)d * nInd + iv) * out.ld + p] = der[iv];
-                if (out.normal)
+                if (out.normal || out.aosNormal)
                     for (int iv = 0; iv < nInd; ++iv) J[d * nInd + iv] = der[iv];
             }
         }
-        if (jac && out.normal) {
+        if (jac && (out.normal || out.aosNormal)) {
             double minor[BSPY_MAX_IND * BSPY_MAX_IND];
             double n[BSPY_MAX_IND + 1];
             const int M = D - 1;
@@ -415,7 +429,10 @@ __global__ void __launch_bounds__(128) eval_generic_kernel(const SplineDev s, co
                 if (out.normalMask & (1u << i)) sq += n[i] * n[i];
             }
             const double len = sqrt(sq);
-            for (int i = 0; i < D; ++i) out.normal[(long long)i * out.ld + p] = out.normalize ? n[i] / len : n[i];
+            if (out.aos)
+                for (int i = 0; i < D; ++i) out.aos[p * out.aosStride + nDep + nDep * nInd + i] = out.normalize ? n[i] / len : n[i];
+            else
+                for (int i = 0; i < D; ++i) out.normal[(long long)i * out.ld + p] = out.normalize ? n[i] / len : n[i];
         }
     }
 }
@@ -540,7 +557,7 @@ int launch_eval(const SplineDev &s, const PointsDev &in, long long N, const WrtD
                 cudaStream_t stream)
 {
     if (N <= 0) return 0;
-    if (!in.perm) {
+    if (!in.perm && !out.aos) {
         const int rc = launch_curve(s, in, N, wrt, out, jac, stream);   // lean single-curve path (curve.cu)
         if (rc != -1000) return rc;
     }

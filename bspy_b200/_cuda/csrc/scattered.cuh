@@ -108,7 +108,7 @@ __device__ __forceinline__ void store_result_record(const SplineDev &s, const Ou
 #pragma unroll
             for (int iv = 0; iv < NIND; ++iv) rec[NDEP + d * NIND + iv] = g[iv][d];
         if constexpr (DN > 0) {
-            if (out.normal) {
+            if (out.normal || out.aosNormal) {
                 double J[NDEP * NIND];
 #pragma unroll
                 for (int d = 0; d < NDEP; ++d)
@@ -400,6 +400,7 @@ int launch_eval(const SplineDev &s, const PointsDev &in, long long N, const WrtD
 
 // cells.cu
 long long binned_workspace(const SplineDev &s, long long N);
+long long binned_workspace(const SplineDev &s, long long N, bool aosOut);
 int eval_binned(const SplineDev &s, PointsDev in, long long N, const WrtDev &wrt, OutDev out, int jac, void *workspace,
                 cudaStream_t stream);
 

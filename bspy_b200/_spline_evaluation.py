@@ -28,12 +28,24 @@ class EvalResult:
     values (nDep, N) | derivative (nDep, N) | jacobian (nDep, nInd, N) |
     normal (len(indices) or max(nInd, nDep), N) | spans (nInd, N) int32.
     Arrays are numpy when the points were numpy / array-like, CPU tensors for CPU tensors and CUDA
-    tensors for CUDA tensors.  For grids, N is replaced by the grid shape."""
+    tensors for CUDA tensors.  For grids, N is replaced by the grid shape.
+
+    ``out_layout="aos"``: ``records`` is the (N, stride) array of per-point records [values | jacobian (d, i) | normal]
+    (stride = record length rounded up to 4 doubles) and values / jacobian / normal are strided VIEWS into it with the
+    shapes above.  ``check_domain="defer"``: ``first_outside`` is the device int64[1] flag the kernels wrote (-1 = every
+    point inside the domain); ``raise_if_outside()`` reads it and raises the reference's ValueError."""
     values: Any = None
     derivative: Any = None
     jacobian: Any = None
     normal: Any = None
     spans: Any = None
+    records: Any = None
+    first_outside: Any = None
+
+    def raise_if_outside(self):
+        if self.first_outside is not None and int(self.first_outside.item()) >= 0:
+            raise ValueError(f"Spline evaluation outside domain: point index {int(self.first_outside.item())}")
+        return self
 
 
 # ----------------------------------------------------------------------------- device residency
@@ -297,8 +309,23 @@ def _raise_outside(self, flag_value, fetch_point):
         raise ValueError(f"Spline evaluation outside domain: {fetch_point(int(flag_value))}")
 
 
+def _record_views(ds, records, jacobian, normal, idx):
+    """values / jacobian / normal as strided views into the (N, stride) record array."""
+    nDep, nInd = ds.nDep, ds.nInd
+    rt = records.T if isinstance(records, torch.Tensor) else records.T            # (stride, N) view
+    vals = rt[:nDep]
+    jac = rt[nDep:nDep + nDep * nInd].reshape(nDep, nInd, -1) if (jacobian or normal) else None
+    nrm = None
+    if normal:
+        at = nDep + nDep * nInd
+        nrm = rt[at:at + ds.normal_dim]
+        if idx is not None:
+            nrm = nrm[idx]
+    return vals, (jac if jacobian else None), nrm
+
+
 def evaluate_points(self, uvw, *, with_respect_to=None, values=True, jacobian=False, normal=False, normalize=True,
-                    indices=None, spans=False, layout="points", check_domain=True, device=None) -> EvalResult:
+                    indices=None, spans=False, layout="points", check_domain=True, device=None, out_layout="soa") -> EvalResult:
     """Evaluate the spline at N points in one go (the vectorised entry point the reference lacks).
 
     uvw : (N, nInd) array-like, numpy array, CPU tensor or CUDA tensor of float64
@@ -307,9 +334,14 @@ def evaluate_points(self, uvw, *, with_respect_to=None, values=True, jacobian=Fa
     values / jacobian / normal / spans : which outputs to produce (one fused pass over the window)
     normalize, indices : as in ``Spline.normal``
     check_domain : raise ``ValueError("Spline evaluation outside domain: ...")`` like the reference
-          when any point is outside the closed domain (costs one device->host flag read)
+          when any point is outside the closed domain (costs one device->host flag read); ``"defer"`` (CUDA inputs):
+          the flag is written on the device and returned as ``first_outside`` without a synchronisation
+    out_layout : ``"soa"`` (default) struct-of-arrays outputs; ``"aos"``: one record [values | jacobian | normal] per
+          point (``records`` (N, stride), the per-point shape of the reference's returns) with values / jacobian /
+          normal as views into it -- big scattered batches are then written straight to their original positions by
+          the cell-sorted kernels, with no un-permute pass over the outputs
 
-    Returns an ``EvalResult`` of struct-of-arrays outputs of the same kind as ``uvw``."""
+    Returns an ``EvalResult`` of outputs of the same kind as ``uvw``."""
     kind = _classify(uvw)
     idx, mask = (None, 0)
     if normal:
@@ -317,6 +349,14 @@ def evaluate_points(self, uvw, *, with_respect_to=None, values=True, jacobian=Fa
     wrt = None if with_respect_to is None else [int(with_respect_to[i]) for i in range(self.nInd)]
     if layout not in ("points", "variables"):
         raise ValueError("layout must be 'points' or 'variables'")
+    if out_layout not in ("soa", "aos"):
+        raise ValueError("out_layout must be 'soa' or 'aos'")
+    aos = out_layout == "aos"
+    if aos and wrt is not None:
+        raise ValueError("out_layout='aos' holds values, jacobian and normal; request with_respect_to with out_layout='soa'")
+    defer = isinstance(check_domain, str) and check_domain == "defer"
+    if defer and kind != "cuda":
+        raise ValueError("check_domain='defer' needs CUDA inputs (host inputs are checked when the results are copied back)")
     request = dict(wrt=wrt, values=bool(values), jacobian=bool(jacobian), normal=bool(normal), normalize=bool(normalize),
                    normal_mask=mask, spans=bool(spans))
 
@@ -330,14 +370,23 @@ def evaluate_points(self, uvw, *, with_respect_to=None, values=True, jacobian=Fa
         ps, vs = (pts.stride(0), pts.stride(1)) if layout == "points" else (pts.stride(1), pts.stride(0))
         ds = device_spline(self, pts.device)
         flag = _cuda.new_flag(pts.device) if check_domain else None
-        out = _cuda.eval_points(ds, pts, ps, vs, N, flag=flag, **request)
-        if check_domain:
+        if aos:
+            rec, sp = _cuda.eval_points_aos(ds, pts, ps, vs, N, jacobian=bool(jacobian), normal=bool(normal), normalize=bool(normalize),
+                                            normal_mask=mask, spans=bool(spans), flag=flag)
+            v, j, nrm = _record_views(ds, rec, jacobian, normal, idx)
+            res = EvalResult(v, None, j, nrm, sp, records=rec)
+        else:
+            out = _cuda.eval_points(ds, pts, ps, vs, N, flag=flag, **request)
+            nrm = out["normal"]
+            if nrm is not None and idx is not None:
+                nrm = nrm[idx]
+            res = EvalResult(out["values"], out["derivative"], out["jacobian"], nrm, out["spans"])
+        if defer:
+            res.first_outside = flag
+        elif check_domain:
             _raise_outside(self, int(flag.item()),
                            lambda p: (pts[p] if layout == "points" else pts[:, p]).cpu().numpy())
-        nrm = out["normal"]
-        if nrm is not None and idx is not None:
-            nrm = nrm[idx]
-        return EvalResult(out["values"], out["derivative"], out["jacobian"], nrm, out["spans"])
+        return res
 
     # ---- host input: chunked H2D -> kernel -> D2H pipeline (bspy_b200._cuda.eval_points_host) ----
     if kind == "numpy":
@@ -349,9 +398,16 @@ def evaluate_points(self, uvw, *, with_respect_to=None, values=True, jacobian=Fa
     if host.dim() != 2 or host.shape[1 if layout == "points" else 0] != self.nInd:
         raise ValueError(f"Incorrect number of parameter values: {tuple(host.shape)}")
     ds = device_spline(self, device)
-    res, first = _cuda.eval_points_host(ds, host, layout, check=check_domain, **request)
+    res, first = _cuda.eval_points_host(ds, host, layout, check=bool(check_domain), aos=aos, **request)
     if first >= 0:
         raise ValueError(f"Spline evaluation outside domain: {(host[first] if layout == 'points' else host[:, first]).numpy()}")
+    if aos:
+        rec = res["records"].numpy() if kind == "numpy" else res["records"]
+        sp = res["spans"]
+        if sp is not None and kind == "numpy":
+            sp = sp.numpy()
+        v, j, nrm = _record_views(ds, rec, jacobian, normal, idx)
+        return EvalResult(v, None, j, nrm, sp, records=rec)
     if res["normal"] is not None and idx is not None:
         res["normal"] = res["normal"][idx]
     if kind == "numpy":
@@ -393,7 +449,8 @@ def evaluate_grid(self, *axes, values=True, jacobian=False, normal=False, normal
     flag = _cuda.new_flag(dev) if check_domain else None
     out = _cuda.eval_grid(ds, d_axes, values=bool(values), jacobian=bool(jacobian), normal=bool(normal),
                           normalize=bool(normalize), normal_mask=mask, flag=flag, **({"out_f32": True} if f32 else {}))
-    if check_domain:
+    defer = isinstance(check_domain, str) and check_domain == "defer"
+    if check_domain and not defer:
         off = int(flag.item())
         if off >= 0:
             shape = [int(a.numel()) for a in d_axes]
@@ -402,7 +459,7 @@ def evaluate_grid(self, *axes, values=True, jacobian=False, normal=False, normal
     nrm = out["normal"]
     if nrm is not None and idx is not None:
         nrm = nrm[idx]
-    res = EvalResult(out["values"], None, out["jacobian"], nrm, None)
+    res = EvalResult(out["values"], None, out["jacobian"], nrm, None, first_outside=flag if defer else None)
     if not on_device:
         conv = (lambda t: None if t is None else t.cpu().numpy()) if kinds <= {"numpy"} else \
                (lambda t: None if t is None else t.cpu())

@@ -159,7 +159,8 @@ class SplineBatch:
         else:
             res = _cuda.eval_many(self.order[0], self.nCoef[0], self.nDep, _ExpandedKnots(k), coefs, ut, deriv1=derivative,
                                   flag=flag, out=out)
-        if check_domain:
+        defer = isinstance(check_domain, str) and check_domain == "defer"
+        if check_domain and not defer:
             off = int(flag.item())
             if off >= 0:
                 s, p = divmod(off, ut.shape[1])
@@ -168,7 +169,7 @@ class SplineBatch:
         if not on_device:
             vals = vals.cpu().numpy()
             der = None if der is None else der.cpu().numpy()
-        return EvalResult(values=vals, derivative=der)
+        return EvalResult(values=vals, derivative=der, first_outside=flag if defer else None)
 
     def _evaluate_per_spline(self, k, coefs, ut, derivative, flag, out):
         """Curves whose order exceeds the warp-per-curve kernel's limit: one scattered-point launch per curve
@@ -206,6 +207,8 @@ class SplineBatch:
         axes = [_to_device(uAxis, self.device).reshape(-1), _to_device(vAxis, self.device).reshape(-1)]
         strides = [0 if k.dim() == 1 else int(k.stride(0)) for k in self.knots]
         request = dict(values=values, jacobian=jacobian, normal=normal, normalize=normalize, normal_mask=mask)
+        defer = isinstance(check_domain, str) and check_domain == "defer"
+        flag = None
         if self.nSplines == 0 or axes[0].numel() == 0 or axes[1].numel() == 0:
             # a rank whose shard is empty (world > nSplines): empty outputs of the right shape, no launch
             nU, nV = int(axes[0].numel()), int(axes[1].numel())
@@ -222,10 +225,10 @@ class SplineBatch:
             flag = _cuda.new_flag(self.device) if check_domain else None
             res = _cuda.eval_grid_batch(self._descriptor(), self.nSplines, strides, int(self.coefs.stride(0)), axes,
                                         flag=flag, out=out, **request, **({"out_f32": True} if f32 else {}))
-            off = int(flag.item()) if check_domain else -1
+            off = int(flag.item()) if (check_domain and not defer) else -1
         else:
             res, off = _cuda.eval_grid_batch_host(self._descriptor(), self.nSplines, strides, int(self.coefs.stride(0)),
-                                                  axes, check=check_domain, **request)
+                                                  axes, check=bool(check_domain), **request)
         if off >= 0:
             nU, nV = int(axes[0].numel()), int(axes[1].numel())
             s, rem = divmod(off, nU * nV)
@@ -234,7 +237,7 @@ class SplineBatch:
         nrm = res.get("normal")
         if nrm is not None and idx is not None:
             nrm = nrm[:, idx]
-        r = EvalResult(values=res.get("values"), jacobian=res.get("jacobian"), normal=nrm)
+        r = EvalResult(values=res.get("values"), jacobian=res.get("jacobian"), normal=nrm, first_outside=flag if defer else None)
         if not on_device:
             conv = lambda t: None if t is None else (t.numpy() if not t.is_cuda else t.cpu().numpy())
             r = EvalResult(values=conv(r.values), jacobian=conv(r.jacobian), normal=conv(r.normal))

@@ -13,7 +13,8 @@ import os
 import torch
 import torch.distributed as dist
 
-__all__ = ["shard_range", "rank_world", "init_from_env", "shard_points", "gather_last_dim"]
+__all__ = ["shard_range", "rank_world", "init_from_env", "shard_points", "gather_last_dim", "gather_records",
+           "bind_to_gpu_numa_node"]
 
 
 def shard_range(n: int, rank: int, world: int):
@@ -80,3 +81,65 @@ def gather_last_dim(local: torch.Tensor, n_total: int, group=None) -> torch.Tens
         lo, hi = shard_range(n_total, r, world)
         out[..., lo:hi] = parts[r][..., : hi - lo]
     return out
+
+
+def gather_records(local: torch.Tensor, n_total: int, out: torch.Tensor = None, group=None) -> torch.Tensor:
+    """All-gather array-of-structs shards ``(n_local, stride)`` (rows split by ``shard_range``) into ``(n_total, stride)``
+    on every rank.  Records are point-major, so each rank's shard is one contiguous block of the result: equal shards
+    go through a single ``all_gather_into_tensor`` straight into ``out`` (no staging copy); ragged shards are padded to
+    the largest one and trimmed."""
+    rank, world = rank_world()
+    stride = local.shape[1]
+    if out is None:
+        out = local.new_empty((n_total, stride))
+    if world == 1:
+        out.copy_(local)
+        return out
+    local = local.contiguous()
+    if n_total % world == 0 and out.is_contiguous():
+        dist.all_gather_into_tensor(out, local, group=group)
+        return out
+    most = (n_total + world - 1) // world
+    padded = local.new_zeros((most, stride))
+    padded[: local.shape[0]] = local
+    parts = local.new_empty((world * most, stride))
+    dist.all_gather_into_tensor(parts, padded, group=group)
+    for r in range(world):
+        lo, hi = shard_range(n_total, r, world)
+        out[lo:hi] = parts[r * most: r * most + hi - lo]
+    return out
+
+
+def bind_to_gpu_numa_node(device_index=None):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off, so that pinned host buffers (first touched by
+    this process) and the copy-engine traffic stay on that node.  Linux sysfs only; returns a short description, or the
+    reason nothing was changed.  Purely a host-side placement hint: results do not depend on it."""
+    try:
+        if not torch.cuda.is_available():
+            return "no CUDA device"
+        idx = torch.cuda.current_device() if device_index is None else int(device_index)
+        props = torch.cuda.get_device_properties(idx)
+        bus = f"{getattr(props, 'pci_domain_id', 0):04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        base = f"/sys/bus/pci/devices/{bus}"
+        with open(f"{base}/local_cpulist") as f:
+            text = f.read().strip()
+        cpus = set()
+        for part in text.split(","):
+            if not part:
+                continue
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0)
+        use = cpus & allowed
+        if not use:
+            return f"{bus}: local cpus {text} not in this process's affinity mask"
+        try:
+            with open(f"{base}/numa_node") as f:
+                node = f.read().strip()
+        except OSError:
+            node = "?"
+        if use != allowed:
+            os.sched_setaffinity(0, use)
+        return f"gpu {idx} ({bus}) numa node {node}: {len(use)} of {len(allowed)} cpus"
+    except Exception as exc:  # pragma: no cover - depends on the box
+        return f"not bound: {type(exc).__name__}: {exc}"

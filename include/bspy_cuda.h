@@ -58,6 +58,8 @@ typedef struct bspy_spline {
 /* what bspy_cuda_eval_* computes */
 #define BSPY_NORMALIZE 1u /* divide the normal by its 2-norm over the selected components */
 #define BSPY_OUT_F32 2u   /* grid entry points, surfaces only: values / jacobian / normal point to float arrays */
+#define BSPY_WANT_JACOBIAN 4u /* bspy_cuda_eval_points_aos: records carry the jacobian after the values       */
+#define BSPY_WANT_NORMAL 8u   /* bspy_cuda_eval_points_aos: ... and the normal after the jacobian             */
 
 /* ---- library ------------------------------------------------------------------------- */
 int bspy_cuda_abi_version(void);
@@ -68,6 +70,11 @@ int64_t bspy_cuda_launch_count(void);
  * the measured best; the environment variable BSPY_<NAME> is read ONCE when the library is first used and this call
  * overrides it (isSet == 0 returns the switch to "unset" = built-in default).  Process-wide; not an evaluation entry. */
 int bspy_cuda_set_option(const char *name, int64_t value, int32_t isSet);
+
+/* Host-pipeline helper: rows x widthBytes 2-D copy between device and PINNED host memory (either direction) on the
+ * stream, one call per output array and chunk instead of one per row (cudaMemcpy2DAsync, cudaMemcpyDefault).        */
+int bspy_cuda_copy_2d(void *dst, int64_t dstPitchBytes, const void *src, int64_t srcPitchBytes,
+                      int64_t widthBytes, int64_t rows, void *stream);
 
 /* ---- knot spans: replaces the search in bspline_values
  *      (bspy/_spline_evaluation.py:7-8: np.searchsorted(knots, u, 'right') clamped to
@@ -120,6 +127,21 @@ int bspy_cuda_eval_points_binned(const bspy_spline *spline, const double *uvw, i
                                  uint32_t normalMask, double *values, double *deriv, double *jacobian,
                                  double *normal, int32_t *spans, int64_t *firstOutside,
                                  void *workspace, int64_t workspaceBytes, void *stream);
+
+/* ---- array-of-structs results: one record per point, records[p * recordStride ..] =
+ *      [ values (nDep) | jacobian (nDep x nInd, [d][i]; with BSPY_WANT_JACOBIAN or BSPY_WANT_NORMAL) |
+ *        normal (max(nInd,nDep); with BSPY_WANT_NORMAL) ], which is the shape the reference returns per point
+ *      (evaluate -> (nDep,), jacobian -> (nDep, nInd), normal -> (D,): bspy/_spline_evaluation.py:140-164, 205-246).
+ *      recordStride (doubles) must be even and >= the record length, records 16-byte aligned; a stride that is a
+ *      multiple of 4 makes every record whole 32-byte sectors: the cell-sorted path for big batches then writes each
+ *      result straight to its point's original position and needs no un-permute pass over the outputs (padding doubles
+ *      of a record may be written as zeros).  workspace: bspy_cuda_aos_workspace_bytes(spline, N) bytes of device
+ *      memory (0 = the direct kernels are used; NULL / too small: the direct kernels are used as well).             */
+int64_t bspy_cuda_aos_workspace_bytes(const bspy_spline *spline, int64_t N);
+int bspy_cuda_eval_points_aos(const bspy_spline *spline, const double *uvw, int64_t pointStride,
+                              int64_t varStride, int64_t N, uint32_t flags, uint32_t normalMask,
+                              double *records, int64_t recordStride, int32_t *spans, int64_t *firstOutside,
+                              void *workspace, int64_t workspaceBytes, void *stream);
 
 /* ---- regular grid: the tensor product of one parameter axis per variable; axis i has
  *      nAxis[i] device doubles.  Outputs as above with N = prod(nAxis) laid out C-order with

@@ -67,9 +67,40 @@ def eval_points(ds, uvw, point_stride, var_stride, N, **request):
     return _evaluate(ds, pts, **request)
 
 
-def eval_points_host(ds, host, layout, *, check=True, chunk=None, **request):
+def record_layout(ds, jacobian, normal):
+    length = ds.nDep + (ds.nDep * ds.nInd if (jacobian or normal) else 0) + (max(ds.nInd, ds.nDep) if normal else 0)
+    return length, (length + 3) // 4 * 4
+
+
+def _records(ds, pts, *, jacobian=False, normal=False, normalize=True, normal_mask=0, spans=False, flag=None):
+    out = _evaluate(ds, pts, values=True, jacobian=jacobian or normal, normal=normal, normalize=normalize, normal_mask=normal_mask,
+                    spans=spans, flag=flag)
+    N = pts.shape[0]
+    length, stride = record_layout(ds, jacobian, normal)
+    rec = torch.zeros((N, stride), dtype=torch.float64)
+    rec[:, :ds.nDep] = out["values"].T
+    at = ds.nDep
+    if jacobian or normal:
+        rec[:, at:at + ds.nDep * ds.nInd] = out["jacobian"].reshape(ds.nDep * ds.nInd, N).T
+        at += ds.nDep * ds.nInd
+    if normal:
+        rec[:, at:at + out["normal"].shape[0]] = out["normal"].T
+    return rec, out["spans"]
+
+
+def eval_points_aos(ds, uvw, point_stride, var_stride, N, **request):
+    pts = torch.as_strided(uvw, (N, ds.nInd), (point_stride, var_stride)).numpy().astype(np.float64)
+    return _records(ds, pts, **request)
+
+
+def eval_points_host(ds, host, layout, *, check=True, chunk=None, aos=False, **request):
     pts = host.numpy() if layout == "points" else host.numpy().T
     flag = new_flag(CPU) if check else None
+    if aos:
+        rec, sp = _records(ds, np.ascontiguousarray(pts), jacobian=request.get("jacobian", False), normal=request.get("normal", False),
+                           normalize=request.get("normalize", True), normal_mask=request.get("normal_mask", 0),
+                           spans=request.get("spans", False), flag=flag)
+        return {"records": rec, "spans": sp}, (int(flag[0]) if check else -1)
     out = _evaluate(ds, np.ascontiguousarray(pts), flag=flag, **request)
     return out, (int(flag[0]) if check else -1)
 
@@ -167,7 +198,7 @@ def collocation(knots, order, u, deriv_orders=None):
 
 def install(monkeypatch):
     from bspy_b200 import _cuda
-    for name in ("device", "new_flag", "launch_count", "eval_points", "eval_points_host", "eval_grid", "spans", "basis", "curvature",
+    for name in ("device", "new_flag", "launch_count", "eval_points", "eval_points_host", "eval_points_aos", "record_layout", "eval_grid", "spans", "basis", "curvature",
                  "contract_axis", "block_accumulate", "normal_from_jacobian", "collocation"):
         monkeypatch.setattr(_cuda, name, globals()[name])
     launches[0] = 0

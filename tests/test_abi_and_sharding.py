@@ -93,10 +93,10 @@ WORKER = r'''
 import os, sys
 sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "tests"))
 import numpy as np, torch, torch.distributed as dist
-from bspy_b200.sharding import init_from_env, shard_points, shard_range, gather_last_dim
+from bspy_b200.sharding import init_from_env, shard_points, shard_range, gather_last_dim, gather_records
 import bspy_b200 as bspy, fake_cuda
 from bspy_b200 import _cuda
-for name in ("device", "new_flag", "launch_count", "eval_points", "eval_points_host", "eval_grid", "spans", "basis"):
+for name in ("device", "new_flag", "launch_count", "eval_points", "eval_points_host", "eval_points_aos", "record_layout", "eval_grid", "spans", "basis"):
     setattr(_cuda, name, getattr(fake_cuda, name))
 rank, world, local = init_from_env("gloo")
 assert world == 2 and dist.get_backend() == "gloo"
@@ -112,6 +112,17 @@ full = gather_last_dim(local_vals, 1001)                               # optiona
 ref = s.evaluate_points(u).values
 assert full.shape == (3, 1001) and np.array_equal(full.numpy(), ref), "gathered shards differ from the unsharded result"
 b = torch.tensor([float(local_vals.shape[1])]); dist.all_reduce(b); assert int(b) == 1001
+# array-of-structs records: ragged shards (1001 points) and even shards (1000 points) through gather_records
+for total in (1001, 1000):
+    pts = u[:total]
+    rec = torch.from_numpy(s.evaluate_points(shard_points(pts, rank, world), jacobian=True, out_layout="aos").records)
+    whole = gather_records(rec, total)
+    want = s.evaluate_points(pts, jacobian=True, out_layout="aos")
+    assert whole.shape == (total, 8) and np.array_equal(whole.numpy(), want.records), "gathered records differ"
+    assert np.array_equal(whole.numpy()[:, :3].T, want.values) and np.array_equal(whole.numpy()[:, 3:6].T, want.jacobian[:, 0])
+# a rank with an empty shard (world > items) still takes part
+tiny = shard_points(u[:1], rank, world)
+assert tiny.shape[0] == (1 if rank == 0 else 0)
 dist.destroy_process_group()
 print("rank", rank, "ok")
 '''

@@ -476,6 +476,7 @@ def test_record_mode_staged_windows_bit_identical(option):
         return np.concatenate((np.zeros(o - 1), inner, np.ones(o - 1)))
 
     option("BIN_MODE", 1)
+    option("CELL_KERNEL", 0)                                        # the all-DFMA kernels; the tensor-pipe cell kernel has its own test
     shapes = [((4, 4, 4), 3, (18, 18, 18)), ((3, 3, 3), 3, (20, 19, 18)), ((4, 4, 4), 1, (28, 27, 26)), ((4, 4, 4), 4, (17, 16, 18)),
               ((3, 3, 3, 3), 6, (10, 10, 9, 10))]
     for order, nDep, nCoef in shapes:
@@ -504,6 +505,82 @@ def test_record_mode_staged_windows_bit_identical(option):
             so = O.OracleSpline.of(s)
             ph = pts[idx].cpu().numpy()
             assert close(a["values"][:, idx].cpu().numpy().T, O.evaluate_vec(so, ph))
+
+
+def _close_t(x, y):
+    """strict bar |x - y| <= 1e-13 + 1e-12 |y| on device tensors, NaNs matching"""
+    return bool(torch.isclose(x, y, rtol=1e-12, atol=1e-13, equal_nan=True).all())
+
+
+def test_cell_kernel_tensor_pipe_and_aos_records(option):
+    """The cell-sorted pipeline with the first contraction stage on the FP64 tensor pipe (eval_cell_mma_kernel) and
+    array-of-structs records written straight to the points' original positions: against the direct thread-per-point
+    kernel (strict bar on every point: the summation order differs in the last variable only), the oracle on a sample,
+    spans bit-exact; struct-of-arrays and array-of-structs outputs of the same request are bit-identical; many small
+    chunks (ragged, straddling tiles), dense and sparse cells, the staged / gather kernels behind the same records."""
+    bspy, _cuda, O, _ = _mods()
+    from bspy_b200._spline_evaluation import device_spline
+    from oracle import c_oracle as CO
+    rng = np.random.default_rng(131)
+
+    def K(o, n):
+        w = rng.uniform(0.25, 1.75, n - o + 1)
+        inner = np.concatenate(([0.0], np.cumsum(w))); inner /= inner[-1]
+        return np.concatenate((np.zeros(o - 1), inner, np.ones(o - 1)))
+
+    shapes = [((4, 4, 4), 3, (18, 18, 18)), ((3, 3, 3), 3, (20, 19, 18)), ((4, 4, 4), 1, (28, 27, 26)), ((3, 3, 3, 3), 6, (10, 10, 9, 10)),
+              ((4, 4, 4), 4, (17, 16, 18)), ((3, 4), 3, (150, 140)), ((5, 4), 3, (40, 30))]
+    for order, nDep, nCoef in shapes:
+        nInd = len(order)
+        s = bspy.Spline(nInd, nDep, order, nCoef, [K(o, n) for o, n in zip(order, nCoef)], rng.standard_normal((nDep, *nCoef)))
+        ds = device_spline(s)
+        cells = int(np.prod([n - o + 1 for o, n in zip(order, nCoef)]))
+        want_normal = abs(nInd - nDep) == 1
+        for N, chunk_log2 in ((64 * cells + 4321, 22), (3 * (1 << 18) + 777, 18), (70_000, 22)):
+            option("BIN_REC_CHUNK_LOG2", chunk_log2)
+            g = torch.Generator(device="cuda").manual_seed(N)
+            pts = torch.rand((N, nInd), dtype=torch.float64, device="cuda", generator=g)
+            pts[7, 0], pts[N - 1, nInd - 1], pts[99, 1] = 0.0, 1.0, float(s.knots[1][order[1] + 2])
+            direct = _cuda.eval_points(ds, pts, nInd, 1, N, binned=False, values=True, jacobian=True, normal=want_normal, spans=True)
+            for cell_kernel in (1, 0):
+                option("CELL_KERNEL", cell_kernel)
+                rec, sp = _cuda.eval_points_aos(ds, pts, nInd, 1, N, jacobian=True, normal=want_normal, spans=True)
+                assert rec.shape == (N, (nDep * (1 + nInd) + (max(nInd, nDep) if want_normal else 0) + 3) // 4 * 4)
+                assert torch.equal(sp, direct["spans"]), (order, nDep, N, cell_kernel)
+                assert _close_t(rec[:, :nDep].T, direct["values"]), (order, nDep, N, cell_kernel)
+                assert _close_t(rec[:, nDep:nDep * (1 + nInd)].T.reshape(nDep, nInd, N), direct["jacobian"]), (order, nDep, N, cell_kernel)
+                if want_normal:
+                    assert _close_t(rec[:, nDep * (1 + nInd):nDep * (1 + nInd) + max(nInd, nDep)].T, direct["normal"])
+                if N >= (1 << 16):                                  # struct-of-arrays through the same sorted records + un-permute
+                    option("BIN_MODE", 1)
+                    soa = _cuda.eval_points(ds, pts, nInd, 1, N, binned=True, values=True, jacobian=True, normal=want_normal)
+                    option("BIN_MODE", None)
+                    assert torch.equal(soa["values"], rec[:, :nDep].T) and \
+                        torch.equal(soa["jacobian"], rec[:, nDep:nDep * (1 + nInd)].T.reshape(nDep, nInd, N)), (order, nDep, N, cell_kernel)
+                values_only, _ = _cuda.eval_points_aos(ds, pts, nInd, 1, N)
+                assert torch.equal(values_only[:, :nDep].T, _cuda.eval_points(ds, pts, nInd, 1, N, binned=False)["values"])
+            option("CELL_KERNEL", None)
+            idx = rng.integers(0, N, 4000)
+            ref = CO.evaluate(s, pts[idx].cpu().numpy(), values=True, jacobian=True, spans=True)
+            assert np.array_equal(sp[:, idx].cpu().numpy().T, ref["spans"])
+            assert close(rec[idx, :nDep].cpu().numpy(), ref["values"])
+            assert close(rec[idx, nDep:nDep * (1 + nInd)].cpu().numpy().reshape(-1, nDep, nInd), ref["jacobian"])
+        # outside the domain: the first offender survives sorting and chunking
+        bad = pts.clone()
+        bad[60_123, nInd - 1] = 1.5
+        bad[65_000, 0] = -0.25
+        flag = _cuda.new_flag(pts.device)
+        _cuda.eval_points_aos(ds, bad, nInd, 1, N, jacobian=True, flag=flag)
+        assert int(flag.item()) == 60_123
+    # the public API: views into the records, host inputs through the chunked pipeline
+    s = bspy.Spline(3, 3, (4, 4, 4), (18, 18, 18), [K(4, 18) for _ in range(3)], rng.standard_normal((3, 18, 18, 18)))
+    pts = torch.rand((150_000, 3), dtype=torch.float64, device="cuda", generator=torch.Generator(device="cuda").manual_seed(8))
+    a = s.evaluate_points(pts, jacobian=True, out_layout="aos", check_domain="defer")
+    b = s.evaluate_points(pts.cpu().numpy(), jacobian=True, out_layout="aos")
+    assert a.records.shape == (150_000, 12) and int(a.first_outside.item()) == -1 and a.raise_if_outside() is a
+    assert np.array_equal(a.records.cpu().numpy(), b.records) and np.array_equal(a.jacobian.cpu().numpy(), b.jacobian)
+    c = s.evaluate_points(pts, jacobian=True)
+    assert _close_t(a.values, c.values) and _close_t(a.jacobian, c.jacobian)
 
 
 def test_curve_replicated_rows_bit_identical(option):
@@ -592,6 +669,7 @@ def test_record_mode_multi_chunk_overlap_bit_identical(option):
     s = bspy.Spline(3, 3, (4, 4, 4), (18, 18, 18), [K(4, 18) for _ in range(3)], rng.standard_normal((3, 18, 18, 18)))
     ds = device_spline(s)
     N = 2 * (1 << 22) + 70_001                                     # three chunks, ragged sparse tail
+    option("CELL_KERNEL", 0)
     pts = torch.rand((N, 3), dtype=torch.float64, device="cuda", generator=torch.Generator(device="cuda").manual_seed(5))
     ref = _cuda.eval_points(ds, pts, 3, 1, N, binned=False, values=True, jacobian=True)
     for flag in ("1", "0"):

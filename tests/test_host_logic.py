@@ -204,6 +204,37 @@ def test_evaluate_points_shapes_and_kinds():
         s.evaluate_grid([0, 1], [0, 1], [0, 1.01])
 
 
+def test_array_of_structs_layout_host_logic():
+    """out_layout="aos": one record [values | jacobian (d, i) | normal] per point, stride rounded up to 4 doubles;
+    values / jacobian / normal are views into the records with the struct-of-arrays shapes."""
+    c = CASES["vol_444_d3"]
+    s = _spline(c)
+    N = c.uvw.shape[0]
+    soa = s.evaluate_points(c.uvw, jacobian=True, spans=True)
+    aos = s.evaluate_points(c.uvw, jacobian=True, spans=True, out_layout="aos")
+    assert aos.records.shape == (N, 12) and isinstance(aos.records, np.ndarray)
+    assert aos.values.shape == (3, N) and aos.jacobian.shape == (3, 3, N) and aos.normal is None
+    assert np.shares_memory(aos.values, aos.records) and np.shares_memory(aos.jacobian, aos.records)
+    assert np.array_equal(aos.values, soa.values) and np.array_equal(aos.jacobian, soa.jacobian) and np.array_equal(aos.spans, soa.spans)
+    assert np.array_equal(aos.records[:, 3:].reshape(N, 3, 3), np.transpose(soa.jacobian, (2, 0, 1)))   # the reference's (nDep, nInd) per point
+    only = s.evaluate_points(torch.from_numpy(c.uvw), out_layout="aos")
+    assert only.records.shape == (N, 4) and isinstance(only.records, torch.Tensor) and only.jacobian is None
+    surf = _spline(CASES["surf_44_d3"]) if "surf_44_d3" in CASES else None
+    if surf is not None:
+        cu = CASES["surf_44_d3"]
+        r = surf.evaluate_points(cu.uvw, normal=True, indices=(2, 0), out_layout="aos")
+        ref = surf.evaluate_points(cu.uvw, normal=True, indices=(2, 0))
+        assert r.records.shape[1] == 12 and r.normal.shape == (2, cu.uvw.shape[0]) and close(r.normal, ref.normal) and r.jacobian is None
+    with pytest.raises(ValueError, match="out_layout"):
+        s.evaluate_points(c.uvw, out_layout="rows")
+    with pytest.raises(ValueError, match="with_respect_to"):
+        s.evaluate_points(c.uvw, with_respect_to=[1, 0, 0], out_layout="aos")
+    with pytest.raises(ValueError, match="defer"):
+        s.evaluate_points(c.uvw, check_domain="defer")
+    with pytest.raises(ValueError, match="outside domain"):
+        s.evaluate_points(np.array([[0.5, 0.5, 1.5]]), out_layout="aos")
+
+
 def test_device_copy_revalidation_and_freeze():
     c = CASES["curve_o4"]
     s = _spline(c)
