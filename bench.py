@@ -216,13 +216,23 @@ class Cfg2Teapot(Workload):
 
     def parity(self):
         """Timed outputs of 8 patches (rim, body, handle, spout, lid knob, lid, two bottoms): the four border rows /
-        columns in full plus 12288 random interior nodes each.  At the singular points of the lid / bottom patches
-        (collapsed control rows) the raw normal is rounding noise and the reference itself returns NaN or an
-        arbitrary unit vector: there NaN-or-unit-length is required, everywhere else the strict bar."""
+        columns in full plus 12288 random interior nodes each.  Values and derivatives: strict bar everywhere.  Unit
+        normals, by how well the cross product is conditioned at the node (|du x dv| against the sum of the magnitudes of
+        the terms it is built from, oracle.normal_abs_vec):
+          well-conditioned (ratio >= 1e-3): strict bar;
+          ill-conditioned (next to the collapsed control rows of the lid / bottom patches the partials themselves cancel;
+            two restatements of the reference already differ by 2.3x the strict bar there): the bar widened by
+            16 eps sum|terms| / |du x dv|;
+          degenerate (the collapsed rows themselves: the raw normal is an exact or inexact zero and the reference returns
+            NaN or an arbitrary unit vector depending on rounding): NaN or unit length."""
         CO = _oracle()
+        from oracle import bspy_oracle as O
         torch, n = self.torch, self.n
         P = Parity()
         rng = np.random.default_rng(22)
+        classes = {"well": 0, "ill": 0, "degenerate": 0}
+        eps = np.finfo(float).eps
+        sp = self.bspy._cuda.spans(torch.from_numpy(self.kn).to(self.dev), 4, self.axis).cpu().numpy()
         for p in (0, 5, 13, 17, 20, 25, 28, 31):
             a = np.concatenate([np.zeros(n, np.int64), np.full(n, n - 1), np.arange(n), np.arange(n), rng.integers(0, n, 12288)])
             b = np.concatenate([np.arange(n), np.arange(n), np.zeros(n, np.int64), np.full(n, n - 1), rng.integers(0, n, 12288)])
@@ -234,23 +244,35 @@ class Cfg2Teapot(Workload):
             uv = np.stack([self.axis_host[a], self.axis_host[b]], axis=1)
             ref = CO.evaluate(s, uv, values=True, jacobian=True, normal=True, normalize=True, spans=True)
             raw = CO.evaluate(s, uv, values=False, normal=True, normalize=False)["normal"]
-            scale = np.abs(ref["jacobian"]).max(axis=(1, 2)) ** 2
-            regular = np.sqrt((raw ** 2).sum(axis=1)) > 1e-9 * np.maximum(scale, 1e-300)
+            with np.errstate(all="ignore"):
+                scale = O.normal_abs_vec(O.OracleSpline(**_payload(s)), uv).max(axis=1)
+                mag = np.sqrt((raw ** 2).sum(axis=1))
+                degenerate = ~(mag > 1e-9 * scale)
+                well = (scale > 0) & (mag >= 1e-3 * scale)
+                ill = ~well & ~degenerate
             P.values(v, ref["values"], f"patch {p} values")
             P.values(j, ref["jacobian"], f"patch {p} jacobian")
-            P.values(nr, ref["normal"], f"patch {p} normal", mask=regular)
-            rest = nr[~regular]
+            P.values(nr, ref["normal"], f"patch {p} normal", mask=well)
+            if ill.any():
+                x, r = nr[ill], ref["normal"][ill]
+                tol = ATOL + RTOL * np.abs(r) + 16 * eps * (scale[ill] / mag[ill])[:, None]
+                if not (np.isfinite(x).all() and np.all(np.abs(x - r) <= tol)):
+                    P.nan_match = False
+                    P.notes.append(f"patch {p}: ill-conditioned normals outside the condition-aware bar")
+            rest = nr[degenerate]
             if rest.size:
                 length = np.sqrt((rest ** 2).sum(axis=1))
                 if not np.all(np.isnan(length) | (np.abs(length - 1.0) < 1e-12)):
                     P.nan_match = False
                     P.notes.append(f"patch {p}: singular-point normal neither NaN nor unit length")
+            classes["well"] += int(well.sum()); classes["ill"] += int(ill.sum()); classes["degenerate"] += int(degenerate.sum())
             # spans of the grid axes through the span kernel of the same library (the grid kernel does not output them)
-            sp = self.bspy._cuda.spans(torch.from_numpy(self.kn).to(self.dev), 4, self.axis).cpu().numpy()
             P.spans(sp[a], ref["spans"][:, 0])
             P.spans(sp[b], ref["spans"][:, 1])
             P.n += len(a)
-        return P.report()
+        rep = P.report()
+        rep["normal_classes"] = classes
+        return rep
 
 
 class ScatteredBase(Workload):

@@ -779,13 +779,15 @@ static int eval_binned_records(const SplineDev &s, PointsDev in, long long N, co
     FixedFn fn = find_fixed(s, jac);
     {
         const int ndt = (int)option(OPT_DEP_TILE, 14);
-        // one dependent variable per pass stores partial records: only where the records are private (workspace)
-        FixedFn tiled = (ndt > 0 && !nN && !userAos) ? find_fixed_tiled(s, jac, ndt) : nullptr;
+        // one dependent variable per pass (smaller accumulator set, more resident warps); no normals there
+        FixedFn tiled = (ndt > 0 && !nN) ? find_fixed_tiled(s, jac, ndt) : nullptr;
         if (tiled) fn = tiled;
     }
-    // evaluation kernel for dense chunks: tensor-pipe cell kernel (value + jacobian requests), else warp-staged
-    // windows, else the L1-gather kernel.  CELL_KERNEL: 0 = never the tensor-pipe kernel, 1 = default
-    const CellEntry *cell = (jac && plainWrt && option(OPT_CELL_KERNEL, 1)) ? find_cell(s) : nullptr;
+    // evaluation kernel for dense chunks: warp-staged windows where compiled, else the L1-gather kernel.  CELL_KERNEL=1
+    // selects the tensor-pipe cell kernel instead (measured SLOWER: 493 vs 326 us per 4 Mi points on config 4, 3400 vs
+    // 1070 us on config 5 -- the T round trip through shared memory saturates the LSU data pipe at 92 % with the FP64
+    // pipe 15 % active, profiles/r02_cfg4_eval_cell_mma_ncu_full.txt; kept as a tested experiment, off by default)
+    const CellEntry *cell = (jac && plainWrt && option(OPT_CELL_KERNEL, 0)) ? find_cell(s) : nullptr;
     const size_t cellSmem = cell ? sizeof(double) * CELL_WARPS * cell->warpDoubles : 0;
     if (cell)
         if (int rc = allow_dynamic_smem(cell->fn, cellSmem)) return rc;
@@ -793,9 +795,13 @@ static int eval_binned_records(const SplineDev &s, PointsDev in, long long N, co
     {
         const int code = (int)option(OPT_STAGED, 0);
         if (code >= 0 && !nN) staged = find_staged(s, jac, code);
-        if (staged)
-            if (int rc = allow_dynamic_smem(staged->fn, sizeof(double) * 4 * 2 * staged->windowDoubles)) return rc;
     }
+    // second-generation staged kernel (span records staged with the window) unless EXP_A=1 or the records are off
+    const bool staged2 = staged && option(OPT_SPAN_RECORDS, 1) && !option(OPT_EXP_A, 0);
+    const FixedFn stagedFn = staged ? (staged2 ? staged->fn2 : staged->fn) : nullptr;
+    const size_t stagedSmem = staged ? sizeof(double) * 4 * 2 * (staged2 ? staged->slotDoubles : staged->windowDoubles) : 0;
+    if (staged)
+        if (int rc = allow_dynamic_smem(stagedFn, stagedSmem)) return rc;
     // per-span records (left knots | reciprocal gaps) for every variable: no divisions in the evaluation kernel
     const double *spanRec[BSPY_MAX_IND] = {};
     {
@@ -876,7 +882,7 @@ static int eval_binned_records(const SplineDev &s, PointsDev in, long long N, co
             // persistent warps over contiguous runs of tiles (window reuse between consecutive tiles)
             long long blocks = (long long)num_sms() * (staged->code % 10);
             if (blocks > (n + 127) / 128) blocks = (n + 127) / 128;
-            staged->fn<<<(unsigned)blocks, 128, sizeof(double) * 4 * 2 * staged->windowDoubles, sEval>>>(s, pin, n, wrt, o2);
+            stagedFn<<<(unsigned)blocks, 128, stagedSmem, sEval>>>(s, pin, n, wrt, o2);
         }
         else
             fn<<<(unsigned)((n + 127) / 128), 128, 0, sEval>>>(s, pin, n, wrt, o2);

@@ -261,6 +261,188 @@ __global__ void __launch_bounds__(128, MINB) eval_staged_kernel(const SplineDev 
     }
 }
 
+// ---- warp-staged windows, second generation: the CELL's span records travel with its window ------------------------
+// All points of a cell share their knot spans, hence their per-span records (left knots | reciprocal gaps).  v1 above
+// still decodes the cell key per lane (three integer divisions by run-time radices) and pulls the records through L1 with
+// per-lane addresses on every tile (ncu: 1.3 long-scoreboard stalls per issue).  Here the warp decodes the key once per
+// cell CHANGE and stages the records next to the window image (cp.async, 16 bytes per lane); a point is then: its
+// 32-byte record (requested one tile ahead), broadcast LDS.128 of the slot's span records, the recurrence, the
+// contraction over the slot's window with immediate offsets.  Same arithmetic per point: bit-identical to v1.
+template <class Ord>
+struct CellRecords {
+    __host__ __device__ static constexpr int stride(int iv)
+    {
+        const int o = Ord::at(iv);
+        return ((o - 1 + o * (o - 1) / 2) + 1) & ~1;
+    }
+    __host__ __device__ static constexpr int offset(int iv)
+    {
+        int at = 0;
+        for (int m = 0; m < iv; ++m) at += stride(m);
+        return at;
+    }
+    static constexpr int size = offset(Ord::n);
+};
+
+// basis values and first derivatives from a span record held in shared memory (16-byte aligned)
+template <int O, bool DER>
+__device__ __forceinline__ void basis_from_shared_record(const double *__restrict__ rec, double u, int d, double (&b0)[O], double (&b1)[O])
+{
+    using R = SpanRec<O>;
+    double r[R::stride > 0 ? R::stride : 1];
+#pragma unroll
+    for (int j = 0; j < R::stride / 2; ++j) {
+        const double2 x = *reinterpret_cast<const double2 *>(rec + 2 * j);
+        r[2 * j] = x.x;
+        r[2 * j + 1] = x.y;
+    }
+    double dl[O > 1 ? O - 1 : 1], rc[O > 1 ? O * (O - 1) / 2 : 1];
+#pragma unroll
+    for (int j = 0; j < O - 1; ++j) dl[j] = u - r[j];
+#pragma unroll
+    for (int j = 0; j < O * (O - 1) / 2; ++j) rc[j] = r[O - 1 + j];
+    basis_core<O, DER>(dl, rc, d, b0, b1);
+}
+
+template <int IV, class Ord, int NDT, bool JAC>
+__device__ __forceinline__ void setup_variable_shared(const double *__restrict__ cellRec, double u, int d, FixedCtx<Ord, NDT, JAC> &c)
+{
+    constexpr int O = Ord::at(IV);
+    double b0[O], b1[O];
+    basis_from_shared_record<O, JAC>(cellRec + CellRecords<Ord>::offset(IV), u, d, b0, b1);
+#pragma unroll
+    for (int j = 0; j < O; ++j) {
+        c.B[IV][j] = b0[j];
+        if constexpr (JAC) c.dB[IV][j] = b1[j];
+    }
+}
+
+// the warp copies window and span records of cell `key` into a slot: [window image | records of variable 0 | 1 | ..]
+template <class Ord, int NDEP>
+__device__ __forceinline__ void stage_cell(const SplineDev &s, const PointsDev &in, int key, double *dst, const int lane)
+{
+    using WS = WindowShape<Ord, NDEP>;
+    using CR = CellRecords<Ord>;
+    stage_window<Ord, NDEP>(s, key, dst, lane);
+    const unsigned recAddr = (unsigned)__cvta_generic_to_shared(dst + WS::size);
+    int k = key;
+#pragma unroll
+    for (int iv = Ord::n - 1; iv >= 0; --iv) {
+        const int m = s.nCoef[iv] - Ord::at(iv) + 1;
+        const int span = k % m;
+        k /= m;
+        constexpr int dummy = 0;
+        (void)dummy;
+        const int st = CR::stride(iv);
+        if (lane < st / 2) {
+            const double *src = in.spanRec[iv] + (long long)span * st + 2 * lane;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(recAddr + (unsigned)(CR::offset(iv) + 2 * lane) * 8u), "l"(src) : "memory");
+        }
+    }
+}
+
+template <int NIND, int O0, int O1, int O2, int O3, int NDEP, bool JAC, int NDT, int MINB>
+__global__ void __launch_bounds__(128, MINB) eval_staged2_kernel(const SplineDev s, const PointsDev in, const long long N,
+                                                                  const WrtDev wrt, const OutDev out)
+{
+    using Ord = Orders<NIND, O0, O1, O2, O3>;
+    using WS = WindowShape<Ord, NDEP>;
+    using CR = CellRecords<Ord>;
+    constexpr int SLOT = WS::size + CR::size;                       // doubles per slot (both parts even: 16-byte aligned)
+    static_assert(NDEP % NDT == 0, "dependent-variable tile must divide nDep");
+    extern __shared__ __align__(16) double stagedWindows[];         // per warp: two slots
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *w0 = stagedWindows + warp * 2 * SLOT;
+    int slotKey0 = -1, slotKey1 = -1;                               // cells held by the two slots (warp-uniform)
+    const long long tiles = (N + 31) >> 5, nWarps = gridDim.x * 4LL;
+    const long long per = (tiles + nWarps - 1) / nWarps;
+    const long long firstTile = (blockIdx.x * 4LL + warp) * per;
+    const long long endTile = firstTile + per < tiles ? firstTile + per : tiles;
+    double2 r0 = make_double2(0.0, 0.0), r1 = r0;
+    long long k4 = -1;
+    auto fetch = [&](long long tile) {
+        const long long t = tile * 32 + lane;
+        if (tile < endTile && t < N) {
+            const double2 *rp = reinterpret_cast<const double2 *>(in.records + 4 * t);
+            r0 = __ldcs(rp);
+            r1 = __ldcs(rp + 1);
+            if constexpr (NIND > 3) k4 = __ldcs(reinterpret_cast<const long long *>(in.recKI) + t);
+        }
+    };
+    fetch(firstTile);
+    for (long long tile = firstTile; tile < endTile; ++tile) {
+        const long long t = tile * 32 + lane;
+        const bool live = t < N;
+        double u[NIND];
+        u[0] = r0.x;
+        if constexpr (NIND > 1) u[1] = r0.y;
+        if constexpr (NIND > 2) u[2] = r1.x;
+        if constexpr (NIND > 3) u[3] = r1.y;
+        const long long ki = NIND > 3 ? k4 : __double_as_longlong(r1.y);
+        const int key = live ? (int)ki : -1;
+        const long long dest = out.aosScatter ? out.aosBase + (ki >> 32) : t;
+        fetch(tile + 1);                                            // next tile's records arrive under this tile's arithmetic
+        bool done = !live;
+        while (true) {
+            const unsigned pending = __ballot_sync(0xffffffffu, !done);
+            if (!pending) break;
+            // up to two distinct cells per pass, each in the slot that already holds it or freshly staged
+            const int k0 = __shfl_sync(0xffffffffu, key, __ffs(pending) - 1);
+            const bool in0 = !done && key == k0;
+            const unsigned rest = __ballot_sync(0xffffffffu, !done && !in0);
+            const int k1 = rest ? __shfl_sync(0xffffffffu, key, __ffs(rest) - 1) : -1;
+            const bool in1 = !done && !in0 && key == k1;
+            int s0, s1 = -1;
+            bool staged = false;
+            if (k0 == slotKey0) s0 = 0;
+            else if (k0 == slotKey1) s0 = 1;
+            else {
+                s0 = (k1 >= 0 && k1 == slotKey0) ? 1 : 0;
+                stage_cell<Ord, NDEP>(s, in, k0, w0 + s0 * SLOT, lane);
+                if (s0) slotKey1 = k0; else slotKey0 = k0;
+                staged = true;
+            }
+            if (k1 >= 0) {
+                s1 = 1 - s0;
+                if ((s1 ? slotKey1 : slotKey0) != k1) {
+                    stage_cell<Ord, NDEP>(s, in, k1, w0 + s1 * SLOT, lane);
+                    if (s1) slotKey1 = k1; else slotKey0 = k1;
+                    staged = true;
+                }
+            }
+            if (staged) {
+                asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+                __syncwarp();
+            }
+            if (in0 || in1) {
+                const double *w = w0 + (in1 ? s1 : s0) * SLOT;
+                FixedCtx<Ord, NDT, JAC> c;
+                setup_variable_shared<0, Ord, NDT, JAC>(w + WS::size, u[0], wrt.d[0], c);
+                if constexpr (NIND > 1) setup_variable_shared<1, Ord, NDT, JAC>(w + WS::size, u[1], wrt.d[1], c);
+                if constexpr (NIND > 2) setup_variable_shared<2, Ord, NDT, JAC>(w + WS::size, u[2], wrt.d[2], c);
+                if constexpr (NIND > 3) setup_variable_shared<3, Ord, NDT, JAC>(w + WS::size, u[3], wrt.d[3], c);
+                double *rec = out.aos + dest * out.aosStride;
+                if constexpr (NDT == NDEP) {
+                    double v[NDEP];
+                    double g[NIND][NDEP];
+                    ContractS<0, Ord, NDEP, NDEP, JAC>::run(w, 0, c, v, g);
+                    store_result_record<NIND, NDEP, JAC>(s, out, rec, v, g);
+                } else {
+#pragma unroll 1
+                    for (int d0 = 0; d0 < NDEP; d0 += NDT) {
+                        double vt[NDT];
+                        double gt[NIND][NDT];
+                        ContractS<0, Ord, NDEP, NDT, JAC>::run(w + d0 * WS::perDepPad, 0, c, vt, gt);
+                        store_result_tile<NIND, NDEP, NDT, JAC>(rec, d0, vt, gt);
+                    }
+                }
+                done = true;
+            }
+            __syncwarp();                                            // slots may be overwritten by the next pass / tile
+        }
+    }
+}
+
 // ---- any-shape kernel -------------------------------------------------------------------------
 // Runtime nInd / orders / nDep.  Per-thread basis rows live in shared memory ([slot][thread]);
 // the window is walked with an odometer over all variables but the last, the last variable is
@@ -487,9 +669,12 @@ FixedFn find_fixed_tiled(const SplineDev &s, int jac, int code)
     return nullptr;
 }
 
-#define BSPY_STAGED(NI, A, B, C, D_, ND, J, NDT, MB)                                                          \
+#define BSPY_STAGED_(NI, A, B, C, D_, ND, J, NDT, MB, OPT)                                                        \
     {NI, {A, B, C, D_}, ND, J, 10 * NDT + MB, eval_staged_kernel<NI, A, B, C, D_, ND, J != 0, NDT, MB>,       \
-     WindowShape<Orders<NI, A, B, C, D_>, ND>::size}
+     WindowShape<Orders<NI, A, B, C, D_>, ND>::size,                                                          \
+     eval_staged2_kernel<NI, A, B, C, D_, ND, J != 0, NDT, MB>,                                               \
+     WindowShape<Orders<NI, A, B, C, D_>, ND>::size + CellRecords<Orders<NI, A, B, C, D_>>::size, OPT}
+#define BSPY_STAGED(NI, A, B, C, D_, ND, J, NDT, MB) BSPY_STAGED_(NI, A, B, C, D_, ND, J, NDT, MB, 0)
 static const StagedEntry kStaged[] = {
     // volumes (measured: tricubic nDep 3, value + jacobian, 379 -> 326 us per 4 Mi points, FP64 pipe 37 -> 50 %);
     // the 4-variate nDep-6 window gained nothing here (register spills once the pass over the dependent variables is
@@ -498,6 +683,9 @@ static const StagedEntry kStaged[] = {
     BSPY_STAGED(3, 4, 4, 4, 0, 1, 0, 1, 4), BSPY_STAGED(3, 4, 4, 4, 0, 1, 1, 1, 4),
     BSPY_STAGED(3, 4, 4, 4, 0, 3, 0, 3, 4), BSPY_STAGED(3, 4, 4, 4, 0, 3, 1, 3, 4),
     BSPY_STAGED(3, 4, 4, 4, 0, 4, 0, 4, 4), BSPY_STAGED(3, 4, 4, 4, 0, 4, 1, 4, 4),
+    // variants selected with STAGED=<10 * deps per pass + CTAs per SM> only
+    BSPY_STAGED_(3, 4, 4, 4, 0, 3, 1, 3, 3, 1),
+    BSPY_STAGED_(4, 3, 3, 3, 3, 6, 1, 1, 4, 1), BSPY_STAGED_(4, 3, 3, 3, 3, 6, 1, 2, 3, 1), BSPY_STAGED_(4, 3, 3, 3, 3, 6, 1, 6, 2, 1),
 };
 
 const StagedEntry *find_staged(const SplineDev &s, int jac, int code)
@@ -506,7 +694,7 @@ const StagedEntry *find_staged(const SplineDev &s, int jac, int code)
         if (e.nInd != s.nInd || e.nDep != s.nDep || e.jac != jac) continue;
         bool same = true;
         for (int i = 0; i < s.nInd; ++i) same &= e.o[i] == s.order[i];
-        if (same && (code == 0 || code == e.code)) return &e;
+        if (same && (code == 0 ? !e.optIn : code == e.code)) return &e;
     }
     return nullptr;
 }

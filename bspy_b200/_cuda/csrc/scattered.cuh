@@ -389,6 +389,9 @@ struct StagedEntry {
     int nInd, o[4], nDep, jac, code;
     FixedFn fn;
     int windowDoubles;
+    FixedFn fn2;          // second generation: the cell's span records are staged with its window
+    int slotDoubles;
+    int optIn;            // only selected by an explicit STAGED=<code> (variants kept for measurement)
 };
 
 FixedFn find_fixed(const SplineDev &s, int jac);

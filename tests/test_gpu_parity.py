@@ -476,7 +476,6 @@ def test_record_mode_staged_windows_bit_identical(option):
         return np.concatenate((np.zeros(o - 1), inner, np.ones(o - 1)))
 
     option("BIN_MODE", 1)
-    option("CELL_KERNEL", 0)                                        # the all-DFMA kernels; the tensor-pipe cell kernel has its own test
     shapes = [((4, 4, 4), 3, (18, 18, 18)), ((3, 3, 3), 3, (20, 19, 18)), ((4, 4, 4), 1, (28, 27, 26)), ((4, 4, 4), 4, (17, 16, 18)),
               ((3, 3, 3, 3), 6, (10, 10, 9, 10))]
     for order, nDep, nCoef in shapes:
@@ -669,11 +668,11 @@ def test_record_mode_multi_chunk_overlap_bit_identical(option):
     s = bspy.Spline(3, 3, (4, 4, 4), (18, 18, 18), [K(4, 18) for _ in range(3)], rng.standard_normal((3, 18, 18, 18)))
     ds = device_spline(s)
     N = 2 * (1 << 22) + 70_001                                     # three chunks, ragged sparse tail
-    option("CELL_KERNEL", 0)
     pts = torch.rand((N, 3), dtype=torch.float64, device="cuda", generator=torch.Generator(device="cuda").manual_seed(5))
     ref = _cuda.eval_points(ds, pts, 3, 1, N, binned=False, values=True, jacobian=True)
-    for flag in ("1", "0"):
-        option("BIN_OVERLAP", int(flag))
+    for flag in ("1", "0", "v1"):
+        option("BIN_OVERLAP", 1 if flag == "v1" else int(flag))
+        option("EXP_A", 1 if flag == "v1" else None)               # v1: first-generation staged kernel (per-lane span records)
         a = _cuda.eval_points(ds, pts, 3, 1, N, binned=True, values=True, jacobian=True)
         torch.cuda.synchronize()
         assert torch.equal(a["values"], ref["values"]) and torch.equal(a["jacobian"], ref["jacobian"]), flag
