@@ -203,7 +203,12 @@ __device__ __forceinline__ int claim_slot(int *cursor, int key, unsigned active)
 
 // exclusive scan of hist[0..cells) in place, one CTA: 4096 counters per round (coalesced 16-byte loads, warp
 // shuffles, one shared-memory hop between the warps), running total carried from round to round
-__global__ void __launch_bounds__(1024) bin_scan_kernel(int *__restrict__ hist, const int cells)
+// evenPad != 0: every cell's segment is rounded up to an even number of slots so that the aligned pairs (2i, 2i+1) of the
+// sorted sequence never straddle a cell (two points per thread share their window loads); the odd cells' spare slot
+// receives a dummy record (NaN parameters, index -1: evaluated, never stored).  hist[cells] receives the total.
+__global__ void __launch_bounds__(1024) bin_scan_kernel(int *__restrict__ hist, const int cells, const int evenPad = 0,
+                                                        double *__restrict__ records = nullptr, int2 *__restrict__ recKI = nullptr,
+                                                        const int nInd = 0)
 {
     __shared__ int warpSum[32];
     __shared__ int carry;
@@ -219,6 +224,8 @@ __global__ void __launch_bounds__(1024) bin_scan_kernel(int *__restrict__ hist, 
             if (i + 1 < cells) c.y = hist[i + 1];
             if (i + 2 < cells) c.z = hist[i + 2];
         }
+        const int4 raw = c;
+        if (evenPad) { c.x = (c.x + 1) & ~1; c.y = (c.y + 1) & ~1; c.z = (c.z + 1) & ~1; c.w = (c.w + 1) & ~1; }
         const int mine = c.x + c.y + c.z + c.w;
         int incl = mine;
 #pragma unroll
@@ -247,10 +254,26 @@ __global__ void __launch_bounds__(1024) bin_scan_kernel(int *__restrict__ hist, 
             if (i + 1 < cells) hist[i + 1] = o.y;
             if (i + 2 < cells) hist[i + 2] = o.z;
         }
+        if (evenPad) {
+            const int cnt[4] = {raw.x, raw.y, raw.z, raw.w}, at[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (i + j < cells && (cnt[j] & 1)) {
+                    const long long pos = at[j] + cnt[j];
+                    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+                    double2 *q = reinterpret_cast<double2 *>(records + 4 * pos);
+                    const long long ki = (-1LL << 32) | (unsigned)(i + j);
+                    q[0] = make_double2(nan, nan);
+                    q[1] = make_double2(nan, nInd <= 3 ? __longlong_as_double(ki) : nan);
+                    if (nInd > 3) recKI[pos] = make_int2(i + j, -1);
+                }
+            }
+        }
         __syncthreads();
         if (threadIdx.x == 1023) carry = start + mine;
         __syncthreads();
     }
+    if (threadIdx.x == 0) hist[cells] = carry;
 }
 
 __global__ void __launch_bounds__(256) bin_scatter_kernel(const int *__restrict__ keys, int *__restrict__ cursor, const int n,
@@ -392,13 +415,56 @@ static bool binning_applies(const SplineDev &s, long long N)
     return find_fixed(s, 0) != nullptr;
 }
 
+struct ImageEntry;
+static const ImageEntry *find_image(const SplineDev &s, int jac, int code);
+
+// run-time shape version of the layout (the builder is not templated)
+struct ImageLayout {
+    int n, nDep, OL, Q, window, recs, size;
+    int recOffset[BSPY_MAX_IND], recStride[BSPY_MAX_IND];
+};
+
+static ImageLayout image_layout(const SplineDev &s)
+{
+    ImageLayout L{};
+    L.n = s.nInd; L.nDep = s.nDep; L.OL = s.order[s.nInd - 1];
+    L.Q = 1;
+    for (int i = 0; i < s.nInd - 1; ++i) L.Q *= s.order[i];
+    L.window = s.nDep * L.Q * 4;
+    int at = 0;
+    for (int i = 0; i < s.nInd; ++i) {
+        L.recOffset[i] = at;
+        L.recStride[i] = span_rec_stride(s.order[i]);
+        at += L.recStride[i];
+    }
+    L.recs = (at + 3) & ~3;
+    L.size = L.window + L.recs;
+    return L;
+}
+
+
+// cell images are built once per call: worth it when the batch holds a few points per cell at least
+static bool images_apply(const SplineDev &s, long long N)
+{
+    const long long code = option(OPT_IMAGE, 0);
+    if (code < 0 || !option(OPT_SPAN_RECORDS, 1)) return false;
+    if (!find_image(s, 1, (int)code) && !find_image(s, 0, (int)code)) return false;
+    return N >= 8 * binned_cells(s);
+}
+
+static long long cell_images_bytes(const SplineDev &s, long long N)
+{
+    if (!images_apply(s, N)) return 0;
+    return 8 * pad64(binned_cells(s) * (long long)image_layout(s).size);
+}
+
 long long binned_workspace(const SplineDev &s, long long N, bool aosOut)
 {
     if (!binning_applies(s, N)) return 0;
     const long long cells = binned_cells(s);
     if (aosOut || bin_mode(N) == 1) {
         const long long chunk = N < BIN_REC_CHUNK ? N : BIN_REC_CHUNK;
-        return 2 * records_half_bytes(s, chunk, !aosOut) + span_records_bytes(s);
+        return 2 * records_half_bytes(s, chunk, !aosOut) + span_records_bytes(s) + cell_images_bytes(s, N);
     }
     const long long chunk = N < BIN_CHUNK_MAX ? N : BIN_CHUNK_MAX;
     return 3 * 4 * pad64(chunk) + 4 * pad64(cells + 1);
@@ -728,6 +794,415 @@ __global__ void __launch_bounds__(CELL_WARPS * 32, MINB) eval_cell_mma_kernel(co
     }
 }
 
+// ---- cell images: one compact, padded copy of every cell's window (+ its span records) in global memory ------------
+// The thread-per-point kernel in cell order walks its window through L1 with run-time strides: 486 scalar loads and
+// ~700 address instructions per point for the 4-variate nDep-6 manifold (ncu: 4.0 long-scoreboard + 1.9 LG-throttle stalls
+// per issue, FP64 pipe 40 %), and the warp-staged shared-memory variant of that shape spills.  Here a pre-pass (once per
+// call) writes, for every cell, the image  [d][q][4]  (q = window position of all variables but the last, rows of the last
+// variable padded to 4 doubles = one 32-byte sector) followed by the cell's span records; the evaluation kernel is then
+// straight-line code per point: one 256-bit load per window row at an immediate offset from the cell's base pointer
+// (all lanes of a warp in the same cell: one broadcast sector from L1), the span records by broadcast loads, no
+// per-lane key decode, no address arithmetic.  Arithmetic and summation order are those of Contract<>: bit-identical.
+template <class Ord, int NDEP>
+struct ImageShape {
+    static constexpr int n = Ord::n;
+    static constexpr int OL = Ord::at(n - 1);
+    __host__ __device__ static constexpr int qstride(int iv)
+    {
+        int st = 1;
+        for (int m = n - 2; m > iv; --m) st *= Ord::at(m);
+        return st;
+    }
+    static constexpr int Q = n > 1 ? qstride(0) * Ord::at(0) : 1;
+    static constexpr int perDep = Q * 4;
+    static constexpr int window = NDEP * perDep;
+    static constexpr int recs = (CellRecords<Ord>::size + 3) & ~3;
+    static constexpr int size = window + recs;                        // doubles per cell: a multiple of 4
+    static_assert(OL <= 4, "rows of the last variable are padded to 4 doubles");
+};
+
+// one warp per cell
+__global__ void __launch_bounds__(256) build_cell_images_kernel(const SplineDev s, const ImageLayout L, const long long cells,
+                                                                const double *const *spanRecUnused, const PointsDev recs,
+                                                                double *__restrict__ images)
+{
+    const int lane = threadIdx.x & 31;
+    for (long long cell = blockIdx.x * 8LL + (threadIdx.x >> 5); cell < cells; cell += gridDim.x * 8LL) {
+        int span[BSPY_MAX_IND];
+        long long base = 0;
+        {
+            long long k = cell;
+            for (int iv = L.n - 1; iv >= 0; --iv) {
+                const int m = s.nCoef[iv] - s.order[iv] + 1;
+                span[iv] = (int)(k % m);
+                k /= m;
+                base += (long long)span[iv] * s.stride[iv];
+            }
+        }
+        double *img = images + cell * L.size;
+        for (int e = lane; e < L.window; e += 32) {
+            const int k = e & 3, row = e >> 2;
+            const int d = row / L.Q;
+            int q = row - d * L.Q;
+            double x = 0.0;
+            if (k < L.OL) {
+                long long src = base + (long long)d * s.depStride + k;
+                for (int iv = L.n - 2; iv >= 0; --iv) {
+                    const int o = s.order[iv];
+                    src += (long long)(q % o) * s.stride[iv];
+                    q /= o;
+                }
+                x = __ldg(s.coefs + src);
+            }
+            img[e] = x;
+        }
+        for (int iv = 0; iv < L.n; ++iv)
+            for (int j = lane; j < L.recStride[iv]; j += 32)
+                img[L.window + L.recOffset[iv] + j] = __ldg(recs.spanRec[iv] + (long long)span[iv] * L.recStride[iv] + j);
+        for (int j = L.recOffset[L.n - 1] + L.recStride[L.n - 1] + lane; j < L.recs; j += 32) img[L.window + j] = 0.0;
+    }
+}
+
+__device__ __forceinline__ void ld_row256(const double *__restrict__ p, double (&x)[4])
+{
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(x[0]), "=d"(x[1]), "=d"(x[2]), "=d"(x[3]) : "l"(p));
+}
+
+// Contract variables L .. n-1 of the image (dependent variables d0 .. d0+NDT-1) at window position q of the outer
+// variables; same recursion and summation order as Contract<>.
+template <int L, class Ord, int NDEP, int NDT, bool JAC>
+struct ContractI {
+    using IS = ImageShape<Ord, NDEP>;
+    __device__ __forceinline__ static void run(const double *__restrict__ img, const int q, const FixedCtx<Ord, NDT, JAC> &c,
+                                               double (&v)[NDT], double (&g)[Ord::n][NDT])
+    {
+        constexpr int O = Ord::at(L);
+#pragma unroll
+        for (int d = 0; d < NDT; ++d) v[d] = 0.0;
+        if constexpr (JAC) {
+#pragma unroll
+            for (int m = L; m < Ord::n; ++m)
+#pragma unroll
+                for (int d = 0; d < NDT; ++d) g[m][d] = 0.0;
+        }
+        if constexpr (L == Ord::n - 1) {
+#pragma unroll
+            for (int d = 0; d < NDT; ++d) {
+                double x[4];
+                ld_row256(img + (d * IS::Q + q) * 4, x);
+#pragma unroll
+                for (int i = 0; i < O; ++i) {
+                    v[d] = fma(x[i], c.B[L][i], v[d]);
+                    if constexpr (JAC) g[L][d] = fma(x[i], c.dB[L][i], g[L][d]);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < O; ++i) {
+                double cv[NDT];
+                double cg[Ord::n][NDT];
+                ContractI<L + 1, Ord, NDEP, NDT, JAC>::run(img, q + i * IS::qstride(L), c, cv, cg);
+#pragma unroll
+                for (int d = 0; d < NDT; ++d) {
+                    v[d] = fma(cv[d], c.B[L][i], v[d]);
+                    if constexpr (JAC) {
+                        g[L][d] = fma(cv[d], c.dB[L][i], g[L][d]);
+#pragma unroll
+                        for (int m = L + 1; m < Ord::n; ++m) g[m][d] = fma(cg[m][d], c.B[L][i], g[m][d]);
+                    }
+                }
+            }
+        }
+    }
+};
+
+template <int IV, class Ord, int NDT, bool JAC>
+__device__ __forceinline__ void setup_variable_image(const double *__restrict__ rec, double u, int d, FixedCtx<Ord, NDT, JAC> &c)
+{
+    constexpr int O = Ord::at(IV);
+    double b0[O], b1[O];
+    basis_from_span_record<O, JAC>(rec + CellRecords<Ord>::offset(IV), u, d, b0, b1);
+#pragma unroll
+    for (int j = 0; j < O; ++j) {
+        c.B[IV][j] = b0[j];
+        if constexpr (JAC) c.dB[IV][j] = b1[j];
+    }
+}
+
+// STAGE: the passes over the dependent variables (rolled loop) leave their results in a [slot][thread] tile of shared
+// memory and every thread then writes its whole record in one go (whole sectors at the record's final position)
+template <int NIND, int O0, int O1, int O2, int O3, int NDEP, bool JAC, int NDT, int MINB, bool STAGE>
+__global__ void __launch_bounds__(128, MINB) eval_image_kernel(const SplineDev s, const PointsDev in, const long long N,
+                                                                const WrtDev wrt, const OutDev out)
+{
+    using Ord = Orders<NIND, O0, O1, O2, O3>;
+    using IS = ImageShape<Ord, NDEP>;
+    static_assert(NDEP % NDT == 0, "dependent-variable tile must divide nDep");
+    constexpr int R = JAC ? NDEP * (1 + NIND) : NDEP;
+    extern __shared__ __align__(16) double recTile[];                // STAGE: R slots x 128 threads
+    const long long t = blockIdx.x * 128LL + threadIdx.x;
+    if (t >= N) return;
+    const double2 *rp = reinterpret_cast<const double2 *>(in.records + 4 * t);
+    const double2 r0 = __ldcs(rp), r1 = __ldcs(rp + 1);
+    double u[NIND];
+    u[0] = r0.x;
+    if constexpr (NIND > 1) u[1] = r0.y;
+    if constexpr (NIND > 2) u[2] = r1.x;
+    if constexpr (NIND > 3) u[3] = r1.y;
+    const long long ki = NIND > 3 ? __ldcs(reinterpret_cast<const long long *>(in.recKI) + t) : __double_as_longlong(r1.y);
+    const long long dest = out.aosScatter ? out.aosBase + (ki >> 32) : t;
+    const double *img = in.images + (long long)(int)ki * IS::size;
+    FixedCtx<Ord, NDT, JAC> c;
+    setup_variable_image<0, Ord, NDT, JAC>(img + IS::window, u[0], wrt.d[0], c);
+    if constexpr (NIND > 1) setup_variable_image<1, Ord, NDT, JAC>(img + IS::window, u[1], wrt.d[1], c);
+    if constexpr (NIND > 2) setup_variable_image<2, Ord, NDT, JAC>(img + IS::window, u[2], wrt.d[2], c);
+    if constexpr (NIND > 3) setup_variable_image<3, Ord, NDT, JAC>(img + IS::window, u[3], wrt.d[3], c);
+    double *rec = out.aos + dest * out.aosStride;
+    if constexpr (NDT == NDEP) {
+        double v[NDEP];
+        double g[NIND][NDEP];
+        ContractI<0, Ord, NDEP, NDEP, JAC>::run(img, 0, c, v, g);
+        store_result_record<NIND, NDEP, JAC>(s, out, rec, v, g);
+    } else {
+        double *mine = recTile + threadIdx.x;
+#pragma unroll 1
+        for (int d0 = 0; d0 < NDEP; d0 += NDT) {
+            double vt[NDT];
+            double gt[NIND][NDT];
+            ContractI<0, Ord, NDEP, NDT, JAC>::run(img + d0 * IS::perDep, 0, c, vt, gt);
+            if constexpr (STAGE) {
+#pragma unroll
+                for (int d = 0; d < NDT; ++d) {
+                    mine[(d0 + d) * 128] = vt[d];
+                    if constexpr (JAC) {
+#pragma unroll
+                        for (int iv = 0; iv < NIND; ++iv) mine[(NDEP + (d0 + d) * NIND + iv) * 128] = gt[iv][d];
+                    }
+                }
+            } else {
+                store_result_tile<NIND, NDEP, NDT, JAC>(rec, d0, vt, gt);
+            }
+        }
+        if constexpr (STAGE) {
+            constexpr int RP = (R + 3) & ~3;
+            double2 *q2 = reinterpret_cast<double2 *>(rec);
+#pragma unroll
+            for (int j = 0; j < RP / 2; ++j) {
+                const double a = 2 * j < R ? mine[(2 * j) * 128] : 0.0, b = 2 * j + 1 < R ? mine[(2 * j + 1) * 128] : 0.0;
+                if (2 * j < out.aosStride) __stcs(q2 + j, make_double2(a, b));
+            }
+        }
+    }
+}
+
+// ---- two points per thread --------------------------------------------------------------------------------------------
+// The innermost contraction stage needs every window coefficient in a register of every lane: 1.5 KB (tricubic, nDep 3) /
+// 3.9 KB (4-variate, nDep 6) per point through the 128 B/clk load-return path of the SM, which is as many cycles as the
+// FP64 pipe needs for the point's arithmetic (ncu: l1tex 68-77 % busy on every variant of the one-point kernels, which is
+// why they all run at the same speed whatever their occupancy or instruction count).  Two points of the SAME cell per
+// thread use every loaded row twice: half the load-return traffic per point, twice the independent FMA chains.  The sort
+// rounds every cell's segment up to an even length (bin_scan_kernel, evenPad), so the aligned pairs of the sorted sequence
+// never straddle a cell; spare slots hold dummy records that are evaluated and not stored.
+template <int L, class Ord, int NDEP, int NDT>
+struct ContractI2 {
+    using IS = ImageShape<Ord, NDEP>;
+    using Ctx = FixedCtx<Ord, NDT, true>;
+    __device__ __forceinline__ static void run(const double *__restrict__ img, const int q, const Ctx &c0, const Ctx &c1,
+                                               double (&v0)[NDT], double (&g0)[Ord::n][NDT], double (&v1)[NDT], double (&g1)[Ord::n][NDT])
+    {
+        constexpr int O = Ord::at(L);
+#pragma unroll
+        for (int d = 0; d < NDT; ++d) { v0[d] = 0.0; v1[d] = 0.0; }
+#pragma unroll
+        for (int m = L; m < Ord::n; ++m)
+#pragma unroll
+            for (int d = 0; d < NDT; ++d) { g0[m][d] = 0.0; g1[m][d] = 0.0; }
+        if constexpr (L == Ord::n - 1) {
+#pragma unroll
+            for (int d = 0; d < NDT; ++d) {
+                double x[4];
+                ld_row256(img + (d * IS::Q + q) * 4, x);
+#pragma unroll
+                for (int i = 0; i < O; ++i) {
+                    v0[d] = fma(x[i], c0.B[L][i], v0[d]);
+                    v1[d] = fma(x[i], c1.B[L][i], v1[d]);
+                    g0[L][d] = fma(x[i], c0.dB[L][i], g0[L][d]);
+                    g1[L][d] = fma(x[i], c1.dB[L][i], g1[L][d]);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < O; ++i) {
+                double cv0[NDT], cv1[NDT];
+                double cg0[Ord::n][NDT], cg1[Ord::n][NDT];
+                ContractI2<L + 1, Ord, NDEP, NDT>::run(img, q + i * IS::qstride(L), c0, c1, cv0, cg0, cv1, cg1);
+#pragma unroll
+                for (int d = 0; d < NDT; ++d) {
+                    v0[d] = fma(cv0[d], c0.B[L][i], v0[d]);
+                    v1[d] = fma(cv1[d], c1.B[L][i], v1[d]);
+                    g0[L][d] = fma(cv0[d], c0.dB[L][i], g0[L][d]);
+                    g1[L][d] = fma(cv1[d], c1.dB[L][i], g1[L][d]);
+#pragma unroll
+                    for (int m = L + 1; m < Ord::n; ++m) {
+                        g0[m][d] = fma(cg0[m][d], c0.B[L][i], g0[m][d]);
+                        g1[m][d] = fma(cg1[m][d], c1.B[L][i], g1[m][d]);
+                    }
+                }
+            }
+        }
+    }
+};
+
+// basis values and first derivatives of TWO parameters of the same span from one read of the span record
+template <int IV, class Ord, int NDT>
+__device__ __forceinline__ void setup_variable_pair(const double *__restrict__ rec, double ua, double ub, FixedCtx<Ord, NDT, true> &ca,
+                                                    FixedCtx<Ord, NDT, true> &cb)
+{
+    constexpr int O = Ord::at(IV);
+    using R = SpanRec<O>;
+    const double *rp0 = rec + CellRecords<Ord>::offset(IV);
+    double r[R::stride > 0 ? R::stride : 1];
+    if constexpr (R::stride > 0) {
+        const double2 *rp = reinterpret_cast<const double2 *>(rp0);
+#pragma unroll
+        for (int j = 0; j < R::stride / 2; ++j) {
+            const double2 x = __ldg(rp + j);
+            r[2 * j] = x.x;
+            r[2 * j + 1] = x.y;
+        }
+    }
+    double rc[O > 1 ? O * (O - 1) / 2 : 1];
+#pragma unroll
+    for (int j = 0; j < O * (O - 1) / 2; ++j) rc[j] = r[O - 1 + j];
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+        const double u = p ? ub : ua;
+        double dl[O > 1 ? O - 1 : 1], b0[O], b1[O];
+#pragma unroll
+        for (int j = 0; j < O - 1; ++j) dl[j] = u - r[j];
+        basis_core<O, true>(dl, rc, 0, b0, b1);
+        FixedCtx<Ord, NDT, true> &c = p ? cb : ca;
+#pragma unroll
+        for (int j = 0; j < O; ++j) { c.B[IV][j] = b0[j]; c.dB[IV][j] = b1[j]; }
+    }
+}
+
+template <int NIND, int O0, int O1, int O2, int O3, int NDEP, int NDT, int MINB>
+__global__ void __launch_bounds__(128, MINB) eval_image2_kernel(const SplineDev s, const PointsDev in, const long long N,
+                                                                 const WrtDev wrt, const OutDev out)
+{
+    using Ord = Orders<NIND, O0, O1, O2, O3>;
+    using IS = ImageShape<Ord, NDEP>;
+    static_assert(NDEP % NDT == 0, "dependent-variable tile must divide nDep");
+    constexpr int R = NDEP * (1 + NIND), RP = (R + 3) & ~3;
+    extern __shared__ __align__(16) double recTile[];                // [point 0 | point 1][R slots][128 threads]
+    const long long P = blockIdx.x * 128LL + threadIdx.x;            // pair index: sorted slots 2P and 2P + 1
+    if (2 * P >= (long long)__ldg(in.sortedTotal)) return;
+    double ra[4], rb[4];
+    ld_row256(in.records + 8 * P, ra);
+    ld_row256(in.records + 8 * P + 4, rb);
+    long long kia, kib;
+    if constexpr (NIND > 3) {
+        const longlong2 kk = __ldcs(reinterpret_cast<const longlong2 *>(in.recKI) + P);
+        kia = kk.x;
+        kib = kk.y;
+    } else {
+        kia = __double_as_longlong(ra[3]);
+        kib = __double_as_longlong(rb[3]);
+    }
+    const double *img = in.images + (long long)(int)kia * IS::size;
+    if (in.prefetchImages) {
+        // the first warp to touch a cell would otherwise take its misses one dependent row at a time: request every
+        // 128-byte line of the image at once (the lanes of a warp ask for the same lines: one request per line)
+        constexpr int lines = (IS::size * 8 + 127) / 128;
+#pragma unroll
+        for (int l = 0; l < lines; ++l) asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char *>(img) + 128 * l));
+    }
+    FixedCtx<Ord, NDT, true> c0, c1;
+    setup_variable_pair<0, Ord, NDT>(img + IS::window, ra[0], rb[0], c0, c1);
+    if constexpr (NIND > 1) setup_variable_pair<1, Ord, NDT>(img + IS::window, ra[1], rb[1], c0, c1);
+    if constexpr (NIND > 2) setup_variable_pair<2, Ord, NDT>(img + IS::window, ra[2], rb[2], c0, c1);
+    if constexpr (NIND > 3) setup_variable_pair<3, Ord, NDT>(img + IS::window, ra[3], rb[3], c0, c1);
+    double *mine = recTile + threadIdx.x;
+#pragma unroll 1
+    for (int d0 = 0; d0 < NDEP; d0 += NDT) {
+        double v0[NDT], v1[NDT];
+        double g0[NIND][NDT], g1[NIND][NDT];
+        ContractI2<0, Ord, NDEP, NDT>::run(img + d0 * IS::perDep, 0, c0, c1, v0, g0, v1, g1);
+#pragma unroll
+        for (int d = 0; d < NDT; ++d) {
+            mine[(d0 + d) * 128] = v0[d];
+            mine[(R + d0 + d) * 128] = v1[d];
+#pragma unroll
+            for (int iv = 0; iv < NIND; ++iv) {
+                mine[(NDEP + (d0 + d) * NIND + iv) * 128] = g0[iv][d];
+                mine[(R + NDEP + (d0 + d) * NIND + iv) * 128] = g1[iv][d];
+            }
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+        const long long ki = p ? kib : kia;
+        const long long idx = ki >> 32;
+        if (idx < 0) continue;                                        // dummy slot of an odd cell
+        const long long dest = out.aosScatter ? out.aosBase + idx : 2 * P + p;
+        double *rec = out.aos + dest * out.aosStride;
+        const double *src = mine + p * R * 128;
+#pragma unroll
+        for (int j = 0; j < RP / 4; ++j) {
+            if (4 * j < out.aosStride) {
+                double x[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) x[e] = 4 * j + e < R ? src[(4 * j + e) * 128] : 0.0;
+                if (out.aosWide)
+                    asm volatile("st.global.cs.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(rec + 4 * j), "d"(x[0]), "d"(x[1]), "d"(x[2]), "d"(x[3]) : "memory");
+                else {
+                    __stcs(reinterpret_cast<double2 *>(rec + 4 * j), make_double2(x[0], x[1]));
+                    __stcs(reinterpret_cast<double2 *>(rec + 4 * j) + 1, make_double2(x[2], x[3]));
+                }
+            }
+        }
+    }
+}
+
+struct ImageEntry {
+    int nInd, o[4], nDep, jac, code;      // code = 1000 * PAIR + 100 * STAGE + 10 * (dependent variables per pass) + CTAs per SM
+    FixedFn fn;
+    int recDoubles;                       // shared memory per thread (STAGE / PAIR), doubles
+    int optIn;
+    int pair;                             // two points per thread: needs even-padded cell segments
+};
+#define BSPY_IMAGE(NI, A, B, C, D_, ND, J, NDT, MB, ST, OPT)                                                            \
+    {NI, {A, B, C, D_}, ND, J, 100 * ST + 10 * NDT + MB, eval_image_kernel<NI, A, B, C, D_, ND, J != 0, NDT, MB, ST != 0>, \
+     ST ? (J ? ND * (1 + NI) : ND) : 0, OPT, 0}
+#define BSPY_IMAGE2(NI, A, B, C, D_, ND, NDT, MB, OPT)                                                                  \
+    {NI, {A, B, C, D_}, ND, 1, 1000 + 10 * NDT + MB, eval_image2_kernel<NI, A, B, C, D_, ND, NDT, MB>, 2 * ND * (1 + NI), OPT, 1}
+static const ImageEntry kImage[] = {
+    // two points per thread (value + jacobian requests)
+    // measured on config 5 (Gpts/s, whole step): 1022 -> 3.60, 1012 -> 3.50, 1013 -> 3.35; one point per thread: 114 -> 2.71,
+    // the L1-gather kernel 2.61
+    BSPY_IMAGE2(4, 3, 3, 3, 3, 6, 2, 2, 0), BSPY_IMAGE2(4, 3, 3, 3, 3, 6, 1, 2, 1), BSPY_IMAGE2(4, 3, 3, 3, 3, 6, 1, 3, 1),
+    BSPY_IMAGE2(3, 4, 4, 4, 0, 3, 1, 3, 1), BSPY_IMAGE2(3, 4, 4, 4, 0, 3, 1, 4, 1), BSPY_IMAGE2(3, 4, 4, 4, 0, 3, 3, 2, 1),
+    // the 4-variate nDep-6 manifold of config 5 (value + jacobian); variants for measurement are opt-in (IMAGE=<code>)
+    BSPY_IMAGE(4, 3, 3, 3, 3, 6, 1, 1, 4, 1, 0),
+    BSPY_IMAGE(4, 3, 3, 3, 3, 6, 1, 1, 4, 0, 1), BSPY_IMAGE(4, 3, 3, 3, 3, 6, 1, 2, 3, 1, 1), BSPY_IMAGE(4, 3, 3, 3, 3, 6, 1, 3, 2, 1, 1),
+    BSPY_IMAGE(4, 3, 3, 3, 3, 6, 1, 1, 3, 1, 1), BSPY_IMAGE(4, 3, 3, 3, 3, 6, 1, 6, 2, 0, 1), BSPY_IMAGE(4, 3, 3, 3, 3, 6, 1, 1, 5, 1, 1),
+    BSPY_IMAGE(4, 3, 3, 3, 3, 6, 0, 6, 4, 0, 0),
+    // tricubic volume (config 4): measured against the warp-staged kernel (10.6 Gpts/s): 34 -> 7.1, pairs 1013 -> 8.1; opt-in
+    BSPY_IMAGE(3, 4, 4, 4, 0, 3, 1, 3, 4, 0, 1), BSPY_IMAGE(3, 4, 4, 4, 0, 3, 1, 3, 3, 0, 1),
+};
+
+static const ImageEntry *find_image(const SplineDev &s, int jac, int code)
+{
+    for (const ImageEntry &e : kImage) {
+        if (e.nInd != s.nInd || e.nDep != s.nDep || e.jac != jac) continue;
+        bool same = true;
+        for (int i = 0; i < s.nInd; ++i) same &= e.o[i] == s.order[i];
+        if (same && (code == 0 ? !e.optIn : code == e.code)) return &e;
+    }
+    return nullptr;
+}
+
 struct CellEntry {
     int nInd, o[4], nDep;
     FixedFn fn;
@@ -759,8 +1234,8 @@ static const CellEntry *find_cell(const SplineDev &s)
 static long long records_half_bytes(const SplineDev &s, long long chunk, bool ownAos)
 {
     const long long cells = binned_cells(s);
-    return 4 * (2 * pad64(chunk) + pad64(cells + 1)) + 8 * pad64(chunk) +
-           8 * (4 * pad64(chunk) + (ownAos ? (long long)aos_stride(s) * pad64(chunk) : 0));
+    const long long slots = pad64(chunk) + pad64(cells);          // sorted slots: cell segments may be padded to even lengths
+    return 4 * (2 * pad64(chunk) + pad64(cells + 1)) + 8 * slots + 8 * (4 * slots + (ownAos ? (long long)aos_stride(s) * slots : 0));
 }
 
 static int eval_binned_records(const SplineDev &s, PointsDev in, long long N, const WrtDev &wrt, OutDev out, int jac,
@@ -816,6 +1291,28 @@ static int eval_binned_records(const SplineDev &s, PointsDev in, long long N, co
             count_launch(s.nInd);
         }
     }
+    // cell images (padded window + span records per cell, built once per call) for the shapes compiled for them
+    const ImageEntry *image = nullptr;
+    const double *images = nullptr;
+    if (images_apply(s, N) && !(cell && option(OPT_CELL_KERNEL, 0))) {
+        image = find_image(s, jac, (int)option(OPT_IMAGE, 0));
+        if (image && nN && (image->pair || (image->code % 100) / 10 != s.nDep)) image = nullptr;   // normals need the whole jacobian in one pass
+        if (image && image->pair && !plainWrt) image = nullptr;
+        if (image && !spanRec[0]) image = nullptr;
+    }
+    if (image) {
+        const ImageLayout L = image_layout(s);
+        double *dst = (double *)((char *)workspace + 2 * half + span_records_bytes(s));
+        PointsDev rp{};
+        for (int i = 0; i < s.nInd; ++i) rp.spanRec[i] = spanRec[i];
+        long long blocks = (cells + 7) / 8;
+        const long long cap = (long long)num_sms() * 8;
+        if (blocks > cap) blocks = cap;
+        build_cell_images_kernel<<<(unsigned)blocks, 256, 0, stream>>>(s, L, cells, nullptr, rp, dst);
+        count_launch(1);
+        images = dst;
+        if (int rc = allow_dynamic_smem(image->fn, sizeof(double) * 128 * image->recDoubles)) return rc;
+    }
     // Sort (and un-permute) of the neighbouring chunks on a second stream under the evaluation of this one: the sort
     // passes are memory / latency bound, the evaluation FP64 bound.  BIN_OVERLAP=0/1 overrides.
     const bool wantOverlap = option(OPT_BIN_OVERLAP, (staged != nullptr || cell != nullptr) ? 1 : 0) != 0;
@@ -835,8 +1332,8 @@ static int eval_binned_records(const SplineDev &s, PointsDev in, long long N, co
         buf[h].keys = (int *)base; buf[h].inv = buf[h].keys + cpad;
         buf[h].hist = buf[h].inv + cpad;
         buf[h].recKI = (int2 *)(buf[h].hist + pad64(cells + 1));
-        buf[h].records = (double *)(buf[h].recKI + cpad);
-        buf[h].aos = buf[h].records + 4 * cpad;
+        buf[h].records = (double *)(buf[h].recKI + cpad + pad64(cells));
+        buf[h].aos = buf[h].records + 4 * (cpad + pad64(cells));
     }
     auto sortChunk = [&](long long c) -> int {
         const Buf &B = buf[c & 1];
@@ -851,7 +1348,8 @@ static int eval_binned_records(const SplineDev &s, PointsDev in, long long N, co
         // four points per thread in flight (measured against one point per thread at full occupancy: keys 106 -> 95 us,
         // scatter 88 -> 71 us per 4 Mi points)
         bin_keys_batched_kernel<4><<<(n + 511) / 512, 128, 0, sSort>>>(s, in, base, n, B.keys, B.hist, B.inv, o1);
-        bin_scan_kernel<<<1, 1024, 0, sSort>>>(B.hist, (int)cells);
+        if (image && image->pair) bin_scan_kernel<<<1, 1024, 0, sSort>>>(B.hist, (int)cells, 1, B.records, B.recKI, s.nInd);
+        else bin_scan_kernel<<<1, 1024, 0, sSort>>>(B.hist, (int)cells);
         bin_scatter_records_batched_kernel<4><<<(n + 511) / 512, 128, 0, sSort>>>(s, in, base, n, B.keys, B.hist, B.records, B.recKI,
                                                                                  B.inv, userAos ? 0 : 1);
         if (overlap) cudaEventRecord(bs->sorted[c & 1], sSort);
@@ -871,9 +1369,18 @@ static int eval_binned_records(const SplineDev &s, PointsDev in, long long N, co
         o2.aosStride = stride;
         if (userAos) { o2.aosScatter = 1; o2.aosBase = base; }
         else { o2.aos = B.aos; o2.aosScatter = 0; o2.aosBase = 0; }
+        o2.aosWide = (stride % 4 == 0 && (reinterpret_cast<uintptr_t>(o2.aos) & 31) == 0) ? 1 : 0;
         // the window-sharing kernels live on reuse: they need cells that hold a few tiles' worth of points (a sparse
         // tail chunk makes every tile straddle several cells); below that the L1-gather kernel is the faster one
-        if (cell && n >= 48 * cells) {
+        pin.images = images;
+        pin.sortedTotal = B.hist + cells;
+        pin.prefetchImages = (int)option(OPT_EXP_B, 1);
+        if (image && image->pair) {
+            const long long pairs = (n + cells + 1) / 2;          // upper bound; the kernel reads the exact slot count
+            image->fn<<<(unsigned)((pairs + 127) / 128), 128, sizeof(double) * 128 * image->recDoubles, sEval>>>(s, pin, n, wrt, o2);
+        } else if (image) {
+            image->fn<<<(unsigned)((n + 127) / 128), 128, sizeof(double) * 128 * image->recDoubles, sEval>>>(s, pin, n, wrt, o2);
+        } else if (cell && n >= 48 * cells) {
             long long blocks = (long long)num_sms() * cell->minBlocks;
             const long long most = (n + 32 * CELL_WARPS - 1) / (32 * CELL_WARPS);
             if (blocks > most) blocks = most;
@@ -1061,6 +1568,7 @@ extern "C" int bspy_cuda_eval_points_aos(const bspy_spline *spline, const double
     out.aosStride = (int)recordStride;
     out.aosNormal = wantNormal ? 1 : 0;
     WrtDev w{};
+    out.aosWide = (recordStride % 4 == 0 && (reinterpret_cast<uintptr_t>(records) & 31) == 0) ? 1 : 0;
     const long long need = binned_workspace(s, N, true);
     if (need && workspace && workspaceBytes >= need) return eval_binned(s, in, N, w, out, jac, workspace, (cudaStream_t)stream);
     return launch_eval(s, in, N, w, out, jac, (cudaStream_t)stream);

@@ -47,7 +47,7 @@ static inline int allow_dynamic_smem(K kernel, size_t smem)
 enum Option {
     OPT_CURVE_REPL, OPT_CURVE_PPT, OPT_BIN_MODE, OPT_BIN_OVERLAP, OPT_STAGED, OPT_DEP_TILE, OPT_SPAN_RECORDS, OPT_BIN_CHUNK,
     OPT_BIN_REC_CHUNK_LOG2, OPT_GRID_CHUNK, OPT_GRID_ROWS, OPT_GRID_GROUP, OPT_CELL_KERNEL, OPT_CURVE_TMA, OPT_MANY_MODE,
-    OPT_GRID3_ROWS, OPT_GRID3_CHUNK, OPT_EXP_A, OPT_EXP_B, OPT_COUNT
+    OPT_GRID3_ROWS, OPT_GRID3_CHUNK, OPT_EXP_A, OPT_EXP_B, OPT_IMAGE, OPT_COUNT
 };
 long long option(Option o, long long unset);
 
@@ -83,6 +83,10 @@ struct PointsDev {
     // per-span records of variable i (left knots | reciprocal knot gaps, SpanRec<order>::stride doubles per span), built
     // once per call by span_records_kernel for the binned path; nullptr: gaps are divided per point
     const double *spanRec[BSPY_MAX_IND];
+    // cell images (eval_image_kernel): images[cell * size ..] = padded window of the cell followed by its span records
+    const double *images;
+    int prefetchImages;       // eval_image2_kernel: request all lines of the cell image up front
+    const int *sortedTotal;   // number of slots of the sorted sequence (cell segments rounded up to even lengths)
 };
 
 struct OutDev {
@@ -101,6 +105,7 @@ struct OutDev {
     int aosStride;
     int aosScatter;
     int aosNormal;      // array-of-structs records carry the normal after the jacobian (out.normal itself stays NULL)
+    int aosWide;        // records are 32-byte aligned with a stride that is a multiple of 4 doubles: 256-bit stores
     long long aosBase;
 };
 

@@ -268,22 +268,6 @@ __global__ void __launch_bounds__(128, MINB) eval_staged_kernel(const SplineDev 
 // cell CHANGE and stages the records next to the window image (cp.async, 16 bytes per lane); a point is then: its
 // 32-byte record (requested one tile ahead), broadcast LDS.128 of the slot's span records, the recurrence, the
 // contraction over the slot's window with immediate offsets.  Same arithmetic per point: bit-identical to v1.
-template <class Ord>
-struct CellRecords {
-    __host__ __device__ static constexpr int stride(int iv)
-    {
-        const int o = Ord::at(iv);
-        return ((o - 1 + o * (o - 1) / 2) + 1) & ~1;
-    }
-    __host__ __device__ static constexpr int offset(int iv)
-    {
-        int at = 0;
-        for (int m = 0; m < iv; ++m) at += stride(m);
-        return at;
-    }
-    static constexpr int size = offset(Ord::n);
-};
-
 // basis values and first derivatives from a span record held in shared memory (16-byte aligned)
 template <int O, bool DER>
 __device__ __forceinline__ void basis_from_shared_record(const double *__restrict__ rec, double u, int d, double (&b0)[O], double (&b1)[O])

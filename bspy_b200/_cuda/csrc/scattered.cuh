@@ -121,6 +121,15 @@ __device__ __forceinline__ void store_result_record(const SplineDev &s, const Ou
             }
         }
     }
+    if (out.aosWide) {
+        // one 32-byte sector per store instruction (STG.256): half the requests of 16-byte stores
+#pragma unroll
+        for (int j = 0; j < RP / 4; ++j)
+            if (4 * j < out.aosStride)
+                asm volatile("st.global.cs.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(recOut + 4 * j), "d"(rec[4 * j]), "d"(rec[4 * j + 1]),
+                             "d"(rec[4 * j + 2]), "d"(rec[4 * j + 3]) : "memory");
+        return;
+    }
     double2 *q = reinterpret_cast<double2 *>(recOut);
 #pragma unroll
     for (int j = 0; j < RP / 2; ++j)
@@ -380,6 +389,23 @@ __device__ __forceinline__ void stage_window(const SplineDev &s, int key, double
         }
     }
 }
+
+// per-span records of all variables of one cell, back to back (each part an even number of doubles)
+template <class Ord>
+struct CellRecords {
+    __host__ __device__ static constexpr int stride(int iv)
+    {
+        const int o = Ord::at(iv);
+        return ((o - 1 + o * (o - 1) / 2) + 1) & ~1;
+    }
+    __host__ __device__ static constexpr int offset(int iv)
+    {
+        int at = 0;
+        for (int m = 0; m < iv; ++m) at += stride(m);
+        return at;
+    }
+    static constexpr int size = offset(Ord::n);
+};
 
 // ---- host side (defined in scattered.cu) ------------------------------------------------------------------------
 typedef void (*FixedFn)(const SplineDev, const PointsDev, const long long, const WrtDev, const OutDev);
