@@ -32,7 +32,7 @@ LIB_PATH = os.environ.get("BSPY_CUDA_LIB") or os.path.join(HERE, "libbspy_cuda.s
 SYMBOLS = (
     "bspy_cuda_abi_version", "bspy_cuda_last_error_string", "bspy_cuda_launch_count", "bspy_cuda_set_option", "bspy_cuda_copy_2d",
     "bspy_cuda_spans", "bspy_cuda_basis", "bspy_cuda_eval_points", "bspy_cuda_eval_points_binned",
-    "bspy_cuda_binned_workspace_bytes", "bspy_cuda_eval_points_aos", "bspy_cuda_aos_workspace_bytes", "bspy_cuda_eval_grid",
+    "bspy_cuda_binned_workspace_bytes", "bspy_cuda_eval_points_aos", "bspy_cuda_aos_workspace_bytes", "bspy_cuda_curve_table_bytes", "bspy_cuda_curve_table_build", "bspy_cuda_eval_grid",
     "bspy_cuda_eval_grid_batch", "bspy_cuda_eval_many", "bspy_cuda_probe_fp64", "bspy_cuda_probe_hbm",
     "bspy_cuda_probe_tiles", "bspy_cuda_curvature", "bspy_cuda_contract_axis", "bspy_cuda_block_accumulate",
     "bspy_cuda_normal_from_jacobian", "bspy_cuda_collocation",
@@ -46,6 +46,7 @@ class CSpline(C.Structure):
         ("order", C.c_int32 * MAX_IND), ("nCoef", C.c_int32 * MAX_IND),
         ("knots", C.c_void_p * MAX_IND), ("coefs", C.c_void_p),
         ("normalSign", C.c_int32), ("reserved", C.c_int32),
+        ("curveTable", C.c_void_p), ("curveTableBytes", C.c_int64),
     ]
 
 
@@ -88,6 +89,7 @@ def library():
             "bspy_cuda_basis": [vp, i32, i32, vp, vp, i64, i32, i32, vp, vp, vp],
             "bspy_cuda_eval_points": [C.POINTER(CSpline), vp, i64, i64, i64, C.POINTER(i32), u32, u32, vp, vp, vp, vp, vp, vp, vp],
             "bspy_cuda_eval_points_binned": [C.POINTER(CSpline), vp, i64, i64, i64, C.POINTER(i32), u32, u32, vp, vp, vp, vp, vp, vp, vp, i64, vp],
+            "bspy_cuda_curve_table_build": [C.POINTER(CSpline), vp, i64, vp],
             "bspy_cuda_eval_points_aos": [C.POINTER(CSpline), vp, i64, i64, i64, u32, u32, vp, i64, vp, vp, vp, i64, vp],
             "bspy_cuda_eval_grid": [C.POINTER(CSpline), C.POINTER(vp), C.POINTER(i64), u32, u32, vp, vp, vp, vp, vp],
             "bspy_cuda_eval_grid_batch": [C.POINTER(CSpline), i64, C.POINTER(i64), i64, C.POINTER(vp), C.POINTER(i64), u32, u32, vp, vp, vp, vp, vp],
@@ -107,9 +109,11 @@ def library():
             fn.restype = C.c_int
         lib.bspy_cuda_binned_workspace_bytes.argtypes = [C.POINTER(CSpline), i64]
         lib.bspy_cuda_binned_workspace_bytes.restype = C.c_int64
+        lib.bspy_cuda_curve_table_bytes.argtypes = [C.POINTER(CSpline)]
+        lib.bspy_cuda_curve_table_bytes.restype = C.c_int64
         lib.bspy_cuda_aos_workspace_bytes.argtypes = [C.POINTER(CSpline), i64]
         lib.bspy_cuda_aos_workspace_bytes.restype = C.c_int64
-        if lib.bspy_cuda_abi_version() != 1:
+        if lib.bspy_cuda_abi_version() != 2:
             raise CudaPathError("libbspy_cuda.so ABI version mismatch; rebuild with python -m bspy_b200._cuda.build --force")
         _lib = lib
     return _lib
@@ -185,6 +189,26 @@ class DeviceSpline:
         c.coefs = self.coefs.data_ptr()
         c.normalSign = self.normal_sign
         self.c = c
+        self.curve_table = None
+
+    def build_curve_table(self):
+        """Curves: build the span tables of this spline once (bspy_cuda_curve_table_build) and attach them to the C
+        struct; big batches then fetch them by TMA instead of rebuilding them in every thread block.  Called by
+        ``freeze()`` / the device cache of ``bspy_b200._spline_evaluation`` when the device copy is made."""
+        if self.nInd != 1 or not self.coefs.is_cuda:
+            return self
+        lib = library()
+        need = int(lib.bspy_cuda_curve_table_bytes(C.byref(self.c)))
+        if need <= 0:
+            return self
+        table = torch.empty(need, dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = lib.bspy_cuda_curve_table_build(C.byref(self.c), _ptr(table), need, _stream(self.device))
+        _check(rc, "bspy_cuda_curve_table_build")
+        self.curve_table = table
+        self.c.curveTable = table.data_ptr()
+        self.c.curveTableBytes = need
+        return self
 
     @property
     def normal_dim(self):

@@ -61,6 +61,8 @@ struct SplineDev {
     long long stride[BSPY_MAX_IND];  // coefficient stride of variable i (elements)
     long long depStride;
     int normalSign;
+    const void *curveTable;          // bspy_spline.curveTable / curveTableBytes (curves: replicated tables, built once)
+    long long curveTableBytes;
 };
 
 struct PointsDev {

@@ -15,6 +15,7 @@ struct CurveParams {
     OutDev out;
     long long N;
     int derivAsValue;   // derivative([1], u): write the first derivative into out.values
+    const void *table;  // caller-owned image of the replicated tables (bspy_cuda_curve_table_build), or nullptr
 };
 
 // results of one point: spans, values (or the first derivative when derivative([1], u) was asked for), jacobian,
@@ -125,47 +126,34 @@ static ReplLayout repl_layout(int O, int nDep, int nCoef, size_t budget)
 // 32 points (44 for the rows, all conflict-free) plus ~22 for the 32 bytes/point of global traffic -- at 132 Gpts/s =
 // 65 % of the HBM roofline; 16-byte global accesses (two consecutive points per thread) change nothing, the pipe
 // charges global traffic by the byte.
-template <int O, int NDEP, bool DER>
-__global__ void __launch_bounds__(repl_threads(O, NDEP), 2) eval_curve_repl_kernel(const CurveParams P, const int buckets)
+// bucket function of the span search: monotone in x (subtraction and multiplication by a positive constant are, so is the
+// saturating conversion); NaN -> 0
+__device__ __forceinline__ int repl_bucket_of(double x, double lo, double scale, int lastBucket)
+{
+    return min(max(__double2int_rz((x - lo) * scale), 0), lastBucket);
+}
+
+// Builds the replicated tables of one curve in shared memory: rows (spans * ROW * CP doubles) | knots (nKnots * KC) |
+// raw coefficients (scratch) | bucket counters (scratch) | tab (buckets unsigned shorts).  Called by every CTA of
+// eval_curve_repl_kernel and once per spline by curve_table_kernel.
+template <int O, int NDEP>
+__device__ __forceinline__ void build_repl_tables(const double *__restrict__ knots, const double *__restrict__ coefs, const int nCoef,
+                                                  const int buckets, double *rows, double *kn, double *raw, int *cnt,
+                                                  unsigned short *tab)
 {
     using R = SpanRec<O>;
     constexpr int ROW = ((O - 1) + O * (O - 1) / 2 + O * NDEP + 1) & ~1, CH = ROW / 2;
     constexpr int CP = REPL_COPIES, KC = REPL_KNOT_COPIES;
-    extern __shared__ __align__(16) double sm[];
-    const int nKnots = O + P.nCoef, spans = P.nCoef - O + 1;
-    double *rows = sm;                                             // spans * ROW * CP
-    double *kn = rows + spans * ROW * CP;                          // nKnots * KC
-    double *raw = kn + nKnots * KC;                                // NDEP * nCoef: the coefficients as they come
-    int *cnt = reinterpret_cast<int *>(raw + NDEP * P.nCoef);      // buckets + 1 (scan scratch)
-    unsigned short *tab = reinterpret_cast<unsigned short *>(cnt + buckets + 2);
+    const int nKnots = O + nCoef, spans = nCoef - O + 1;
     const int lane = threadIdx.x & 31;
-    // the first round of parameters travels from HBM while the tables are built
-    const long long stride = (long long)gridDim.x * blockDim.x;          // threads of the grid
-    const long long first = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    // point of (round, k) = first + (2 * round + k) * stride
-    const long long pstep = stride, rstep = 2 * stride;
-    const long long pfirst = first;
-    const double *up = P.in.uvw + pfirst * P.in.pointStride;
-    const long long ustep = pstep * P.in.pointStride, urstep = rstep * P.in.pointStride;
-    double un[REPL_U];
-    auto fetch = [&](const double *src, long long p0) {
-#pragma unroll
-        for (int k = 0; k < REPL_U; ++k)
-            if (p0 + k * pstep < P.N) un[k] = __ldcs(src + k * ustep);
-    };
-    un[0] = un[1] = 0.0;
-    fetch(up, pfirst);
     // knots (every copy) and coefficients in one DRAM round trip
-    for (int i = threadIdx.x; i < nKnots * KC; i += blockDim.x) kn[i] = __ldg(P.knots + i / KC);
-    for (int i = threadIdx.x; i < NDEP * P.nCoef; i += blockDim.x) raw[i] = __ldg(P.coefs + i);
+    for (int i = threadIdx.x; i < nKnots * KC; i += blockDim.x) kn[i] = __ldg(knots + i / KC);
+    for (int i = threadIdx.x; i < NDEP * nCoef; i += blockDim.x) raw[i] = __ldg(coefs + i);
     for (int i = threadIdx.x; i <= buckets; i += blockDim.x) cnt[i] = 0;
     __syncthreads();
-    const double lo = kn[(O - 1) * KC], hi = kn[P.nCoef * KC];
+    const double lo = kn[(O - 1) * KC], hi = kn[nCoef * KC];
     const double scale = (double)buckets / (hi - lo);
     const int lastBucket = buckets - 1;
-    // monotone in x (subtraction and multiplication by a positive constant are, so is the saturating conversion);
-    // NaN -> 0
-    auto bucket_of = [&](double x) -> int { return min(max(__double2int_rz((x - lo) * scale), 0), lastBucket); };
     // rows (copy 0 is written first, then replicated) and the bucket histogram of the interior knots
     for (int sp = threadIdx.x; sp < spans; sp += blockDim.x) {
         const int ix = O + sp;
@@ -180,14 +168,14 @@ __global__ void __launch_bounds__(repl_threads(O, NDEP), 2) eval_curve_repl_kern
 #pragma unroll
         for (int j = 0; j < O; ++j)
 #pragma unroll
-            for (int d = 0; d < NDEP; ++d) r[R::used + j * NDEP + d] = raw[d * P.nCoef + (sp + j)];
+            for (int d = 0; d < NDEP; ++d) r[R::used + j * NDEP + d] = raw[d * nCoef + (sp + j)];
         if (ROW > R::used + O * NDEP) r[ROW - 1] = 0.0;
 #pragma unroll
         for (int j = 0; j < CH; ++j)
             *reinterpret_cast<double2 *>(rows + 2 * ((sp * CH + j) * CP)) = make_double2(r[2 * j], r[2 * j + 1]);
     }
     // interior knots O .. nCoef-1 (the candidates of the span search) into their buckets
-    for (int i = O + threadIdx.x; i < P.nCoef; i += blockDim.x) atomicAdd(cnt + bucket_of(kn[i * KC]) + 1, 1);
+    for (int i = O + threadIdx.x; i < nCoef; i += blockDim.x) atomicAdd(cnt + repl_bucket_of(kn[i * KC], lo, scale, lastBucket) + 1, 1);
     __syncthreads();
     // replicate the rows
     {
@@ -214,27 +202,45 @@ __global__ void __launch_bounds__(repl_threads(O, NDEP), 2) eval_curve_repl_kern
         }
     }
     __syncthreads();
+}
+
+// The point loop of the replicated-row kernels: REPL_U points per thread and round; the parameters of the next round
+// are requested before this round's arithmetic (the loop is otherwise a chain DRAM load -> table -> row -> arithmetic ->
+// store per point).  un[] holds the first round's parameters, requested by the caller before the tables were ready.
+template <int O, int NDEP, bool DER, int REPL_U>
+__device__ __forceinline__ void repl_point_loop(const CurveParams &P, const int buckets, const double *rows, const double *kn,
+                                                const unsigned short *tab, double (&un)[REPL_U], const double *up,
+                                                const long long pfirst, const long long pstep, const long long rstep)
+{
+    using R = SpanRec<O>;
+    constexpr int ROW = ((O - 1) + O * (O - 1) / 2 + O * NDEP + 1) & ~1, CH = ROW / 2;
+    constexpr int CP = REPL_COPIES, KC = REPL_KNOT_COPIES;
+    const int lane = threadIdx.x & 31;
+    const long long ustep = pstep * P.in.pointStride, urstep = rstep * P.in.pointStride;
+    const double lo = kn[(O - 1) * KC], hi = kn[P.nCoef * KC];
+    const double scale = (double)buckets / (hi - lo);
+    const int lastBucket = buckets - 1;
     // rows of this lane's copy start at myRows, O rows before span 0 so that the span index addresses them directly
     const double2 *myRows = reinterpret_cast<const double2 *>(rows) + (lane & (CP - 1)) - O * CH * CP;
     const double *myKnots = kn + (lane & (KC - 1));
     const OutDev &out = P.out;
     const bool report = out.firstOutside != nullptr;
     const int nCoef = P.nCoef;
-    // REPL_U points per thread and round; the parameters of the next round are requested before this round's
-    // arithmetic (the loop is otherwise a chain DRAM load -> table -> row -> arithmetic -> store per point)
     for (long long p0 = pfirst; p0 < P.N; p0 += rstep) {
         double u[REPL_U];
 #pragma unroll
         for (int k = 0; k < REPL_U; ++k) u[k] = un[k];
         up += urstep;
-        fetch(up, p0 + rstep);
+#pragma unroll
+        for (int k = 0; k < REPL_U; ++k)
+            if (p0 + rstep + k * pstep < P.N) un[k] = __ldcs(up + k * ustep);
 #pragma unroll
         for (int k = 0; k < REPL_U; ++k) {
             const long long p = p0 + k * pstep;
             if (p >= P.N) break;
             const double uk = u[k];
             if (report && ((uk < lo) | (uk > hi))) report_outside((int64_t *)out.firstOutside, p);
-            int ix = tab[bucket_of(uk)];
+            int ix = tab[repl_bucket_of(uk, lo, scale, lastBucket)];
             while (ix < nCoef && myKnots[ix * KC] <= uk) ++ix;
             if (uk != uk) ix = nCoef;
             double r[ROW];
@@ -268,6 +274,132 @@ __global__ void __launch_bounds__(repl_threads(O, NDEP), 2) eval_curve_repl_kern
     }
 }
 
+// Measured (ncu, config 1 at 2e7 points): the LSU data pipe is 97 % busy -- 51 shared-memory wavefronts per warp of
+// 32 points (44 for the rows, all conflict-free) plus ~22 for the 32 bytes/point of global traffic -- at 132 Gpts/s =
+// 65 % of the HBM roofline; 16-byte global accesses (two consecutive points per thread) change nothing, the pipe
+// charges global traffic by the byte.
+template <int O, int NDEP, bool DER>
+__global__ void __launch_bounds__(repl_threads(O, NDEP), 2) eval_curve_repl_kernel(const CurveParams P, const int buckets)
+{
+    constexpr int ROW = ((O - 1) + O * (O - 1) / 2 + O * NDEP + 1) & ~1;
+    constexpr int CP = REPL_COPIES, KC = REPL_KNOT_COPIES;
+    extern __shared__ __align__(16) double sm[];
+    const int nKnots = O + P.nCoef, spans = P.nCoef - O + 1;
+    double *rows = sm;                                             // spans * ROW * CP
+    double *kn = rows + spans * ROW * CP;                          // nKnots * KC
+    double *raw = kn + nKnots * KC;                                // NDEP * nCoef: the coefficients as they come
+    int *cnt = reinterpret_cast<int *>(raw + NDEP * P.nCoef);      // buckets + 1 (scan scratch)
+    unsigned short *tab = reinterpret_cast<unsigned short *>(cnt + buckets + 2);
+    // the first round of parameters travels from HBM while the tables are built
+    const long long stride = (long long)gridDim.x * blockDim.x;          // threads of the grid
+    const long long pfirst = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    // point of (round, k) = first + (2 * round + k) * stride
+    const long long pstep = stride, rstep = REPL_U * stride;
+    const double *up = P.in.uvw + pfirst * P.in.pointStride;
+    double un[REPL_U];
+#pragma unroll
+    for (int k = 0; k < REPL_U; ++k) un[k] = pfirst + k * pstep < P.N ? __ldcs(up + k * pstep * P.in.pointStride) : 0.0;
+    build_repl_tables<O, NDEP>(P.knots, P.coefs, P.nCoef, buckets, rows, kn, raw, cnt, tab);
+    repl_point_loop<O, NDEP, DER, REPL_U>(P, buckets, rows, kn, tab, un, up, pfirst, pstep, rstep);
+}
+
+// ---- the tables built ONCE per spline and pulled in by TMA ------------------------------------------------------------
+// At the specified size of config 1 (1e6 points, 32 MB of traffic = 4.9 us at the HBM roofline) the kernel above spends
+// about half of its 21 us building the 95 KB of replicated tables in each of its 296 CTAs.  The tables depend on the
+// spline only, so curve_table_kernel writes them once into a caller-owned image (rows | knots | tab; Python keeps it on the
+// DeviceSpline next to the knots and coefficients) and eval_curve_tab_kernel -- one CTA of 1024 threads per SM -- fetches
+// the image with bulk asynchronous copies (cp.async.bulk global -> shared, completion on an mbarrier: SASS UBLKCP +
+// SYNCS) while its first round of parameters is already travelling from HBM.
+constexpr int TAB_THREADS = 1024;
+
+struct TableLayout {
+    int buckets;
+    size_t rowsBytes, knotBytes, tabBytes, bytes;   // bytes: the whole image, a multiple of 16
+};
+
+static TableLayout table_layout(int O, int nDep, int nCoef)
+{
+    TableLayout T{};
+    const ReplLayout L = repl_layout(O, nDep, nCoef, 200 * 1024);
+    if (!L.bytes) return T;
+    const int rowDoubles = ((O - 1) + O * (O - 1) / 2 + O * nDep + 1) & ~1;
+    T.buckets = L.buckets;
+    T.rowsBytes = sizeof(double) * (size_t)(nCoef - O + 1) * rowDoubles * REPL_COPIES;
+    T.knotBytes = sizeof(double) * (size_t)(O + nCoef) * REPL_KNOT_COPIES;
+    T.tabBytes = (sizeof(unsigned short) * (size_t)L.buckets + 15) & ~(size_t)15;
+    T.bytes = T.rowsBytes + T.knotBytes + T.tabBytes;
+    return T;
+}
+
+template <int O, int NDEP>
+__global__ void __launch_bounds__(512) curve_table_kernel(const double *__restrict__ knots, const double *__restrict__ coefs,
+                                                          const int nCoef, const int buckets, unsigned char *__restrict__ image,
+                                                          const TableLayout T)
+{
+    constexpr int ROW = ((O - 1) + O * (O - 1) / 2 + O * NDEP + 1) & ~1;
+    constexpr int CP = REPL_COPIES, KC = REPL_KNOT_COPIES;
+    extern __shared__ __align__(16) double sm[];
+    const int nKnots = O + nCoef, spans = nCoef - O + 1;
+    double *rows = sm;
+    double *kn = rows + spans * ROW * CP;
+    double *raw = kn + nKnots * KC;
+    int *cnt = reinterpret_cast<int *>(raw + NDEP * nCoef);
+    unsigned short *tab = reinterpret_cast<unsigned short *>(cnt + buckets + 2);
+    build_repl_tables<O, NDEP>(knots, coefs, nCoef, buckets, rows, kn, raw, cnt, tab);
+    double *gRows = reinterpret_cast<double *>(image);
+    double *gKn = reinterpret_cast<double *>(image + T.rowsBytes);
+    unsigned short *gTab = reinterpret_cast<unsigned short *>(image + T.rowsBytes + T.knotBytes);
+    for (int i = threadIdx.x; i < spans * ROW * CP; i += blockDim.x) gRows[i] = rows[i];
+    for (int i = threadIdx.x; i < nKnots * KC; i += blockDim.x) gKn[i] = kn[i];
+    for (int i = threadIdx.x; i < (int)(T.tabBytes / 2); i += blockDim.x) gTab[i] = i < buckets ? tab[i] : (unsigned short)0;
+}
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+// U = points per thread and round: 2 for long streams (the next round's parameters travel under this round's
+// arithmetic); 8 when the whole batch is a round or two -- config 1 as specified: 6.6 points per thread, all of them
+// requested before the image has even arrived
+template <int O, int NDEP, bool DER, int U = REPL_U>
+__global__ void __launch_bounds__(TAB_THREADS, 1) eval_curve_tab_kernel(const CurveParams P, const TableLayout T)
+{
+    extern __shared__ __align__(128) unsigned char image[];
+    __shared__ __align__(8) unsigned long long mbar;
+    const unsigned bar = smem_u32(&mbar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        // one elected thread arms the barrier with the byte count and issues the bulk copies (64 KB pieces)
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((unsigned)T.bytes) : "memory");
+        const unsigned char *src = reinterpret_cast<const unsigned char *>(P.table);
+        for (size_t at = 0; at < T.bytes; at += 65536) {
+            const unsigned n = (unsigned)(T.bytes - at < 65536 ? T.bytes - at : 65536);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(image + at)),
+                         "l"(src + at), "r"(n), "r"(bar)
+                         : "memory");
+        }
+    }
+    // the first round of parameters travels from HBM while the image arrives
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long pfirst = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long pstep = stride, rstep = U * stride;
+    const double *up = P.in.uvw + pfirst * P.in.pointStride;
+    double un[U];
+#pragma unroll
+    for (int k = 0; k < U; ++k) un[k] = pfirst + k * pstep < P.N ? __ldcs(up + k * pstep * P.in.pointStride) : 0.0;
+    {
+        unsigned done = 0;
+        while (!done)
+            asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(bar) : "memory");
+    }
+    const double *rows = reinterpret_cast<const double *>(image);
+    const double *kn = reinterpret_cast<const double *>(image + T.rowsBytes);
+    const unsigned short *tab = reinterpret_cast<const unsigned short *>(image + T.rowsBytes + T.knotBytes);
+    repl_point_loop<O, NDEP, DER, U>(P, T.buckets, rows, kn, tab, un, up, pfirst, pstep, rstep);
+}
+
 template <int O, int NDEP, bool DER>
 static int launch_curve3(const CurveParams &P, size_t smem, cudaStream_t stream)
 {
@@ -277,6 +409,19 @@ static int launch_curve3(const CurveParams &P, size_t smem, cudaStream_t stream)
         const long long re = option(OPT_CURVE_REPL, -1);
         const long long minN = re >= 0 ? (re ? 0 : (1LL << 62)) : 131072;
         const ReplLayout L = repl_layout(O, NDEP, P.nCoef, 100 * 1024);
+        if (P.N >= minN && L.bytes && !P.in.grid && P.nCoef < 65535 && P.table && option(OPT_CURVE_TMA, 1)) {
+            // tables built once per spline (caller-owned image), one 1024-thread CTA per SM, image fetched by TMA
+            const TableLayout T = table_layout(O, NDEP, P.nCoef);
+            if (int rc = allow_dynamic_smem(eval_curve_tab_kernel<O, NDEP, DER>, T.bytes)) return rc;
+            long long blocks = (P.N + TAB_THREADS * 4 - 1) / (TAB_THREADS * 4);
+            const long long cap = num_sms();
+            if (blocks > cap) blocks = cap;
+            // (eight points per thread requested up front for short batches were measured slower at 1e6 points:
+            // 19.0 against 16.7 us)
+            eval_curve_tab_kernel<O, NDEP, DER><<<(unsigned)blocks, TAB_THREADS, T.bytes, stream>>>(P, T);
+            count_launch();
+            return check_launch("bspy_cuda_eval_points(curve, cached tables)");
+        }
         if (P.N >= minN && L.bytes && !P.in.grid && P.nCoef < 65535) {
             if (int rc = allow_dynamic_smem(eval_curve_repl_kernel<O, NDEP, DER>, L.bytes)) return rc;
             const int threads = repl_threads(O, NDEP);
@@ -324,6 +469,8 @@ int launch_curve(const SplineDev &s, const PointsDev &in, long long N, const Wrt
     CurveParams P{};
     P.knots = s.knots[0]; P.coefs = s.coefs; P.nCoef = nCoef; P.normalSign = s.normalSign;
     P.in = in; P.out = out; P.N = N;
+    // caller-owned table image: trusted only when its size is exactly what this shape needs
+    P.table = (s.curveTable && s.curveTableBytes == (long long)table_layout(O, s.nDep, nCoef).bytes && s.curveTableBytes > 0) ? s.curveTable : nullptr;
     P.derivAsValue = (!jac && wrt.d[0] == 1) ? 1 : 0;
     const bool der = jac || wrt.d[0] == 1;
     switch (O) {
@@ -336,4 +483,58 @@ int launch_curve(const SplineDev &s, const PointsDev &in, long long N, const Wrt
     }
 }
 
+template <int O>
+static int build_table2(const bspy_spline *sp, const TableLayout &T, void *table, cudaStream_t stream)
+{
+    const int nCoef = sp->nCoef[0];
+    const ReplLayout L = repl_layout(O, sp->nDep, nCoef, 200 * 1024);
+    const double *kn = sp->knots[0], *cf = sp->coefs;
+    unsigned char *img = (unsigned char *)table;
+#define BSPY_TABLE_CASE(ND)                                                                                          \
+    case ND:                                                                                                        \
+        if (int rc = allow_dynamic_smem(curve_table_kernel<O, ND>, L.bytes)) return rc;                             \
+        curve_table_kernel<O, ND><<<1, 512, L.bytes, stream>>>(kn, cf, nCoef, T.buckets, img, T);                   \
+        break;
+    switch (sp->nDep) {
+        BSPY_TABLE_CASE(1) BSPY_TABLE_CASE(2) BSPY_TABLE_CASE(3) BSPY_TABLE_CASE(4)
+        default: return BSPY_E_UNSUPPORTED;
+    }
+#undef BSPY_TABLE_CASE
+    count_launch();
+    return check_launch("bspy_cuda_curve_table_build");
+}
+
+static bool table_shape_ok(const bspy_spline *sp)
+{
+    return sp && sp->nInd == 1 && sp->order[0] >= 1 && sp->order[0] <= 6 && sp->nDep >= 1 && sp->nDep <= 4 &&
+           sp->nCoef[0] >= sp->order[0] && sp->nCoef[0] < 65535 && sp->knots[0] && sp->coefs;
+}
+
 }  // namespace bspy
+
+using namespace bspy;
+
+extern "C" int64_t bspy_cuda_curve_table_bytes(const bspy_spline *spline)
+{
+    if (!table_shape_ok(spline)) return 0;
+    const TableLayout T = table_layout(spline->order[0], spline->nDep, spline->nCoef[0]);
+    return T.bytes <= 200 * 1024 ? (int64_t)T.bytes : 0;
+}
+
+extern "C" int bspy_cuda_curve_table_build(const bspy_spline *spline, void *table, int64_t tableBytes, void *stream)
+{
+    const int64_t need = bspy_cuda_curve_table_bytes(spline);
+    if (!need || !table || tableBytes < need || (reinterpret_cast<uintptr_t>(table) & 15)) {
+        set_error("bspy_cuda_curve_table_build: not a curve shape with tables, or table NULL / too small / not 16-byte aligned");
+        return BSPY_E_ARG;
+    }
+    const TableLayout T = table_layout(spline->order[0], spline->nDep, spline->nCoef[0]);
+    switch (spline->order[0]) {
+        case 1: return build_table2<1>(spline, T, table, (cudaStream_t)stream);
+        case 2: return build_table2<2>(spline, T, table, (cudaStream_t)stream);
+        case 3: return build_table2<3>(spline, T, table, (cudaStream_t)stream);
+        case 4: return build_table2<4>(spline, T, table, (cudaStream_t)stream);
+        case 5: return build_table2<5>(spline, T, table, (cudaStream_t)stream);
+        default: return build_table2<6>(spline, T, table, (cudaStream_t)stream);
+    }
+}

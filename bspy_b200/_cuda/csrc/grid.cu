@@ -351,6 +351,7 @@ __global__ void __launch_bounds__(GRID_WARPS * 32, 2) grid2_dmma_kernel(const Gr
 constexpr int GRID3_TCAP = 32;        // coefficient columns a chunk may touch in the banded path
 constexpr int GRID3_TS = GRID3_TCAP + 4;   // row stride of the staged T: == 4 (mod 32) doubles, A-fragment loads take 2 wavefronts
 constexpr int GRID3_BAND_ROWS = 16;   // rows of a tile in the banded path
+constexpr int GRID3_SJ = 8;           // v-coefficient rows the rows of a tile may touch together in the separable first stage
 
 struct Grid3Params {
     const double *knots[3], *coefs;
@@ -379,6 +380,7 @@ __global__ void __launch_bounds__(GRID_WARPS * 32, 2) grid3_dmma_kernel(const Gr
     int *krange = spanVr + GRID_TILE_ROWS;                      // [0] = min first coefficient, [1] = max span of the chunk
     // first-stage contraction of the tile, T[kind*NDEP+d][row][k'] (k' = coefficient index - krange[0]), 8-byte aligned
     double *Tsm = reinterpret_cast<double *>(krange + 2);       // 3 * NDEP * GRID3_BAND_ROWS * GRID3_TS
+    double *Ssm = Tsm + 3 * NDEP * GRID3_BAND_ROWS * GRID3_TS;  // u-contracted coefficients: 2 * NDEP * GRID3_SJ * GRID3_TS
 
     const long long tile = blockIdx.x;
     const int cc = (int)(tile % P.colChunks);
@@ -458,6 +460,62 @@ __global__ void __launch_bounds__(GRID_WARPS * 32, 2) grid3_dmma_kernel(const Gr
     // L2 (measured: 11.5 Gpts/s at ~6.6 TB/s of L2 traffic on a 512^3 grid of a 32^3-coefficient volume).
     const int kmin = krange[0], range = krange[1] - krange[0];
     if (range > 0 && range <= GRID3_TCAP && P.tileRows <= GRID3_BAND_ROWS) {
+        // Separable first stage.  The rows of a tile are consecutive (a, b) grid nodes: when they share a (tileRows
+        // divides n[1], the usual case) the u contraction S[kind][d][jj][k'] = sum_i {Bu,dBu}[i] C[d][su-ou+i][jlo+jj][kmin+k']
+        // is common to all of them -- 4 loads per entry once per tile instead of 16 per entry and row -- and every row
+        // finishes with its own v basis out of shared memory.
+        const long long lastRow = (row0 + P.tileRows < nRows ? row0 + P.tileRows : nRows) - 1;
+        int jlo = 0x7fffffff, jhi = 0;
+        for (int r = 0; r <= (int)(lastRow - row0); ++r) {
+            jlo = min(jlo, spanVr[r] - P.o[1]);
+            jhi = max(jhi, spanVr[r]);
+        }
+        const bool separable = (row0 / P.n[1]) == (lastRow / P.n[1]) && jhi - jlo <= GRID3_SJ;
+        if (separable) {
+            const int jr = jhi - jlo, su = spanU[0];
+            for (int item = threadIdx.x; item < NDEP * jr * GRID3_TS; item += blockDim.x) {
+                const int kp = item % GRID3_TS, rest = item / GRID3_TS;
+                const int jj = rest % jr, dd = rest / jr;
+                double a0 = 0.0, a1 = 0.0;
+                if (kp < range) {
+                    const double *cp = P.coefs + dd * P.depStride + (long long)(su - P.o[0]) * s0 + (long long)(jlo + jj) * s1 + (kmin + kp);
+#pragma unroll
+                    for (int i = 0; i < MAXO; ++i)
+                        if (i < P.o[0]) {
+                            const double x = __ldg(cp + i * s0);
+                            a0 = fma(x, tabU[i * GRID_TILE_ROWS], a0);
+                            a1 = fma(x, tabU[(MAXO + i) * GRID_TILE_ROWS], a1);
+                        }
+                }
+                Ssm[((0 * NDEP + dd) * GRID3_SJ + jj) * GRID3_TS + kp] = a0;
+                Ssm[((1 * NDEP + dd) * GRID3_SJ + jj) * GRID3_TS + kp] = a1;
+            }
+            __syncthreads();
+            for (int item = threadIdx.x; item < P.tileRows * GRID3_TS; item += blockDim.x) {
+                const int r = item / GRID3_TS, kp = item - r * GRID3_TS;
+                const bool liveItem = kp < range && row0 + r < nRows;
+                const int j0 = liveItem ? spanVr[r] - P.o[1] - jlo : 0;
+#pragma unroll
+                for (int dd = 0; dd < NDEP; ++dd) {
+                    double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+                    if (liveItem) {
+#pragma unroll
+                        for (int j = 0; j < MAXO; ++j)
+                            if (j < P.o[1]) {
+                                const double x0 = Ssm[((0 * NDEP + dd) * GRID3_SJ + j0 + j) * GRID3_TS + kp];
+                                const double x1 = Ssm[((1 * NDEP + dd) * GRID3_SJ + j0 + j) * GRID3_TS + kp];
+                                const double bv = tabV[j * GRID_TILE_ROWS + r];
+                                t0 = fma(x0, bv, t0);
+                                t1 = fma(x1, bv, t1);
+                                t2 = fma(x0, tabV[(MAXO + j) * GRID_TILE_ROWS + r], t2);
+                            }
+                    }
+                    Tsm[((0 * NDEP + dd) * GRID3_BAND_ROWS + r) * GRID3_TS + kp] = t0;
+                    Tsm[((1 * NDEP + dd) * GRID3_BAND_ROWS + r) * GRID3_TS + kp] = t1;
+                    Tsm[((2 * NDEP + dd) * GRID3_BAND_ROWS + r) * GRID3_TS + kp] = t2;
+                }
+            }
+        } else
         for (int item = threadIdx.x; item < P.tileRows * GRID3_TS; item += blockDim.x) {
             const int r = item / GRID3_TS, kp = item - r * GRID3_TS;
             const bool liveItem = kp < range && row0 + r < nRows;
@@ -763,7 +821,7 @@ static int launch_grid3(const Grid3Params &P, cudaStream_t stream)
 {
     const size_t smem = sizeof(double) * (2 * MAXO * (P.chunkCols + 2) + 4 * MAXO * GRID_TILE_ROWS) +
                         sizeof(int) * (P.chunkCols + 2 * GRID_TILE_ROWS + 2) +
-                        sizeof(double) * (3 * NDEP * GRID3_BAND_ROWS * GRID3_TS);
+                        sizeof(double) * (3 * NDEP * GRID3_BAND_ROWS * GRID3_TS + 2 * NDEP * GRID3_SJ * GRID3_TS);
     if (int rc = allow_dynamic_smem(grid3_dmma_kernel<NDEP, MAXO>, smem)) return rc;
     const long long tiles = P.colChunks * P.rowBlocks;
     if (tiles > 0x7fffffffLL) { set_error("grid too large for one launch"); return BSPY_E_UNSUPPORTED; }
@@ -796,13 +854,15 @@ static int grid3_run(const bspy_spline *sp, const double *const *axes, const int
     P.vec = 1;
     if (P.n[2] % 2 == 0 && aligned_to(values, 16) && aligned_to(jacobian, 16)) P.vec = 2;
     if (P.n[2] % 4 == 0 && aligned_to(values, 32) && aligned_to(jacobian, 32)) P.vec = 4;
-    const long long cap = 256;
+    // measured on the 512^3 grid of the config-4 volume (value + jacobian): 128 / 256 / 512 columns -> 46.1 / 53.2 / 62.2 Gpts/s
+    const long long cap = option(OPT_GRID3_CHUNK, 512);
     const long long chunks = (P.n[2] + cap - 1) / cap;
     long long per = (P.n[2] + chunks - 1) / chunks;
     per = (per + GRID_STEP - 1) / GRID_STEP * GRID_STEP;
     P.chunkCols = (int)per;
     P.colChunks = (int)((P.n[2] + per - 1) / per);
-    P.tileRows = GRID3_BAND_ROWS;
+    P.tileRows = (int)option(OPT_GRID3_ROWS, GRID3_BAND_ROWS);
+    if (P.tileRows < 8 || P.tileRows > GRID3_BAND_ROWS || P.tileRows % 8) P.tileRows = GRID3_BAND_ROWS;
     P.rowBlocks = (P.n[0] * P.n[1] + P.tileRows - 1) / P.tileRows;
     const bool small = P.o[0] <= 4 && P.o[1] <= 4 && P.o[2] <= 4;
     switch (sp->nDep) {

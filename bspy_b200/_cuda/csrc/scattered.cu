@@ -704,6 +704,8 @@ int make_spline_dev(const bspy_spline *sp, SplineDev &s, const char *who)
     s.nDep = sp->nDep;
     s.coefs = sp->coefs;
     s.normalSign = sp->normalSign < 0 ? -1 : 1;
+    s.curveTable = sp->curveTable;
+    s.curveTableBytes = sp->curveTableBytes;
     long long stride = 1;
     for (int i = sp->nInd - 1; i >= 0; --i) {
         if (sp->order[i] < 1 || sp->nCoef[i] < sp->order[i] || !sp->knots[i]) {

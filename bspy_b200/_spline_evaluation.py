@@ -95,6 +95,8 @@ def device_spline(self, dev=None) -> _cuda.DeviceSpline:
     res.ds = _cuda.DeviceSpline(self.nInd, self.nDep, self.order, self.nCoef,
                                 [torch.from_numpy(k).to(dev) for k in res.knots_host],
                                 torch.from_numpy(res.coefs_host).to(dev), _normal_sign(self))
+    if self.nInd == 1:
+        res.ds.build_curve_table()          # span tables of the curve, once per upload (fetched by TMA by big batches)
     cache[dev] = res
     return res.ds
 

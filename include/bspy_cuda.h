@@ -35,7 +35,7 @@ extern "C" {
 
 #define BSPY_MAX_IND 8     /* independent variables supported by the kernels            */
 #define BSPY_MAX_ORDER 32  /* polynomial order per variable supported by the kernels    */
-#define BSPY_ABI_VERSION 1
+#define BSPY_ABI_VERSION 2
 
 /* error codes (negative returns) */
 #define BSPY_E_ARG (-1)          /* NULL / negative / inconsistent argument              */
@@ -53,6 +53,11 @@ typedef struct bspy_spline {
     const double *coefs;               /* device; (nDep, nCoef[0..nInd-1]) C-contiguous   */
     int32_t normalSign;                /* -1 iff metadata["negateNormal"], else +1         */
     int32_t reserved;
+    /* curves (nInd == 1) only, optional: device image of the span tables of this curve, built ONCE per spline
+     * by bspy_cuda_curve_table_build into caller-owned memory (bspy_cuda_curve_table_bytes bytes); big batches
+     * then fetch it by TMA instead of rebuilding it in every thread block.  NULL / 0: tables are rebuilt per call. */
+    const void *curveTable;
+    int64_t curveTableBytes;
 } bspy_spline;
 
 /* what bspy_cuda_eval_* computes */
@@ -112,6 +117,12 @@ int bspy_cuda_eval_points(const bspy_spline *spline, const double *uvw, int64_t 
                           int64_t varStride, int64_t N, const int32_t *wrt, uint32_t flags,
                           uint32_t normalMask, double *values, double *deriv, double *jacobian,
                           double *normal, int32_t *spans, int64_t *firstOutside, void *stream);
+
+/* ---- span tables of one curve (see bspy_spline.curveTable): bytes needed (0: shape without tables -- nInd != 1,
+ *      order > 6, nDep > 4, or tables larger than shared memory) and the build (one small kernel on `stream`; the
+ *      image must be rebuilt when knots or coefficients change, like the device copies themselves).              */
+int64_t bspy_cuda_curve_table_bytes(const bspy_spline *spline);
+int bspy_cuda_curve_table_build(const bspy_spline *spline, void *table, int64_t tableBytes, void *stream);
 
 /* ---- the same with cell binning for big scattered batches: the points of each 512 Ki chunk are
  *      counting-sorted by knot-span cell (in `workspace`, caller-owned device memory) so that the

@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol():
     out = subprocess.run(["nm", "-D", "--defined-only", _cuda.LIB_PATH], capture_output=True, text=True).stdout
     exported = sorted(set(re.findall(r"\b(bspy_cuda_\w+)\b", out)))
     assert exported == declared
-    assert lib.bspy_cuda_abi_version() == 1
+    assert lib.bspy_cuda_abi_version() == 2
 
 
 def test_library_is_sm100a_with_dmma_and_lineinfo():
@@ -42,13 +42,18 @@ def test_library_is_sm100a_with_dmma_and_lineinfo():
     sass = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN4bspy17grid2_dmma_kernelILi3ELi4ELb0EEEvNS_11Grid2ParamsE", _cuda.LIB_PATH],
                           capture_output=True, text=True).stdout
     assert "DMMA" in sass, "the grid kernel must run on the FP64 tensor pipe"
+    sass = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN4bspy21eval_curve_tab_kernelILi4ELi3ELb0EEEvNS_11CurveParamsENS_11TableLayoutE",
+                           _cuda.LIB_PATH], capture_output=True, text=True).stdout
+    assert "UBLKCP" in sass and "SYNCS" in sass, "the cached curve tables must arrive by bulk asynchronous copy (TMA) on an mbarrier"
 
 
 def test_struct_layout_matches_header():
     from bspy_b200 import _cuda
-    # int32 x2, int32[8] x2, ptr[8], ptr, int32 x2  ->  8 + 64 + 64 + 8 + 8 = 152 bytes on LP64
-    assert C.sizeof(_cuda.CSpline) == 152
+    # int32 x2, int32[8] x2, ptr[8], ptr, int32 x2, ptr, int64  ->  8 + 64 + 64 + 8 + 8 + 8 + 8 = 168 bytes on LP64
+    assert C.sizeof(_cuda.CSpline) == 168
     assert _cuda.CSpline.knots.offset == 72 and _cuda.CSpline.coefs.offset == 136 and _cuda.CSpline.normalSign.offset == 144
+    assert _cuda.CSpline.curveTable.offset == 152 and _cuda.CSpline.curveTableBytes.offset == 160
+    assert _cuda.library().bspy_cuda_abi_version() == 2
 
 
 def test_argument_errors_are_status_codes():

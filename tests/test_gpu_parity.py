@@ -624,6 +624,16 @@ def test_curve_replicated_rows_bit_identical(option):
             a = _cuda.eval_points(ds, u, 1, 1, N, **request)
             option("CURVE_REPL", 0)
             b = _cuda.eval_points(ds, u, 1, 1, N, **request)
+            option("CURVE_REPL", 1)
+            option("CURVE_TMA", 0)                                  # tables rebuilt in every thread block (no cached image)
+            c2 = _cuda.eval_points(ds, u, 1, 1, N, **request)
+            option("CURVE_TMA", None)
+            for key in a:
+                if a[key] is not None:
+                    x, y = a[key], c2[key]
+                    if x.dtype.is_floating_point:
+                        x, y = torch.nan_to_num(x, nan=-7.0), torch.nan_to_num(y, nan=-7.0)
+                    assert torch.equal(x, y), (order, nDep, nCoef, key, "cached tables vs per-block tables")
             for key in a:
                 assert (a[key] is None) == (b[key] is None)
                 if a[key] is not None:
