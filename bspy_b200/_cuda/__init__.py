@@ -34,7 +34,7 @@ SYMBOLS = (
     "bspy_cuda_spans", "bspy_cuda_basis", "bspy_cuda_eval_points", "bspy_cuda_eval_points_binned",
     "bspy_cuda_binned_workspace_bytes", "bspy_cuda_eval_points_aos", "bspy_cuda_aos_workspace_bytes", "bspy_cuda_curve_table_bytes", "bspy_cuda_curve_table_build", "bspy_cuda_eval_grid",
     "bspy_cuda_eval_grid_batch", "bspy_cuda_eval_many", "bspy_cuda_probe_fp64", "bspy_cuda_probe_hbm",
-    "bspy_cuda_probe_tiles", "bspy_cuda_curvature", "bspy_cuda_contract_axis", "bspy_cuda_block_accumulate",
+    "bspy_cuda_probe_tiles", "bspy_cuda_curvature", "bspy_cuda_curvature_points", "bspy_cuda_contract_axis", "bspy_cuda_block_accumulate",
     "bspy_cuda_normal_from_jacobian", "bspy_cuda_collocation",
 )
 
@@ -98,6 +98,7 @@ def library():
             "bspy_cuda_probe_hbm": [i32, vp, vp, i64, C.POINTER(C.c_double), vp],
             "bspy_cuda_probe_tiles": [vp, i32, i64, i64, i32, i32, C.POINTER(C.c_double), vp],
             "bspy_cuda_curvature": [i32, i32, i32, i64, vp, vp, vp, vp, vp],
+            "bspy_cuda_curvature_points": [C.POINTER(CSpline), vp, i64, i64, i64, vp, vp, vp],
             "bspy_cuda_contract_axis": [vp, i64, i64, i64, i32, i32, vp, vp, vp],
             "bspy_cuda_block_accumulate": [vp, i64, vp, i64, i32, C.POINTER(i32), i64, vp],
             "bspy_cuda_normal_from_jacobian": [vp, i32, i32, i64, i32, u32, u32, vp, vp],
@@ -391,6 +392,20 @@ def curvature(nInd, nDep, graph, d1, d2, normal):
         rc = library().bspy_cuda_curvature(int(nInd), int(nDep), int(bool(graph)), int(N), _ptr(_f64(d1, dev)), _ptr(_f64(d2, dev)),
                                            _ptr(normal), _ptr(out), _stream(dev))
     _check(rc, "bspy_cuda_curvature")
+    return out
+
+
+CURVATURE_MAX_ORDER = 8
+
+
+def curvature_points(ds: DeviceSpline, uvw, point_stride, var_stride, N, flag=None):
+    """Launch bspy_cuda_curvature_points (one fused pass per point); returns (N,) float64 on the device."""
+    dev = ds.device
+    out = torch.empty(N, dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        rc = library().bspy_cuda_curvature_points(C.byref(ds.c), _ptr(uvw), int(point_stride), int(var_stride), int(N), _ptr(out),
+                                                  _ptr(flag), _stream(dev))
+    _check(rc, "bspy_cuda_curvature_points")
     return out
 
 

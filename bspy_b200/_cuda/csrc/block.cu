@@ -127,6 +127,137 @@ __global__ void __launch_bounds__(128) normal_from_jacobian_kernel(const double 
     }
 }
 
+int make_spline_dev(const bspy_spline *sp, SplineDev &s, const char *who);
+
+// ---- curvature in one pass -------------------------------------------------------------------------------
+// bspy/_spline_evaluation.py:80-107 for N points of a curve (nInd == 1) or surface (nInd == 2): the reference makes two
+// (curves) or five derivative calls plus a normal per point; here one thread walks the point's coefficient window ONCE with
+// the basis values, first and second derivatives of every variable (relaxed recurrence on the knots, like eval_generic)
+// and finishes with the curvature formula -- no intermediate derivative arrays.  Orders up to 8, nDep up to 3 (nDep == 1:
+// the graph of the function, x(u) = u, like the reference's self.graph()).
+constexpr int CURV_MAXO = 8;
+
+__device__ __forceinline__ void basis_local(const double *__restrict__ knots, const int order, const int ix, const double u,
+                                            const int deriv, double (&b)[CURV_MAXO])
+{
+#pragma unroll
+    for (int j = 0; j < CURV_MAXO; ++j) b[j] = 0.0;
+    if (deriv >= order) return;
+    b[order - 1] = 1.0;
+    const int nValue = order - deriv;
+    for (int deg = 1; deg < order; ++deg) {
+        int slot = order - deg;
+        for (int i = ix - deg; i < ix; ++i, ++slot) {
+            const double ki = __ldg(knots + i);
+            const double gap = __ldg(knots + i + deg) - ki;
+            // static indexing only (the array lives in registers): walk the slots with a compile-time loop
+#pragma unroll
+            for (int sl = 1; sl < CURV_MAXO; ++sl) {
+                if (sl == slot) {
+                    if (deg < nValue) {
+                        const double a = (u - ki) / gap;
+                        b[sl - 1] = fma(1.0 - a, b[sl], b[sl - 1]);
+                        b[sl] *= a;
+                    } else {
+                        const double a = (double)deg / gap;
+                        b[sl - 1] = fma(-a, b[sl], b[sl - 1]);
+                        b[sl] *= a;
+                    }
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) curvature_points_kernel(const SplineDev s, const double *__restrict__ uvw, const long long pointStride,
+                                                               const long long varStride, const long long N, double *__restrict__ out,
+                                                               long long *firstOutside)
+{
+    const int nDep = s.nDep;
+    const bool graph = nDep == 1;
+    for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < N; p += (long long)gridDim.x * blockDim.x) {
+        double B[2][3][CURV_MAXO];
+        int ix[2] = {0, 0};
+        bool outside = false;
+        for (int iv = 0; iv < s.nInd; ++iv) {
+            const double *k = s.knots[iv];
+            const int o = s.order[iv];
+            const double u = __ldg(uvw + p * pointStride + iv * varStride);
+            outside |= (u < __ldg(k + o - 1)) | (u > __ldg(k + s.nCoef[iv]));
+            ix[iv] = span_search(k, o + s.nCoef[iv], o, u);
+            basis_local(k, o, ix[iv], u, 0, B[iv][0]);
+            basis_local(k, o, ix[iv], u, 1, B[iv][1]);
+            basis_local(k, o, ix[iv], u, 2, B[iv][2]);
+        }
+        if (outside && firstOutside) report_outside((int64_t *)firstOutside, p);
+        if (s.nInd == 1) {
+            double fp[3] = {0, 0, 0}, fpp[3] = {0, 0, 0};
+            const int o = s.order[0];
+            for (int d = 0; d < nDep; ++d) {
+                const double *c = s.coefs + d * s.depStride + (ix[0] - o);
+                double a1 = 0.0, a2 = 0.0;
+#pragma unroll
+                for (int j = 0; j < CURV_MAXO; ++j)
+                    if (j < o) {
+                        const double x = __ldg(c + j);
+                        a1 = fma(x, B[0][1][j], a1);
+                        a2 = fma(x, B[0][2][j], a2);
+                    }
+                fp[d] = a1;
+                fpp[d] = a2;
+            }
+            double pp = graph ? 1.0 : 0.0, pq = 0.0, qq = 0.0;     // f'.f', f'.f'', f''.f''
+            for (int d = 0; d < nDep; ++d) {
+                pp = fma(fp[d], fp[d], pp);
+                pq = fma(fp[d], fpp[d], pq);
+                qq = fma(fpp[d], fpp[d], qq);
+            }
+            double num;
+            if (graph) num = fpp[0];                                // (1, f') x (0, f'')
+            else if (nDep == 2) num = fp[0] * fpp[1] - fp[1] * fpp[0];
+            else num = sqrt(qq * pp - pq * pq);
+            out[p] = num / (pp * sqrt(pp));
+        } else {
+            double su[3] = {0, 0, 0}, sv[3] = {0, 0, 0}, suu[3] = {0, 0, 0}, suv[3] = {0, 0, 0}, svv[3] = {0, 0, 0};
+            const int ou = s.order[0], ov = s.order[1];
+            for (int d = 0; d < nDep; ++d) {
+                const double *c = s.coefs + d * s.depStride + (long long)(ix[0] - ou) * s.stride[0] + (ix[1] - ov);
+                double a_u = 0.0, a_v = 0.0, a_uu = 0.0, a_uv = 0.0, a_vv = 0.0;
+#pragma unroll
+                for (int i = 0; i < CURV_MAXO; ++i)
+                    if (i < ou) {
+                        double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+#pragma unroll
+                        for (int j = 0; j < CURV_MAXO; ++j)
+                            if (j < ov) {
+                                const double x = __ldg(c + i * s.stride[0] + j);
+                                t0 = fma(x, B[1][0][j], t0);
+                                t1 = fma(x, B[1][1][j], t1);
+                                t2 = fma(x, B[1][2][j], t2);
+                            }
+                        a_u = fma(B[0][1][i], t0, a_u);
+                        a_v = fma(B[0][0][i], t1, a_v);
+                        a_uu = fma(B[0][2][i], t0, a_uu);
+                        a_uv = fma(B[0][1][i], t1, a_uv);
+                        a_vv = fma(B[0][0][i], t2, a_vv);
+                    }
+                const int dd = graph ? 2 : d;
+                su[dd] = a_u; sv[dd] = a_v; suu[dd] = a_uu; suv[dd] = a_uv; svv[dd] = a_vv;
+            }
+            if (graph) { su[0] = 1.0; sv[1] = 1.0; }
+            double n[3] = {su[1] * sv[2] - su[2] * sv[1], su[2] * sv[0] - su[0] * sv[2], su[0] * sv[1] - su[1] * sv[0]};
+            const double len = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+            double E = 0, F = 0, G = 0, L = 0, M = 0, Nn = 0;
+            for (int d = 0; d < 3; ++d) {
+                const double nd = n[d] / len;
+                E = fma(su[d], su[d], E); F = fma(su[d], sv[d], F); G = fma(sv[d], sv[d], G);
+                L = fma(suu[d], nd, L); M = fma(suv[d], nd, M); Nn = fma(svv[d], nd, Nn);
+            }
+            out[p] = (L * Nn - M * M) / (E * G - F * F);
+        }
+    }
+}
+
 }  // namespace bspy
 
 using namespace bspy;
@@ -212,4 +343,26 @@ extern "C" int bspy_cuda_collocation(const double *knots, int32_t nKnots, int32_
     collocation_kernel<<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(knots, nKnots, order, u, derivOrders, N, spansOut, A, ldA);
     count_launch();
     return check_launch("bspy_cuda_collocation");
+}
+
+extern "C" int bspy_cuda_curvature_points(const bspy_spline *spline, const double *uvw, int64_t pointStride, int64_t varStride,
+                                          int64_t N, double *out, int64_t *firstOutside, void *stream)
+{
+    SplineDev s;
+    int rc = make_spline_dev(spline, s, "bspy_cuda_curvature_points");
+    if (rc) return rc;
+    if (!uvw || !out || N < 0) { set_error("bspy_cuda_curvature_points: bad argument"); return BSPY_E_ARG; }
+    const bool shape = (s.nInd == 1 && s.nDep >= 1 && s.nDep <= 3) || (s.nInd == 2 && (s.nDep == 3 || s.nDep == 1));
+    if (!shape || s.order[0] > CURV_MAXO || (s.nInd == 2 && s.order[1] > CURV_MAXO)) {
+        set_error("bspy_cuda_curvature_points: curves of nDep 1..3 and surfaces of nDep 3 / 1 with orders <= %d", CURV_MAXO);
+        return BSPY_E_UNSUPPORTED;
+    }
+    if (N == 0) return 0;
+    long long blocks = (N + 127) / 128;
+    const long long cap = (long long)num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    curvature_points_kernel<<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(s, uvw, pointStride, varStride, N, out,
+                                                                                (long long *)firstOutside);
+    count_launch();
+    return check_launch("bspy_cuda_curvature_points");
 }

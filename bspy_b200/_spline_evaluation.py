@@ -463,9 +463,14 @@ def evaluate_grid(self, *axes, values=True, jacobian=False, normal=False, normal
         nrm = nrm[idx]
     res = EvalResult(out["values"], None, out["jacobian"], nrm, None, first_outside=flag if defer else None)
     if not on_device:
-        conv = (lambda t: None if t is None else t.cpu().numpy()) if kinds <= {"numpy"} else \
-               (lambda t: None if t is None else t.cpu())
-        res = EvalResult(conv(res.values), None, conv(res.jacobian), conv(res.normal), None)
+        # results go back through pinned staging buffers (recycled by torch's host allocator), all copies in flight together
+        host = {}
+        for name in ("values", "jacobian", "normal"):
+            t = getattr(res, name)
+            host[name] = None if t is None else torch.empty(t.shape, dtype=t.dtype, pin_memory=True).copy_(t, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        conv = (lambda t: None if t is None else t.numpy()) if kinds <= {"numpy"} else (lambda t: t)
+        res = EvalResult(conv(host["values"]), None, conv(host["jacobian"]), conv(host["normal"]), None)
     return res
 
 
@@ -488,6 +493,14 @@ def curvature_points(self, uvw, check_domain=True, device=None):
         dev = _cuda.device(device)
         pts = torch.from_numpy(np.ascontiguousarray(np.asarray(uvw, dtype=np.float64))).to(dev)
     pts = pts.reshape(-1, self.nInd)
+    if max(self.order) <= _cuda.CURVATURE_MAX_ORDER and self.nDep <= 3:
+        # one fused launch: second-derivative basis rows + one window walk + the curvature formula per point
+        ds = device_spline(self, pts.device)
+        flag = _cuda.new_flag(pts.device) if check_domain else None
+        k = _cuda.curvature_points(ds, pts, pts.stride(0), pts.stride(1), pts.shape[0], flag=flag)
+        if check_domain:
+            _raise_outside(self, int(flag.item()), lambda p: pts[p].cpu().numpy())
+        return k if on_device else k.cpu().numpy()
     ev = lambda **kw: evaluate_points(self, pts, values=False, check_domain=kw.pop("check", False), **kw)
     if self.nInd == 1:
         d1 = ev(with_respect_to=[1], check=check_domain).derivative

@@ -195,6 +195,13 @@ int bspy_cuda_eval_many(int32_t order, int32_t nCoef, int32_t nDep, int64_t nSpl
 int bspy_cuda_curvature(int32_t nInd, int32_t nDep, int32_t graph, int64_t N, const double *d1,
                         const double *d2, const double *normal, double *out, void *stream);
 
+/*      bspy_cuda_curvature_points: the same from the spline itself, one fused pass per point (basis values, first and
+ *      second derivatives of every variable, one walk over the coefficient window, curvature formula): curves of nDep
+ *      1..3 and surfaces of nDep 3 or 1 (nDep == 1: graph of the function) with orders <= 8; BSPY_E_UNSUPPORTED otherwise
+ *      (callers then compose bspy_cuda_eval_points passes + bspy_cuda_curvature).  firstOutside as in eval_points.   */
+int bspy_cuda_curvature_points(const bspy_spline *spline, const double *uvw, int64_t pointStride,
+                               int64_t varStride, int64_t N, double *out, int64_t *firstOutside, void *stream);
+
 /* ---- Spline.contract and SplineBlock -------------------------------------------------
  *      bspy_cuda_contract_axis: out[a, b] = sum_j coefs[a, first + j, b] * basis[j], a < outer, b < inner, j < order:
  *      one variable of a C-contiguous coefficient array (outer, n, inner) contracted against the `order` non-zero

@@ -321,6 +321,42 @@ def curvature_vec(s, uvw):
         return (L * Nn - M ** 2) / (E * G - F ** 2)
 
 
+def curvature_condition_vec(s, uvw):
+    """Relative condition number of the curvature formula at N points: sum of |terms| over |result| of every difference
+    in it (the cross-product numerator, L N - M^2, E G - F^2).  Where it is large the reference's own value carries a
+    relative error of about eps * condition, whatever computes the derivatives; tests use it to state the curvature bar
+    (strict 1e-12 relative where the condition is <= 100)."""
+    uvw = np.asarray(uvw, dtype=np.float64).reshape(-1, s.nInd)
+    N = uvw.shape[0]
+    graph = s.nDep == 1
+    with np.errstate(all="ignore"):
+        if s.nInd == 1:
+            fp, fpp = derivative_vec(s, [1], uvw), derivative_vec(s, [2], uvw)
+            if graph:
+                fp = np.concatenate([np.ones((N, 1)), fp], axis=1)
+                fpp = np.concatenate([np.zeros((N, 1)), fpp], axis=1)
+            pp, pq, qq = (fp * fp).sum(1), (fp * fpp).sum(1), (fpp * fpp).sum(1)
+            if fp.shape[1] == 2:
+                a, b = fp[:, 0] * fpp[:, 1], fp[:, 1] * fpp[:, 0]
+                return (np.abs(a) + np.abs(b)) / np.abs(a - b)
+            return (qq * pp + pq ** 2) / np.abs(qq * pp - pq ** 2)
+        d = {w: derivative_vec(s, list(w), uvw) for w in ((1, 0), (0, 1), (2, 0), (1, 1), (0, 2))}
+        if graph:
+            z, o = np.zeros((N, 1)), np.ones((N, 1))
+            su, sv = np.hstack([o, z, d[1, 0]]), np.hstack([z, o, d[0, 1]])
+            suu, suv, svv = (np.hstack([z, z, d[w]]) for w in ((2, 0), (1, 1), (0, 2)))
+        else:
+            su, sv, suu, suv, svv = d[1, 0], d[0, 1], d[2, 0], d[1, 1], d[0, 2]
+        n = np.cross(su, sv)
+        nlen = np.sqrt((n * n).sum(1))
+        n = n / nlen[:, None]
+        E, F, G = (su * su).sum(1), (su * sv).sum(1), (sv * sv).sum(1)
+        L, M, Nn = (suu * n).sum(1), (suv * n).sum(1), (svv * n).sum(1)
+        dots = sum((np.abs(x * n)).sum(1) / np.maximum(np.abs((x * n).sum(1)), 1e-300) for x in (suu, suv, svv)) / 3
+        cross = np.sqrt(E * G) / nlen
+        return (np.abs(L * Nn) + M ** 2) / np.abs(L * Nn - M ** 2) + (E * G + F ** 2) / np.abs(E * G - F ** 2) + dots + cross
+
+
 # ------------------------------------------------------------- conditioning of the sums
 # The parity bar of the path is |x - ref| <= 1e-13 + 1e-12*|ref|.  A value/derivative is a
 # sum of products coefficient x basis values; any implementation that adds those terms in a

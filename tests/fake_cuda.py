@@ -155,6 +155,21 @@ def curvature(nInd, nDep, graph, d1, d2, normal):
         return torch.from_numpy((L * Nn - M ** 2) / (E * G - F ** 2))
 
 
+CURVATURE_MAX_ORDER = 8
+
+
+def curvature_points(ds, uvw, point_stride, var_stride, N, flag=None):
+    launches[0] += 1
+    pts = torch.as_strided(uvw, (N, ds.nInd), (point_stride, var_stride)).numpy().astype(np.float64)
+    s = _ospline(ds)
+    if flag is not None:
+        bad = O.check_domain_vec(s, pts)
+        if bad >= 0:
+            flag[0] = bad
+    with np.errstate(all="ignore"):
+        return torch.from_numpy(np.ascontiguousarray(O.curvature_vec(s, pts)))
+
+
 def contract_axis(coefs, axis, first, order, basis):
     launches[0] += 1
     c = np.moveaxis(coefs.numpy(), axis, -1)[..., first:first + order]
@@ -198,7 +213,7 @@ def collocation(knots, order, u, deriv_orders=None):
 
 def install(monkeypatch):
     from bspy_b200 import _cuda
-    for name in ("device", "new_flag", "launch_count", "eval_points", "eval_points_host", "eval_points_aos", "record_layout", "eval_grid", "spans", "basis", "curvature",
+    for name in ("device", "new_flag", "launch_count", "eval_points", "eval_points_host", "eval_points_aos", "record_layout", "eval_grid", "spans", "basis", "curvature", "curvature_points", "CURVATURE_MAX_ORDER",
                  "contract_axis", "block_accumulate", "normal_from_jacobian", "collocation"):
         monkeypatch.setattr(_cuda, name, globals()[name])
     launches[0] = 0

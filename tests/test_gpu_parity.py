@@ -67,6 +67,21 @@ def test_spans_and_basis_bit_exact(c):
     assert ix == c["spans"][7, 0] and np.array_equal(b, c["basis0_d0"][7], equal_nan=True)
 
 
+# The reference's own fixtures with nearly coincident knots (trim-issue.json: a knot gap of 1.9e-6 at order 7; the offset /
+# reverse / Patterson / TomsNasty files) have derivative basis values up to 5e5 that cancel: ANY summation order other than
+# numpy's differs from the reference by a few eps * sum|terms| there, the C restatement of the reference included.  Those
+# files -- and only those -- are held to the condition-aware bar; the 23 synthetic cases to the strict bar
+# |x - ref| <= 1e-13 + 1e-12 |ref|.  profiles/r02_parity_table.md lists, per fixture, how far the CUDA path actually is
+# from the STRICT bar (tools/parity_table.py).
+ILL_CONDITIONED = ("trim0", "reverse0", "offset0", "offset1", "offset2", "offset3", "offset4", "patterson0", "patterson1", "tomsnasty0")
+
+
+def _bar(c, x, ref, scale, k=16.0):
+    if c.tag in ILL_CONDITIONED:
+        return close_cond(x, ref, scale, k=k)
+    return close(x, ref)
+
+
 @pytest.mark.parametrize("c", CASES, ids=lambda c: c.tag)
 def test_points_vs_reference(c):
     _, _, O, _ = _mods()
@@ -74,20 +89,23 @@ def test_points_vs_reference(c):
     r = s.evaluate_points(c.uvw, values=True, jacobian=True, spans=True)
     assert np.array_equal(r.spans.T, c["spans"])
     S0 = O.derivative_abs_vec(so, [0] * c.nInd, c.uvw)
-    assert close_cond(r.values.T, c["values"], S0), c.tag
+    assert _bar(c, r.values.T, c["values"], S0), c.tag
     SJ = O.jacobian_abs_vec(so, c.uvw)
-    assert close_cond(np.transpose(r.jacobian, (2, 0, 1)), c["jacobian"], SJ), c.tag
+    assert _bar(c, np.transpose(r.jacobian, (2, 0, 1)), c["jacobian"], SJ), c.tag
     for w in c.meta["wrt"]:
         ref = c["deriv_" + "_".join(map(str, w))]
         got = s.evaluate_points(c.uvw, values=False, with_respect_to=w).derivative.T
-        assert close_cond(got, ref, O.derivative_abs_vec(so, w, c.uvw)), (c.tag, w)
+        assert _bar(c, got, ref, O.derivative_abs_vec(so, w, c.uvw)), (c.tag, w)
         if w[0] >= c.order[0]:
             assert not got.any()
     # values-only pass (different kernel instantiation) and CUDA-tensor input, (nInd, N) layout
     pts = torch.from_numpy(np.ascontiguousarray(c.uvw.T)).cuda()
     r2 = s.evaluate_points(pts, layout="variables")
     assert isinstance(r2.values, torch.Tensor) and r2.values.is_cuda
-    assert close_cond(r2.values.cpu().numpy().T, c["values"], S0)
+    assert _bar(c, r2.values.cpu().numpy().T, c["values"], S0)
+    # array-of-structs records of the same request: the same numbers
+    r3 = s.evaluate_points(c.uvw, jacobian=True, out_layout="aos")
+    assert np.array_equal(r3.values, r.values, equal_nan=True) and np.array_equal(r3.jacobian, r.jacobian, equal_nan=True)
 
 
 @pytest.mark.parametrize("c", [c for c in CASES if c.meta["normal"]], ids=lambda c: c.tag)
@@ -749,22 +767,68 @@ def test_batch_api_variants():
     assert g.values.shape == (c.nDep, c.uvw.shape[0]) and close(g.values.T, c["values"]) and close(g.jacobian[:, 0].T, c["jacobian"][:, :, 0])
 
 
+def _curvature_close(k, want, cond):
+    """strict bar (1e-12 relative, 1e-13 absolute) where the formula is well-conditioned (condition <= 100); elsewhere the
+    relative bar is 45 eps x condition -- what the reference's own value is uncertain by; NaN / inf must match"""
+    k, want, cond = np.asarray(k), np.asarray(want), np.asarray(cond)
+    fin = np.isfinite(want)
+    if not np.array_equal(np.isnan(k), np.isnan(want)):
+        return False
+    with np.errstate(all="ignore"):
+        rtol = np.where(cond <= 100.0, 1e-12, 1e-14 * cond)
+        return bool(np.all(np.abs(k - want)[fin] <= (1e-13 + rtol * np.abs(want))[fin]))
+
+
 def test_curvature_vs_reference():
-    """batched curvature (curves nDep 1/2/3, surfaces nDep 3 and graph of a scalar function)
-    against Spline.curvature of the reference."""
+    """batched curvature (curves nDep 1/2/3, surfaces nDep 3 and graph of a scalar function) in one
+    fused pass against Spline.curvature of the reference: 1e-12 relative wherever the formula is well-conditioned."""
+    _, _cuda, O, _ = _mods()
     ref = load_npz("ref_curvature.npz")
     by_tag = {c.tag: c for c in CASES}
+    strict = 0
     for tag, want in ref.items():
         c = by_tag[tag]
         s = _spline(c)
+        cond = O.curvature_condition_vec(_ospline(c), c.uvw)
         k = s.curvature_points(c.uvw)
-        ok = np.isfinite(want)
         assert k.shape == want.shape
-        assert np.allclose(k[ok], want[ok], rtol=1e-8, atol=1e-8 * max(1.0, np.abs(want[ok]).max())), tag
+        assert _curvature_close(k, want, cond), (tag, np.nanmax(np.abs(k - want) / np.abs(want)))
+        strict += int((np.isfinite(want) & (cond <= 100.0)).sum())
         kd = s.curvature_points(torch.from_numpy(c.uvw).cuda())
         assert kd.is_cuda and np.array_equal(kd.cpu().numpy(), k, equal_nan=True)
-        p = int(np.flatnonzero(ok)[5])
-        assert np.isclose(s.curvature(c.uvw[p] if c.nInd > 1 else c.uvw[p, 0]), want[p], rtol=1e-8, atol=1e-8)
+        p = int(np.flatnonzero(np.isfinite(want))[5])
+        assert _curvature_close([s.curvature(c.uvw[p] if c.nInd > 1 else c.uvw[p, 0])], [want[p]], [cond[p]])
+        # the composed path (derivative passes + bspy_cuda_curvature) stays available for shapes the fused kernel does not take
+        d1 = s.evaluate_points(c.uvw, values=False, with_respect_to=[1] + [0] * (c.nInd - 1)).derivative
+        assert d1.shape == (c.nDep, c.uvw.shape[0])
+    assert strict >= 300, strict                                    # most samples are held to the strict bar
+
+
+def test_curvature_known_answers():
+    """The reference's own curvature test (tests/bspy_test.py:693-700) on the GPU path: the section curve has curvature 1 at
+    u = 0 and 2 at u = 1 (2e-15), mySurface has Gaussian curvature 1.024 at (0.25, 0.5) (1e-14); plus the reference's values
+    on the planar projection at 101 parameters and on a 7 x 7 grid of the surface."""
+    bspy, _, O, _ = _mods()
+    a = load_npz("ref_curvature_kat.npz")
+
+    def spline(tag):
+        nInd = int(a[f"{tag}/nInd"])
+        return bspy.Spline(nInd, int(a[f"{tag}/nDep"]), tuple(a[f"{tag}/order"]), tuple(a[f"{tag}/nCoef"]),
+                           [a[f"{tag}/knots{i}"] for i in range(nInd)], a[f"{tag}/coefs"])
+
+    section = spline("section")
+    assert abs(section.curvature(0.0) - 1.0) < 2.0e-15 and abs(section.curvature(1.0) - 2.0) < 2.0e-15
+    k = section.curvature_points(a["section/u"])
+    assert np.all(np.abs(k - a["section/curvature"]) < 2.0e-15)
+    planar = spline("planar")
+    kp = planar.curvature_points(a["planar/u"])
+    so = O.OracleSpline.of(planar)
+    assert _curvature_close(kp, a["planar/curvature"], O.curvature_condition_vec(so, a["planar/u"][:, None]))
+    surface = spline("surface")
+    assert abs(surface.curvature([0.25, 0.5]) - 1.024) < 1.0e-14
+    ks = surface.curvature_points(a["surface/uv"])
+    assert abs(ks[0] - 1.024) < 1.0e-14
+    assert _curvature_close(ks, a["surface/curvature"], O.curvature_condition_vec(O.OracleSpline.of(surface), a["surface/uv"]))
 
 
 def test_grid_edge_cases():
@@ -985,3 +1049,24 @@ def test_grid_float32_outputs():
     vol = _spline([c for c in CASES if c.tag == "vol_444_d3"][0])
     with pytest.raises(NotImplementedError):
         vol.evaluate_grid(*[np.linspace(0, 1, 5)] * 3, dtype=np.float32)
+
+
+@pytest.mark.parametrize("cfg,scale", [("cfg2", 1.0), ("cfg1", 1.0), ("cfg3", 0.12), ("cfg4", 0.06), ("cfg4_soa", 0.06), ("cfg5", 0.03),
+                                       ("cfg5_soa", 0.03), ("grid3", 0.5)])
+def test_bench_shapes_at_bench_tile_paths(cfg, scale):
+    """The BASELINE configurations through the public API and the DEFAULT dispatch at sizes that reach the same kernels and
+    tile paths as the bench: the teapot at the full 2048 x 2048 grid per patch (border rows / columns in full + random interior
+    of 8 patches incl. lid and bottom), 1.2e5 curves of config 3, 6e6 points of config 4 and 3.75e6 points of config 5
+    (cell-sorted pipeline, array-of-structs and struct-of-arrays outputs, value + jacobian), the 256^3 volume grid -- each
+    against the C restatement of the reference on a >= 1e5-point sample of the outputs: strict bar, spans ==.  This is the
+    parity block of bench.py (same code), so a green test here is what the bench line's "parity" reports."""
+    import bench
+    wl = bench.CONFIGS[cfg]()
+    wl.setup(torch.device("cuda", torch.cuda.current_device()), 0, scale)
+    wl.step()
+    torch.cuda.synchronize()
+    assert wl.flags_ok()
+    rep = wl.parity()
+    assert rep["ok"] and rep["spans_equal"] and rep["nan_match"] and rep["worst_ratio"] <= 1.0 and rep["n"] >= 100_000, rep
+    wl.teardown()
+    torch.cuda.empty_cache()
