@@ -1271,6 +1271,16 @@ static int eval_binned_records(const SplineDev &s, PointsDev in, long long N, co
         const int code = (int)option(OPT_STAGED, 0);
         if (code >= 0 && !nN) staged = find_staged(s, jac, code);
     }
+    // two points per lane on staged windows (value + jacobian requests).  STAGED_PAIR=<10 * deps per pass + CTAs per SM> selects
+    // it; measured on config 4 (whole step, Gpts/s): 13 -> 9.15, 12 -> 9.49, 32 -> 9.61, 14 -> 8.13 against 10.5 for one point
+    // per lane (eval_staged2_kernel) -- unlike the 4-variate manifold, where two points per thread gave +38 %, the tricubic
+    // kernel loses more to the lower occupancy (168-246 registers) than it gains from halving the window loads.  Off by default.
+    const StagedEntry *stagedPair = nullptr;
+    if (jac && plainWrt && !nN && option(OPT_SPAN_RECORDS, 1) && option(OPT_STAGED_PAIR, -1) >= 0 && !(cell != nullptr))
+        stagedPair = find_staged_pair(s, (int)option(OPT_STAGED_PAIR, -1));
+    const size_t stagedPairSmem = stagedPair ? sizeof(double) * 4 * stagedPair->windowDoubles : 0;
+    if (stagedPair)
+        if (int rc = allow_dynamic_smem(stagedPair->fn, stagedPairSmem)) return rc;
     // second-generation staged kernel (span records staged with the window) unless EXP_A=1 or the records are off
     const bool staged2 = staged && option(OPT_SPAN_RECORDS, 1) && !option(OPT_EXP_A, 0);
     const FixedFn stagedFn = staged ? (staged2 ? staged->fn2 : staged->fn) : nullptr;
@@ -1294,7 +1304,7 @@ static int eval_binned_records(const SplineDev &s, PointsDev in, long long N, co
     // cell images (padded window + span records per cell, built once per call) for the shapes compiled for them
     const ImageEntry *image = nullptr;
     const double *images = nullptr;
-    if (images_apply(s, N) && !(cell && option(OPT_CELL_KERNEL, 0))) {
+    if (images_apply(s, N) && !(cell && option(OPT_CELL_KERNEL, 0)) && !stagedPair) {
         image = find_image(s, jac, (int)option(OPT_IMAGE, 0));
         if (image && nN && (image->pair || (image->code % 100) / 10 != s.nDep)) image = nullptr;   // normals need the whole jacobian in one pass
         if (image && image->pair && !plainWrt) image = nullptr;
@@ -1313,9 +1323,12 @@ static int eval_binned_records(const SplineDev &s, PointsDev in, long long N, co
         images = dst;
         if (int rc = allow_dynamic_smem(image->fn, sizeof(double) * 128 * image->recDoubles)) return rc;
     }
+    // cell segments are padded to even lengths for the chunks a two-points-per-thread kernel evaluates (the staged pair
+    // kernel only takes dense chunks: a sparse tail chunk is sorted without padding and goes to the one-point kernels)
+    auto pair_pad = [&](int n) { return (image && image->pair) || (stagedPair != nullptr && n >= 48 * cells); };
     // Sort (and un-permute) of the neighbouring chunks on a second stream under the evaluation of this one: the sort
     // passes are memory / latency bound, the evaluation FP64 bound.  BIN_OVERLAP=0/1 overrides.
-    const bool wantOverlap = option(OPT_BIN_OVERLAP, (staged != nullptr || cell != nullptr) ? 1 : 0) != 0;
+    const bool wantOverlap = option(OPT_BIN_OVERLAP, (staged != nullptr || cell != nullptr || stagedPair != nullptr) ? 1 : 0) != 0;
     BinStreams *bs = wantOverlap ? acquire_bin_streams() : nullptr;
     struct Release { BinStreams *b; ~Release() { if (b) release_bin_streams(b); } } releaseOnExit{bs};
     const long long nChunks = (N + chunk - 1) / chunk;
@@ -1348,7 +1361,7 @@ static int eval_binned_records(const SplineDev &s, PointsDev in, long long N, co
         // four points per thread in flight (measured against one point per thread at full occupancy: keys 106 -> 95 us,
         // scatter 88 -> 71 us per 4 Mi points)
         bin_keys_batched_kernel<4><<<(n + 511) / 512, 128, 0, sSort>>>(s, in, base, n, B.keys, B.hist, B.inv, o1);
-        if (image && image->pair) bin_scan_kernel<<<1, 1024, 0, sSort>>>(B.hist, (int)cells, 1, B.records, B.recKI, s.nInd);
+        if (pair_pad(n)) bin_scan_kernel<<<1, 1024, 0, sSort>>>(B.hist, (int)cells, 1, B.records, B.recKI, s.nInd);
         else bin_scan_kernel<<<1, 1024, 0, sSort>>>(B.hist, (int)cells);
         bin_scatter_records_batched_kernel<4><<<(n + 511) / 512, 128, 0, sSort>>>(s, in, base, n, B.keys, B.hist, B.records, B.recKI,
                                                                                  B.inv, userAos ? 0 : 1);
@@ -1380,6 +1393,10 @@ static int eval_binned_records(const SplineDev &s, PointsDev in, long long N, co
             image->fn<<<(unsigned)((pairs + 127) / 128), 128, sizeof(double) * 128 * image->recDoubles, sEval>>>(s, pin, n, wrt, o2);
         } else if (image) {
             image->fn<<<(unsigned)((n + 127) / 128), 128, sizeof(double) * 128 * image->recDoubles, sEval>>>(s, pin, n, wrt, o2);
+        } else if (stagedPair && n >= 48 * cells) {
+            long long blocks = (long long)num_sms() * (stagedPair->code % 10);
+            if (blocks > (n + 255) / 256) blocks = (n + 255) / 256;
+            stagedPair->fn<<<(unsigned)blocks, 128, stagedPairSmem, sEval>>>(s, pin, n, wrt, o2);
         } else if (cell && n >= 48 * cells) {
             long long blocks = (long long)num_sms() * cell->minBlocks;
             const long long most = (n + 32 * CELL_WARPS - 1) / (32 * CELL_WARPS);

@@ -427,6 +427,220 @@ __global__ void __launch_bounds__(128, MINB) eval_staged2_kernel(const SplineDev
     }
 }
 
+// ---- warp-staged windows, two points of the same cell per lane ---------------------------------------------------------
+// The load-return path of the SM (128 B/clk) has to deliver every window coefficient to every lane: 1.5 KB per point of a
+// tricubic nDep-3 spline, as many cycles as the FP64 pipe needs for the point (ncu: l1tex 68 %, FP64 57 % -- neither full,
+// the warps wait on both).  Two points per lane use every LDS.128 twice and carry twice the independent FMA chains.  The
+// sort pads every cell's segment to an even length (bin_scan_kernel, evenPad): the aligned pairs of the sorted sequence
+// never straddle a cell, spare slots hold dummy records (index -1: evaluated, never stored).  A tile is 64 sorted slots,
+// lane l takes slots 2l and 2l+1; the two-slot window logic of eval_staged2_kernel applies per pair.  One dependent variable
+// per pass (NDT), results collected in a [slot][lane] tile of shared memory and stored as whole 32-byte sectors.
+template <int L, class Ord, int NDEP, int NDT>
+struct ContractS2 {
+    using WS = WindowShape<Ord, NDEP>;
+    using Ctx = FixedCtx<Ord, NDT, true>;
+    __device__ __forceinline__ static void run(const double *__restrict__ w, const int off, const Ctx &c0, const Ctx &c1,
+                                               double (&v0)[NDT], double (&g0)[Ord::n][NDT], double (&v1)[NDT], double (&g1)[Ord::n][NDT])
+    {
+        constexpr int O = Ord::at(L);
+#pragma unroll
+        for (int d = 0; d < NDT; ++d) { v0[d] = 0.0; v1[d] = 0.0; }
+#pragma unroll
+        for (int m = L; m < Ord::n; ++m)
+#pragma unroll
+            for (int d = 0; d < NDT; ++d) { g0[m][d] = 0.0; g1[m][d] = 0.0; }
+        if constexpr (L == Ord::n - 1) {
+#pragma unroll
+            for (int d = 0; d < NDT; ++d) {
+                double x[O];
+                load_run<O>(w, off + d * WS::perDepPad, x);
+#pragma unroll
+                for (int i = 0; i < O; ++i) {
+                    v0[d] = fma(x[i], c0.B[L][i], v0[d]);
+                    v1[d] = fma(x[i], c1.B[L][i], v1[d]);
+                    g0[L][d] = fma(x[i], c0.dB[L][i], g0[L][d]);
+                    g1[L][d] = fma(x[i], c1.dB[L][i], g1[L][d]);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < O; ++i) {
+                double cv0[NDT], cv1[NDT];
+                double cg0[Ord::n][NDT], cg1[Ord::n][NDT];
+                ContractS2<L + 1, Ord, NDEP, NDT>::run(w, off + i * WS::stride(L), c0, c1, cv0, cg0, cv1, cg1);
+#pragma unroll
+                for (int d = 0; d < NDT; ++d) {
+                    v0[d] = fma(cv0[d], c0.B[L][i], v0[d]);
+                    v1[d] = fma(cv1[d], c1.B[L][i], v1[d]);
+                    g0[L][d] = fma(cv0[d], c0.dB[L][i], g0[L][d]);
+                    g1[L][d] = fma(cv1[d], c1.dB[L][i], g1[L][d]);
+#pragma unroll
+                    for (int m = L + 1; m < Ord::n; ++m) {
+                        g0[m][d] = fma(cg0[m][d], c0.B[L][i], g0[m][d]);
+                        g1[m][d] = fma(cg1[m][d], c1.B[L][i], g1[m][d]);
+                    }
+                }
+            }
+        }
+    }
+};
+
+template <int IV, class Ord, int NDT>
+__device__ __forceinline__ void setup_variable_shared_pair(const double *__restrict__ cellRec, double ua, double ub,
+                                                           FixedCtx<Ord, NDT, true> &ca, FixedCtx<Ord, NDT, true> &cb)
+{
+    constexpr int O = Ord::at(IV);
+    using R = SpanRec<O>;
+    const double *rec = cellRec + CellRecords<Ord>::offset(IV);
+    double r[R::stride > 0 ? R::stride : 1];
+#pragma unroll
+    for (int j = 0; j < R::stride / 2; ++j) {
+        const double2 x = *reinterpret_cast<const double2 *>(rec + 2 * j);
+        r[2 * j] = x.x;
+        r[2 * j + 1] = x.y;
+    }
+    double rc[O > 1 ? O * (O - 1) / 2 : 1];
+#pragma unroll
+    for (int j = 0; j < O * (O - 1) / 2; ++j) rc[j] = r[O - 1 + j];
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+        const double u = p ? ub : ua;
+        double dl[O > 1 ? O - 1 : 1], b0[O], b1[O];
+#pragma unroll
+        for (int j = 0; j < O - 1; ++j) dl[j] = u - r[j];
+        basis_core<O, true>(dl, rc, 0, b0, b1);
+        FixedCtx<Ord, NDT, true> &c = p ? cb : ca;
+#pragma unroll
+        for (int j = 0; j < O; ++j) { c.B[IV][j] = b0[j]; c.dB[IV][j] = b1[j]; }
+    }
+}
+
+template <int NIND, int O0, int O1, int O2, int O3, int NDEP, int NDT, int MINB>
+__global__ void __launch_bounds__(128, MINB) eval_staged_pair_kernel(const SplineDev s, const PointsDev in, const long long N,
+                                                                      const WrtDev wrt, const OutDev out)
+{
+    using Ord = Orders<NIND, O0, O1, O2, O3>;
+    using WS = WindowShape<Ord, NDEP>;
+    using CR = CellRecords<Ord>;
+    constexpr int SLOT = WS::size + CR::size;
+    constexpr int R = NDEP * (1 + NIND), RP = (R + 3) & ~3;
+    static_assert(NDEP % NDT == 0, "dependent-variable tile must divide nDep");
+    extern __shared__ __align__(16) double stagedWindows[];         // per warp: two slots | result tile [2][R][32]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *w0 = stagedWindows + warp * (2 * SLOT + 2 * R * 32);
+    double *mine = w0 + 2 * SLOT + lane;                            // results of this lane: mine[(p * R + slot) * 32]
+    int slotKey0 = -1, slotKey1 = -1;
+    const long long total = __ldg(in.sortedTotal);                  // slots of the sorted sequence (segments padded to even)
+    const long long tiles = (total + 63) >> 6, nWarps = gridDim.x * 4LL;
+    const long long per = (tiles + nWarps - 1) / nWarps;
+    const long long firstTile = (blockIdx.x * 4LL + warp) * per;
+    const long long endTile = firstTile + per < tiles ? firstTile + per : tiles;
+    double2 ra0 = make_double2(0.0, 0.0), ra1 = ra0, rb0 = ra0, rb1 = ra0;
+    longlong2 kk = make_longlong2(-1, -1);
+    auto fetch = [&](long long tile) {
+        const long long t = tile * 64 + 2 * lane;
+        if (tile < endTile && t < total) {
+            const double2 *rp = reinterpret_cast<const double2 *>(in.records + 4 * t);
+            ra0 = __ldcs(rp); ra1 = __ldcs(rp + 1); rb0 = __ldcs(rp + 2); rb1 = __ldcs(rp + 3);
+            if constexpr (NIND > 3) kk = __ldcs(reinterpret_cast<const longlong2 *>(in.recKI + t));
+        }
+    };
+    fetch(firstTile);
+    for (long long tile = firstTile; tile < endTile; ++tile) {
+        const long long t = tile * 64 + 2 * lane;
+        const bool live = t < total;
+        double ua[NIND], ub[NIND];
+        ua[0] = ra0.x; ub[0] = rb0.x;
+        if constexpr (NIND > 1) { ua[1] = ra0.y; ub[1] = rb0.y; }
+        if constexpr (NIND > 2) { ua[2] = ra1.x; ub[2] = rb1.x; }
+        if constexpr (NIND > 3) { ua[3] = ra1.y; ub[3] = rb1.y; }
+        const long long kia = NIND > 3 ? kk.x : __double_as_longlong(ra1.y), kib = NIND > 3 ? kk.y : __double_as_longlong(rb1.y);
+        const int key = live ? (int)kia : -1;
+        fetch(tile + 1);
+        bool done = !live;
+        while (true) {
+            const unsigned pending = __ballot_sync(0xffffffffu, !done);
+            if (!pending) break;
+            const int k0 = __shfl_sync(0xffffffffu, key, __ffs(pending) - 1);
+            const bool in0 = !done && key == k0;
+            const unsigned rest = __ballot_sync(0xffffffffu, !done && !in0);
+            const int k1 = rest ? __shfl_sync(0xffffffffu, key, __ffs(rest) - 1) : -1;
+            const bool in1 = !done && !in0 && key == k1;
+            int s0, s1 = -1;
+            bool staged = false;
+            if (k0 == slotKey0) s0 = 0;
+            else if (k0 == slotKey1) s0 = 1;
+            else {
+                s0 = (k1 >= 0 && k1 == slotKey0) ? 1 : 0;
+                stage_cell<Ord, NDEP>(s, in, k0, w0 + s0 * SLOT, lane);
+                if (s0) slotKey1 = k0; else slotKey0 = k0;
+                staged = true;
+            }
+            if (k1 >= 0) {
+                s1 = 1 - s0;
+                if ((s1 ? slotKey1 : slotKey0) != k1) {
+                    stage_cell<Ord, NDEP>(s, in, k1, w0 + s1 * SLOT, lane);
+                    if (s1) slotKey1 = k1; else slotKey0 = k1;
+                    staged = true;
+                }
+            }
+            if (staged) {
+                asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+                __syncwarp();
+            }
+            if (in0 || in1) {
+                const double *w = w0 + (in1 ? s1 : s0) * SLOT;
+                FixedCtx<Ord, NDT, true> c0, c1;
+                setup_variable_shared_pair<0, Ord, NDT>(w + WS::size, ua[0], ub[0], c0, c1);
+                if constexpr (NIND > 1) setup_variable_shared_pair<1, Ord, NDT>(w + WS::size, ua[1], ub[1], c0, c1);
+                if constexpr (NIND > 2) setup_variable_shared_pair<2, Ord, NDT>(w + WS::size, ua[2], ub[2], c0, c1);
+                if constexpr (NIND > 3) setup_variable_shared_pair<3, Ord, NDT>(w + WS::size, ua[3], ub[3], c0, c1);
+#pragma unroll 1
+                for (int d0 = 0; d0 < NDEP; d0 += NDT) {
+                    double v0[NDT], v1[NDT];
+                    double g0[NIND][NDT], g1[NIND][NDT];
+                    ContractS2<0, Ord, NDEP, NDT>::run(w + d0 * WS::perDepPad, 0, c0, c1, v0, g0, v1, g1);
+#pragma unroll
+                    for (int d = 0; d < NDT; ++d) {
+                        mine[(d0 + d) * 32] = v0[d];
+                        mine[(R + d0 + d) * 32] = v1[d];
+#pragma unroll
+                        for (int iv = 0; iv < NIND; ++iv) {
+                            mine[(NDEP + (d0 + d) * NIND + iv) * 32] = g0[iv][d];
+                            mine[(R + NDEP + (d0 + d) * NIND + iv) * 32] = g1[iv][d];
+                        }
+                    }
+                }
+#pragma unroll
+                for (int p = 0; p < 2; ++p) {
+                    const long long ki = p ? kib : kia;
+                    const long long idx = ki >> 32;
+                    if (idx < 0) continue;                          // dummy slot of an odd cell
+                    const long long dest = out.aosScatter ? out.aosBase + idx : t + p;
+                    double *rec = out.aos + dest * out.aosStride;
+                    const double *src = mine + p * R * 32;
+#pragma unroll
+                    for (int j = 0; j < RP / 4; ++j) {
+                        if (4 * j < out.aosStride) {
+                            double x[4];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) x[e] = 4 * j + e < R ? src[(4 * j + e) * 32] : 0.0;
+                            if (out.aosWide)
+                                asm volatile("st.global.cs.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(rec + 4 * j), "d"(x[0]), "d"(x[1]), "d"(x[2]), "d"(x[3]) : "memory");
+                            else {
+                                __stcs(reinterpret_cast<double2 *>(rec + 4 * j), make_double2(x[0], x[1]));
+                                __stcs(reinterpret_cast<double2 *>(rec + 4 * j) + 1, make_double2(x[2], x[3]));
+                            }
+                        }
+                    }
+                }
+                done = true;
+            }
+            __syncwarp();
+        }
+    }
+}
+
 // ---- any-shape kernel -------------------------------------------------------------------------
 // Runtime nInd / orders / nDep.  Per-thread basis rows live in shared memory ([slot][thread]);
 // the window is walked with an odometer over all variables but the last, the last variable is
@@ -671,6 +885,27 @@ static const StagedEntry kStaged[] = {
     BSPY_STAGED_(3, 4, 4, 4, 0, 3, 1, 3, 3, 1),
     BSPY_STAGED_(4, 3, 3, 3, 3, 6, 1, 1, 4, 1), BSPY_STAGED_(4, 3, 3, 3, 3, 6, 1, 2, 3, 1), BSPY_STAGED_(4, 3, 3, 3, 3, 6, 1, 6, 2, 1),
 };
+
+// two points per lane (value + jacobian).  code = 10 * (dependent variables per pass) + CTAs per SM; windowDoubles holds the
+// per-warp shared memory in doubles: two slots (window + cell records) and the result tile of the lane pairs
+#define BSPY_STAGED_PAIR(NI, A, B, C, D_, ND, NDT, MB, OPT)                                                     \
+    {NI, {A, B, C, D_}, ND, 1, 10 * NDT + MB, eval_staged_pair_kernel<NI, A, B, C, D_, ND, NDT, MB>,           \
+     2 * (WindowShape<Orders<NI, A, B, C, D_>, ND>::size + CellRecords<Orders<NI, A, B, C, D_>>::size) + 2 * ND * (1 + NI) * 32, nullptr, 0, OPT}
+static const StagedEntry kStagedPair[] = {
+    BSPY_STAGED_PAIR(3, 4, 4, 4, 0, 3, 1, 3, 0), BSPY_STAGED_PAIR(3, 4, 4, 4, 0, 3, 1, 2, 1), BSPY_STAGED_PAIR(3, 4, 4, 4, 0, 3, 3, 2, 1),
+    BSPY_STAGED_PAIR(3, 4, 4, 4, 0, 3, 1, 4, 1),
+};
+
+const StagedEntry *find_staged_pair(const SplineDev &s, int code)
+{
+    for (const StagedEntry &e : kStagedPair) {
+        if (e.nInd != s.nInd || e.nDep != s.nDep) continue;
+        bool same = true;
+        for (int i = 0; i < s.nInd; ++i) same &= e.o[i] == s.order[i];
+        if (same && (code == 0 ? !e.optIn : code == e.code)) return &e;
+    }
+    return nullptr;
+}
 
 const StagedEntry *find_staged(const SplineDev &s, int jac, int code)
 {

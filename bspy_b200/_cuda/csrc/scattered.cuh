@@ -423,6 +423,7 @@ struct StagedEntry {
 FixedFn find_fixed(const SplineDev &s, int jac);
 FixedFn find_fixed_tiled(const SplineDev &s, int jac, int code);
 const StagedEntry *find_staged(const SplineDev &s, int jac, int code);
+const StagedEntry *find_staged_pair(const SplineDev &s, int code);   // windowDoubles = per-warp HALF: slot + result tile of one point
 int make_spline_dev(const bspy_spline *sp, SplineDev &s, const char *who);
 int launch_eval(const SplineDev &s, const PointsDev &in, long long N, const WrtDev &wrt, const OutDev &out, int jac,
                 cudaStream_t stream);

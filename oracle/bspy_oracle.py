@@ -357,6 +357,53 @@ def curvature_condition_vec(s, uvw):
         return (np.abs(L * Nn) + M ** 2) / np.abs(L * Nn - M ** 2) + (E * G + F ** 2) / np.abs(E * G - F ** 2) + dots + cross
 
 
+def _curvature_formula(nInd, ders):
+    """reference ``:80-107`` from the derivative arrays (each (N, nDep'))"""
+    with np.errstate(all="ignore"):
+        if nInd == 1:
+            fp, fpp = ders
+            pp, pq, qq = (fp * fp).sum(1), (fp * fpp).sum(1), (fpp * fpp).sum(1)
+            num = fp[:, 0] * fpp[:, 1] - fp[:, 1] * fpp[:, 0] if fp.shape[1] == 2 else np.sqrt(qq * pp - pq ** 2)
+            return num / pp ** 1.5
+        su, sv, suu, suv, svv = ders
+        n = np.cross(su, sv)
+        n = n / np.sqrt((n * n).sum(1))[:, None]
+        E, F, G = (su * su).sum(1), (su * sv).sum(1), (sv * sv).sum(1)
+        L, M, Nn = (suu * n).sum(1), (suv * n).sum(1), (svv * n).sum(1)
+        return (L * Nn - M ** 2) / (E * G - F ** 2)
+
+
+def curvature_uncertainty_vec(s, uvw, k=16.0, trials=12, seed=7):
+    """How much the reference's curvature at N points moves when every derivative entering the formula is perturbed by its
+    own rounding uncertainty k * eps * sum|terms| (derivative_abs_vec): the largest |change| over a few random sign
+    patterns.  Where derivatives are sums that cancel (flat regions of examples/TomsNasty.json: sum|terms| / |value| up to
+    1e17) the formula amplifies rounding noise and the reference's value is only defined to that uncertainty -- for anything
+    that adds the terms in another order than numpy.  Tests state the curvature bar as strict + this."""
+    uvw = np.asarray(uvw, dtype=np.float64).reshape(-1, s.nInd)
+    N = uvw.shape[0]
+    graph = s.nDep == 1
+    wrts = ([1], [2]) if s.nInd == 1 else ([1, 0], [0, 1], [2, 0], [1, 1], [0, 2])
+    with np.errstate(all="ignore"):
+        ders = [derivative_vec(s, list(w), uvw) for w in wrts]
+        unc = [k * np.finfo(float).eps * derivative_abs_vec(s, list(w), uvw) for w in wrts]
+
+        def lift(arrs):
+            if not graph:
+                return arrs
+            z, o = np.zeros((N, 1)), np.ones((N, 1))
+            if s.nInd == 1:
+                return [np.hstack([o, arrs[0]]), np.hstack([z, arrs[1]])]
+            return [np.hstack([o, z, arrs[0]]), np.hstack([z, o, arrs[1]])] + [np.hstack([z, z, a]) for a in arrs[2:]]
+
+        base = _curvature_formula(s.nInd, lift(ders))
+        rng = np.random.default_rng(seed)
+        worst = np.zeros(N)
+        for _ in range(trials):
+            moved = [d + u * rng.choice([-1.0, 1.0], size=d.shape) for d, u in zip(ders, unc)]
+            worst = np.fmax(worst, np.abs(_curvature_formula(s.nInd, lift(moved)) - base))
+        return np.where(np.isfinite(worst), worst, np.inf)
+
+
 # ------------------------------------------------------------- conditioning of the sums
 # The parity bar of the path is |x - ref| <= 1e-13 + 1e-12*|ref|.  A value/derivative is a
 # sum of products coefficient x basis values; any implementation that adds those terms in a

@@ -767,41 +767,44 @@ def test_batch_api_variants():
     assert g.values.shape == (c.nDep, c.uvw.shape[0]) and close(g.values.T, c["values"]) and close(g.jacobian[:, 0].T, c["jacobian"][:, :, 0])
 
 
-def _curvature_close(k, want, cond):
-    """strict bar (1e-12 relative, 1e-13 absolute) where the formula is well-conditioned (condition <= 100); elsewhere the
-    relative bar is 45 eps x condition -- what the reference's own value is uncertain by; NaN / inf must match"""
-    k, want, cond = np.asarray(k), np.asarray(want), np.asarray(cond)
+def _curvature_close(k, want, uncertainty):
+    """|k - want| <= 1e-13 + 1e-12 |want| + the uncertainty of the reference's own value (oracle.curvature_uncertainty_vec:
+    how far the formula moves when its derivative inputs move by their rounding uncertainty); NaN / inf must match"""
+    k, want, uncertainty = np.asarray(k), np.asarray(want), np.asarray(uncertainty)
     fin = np.isfinite(want)
     if not np.array_equal(np.isnan(k), np.isnan(want)):
         return False
     with np.errstate(all="ignore"):
-        rtol = np.where(cond <= 100.0, 1e-12, 1e-14 * cond)
-        return bool(np.all(np.abs(k - want)[fin] <= (1e-13 + rtol * np.abs(want))[fin]))
+        return bool(np.all(np.abs(k - want)[fin] <= (1e-13 + 1e-12 * np.abs(want) + uncertainty)[fin]))
 
 
 def test_curvature_vs_reference():
     """batched curvature (curves nDep 1/2/3, surfaces nDep 3 and graph of a scalar function) in one
-    fused pass against Spline.curvature of the reference: 1e-12 relative wherever the formula is well-conditioned."""
+    fused pass against Spline.curvature of the reference.  Bar: 1e-12 relative (+1e-13) plus the uncertainty the reference's
+    own value has at the point; on the well-conditioned samples (uncertainty below a tenth of the strict bar: most of them)
+    that IS the strict bar."""
     _, _cuda, O, _ = _mods()
     ref = load_npz("ref_curvature.npz")
     by_tag = {c.tag: c for c in CASES}
-    strict = 0
+    strict = total = 0
     for tag, want in ref.items():
         c = by_tag[tag]
         s = _spline(c)
-        cond = O.curvature_condition_vec(_ospline(c), c.uvw)
+        unc = O.curvature_uncertainty_vec(_ospline(c), c.uvw)
         k = s.curvature_points(c.uvw)
         assert k.shape == want.shape
-        assert _curvature_close(k, want, cond), (tag, np.nanmax(np.abs(k - want) / np.abs(want)))
-        strict += int((np.isfinite(want) & (cond <= 100.0)).sum())
+        assert _curvature_close(k, want, unc), tag
+        fin = np.isfinite(want)
+        strict += int((fin & (unc <= 0.1 * (1e-13 + 1e-12 * np.abs(want)))).sum())
+        total += int(fin.sum())
         kd = s.curvature_points(torch.from_numpy(c.uvw).cuda())
         assert kd.is_cuda and np.array_equal(kd.cpu().numpy(), k, equal_nan=True)
-        p = int(np.flatnonzero(np.isfinite(want))[5])
-        assert _curvature_close([s.curvature(c.uvw[p] if c.nInd > 1 else c.uvw[p, 0])], [want[p]], [cond[p]])
+        p = int(np.flatnonzero(fin)[5])
+        assert _curvature_close([s.curvature(c.uvw[p] if c.nInd > 1 else c.uvw[p, 0])], [want[p]], [unc[p]])
         # the composed path (derivative passes + bspy_cuda_curvature) stays available for shapes the fused kernel does not take
         d1 = s.evaluate_points(c.uvw, values=False, with_respect_to=[1] + [0] * (c.nInd - 1)).derivative
         assert d1.shape == (c.nDep, c.uvw.shape[0])
-    assert strict >= 300, strict                                    # most samples are held to the strict bar
+    assert strict >= 0.6 * total, (strict, total)                   # most samples are effectively held to the strict bar
 
 
 def test_curvature_known_answers():
@@ -823,12 +826,12 @@ def test_curvature_known_answers():
     planar = spline("planar")
     kp = planar.curvature_points(a["planar/u"])
     so = O.OracleSpline.of(planar)
-    assert _curvature_close(kp, a["planar/curvature"], O.curvature_condition_vec(so, a["planar/u"][:, None]))
+    assert _curvature_close(kp, a["planar/curvature"], O.curvature_uncertainty_vec(so, a["planar/u"][:, None]))
     surface = spline("surface")
     assert abs(surface.curvature([0.25, 0.5]) - 1.024) < 1.0e-14
     ks = surface.curvature_points(a["surface/uv"])
     assert abs(ks[0] - 1.024) < 1.0e-14
-    assert _curvature_close(ks, a["surface/curvature"], O.curvature_condition_vec(O.OracleSpline.of(surface), a["surface/uv"]))
+    assert _curvature_close(ks, a["surface/curvature"], O.curvature_uncertainty_vec(O.OracleSpline.of(surface), a["surface/uv"]))
 
 
 def test_grid_edge_cases():
