@@ -219,12 +219,28 @@ def _normal_request(self, indices):
     idx = [int(i) for i in indices]
     if any(i < 0 or i >= D for i in idx):
         raise IndexError(f"normal index out of range for a normal of length {D}")
-    if len(set(idx)) != len(idx):
-        raise NotImplementedError("duplicate normal indices are not supported by the CUDA path")
     mask = 0
     for i in idx:
         mask |= 1 << i
+    if len(set(idx)) != len(idx):
+        # repeated indices (the reference allows them, bspy/_spline_evaluation.py:234-240, and counts a repeated component
+        # once per repetition in the norm): the kernels normalise over a component SET, so such requests take the raw
+        # normal from the kernel and are rescaled by _normalize_selected below
+        return _Repeated(idx), mask
     return idx, mask
+
+
+class _Repeated(list):
+    """marker: an ``indices`` list with repetitions"""
+
+
+def _normalize_selected(raw, idx):
+    """raw normals (D, N) -> components ``idx`` divided by the 2-norm of that (possibly repeating) selection"""
+    sel = raw[list(idx)]
+    if isinstance(sel, torch.Tensor):
+        return sel / torch.sqrt((sel * sel).sum(dim=0))
+    with np.errstate(all="ignore"):
+        return sel / np.sqrt((sel * sel).sum(axis=0))
 
 
 def normal(self, uvw, normalize=True, indices=None):
@@ -233,9 +249,12 @@ def normal(self, uvw, normalize=True, indices=None):
     uvw = np.atleast_1d(uvw)
     idx, mask = _normal_request(self, indices)
     uvw = _single_point(self, uvw)
-    out = _launch_single(self, uvw, values=False, normal=True, normalize=bool(normalize), normal_mask=mask)
+    repeated = isinstance(idx, _Repeated)
+    out = _launch_single(self, uvw, values=False, normal=True, normalize=bool(normalize) and not repeated, normal_mask=mask)
     n = out["normal"][:, 0].cpu().numpy()
-    if idx is not None:
+    if repeated and normalize:
+        n = _normalize_selected(n[:, None], idx)[:, 0]
+    elif idx is not None:
         n = n[idx]
     dt = np.asarray(self.coefs).dtype if hasattr(self, "coefs") else getattr(self, "coefsDtype", np.float64)
     return n.astype(dt if np.issubdtype(dt, np.floating) else np.float64, copy=False)
@@ -354,13 +373,20 @@ def evaluate_points(self, uvw, *, with_respect_to=None, values=True, jacobian=Fa
     if out_layout not in ("soa", "aos"):
         raise ValueError("out_layout must be 'soa' or 'aos'")
     aos = out_layout == "aos"
+    repeated = isinstance(idx, _Repeated)            # indices with repetitions: raw normals from the kernel, rescaled here
+    unit = bool(normalize) and not repeated
     if aos and wrt is not None:
         raise ValueError("out_layout='aos' holds values, jacobian and normal; request with_respect_to with out_layout='soa'")
     defer = isinstance(check_domain, str) and check_domain == "defer"
     if defer and kind != "cuda":
         raise ValueError("check_domain='defer' needs CUDA inputs (host inputs are checked when the results are copied back)")
-    request = dict(wrt=wrt, values=bool(values), jacobian=bool(jacobian), normal=bool(normal), normalize=bool(normalize),
+    request = dict(wrt=wrt, values=bool(values), jacobian=bool(jacobian), normal=bool(normal), normalize=unit,
                    normal_mask=mask, spans=bool(spans))
+
+    def pick(nrm):
+        if nrm is None or idx is None:
+            return nrm
+        return _normalize_selected(nrm, idx) if (repeated and normalize) else nrm[list(idx)]
 
     if kind == "cuda":
         pts = uvw if uvw.dtype == torch.float64 else uvw.to(torch.float64)
@@ -373,16 +399,13 @@ def evaluate_points(self, uvw, *, with_respect_to=None, values=True, jacobian=Fa
         ds = device_spline(self, pts.device)
         flag = _cuda.new_flag(pts.device) if check_domain else None
         if aos:
-            rec, sp = _cuda.eval_points_aos(ds, pts, ps, vs, N, jacobian=bool(jacobian), normal=bool(normal), normalize=bool(normalize),
+            rec, sp = _cuda.eval_points_aos(ds, pts, ps, vs, N, jacobian=bool(jacobian), normal=bool(normal), normalize=unit,
                                             normal_mask=mask, spans=bool(spans), flag=flag)
-            v, j, nrm = _record_views(ds, rec, jacobian, normal, idx)
-            res = EvalResult(v, None, j, nrm, sp, records=rec)
+            v, j, nrm = _record_views(ds, rec, jacobian, normal, None)
+            res = EvalResult(v, None, j, pick(nrm), sp, records=rec)
         else:
             out = _cuda.eval_points(ds, pts, ps, vs, N, flag=flag, **request)
-            nrm = out["normal"]
-            if nrm is not None and idx is not None:
-                nrm = nrm[idx]
-            res = EvalResult(out["values"], out["derivative"], out["jacobian"], nrm, out["spans"])
+            res = EvalResult(out["values"], out["derivative"], out["jacobian"], pick(out["normal"]), out["spans"])
         if defer:
             res.first_outside = flag
         elif check_domain:
@@ -408,13 +431,11 @@ def evaluate_points(self, uvw, *, with_respect_to=None, values=True, jacobian=Fa
         sp = res["spans"]
         if sp is not None and kind == "numpy":
             sp = sp.numpy()
-        v, j, nrm = _record_views(ds, rec, jacobian, normal, idx)
-        return EvalResult(v, None, j, nrm, sp, records=rec)
-    if res["normal"] is not None and idx is not None:
-        res["normal"] = res["normal"][idx]
+        v, j, nrm = _record_views(ds, rec, jacobian, normal, None)
+        return EvalResult(v, None, j, pick(nrm), sp, records=rec)
     if kind == "numpy":
         res = {k: (None if v is None else v.numpy()) for k, v in res.items()}
-    return EvalResult(res["values"], res["derivative"], res["jacobian"], res["normal"], res["spans"])
+    return EvalResult(res["values"], res["derivative"], res["jacobian"], pick(res["normal"]), res["spans"])
 
 
 def evaluate_grid(self, *axes, values=True, jacobian=False, normal=False, normalize=True, indices=None,
@@ -440,6 +461,8 @@ def evaluate_grid(self, *axes, values=True, jacobian=False, normal=False, normal
     idx, mask = (None, 0)
     if normal:
         idx, mask = _normal_request(self, indices)
+        if isinstance(idx, _Repeated):
+            raise NotImplementedError("repeated normal indices: use evaluate_points / normal (grids normalise over a component set)")
     dev = axes[0].device if on_device else _cuda.device(device)
     ds = device_spline(self, dev)
     d_axes = []

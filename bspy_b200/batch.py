@@ -203,6 +203,8 @@ class SplineBatch:
         idx, mask = (None, 0)
         if normal:
             idx, mask = _normal_request(self, indices)
+            if type(idx).__name__ == "_Repeated":
+                raise NotImplementedError("repeated normal indices: use Spline.evaluate_points / Spline.normal")
         on_device = all(isinstance(a, torch.Tensor) and a.is_cuda for a in (uAxis, vAxis))
         axes = [_to_device(uAxis, self.device).reshape(-1), _to_device(vAxis, self.device).reshape(-1)]
         strides = [0 if k.dim() == 1 else int(k.stride(0)) for k in self.knots]

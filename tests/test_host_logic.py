@@ -10,7 +10,10 @@ import torch
 
 import bspy_b200 as bspy
 from bspy_b200 import _cuda
+import os
 import fake_cuda
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 from golden_io import close, load_cases, load_npz
 
 CASES = {c.tag: c for c in load_cases()}
@@ -174,8 +177,7 @@ def test_errors():
     pts = np.array([[0.1, 0.2], [0.3, 7.0]])
     with pytest.raises(ValueError, match="Spline evaluation outside domain: \\[0.3 7. \\]"):
         s.evaluate_points(pts)
-    with pytest.raises(NotImplementedError, match="duplicate"):
-        s.normal([0.5, 0.5], True, (0, 0))
+    assert np.allclose(s.normal([0.5, 0.5], True, (0, 0)), np.sign(s.normal([0.5, 0.5], False)[0]) * np.sqrt(0.5))   # repeated indices: norm over both
     with pytest.raises(IndexError):
         s.normal([0.5, 0.5], True, (5,))
     nan = s(np.nan, 0.5)                                                     # NaN passes the domain test, as in the reference
@@ -202,6 +204,28 @@ def test_evaluate_points_shapes_and_kinds():
     assert close(g.values[:, 1, 2, 3], s([0.5, 2 / 3, 0.75]))
     with pytest.raises(ValueError, match="outside domain"):
         s.evaluate_grid([0, 1], [0, 1], [0, 1.01])
+
+
+def test_import_shim_and_repeated_normal_indices():
+    """`import bspy` through shim/ resolves to this package (north star: "a new bspy/_cuda module"); repeated normal indices
+    count once per repetition in the norm, like the reference (bspy/_spline_evaluation.py:234-244)."""
+    import subprocess, sys
+    code = ("import sys; sys.path[:0] = [%r, %r]; import bspy, bspy._cuda, bspy_b200; "
+            "assert bspy.Spline is bspy_b200.Spline and bspy._cuda is bspy_b200._cuda and 'bspy_cuda_eval_points' in bspy._cuda.SYMBOLS; print('ok')"
+            % (os.path.join(ROOT, "shim"), ROOT))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-800:]
+    c = CASES["surf_34"]
+    s = _spline(c)
+    raw = s.evaluate_points(c.uvw[:7], values=False, normal=True, normalize=False).normal
+    rep = s.evaluate_points(c.uvw[:7], values=False, normal=True, indices=(2, 0, 2)).normal
+    want = raw[[2, 0, 2]] / np.sqrt((raw[[2, 0, 2]] ** 2).sum(axis=0))
+    assert rep.shape == (3, 7) and np.allclose(rep, want, rtol=1e-15)
+    one = s.normal(c.uvw[3], True, (2, 0, 2))
+    assert np.allclose(one, want[:, 3], rtol=1e-15)
+    assert np.array_equal(s.evaluate_points(c.uvw[:7], values=False, normal=True, normalize=False, indices=(1, 1)).normal, raw[[1, 1]])
+    with pytest.raises(NotImplementedError):
+        s.evaluate_grid([0.1, 0.2], [0.3], normal=True, indices=(0, 0))
 
 
 def test_array_of_structs_layout_host_logic():
