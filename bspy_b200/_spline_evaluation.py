@@ -490,8 +490,10 @@ def evaluate_grid(self, *axes, values=True, jacobian=False, normal=False, normal
         host = {}
         for name in ("values", "jacobian", "normal"):
             t = getattr(res, name)
-            host[name] = None if t is None else torch.empty(t.shape, dtype=t.dtype, pin_memory=True).copy_(t, non_blocking=True)
-        torch.cuda.current_stream(dev).synchronize()
+            host[name] = None if t is None else \
+                (torch.empty(t.shape, dtype=t.dtype, pin_memory=True).copy_(t, non_blocking=True) if t.is_cuda else t)
+        if dev.type == "cuda":
+            torch.cuda.current_stream(dev).synchronize()
         conv = (lambda t: None if t is None else t.numpy()) if kinds <= {"numpy"} else (lambda t: t)
         res = EvalResult(conv(host["values"]), None, conv(host["jacobian"]), conv(host["normal"]), None)
     return res
