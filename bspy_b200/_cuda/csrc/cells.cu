@@ -1262,7 +1262,7 @@ static int eval_binned_records(const SplineDev &s, PointsDev in, long long N, co
     // selects the tensor-pipe cell kernel instead (measured SLOWER: 493 vs 326 us per 4 Mi points on config 4, 3400 vs
     // 1070 us on config 5 -- the T round trip through shared memory saturates the LSU data pipe at 92 % with the FP64
     // pipe 15 % active, profiles/r02_cfg4_eval_cell_mma_ncu_full.txt; kept as a tested experiment, off by default)
-    const CellEntry *cell = (jac && plainWrt && option(OPT_CELL_KERNEL, 0)) ? find_cell(s) : nullptr;
+    const CellEntry *cell = (jac && plainWrt && option(OPT_CELL_KERNEL, 0) == 1) ? find_cell(s) : nullptr;
     const size_t cellSmem = cell ? sizeof(double) * CELL_WARPS * cell->warpDoubles : 0;
     if (cell)
         if (int rc = allow_dynamic_smem(cell->fn, cellSmem)) return rc;
@@ -1304,7 +1304,7 @@ static int eval_binned_records(const SplineDev &s, PointsDev in, long long N, co
     // cell images (padded window + span records per cell, built once per call) for the shapes compiled for them
     const ImageEntry *image = nullptr;
     const double *images = nullptr;
-    if (images_apply(s, N) && !(cell && option(OPT_CELL_KERNEL, 0)) && !stagedPair) {
+    if (images_apply(s, N) && !cell && !stagedPair) {
         image = find_image(s, jac, (int)option(OPT_IMAGE, 0));
         if (image && nN && (image->pair || (image->code % 100) / 10 != s.nDep)) image = nullptr;   // normals need the whole jacobian in one pass
         if (image && image->pair && !plainWrt) image = nullptr;

@@ -61,6 +61,38 @@ __global__ void __launch_bounds__(256) probe_mixed_kernel(int iters, double *sin
     if (r == 123.456) sink[0] = r;
 }
 
+// DFMA as the contraction kernels issue it: a register-tiled outer product acc[i][j] += x[i] * b[j] (three distinct,
+// varying register operands per instruction, no constant operand in the reuse cache)
+__global__ void __launch_bounds__(256) probe_dfma_tile_kernel(int iters, double *sink)
+{
+    double x[4], b[4], acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        x[i] = 1.0 + threadIdx.x * 1e-9 + i * 1e-7;
+        b[i] = 1.0 - threadIdx.x * 1e-9 - i * 1e-7;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = i + j;
+    }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = fma(x[i], b[j], acc[i][j]);
+        // keep x / b varying without extra FP64 work: integer twiddle of the low mantissa bits
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            x[i] = __longlong_as_double(__double_as_longlong(x[i]) ^ (long long)(it & 1));
+            b[i] = __longlong_as_double(__double_as_longlong(b[i]) ^ (long long)(it & 2));
+        }
+    }
+    double r = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) r += acc[i][j];
+    if (r == 123.456) sink[0] = r;
+}
+
 __global__ void __launch_bounds__(256) probe_copy_kernel(const double2 *__restrict__ src, double2 *__restrict__ dst, long long n2)
 {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x)
@@ -136,6 +168,11 @@ extern "C" int bspy_cuda_probe_fp64(int32_t kind, int32_t iters, double *sink, d
     } else if (kind == 1) {
         probe_dmma_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(iters, sink);
         if (flopsOut_host) *flopsOut_host = (double)blocks * (threads / 32) * (double)iters * 4.0 * 512.0;
+    } else if (kind >= 4) {
+        // kind 4: outer-product DFMA at 8 CTAs of 256 threads per SM; kind 5: the same at 2 CTAs per SM (4 warps per scheduler)
+        const int b2 = kind == 5 ? num_sms() * 2 : blocks;
+        probe_dfma_tile_kernel<<<b2, threads, 0, (cudaStream_t)stream>>>(iters, sink);
+        if (flopsOut_host) *flopsOut_host = (double)b2 * threads * (double)iters * 16.0 * 2.0;
     } else {
         // kind 2: DMMA and DFMA interleaved in every warp; kind 3: alternate warps
         probe_mixed_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(iters, sink, kind == 3);

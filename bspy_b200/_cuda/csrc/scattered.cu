@@ -268,26 +268,6 @@ __global__ void __launch_bounds__(128, MINB) eval_staged_kernel(const SplineDev 
 // cell CHANGE and stages the records next to the window image (cp.async, 16 bytes per lane); a point is then: its
 // 32-byte record (requested one tile ahead), broadcast LDS.128 of the slot's span records, the recurrence, the
 // contraction over the slot's window with immediate offsets.  Same arithmetic per point: bit-identical to v1.
-// basis values and first derivatives from a span record held in shared memory (16-byte aligned)
-template <int O, bool DER>
-__device__ __forceinline__ void basis_from_shared_record(const double *__restrict__ rec, double u, int d, double (&b0)[O], double (&b1)[O])
-{
-    using R = SpanRec<O>;
-    double r[R::stride > 0 ? R::stride : 1];
-#pragma unroll
-    for (int j = 0; j < R::stride / 2; ++j) {
-        const double2 x = *reinterpret_cast<const double2 *>(rec + 2 * j);
-        r[2 * j] = x.x;
-        r[2 * j + 1] = x.y;
-    }
-    double dl[O > 1 ? O - 1 : 1], rc[O > 1 ? O * (O - 1) / 2 : 1];
-#pragma unroll
-    for (int j = 0; j < O - 1; ++j) dl[j] = u - r[j];
-#pragma unroll
-    for (int j = 0; j < O * (O - 1) / 2; ++j) rc[j] = r[O - 1 + j];
-    basis_core<O, DER>(dl, rc, d, b0, b1);
-}
-
 template <int IV, class Ord, int NDT, bool JAC>
 __device__ __forceinline__ void setup_variable_shared(const double *__restrict__ cellRec, double u, int d, FixedCtx<Ord, NDT, JAC> &c)
 {

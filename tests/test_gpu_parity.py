@@ -546,7 +546,8 @@ def test_cell_kernel_tensor_pipe_and_aos_records(option):
         return np.concatenate((np.zeros(o - 1), inner, np.ones(o - 1)))
 
     shapes = [((4, 4, 4), 3, (18, 18, 18)), ((3, 3, 3), 3, (20, 19, 18)), ((4, 4, 4), 1, (28, 27, 26)), ((3, 3, 3, 3), 6, (10, 10, 9, 10)),
-              ((4, 4, 4), 4, (17, 16, 18)), ((3, 4), 3, (150, 140)), ((5, 4), 3, (40, 30))]
+              ((4, 4, 4), 4, (17, 16, 18)), ((3, 4), 3, (150, 140)), ((5, 4), 3, (40, 30)), ((3, 3, 3), 2, (12, 21, 13)),
+              ((4, 4, 4), 2, (9, 8, 30))]
     for order, nDep, nCoef in shapes:
         nInd = len(order)
         s = bspy.Spline(nInd, nDep, order, nCoef, [K(o, n) for o, n in zip(order, nCoef)], rng.standard_normal((nDep, *nCoef)))

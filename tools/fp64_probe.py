@@ -5,7 +5,8 @@ import torch
 from bspy_b200 import _cuda
 
 dev = torch.device("cuda:0")
-for kind, name in ((0, "dfma"), (1, "dmma"), (2, "dmma+dfma interleaved per warp"), (3, "dmma / dfma on alternate warps")):
+for kind, name in ((0, "dfma"), (1, "dmma"), (2, "dmma+dfma interleaved per warp"), (3, "dmma / dfma on alternate warps"),
+                   (4, "dfma outer-product tile (3 varying operands), 16 warps per scheduler"), (5, "the same at 4 warps per scheduler")):
     _cuda.probe_fp64(kind, 2000, dev)
     torch.cuda.synchronize()
     best = 0.0
