@@ -1404,7 +1404,9 @@ static int eval_binned_records(const SplineDev &s, PointsDev in, long long N, co
             cell->fn<<<(unsigned)blocks, CELL_WARPS * 32, cellSmem, sEval>>>(s, pin, n, wrt, o2);
         } else if (staged && n >= 48 * cells) {
             // persistent warps over contiguous runs of tiles (window reuse between consecutive tiles)
-            long long blocks = (long long)num_sms() * (staged->code % 10);
+            // STAGED_WAVES > 1: that many times more, shorter CTAs (runs of tiles stay long enough for the window reuse), so
+            // that CTAs retire all along the kernel and the high-priority sort stream finds room before the tail
+            long long blocks = (long long)num_sms() * (staged->code % 10) * option(OPT_STAGED_WAVES, 1);
             if (blocks > (n + 127) / 128) blocks = (n + 127) / 128;
             stagedFn<<<(unsigned)blocks, 128, stagedSmem, sEval>>>(s, pin, n, wrt, o2);
         }

@@ -47,7 +47,7 @@ static inline int allow_dynamic_smem(K kernel, size_t smem)
 enum Option {
     OPT_CURVE_REPL, OPT_CURVE_PPT, OPT_BIN_MODE, OPT_BIN_OVERLAP, OPT_STAGED, OPT_DEP_TILE, OPT_SPAN_RECORDS, OPT_BIN_CHUNK,
     OPT_BIN_REC_CHUNK_LOG2, OPT_GRID_CHUNK, OPT_GRID_ROWS, OPT_GRID_GROUP, OPT_CELL_KERNEL, OPT_CURVE_TMA, OPT_MANY_MODE,
-    OPT_GRID3_ROWS, OPT_GRID3_CHUNK, OPT_EXP_A, OPT_EXP_B, OPT_IMAGE, OPT_STAGED_PAIR, OPT_COUNT
+    OPT_GRID3_ROWS, OPT_GRID3_CHUNK, OPT_EXP_A, OPT_EXP_B, OPT_IMAGE, OPT_STAGED_PAIR, OPT_STAGED_WAVES, OPT_CURVE_POLY, OPT_COUNT
 };
 long long option(Option o, long long unset);
 

@@ -103,6 +103,9 @@ constexpr int REPL_COPIES = 8, REPL_KNOT_COPIES = 16;   // measured at 1e8 point
 constexpr int REPL_U = 2;
 constexpr int repl_threads(int O, int nDep) { return ((O - 1) + O * (O - 1) / 2 + O * nDep) <= 24 ? 512 : 256; }
 
+// doubles of a polynomial row: O x nDep coefficients + the mid-span, rounded up to whole 16-byte chunks
+__host__ __device__ constexpr int poly_row_doubles(int O, int nDep) { return (O * nDep + 2) & ~1; }
+
 struct ReplLayout {
     int buckets;         // power of two
     size_t bytes;        // 0: the replicated tables do not fit
@@ -207,13 +210,16 @@ __device__ __forceinline__ void build_repl_tables(const double *__restrict__ kno
 // The point loop of the replicated-row kernels: REPL_U points per thread and round; the parameters of the next round
 // are requested before this round's arithmetic (the loop is otherwise a chain DRAM load -> table -> row -> arithmetic ->
 // store per point).  un[] holds the first round's parameters, requested by the caller before the tables were ready.
-template <int O, int NDEP, bool DER, int REPL_U>
+// POLY (value-only requests on a validated table image, see curve_table_kernel): the row of a span is its polynomial in
+// powers of (u - mid-span) -- { c_0[d], .., c_{O-1}[d], m } -- and a point is one row fetch and a Horner evaluation.
+template <int O, int NDEP, bool DER, int REPL_U, bool POLY = false>
 __device__ __forceinline__ void repl_point_loop(const CurveParams &P, const int buckets, const double *rows, const double *kn,
                                                 const unsigned short *tab, double (&un)[REPL_U], const double *up,
                                                 const long long pfirst, const long long pstep, const long long rstep)
 {
     using R = SpanRec<O>;
-    constexpr int ROW = ((O - 1) + O * (O - 1) / 2 + O * NDEP + 1) & ~1, CH = ROW / 2;
+    static_assert(!(POLY && DER), "polynomial rows serve value-only requests");
+    constexpr int ROW = POLY ? poly_row_doubles(O, NDEP) : ((O - 1) + O * (O - 1) / 2 + O * NDEP + 1) & ~1, CH = ROW / 2;
     constexpr int CP = REPL_COPIES, KC = REPL_KNOT_COPIES;
     const int lane = threadIdx.x & 31;
     const long long ustep = pstep * P.in.pointStride, urstep = rstep * P.in.pointStride;
@@ -251,24 +257,36 @@ __device__ __forceinline__ void repl_point_loop(const CurveParams &P, const int 
                 r[2 * j] = x.x;
                 r[2 * j + 1] = x.y;
             }
-            double dl[O > 1 ? O - 1 : 1], rc[O > 1 ? O * (O - 1) / 2 : 1];
-#pragma unroll
-            for (int j = 0; j < O - 1; ++j) dl[j] = uk - r[j];
-#pragma unroll
-            for (int j = 0; j < O * (O - 1) / 2; ++j) rc[j] = r[O - 1 + j];
-            double b0[O], b1[O];
-            basis_core<O, DER>(dl, rc, 0, b0, b1);
             double v[NDEP], g[NDEP];
-#pragma unroll
-            for (int d = 0; d < NDEP; ++d) { v[d] = 0.0; g[d] = 0.0; }
-#pragma unroll
-            for (int j = 0; j < O; ++j)
+            if constexpr (POLY) {
+                const double t = uk - r[O * NDEP];
 #pragma unroll
                 for (int d = 0; d < NDEP; ++d) {
-                    const double x = r[R::used + j * NDEP + d];
-                    v[d] = fma(x, b0[j], v[d]);
-                    if (DER) g[d] = fma(x, b1[j], g[d]);
+                    double h = r[(O - 1) * NDEP + d];
+#pragma unroll
+                    for (int k = O - 2; k >= 0; --k) h = fma(h, t, r[k * NDEP + d]);
+                    v[d] = h;
+                    g[d] = 0.0;
                 }
+            } else {
+                double dl[O > 1 ? O - 1 : 1], rc[O > 1 ? O * (O - 1) / 2 : 1];
+#pragma unroll
+                for (int j = 0; j < O - 1; ++j) dl[j] = uk - r[j];
+#pragma unroll
+                for (int j = 0; j < O * (O - 1) / 2; ++j) rc[j] = r[O - 1 + j];
+                double b0[O], b1[O];
+                basis_core<O, DER>(dl, rc, 0, b0, b1);
+#pragma unroll
+                for (int d = 0; d < NDEP; ++d) { v[d] = 0.0; g[d] = 0.0; }
+#pragma unroll
+                for (int j = 0; j < O; ++j)
+#pragma unroll
+                    for (int d = 0; d < NDEP; ++d) {
+                        const double x = r[R::used + j * NDEP + d];
+                        v[d] = fma(x, b0[j], v[d]);
+                        if (DER) g[d] = fma(x, b1[j], g[d]);
+                    }
+            }
             store_curve_point<NDEP, DER>(P, p, ix, v, g);
         }
     }
@@ -312,9 +330,12 @@ __global__ void __launch_bounds__(repl_threads(O, NDEP), 2) eval_curve_repl_kern
 // SYNCS) while its first round of parameters is already travelling from HBM.
 constexpr int TAB_THREADS = 1024;
 
+// image = recurrence rows | knots | bucket table | polynomial rows | 16-byte trailer (int: polynomial rows validated).
+// Derivative requests fetch the first three parts (cdbBytes), value-only requests the last four (polyFetch bytes from
+// offset rowsBytes) and fall back to the first three when the trailer says the polynomial rows did not pass.
 struct TableLayout {
     int buckets;
-    size_t rowsBytes, knotBytes, tabBytes, bytes;   // bytes: the whole image, a multiple of 16
+    size_t rowsBytes, knotBytes, tabBytes, polyBytes, cdbBytes, polyFetch, bytes;   // bytes: the whole image, a multiple of 16
 };
 
 static TableLayout table_layout(int O, int nDep, int nCoef)
@@ -327,7 +348,10 @@ static TableLayout table_layout(int O, int nDep, int nCoef)
     T.rowsBytes = sizeof(double) * (size_t)(nCoef - O + 1) * rowDoubles * REPL_COPIES;
     T.knotBytes = sizeof(double) * (size_t)(O + nCoef) * REPL_KNOT_COPIES;
     T.tabBytes = (sizeof(unsigned short) * (size_t)L.buckets + 15) & ~(size_t)15;
-    T.bytes = T.rowsBytes + T.knotBytes + T.tabBytes;
+    T.polyBytes = sizeof(double) * (size_t)(nCoef - O + 1) * poly_row_doubles(O, nDep) * REPL_COPIES;
+    T.cdbBytes = T.rowsBytes + T.knotBytes + T.tabBytes;
+    T.polyFetch = T.knotBytes + T.tabBytes + T.polyBytes + 16;
+    T.bytes = T.cdbBytes + T.polyBytes + 16;
     return T;
 }
 
@@ -352,6 +376,101 @@ __global__ void __launch_bounds__(512) curve_table_kernel(const double *__restri
     for (int i = threadIdx.x; i < spans * ROW * CP; i += blockDim.x) gRows[i] = rows[i];
     for (int i = threadIdx.x; i < nKnots * KC; i += blockDim.x) gKn[i] = kn[i];
     for (int i = threadIdx.x; i < (int)(T.tabBytes / 2); i += blockDim.x) gTab[i] = i < buckets ? tab[i] : (unsigned short)0;
+    // polynomial rows: c_k[d] = S^(k)(m)[d] / k! at the mid-span m (Cox-de Boor with k derivative stages, from the span's own
+    // reciprocal gaps), and their validation, span by span:
+    //   * conditioning: sum_k |c_k| (h/2)^k <= 16 max_j |coef_j| over the span's window -- the Horner terms are then at most
+    //     16 times the terms of the recurrence's convex combination, and so is the rounding error (a few eps times the terms
+    //     either way: ~1e-14 for coefficients of order one).  Every knot gap of the derivative stages contains the span itself,
+    //     so the ratio is bounded by ~3^(O-1) whatever the knots; cubics pass, rough data of order 5 and up may not;
+    //   * agreement: at nine parameters of the span the Horner value matches the recurrence to a quarter of the parity bar
+    //     |x - ref| <= 1e-13 + 1e-12 |ref|, widened by 4 eps max|coef| (where the value cancels, both forms carry that much);
+    //   * an empty first / last span (the recurrence gives inf / NaN there, which a row would not reproduce entry for entry).
+    // One failing span clears the flag and value-only requests keep the recurrence rows.
+    constexpr int PROW = poly_row_doubles(O, NDEP), PCH = PROW / 2;
+    double *gPoly = reinterpret_cast<double *>(image + T.cdbBytes);
+    __shared__ int polyOk;
+    if (threadIdx.x == 0) polyOk = 1;
+    __syncthreads();
+    for (int sp = threadIdx.x; sp < spans; sp += blockDim.x) {
+        const int ix = O + sp;
+        double left[O > 1 ? O - 1 : 1], rc[O > 1 ? O * (O - 1) / 2 : 1];
+#pragma unroll
+        for (int j = 0; j < O - 1; ++j) left[j] = kn[(ix - (O - 1) + j) * KC];
+        int at = 0;
+#pragma unroll
+        for (int deg = 1; deg < O; ++deg)
+#pragma unroll
+            for (int t = 0; t < deg; ++t) rc[at++] = 1.0 / (kn[(ix + t) * KC] - kn[(ix - deg + t) * KC]);
+        const double k0 = kn[(ix - 1) * KC], k1 = kn[ix * KC], m = 0.5 * (k0 + k1), h = k1 - k0;
+        double dl[O > 1 ? O - 1 : 1];
+#pragma unroll
+        for (int j = 0; j < O - 1; ++j) dl[j] = m - left[j];
+        double row[PROW];
+        double invFact = 1.0;
+#pragma unroll
+        for (int k = 0; k < O; ++k) {
+            double bk[O], unused[O];
+            basis_core<O, false>(dl, rc, k, bk, unused);
+            if (k > 1) invFact /= (double)k;
+#pragma unroll
+            for (int d = 0; d < NDEP; ++d) {
+                double acc = 0.0;
+#pragma unroll
+                for (int j = 0; j < O; ++j) acc = fma(raw[d * nCoef + sp + j], bk[j], acc);
+                row[k * NDEP + d] = acc * invFact;
+            }
+        }
+        row[O * NDEP] = m;
+        if (PROW > O * NDEP + 1) row[O * NDEP + 1] = 0.0;
+#pragma unroll
+        for (int j = 0; j < PCH; ++j)
+#pragma unroll
+            for (int q = 0; q < CP; ++q)
+                *reinterpret_cast<double2 *>(gPoly + 2 * ((sp * PCH + j) * CP + q)) = make_double2(row[2 * j], row[2 * j + 1]);
+        bool ok = true;
+        double cmax[NDEP];
+#pragma unroll
+        for (int d = 0; d < NDEP; ++d) {
+            cmax[d] = 0.0;
+#pragma unroll
+            for (int j = 0; j < O; ++j) cmax[d] = fmax(cmax[d], fabs(raw[d * nCoef + sp + j]));
+        }
+        if (h > 0.0) {
+#pragma unroll
+            for (int d = 0; d < NDEP; ++d) {
+                double terms = 0.0, tk = 1.0;
+#pragma unroll
+                for (int k = 0; k < O; ++k) { terms = fma(fabs(row[k * NDEP + d]), tk, terms); tk *= 0.5 * h; }
+                if (!(terms <= 16.0 * cmax[d])) ok = false;
+            }
+            for (int sidx = 0; sidx <= 8; ++sidx) {
+                const double u = sidx == 8 ? k1 : k0 + h * (0.125 * sidx);
+                double du[O > 1 ? O - 1 : 1], b0[O], unused[O];
+#pragma unroll
+                for (int j = 0; j < O - 1; ++j) du[j] = u - left[j];
+                basis_core<O, false>(du, rc, 0, b0, unused);
+                const double t = u - m;
+#pragma unroll
+                for (int d = 0; d < NDEP; ++d) {
+                    double ref = 0.0;
+#pragma unroll
+                    for (int j = 0; j < O; ++j) ref = fma(raw[d * nCoef + sp + j], b0[j], ref);
+                    double hv = row[(O - 1) * NDEP + d];
+#pragma unroll
+                    for (int k = O - 2; k >= 0; --k) hv = fma(hv, t, row[k * NDEP + d]);
+                    if (!(fabs(hv - ref) <= 0.25 * (1e-13 + 1e-12 * fabs(ref)) + 8.9e-16 * cmax[d])) ok = false;   // NaN / inf fail too
+                }
+            }
+        } else if (sp == 0 || sp == spans - 1 || !(h == 0.0)) {
+            ok = false;                                   // empty end span, or knots that are not ascending / not finite
+        }
+        if (!ok) polyOk = 0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int *flag = reinterpret_cast<int *>(image + T.cdbBytes + T.polyBytes);
+        flag[0] = polyOk; flag[1] = 0; flag[2] = 0; flag[3] = 0;
+    }
 }
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -359,7 +478,26 @@ __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)_
 // U = points per thread and round: 2 for long streams (the next round's parameters travel under this round's
 // arithmetic); 8 when the whole batch is a round or two -- config 1 as specified: 6.6 points per thread, all of them
 // requested before the image has even arrived
-template <int O, int NDEP, bool DER, int U = REPL_U>
+// one elected thread arms the barrier with the byte count and issues the bulk copies (64 KB pieces)
+__device__ __forceinline__ void tma_fetch(unsigned char *dst, const unsigned char *src, const size_t bytes, const unsigned bar)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((unsigned)bytes) : "memory");
+    for (size_t at = 0; at < bytes; at += 65536) {
+        const unsigned n = (unsigned)(bytes - at < 65536 ? bytes - at : 65536);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst + at)),
+                     "l"(src + at), "r"(n), "r"(bar)
+                     : "memory");
+    }
+}
+
+__device__ __forceinline__ void mbar_wait(const unsigned bar, const unsigned parity)
+{
+    unsigned done = 0;
+    while (!done)
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+}
+
+template <int O, int NDEP, bool DER, int U = REPL_U, bool POLY = false>
 __global__ void __launch_bounds__(TAB_THREADS, 1) eval_curve_tab_kernel(const CurveParams P, const TableLayout T)
 {
     extern __shared__ __align__(128) unsigned char image[];
@@ -370,16 +508,10 @@ __global__ void __launch_bounds__(TAB_THREADS, 1) eval_curve_tab_kernel(const Cu
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    const unsigned char *src = reinterpret_cast<const unsigned char *>(P.table);
     if (threadIdx.x == 0) {
-        // one elected thread arms the barrier with the byte count and issues the bulk copies (64 KB pieces)
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((unsigned)T.bytes) : "memory");
-        const unsigned char *src = reinterpret_cast<const unsigned char *>(P.table);
-        for (size_t at = 0; at < T.bytes; at += 65536) {
-            const unsigned n = (unsigned)(T.bytes - at < 65536 ? T.bytes - at : 65536);
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(image + at)),
-                         "l"(src + at), "r"(n), "r"(bar)
-                         : "memory");
-        }
+        if constexpr (POLY) tma_fetch(image, src + T.rowsBytes, T.polyFetch, bar);   // knots | bucket table | polynomial rows | flag
+        else tma_fetch(image, src, T.cdbBytes, bar);
     }
     // the first round of parameters travels from HBM while the image arrives
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -389,10 +521,23 @@ __global__ void __launch_bounds__(TAB_THREADS, 1) eval_curve_tab_kernel(const Cu
     double un[U];
 #pragma unroll
     for (int k = 0; k < U; ++k) un[k] = pfirst + k * pstep < P.N ? __ldcs(up + k * pstep * P.in.pointStride) : 0.0;
-    {
-        unsigned done = 0;
-        while (!done)
-            asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(bar) : "memory");
+    mbar_wait(bar, 0);
+    if constexpr (POLY) {
+        const bool valid = *reinterpret_cast<const int *>(image + T.polyFetch - 16) != 0;
+        if (valid) {
+            const double *kn = reinterpret_cast<const double *>(image);
+            const unsigned short *tab = reinterpret_cast<const unsigned short *>(image + T.knotBytes);
+            const double *rows = reinterpret_cast<const double *>(image + T.knotBytes + T.tabBytes);
+            repl_point_loop<O, NDEP, DER, U, true>(P, T.buckets, rows, kn, tab, un, up, pfirst, pstep, rstep);
+            return;
+        }
+        // the polynomial rows of this spline did not pass their validation: fetch the recurrence rows instead (rare)
+        __syncthreads();                                              // everybody has read the flag
+        if (threadIdx.x == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            tma_fetch(image, src, T.cdbBytes, bar);
+        }
+        mbar_wait(bar, 1);
     }
     const double *rows = reinterpret_cast<const double *>(image);
     const double *kn = reinterpret_cast<const double *>(image + T.rowsBytes);
@@ -412,13 +557,23 @@ static int launch_curve3(const CurveParams &P, size_t smem, cudaStream_t stream)
         if (P.N >= minN && L.bytes && !P.in.grid && P.nCoef < 65535 && P.table && option(OPT_CURVE_TMA, 1)) {
             // tables built once per spline (caller-owned image), one 1024-thread CTA per SM, image fetched by TMA
             const TableLayout T = table_layout(O, NDEP, P.nCoef);
-            if (int rc = allow_dynamic_smem(eval_curve_tab_kernel<O, NDEP, DER>, T.bytes)) return rc;
             long long blocks = (P.N + TAB_THREADS * 4 - 1) / (TAB_THREADS * 4);
             const long long cap = num_sms();
             if (blocks > cap) blocks = cap;
             // (eight points per thread requested up front for short batches were measured slower at 1e6 points:
             // 19.0 against 16.7 us)
-            eval_curve_tab_kernel<O, NDEP, DER><<<(unsigned)blocks, TAB_THREADS, T.bytes, stream>>>(P, T);
+            if constexpr (!DER && O >= 2) {
+                // value-only requests: polynomial rows (CURVE_POLY=0: recurrence rows, bit-identical to the other curve kernels)
+                if (option(OPT_CURVE_POLY, 1)) {
+                    const size_t smem = T.polyFetch > T.cdbBytes ? T.polyFetch : T.cdbBytes;   // room for the fallback
+                    if (int rc = allow_dynamic_smem(eval_curve_tab_kernel<O, NDEP, false, REPL_U, true>, smem)) return rc;
+                    eval_curve_tab_kernel<O, NDEP, false, REPL_U, true><<<(unsigned)blocks, TAB_THREADS, smem, stream>>>(P, T);
+                    count_launch();
+                    return check_launch("bspy_cuda_eval_points(curve, cached polynomial rows)");
+                }
+            }
+            if (int rc = allow_dynamic_smem(eval_curve_tab_kernel<O, NDEP, DER>, T.cdbBytes)) return rc;
+            eval_curve_tab_kernel<O, NDEP, DER><<<(unsigned)blocks, TAB_THREADS, T.cdbBytes, stream>>>(P, T);
             count_launch();
             return check_launch("bspy_cuda_eval_points(curve, cached tables)");
         }
@@ -518,7 +673,7 @@ extern "C" int64_t bspy_cuda_curve_table_bytes(const bspy_spline *spline)
 {
     if (!table_shape_ok(spline)) return 0;
     const TableLayout T = table_layout(spline->order[0], spline->nDep, spline->nCoef[0]);
-    return T.bytes <= 200 * 1024 ? (int64_t)T.bytes : 0;
+    return (T.bytes && T.cdbBytes <= 200 * 1024) ? (int64_t)T.bytes : 0;
 }
 
 extern "C" int bspy_cuda_curve_table_build(const bspy_spline *spline, void *table, int64_t tableBytes, void *stream)

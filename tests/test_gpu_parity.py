@@ -638,6 +638,7 @@ def test_curve_replicated_rows_bit_identical(option):
         if nDep == 2:
             requests.append(dict(values=True, jacobian=True, normal=True))
             requests.append(dict(values=False, normal=True, normalize=False))
+        option("CURVE_POLY", 0)                                      # recurrence rows for value-only requests too: the bit-for-bit comparisons
         for request in requests:
             option("CURVE_REPL", 1)
             a = _cuda.eval_points(ds, u, 1, 1, N, **request)
@@ -660,8 +661,38 @@ def test_curve_replicated_rows_bit_identical(option):
                     if x.dtype.is_floating_point:
                         x, y = torch.nan_to_num(x, nan=-7.0), torch.nan_to_num(y, nan=-7.0)
                     assert torch.equal(x, y), (order, nDep, nCoef, key)
-        # default dispatch (replicated rows for this N) against the oracle: spans bit-exact, values within tolerance
+        # value-only requests on the cached tables read per-span polynomial rows (validated against the recurrence when the
+        # table is built): spans bit-exact, values inside the strict bar of the recurrence rows
         option("CURVE_REPL", None)
+        rec_rows = _cuda.eval_points(ds, u, 1, 1, N, values=True, spans=True)
+        option("CURVE_POLY", None)
+        poly_rows = _cuda.eval_points(ds, u, 1, 1, N, values=True, spans=True)
+        assert torch.equal(poly_rows["spans"], rec_rows["spans"]), (order, nDep, nCoef)
+        assert _close_t(poly_rows["values"], rec_rows["values"]), (order, nDep, nCoef)
+        if (order, nDep, nCoef, clamp, cluster) == (4, 3, 64, True, False):       # the shape of config 1: the rows must be in use
+            assert not torch.equal(torch.nan_to_num(poly_rows["values"]), torch.nan_to_num(rec_rows["values"])), "polynomial rows not in use"
+        if ds.curve_table is not None:
+            # a table whose rows failed the validation of the build (flag in the image's 16-byte trailer cleared): the kernel
+            # fetches the recurrence rows instead -- bit-identical to them
+            saved = ds.curve_table[-16:].clone()
+            ds.curve_table[-16:] = 0
+            fallback = _cuda.eval_points(ds, u, 1, 1, N, values=True, spans=True)
+            ds.curve_table[-16:] = saved
+            assert torch.equal(fallback["spans"], rec_rows["spans"])
+            assert torch.equal(torch.nan_to_num(fallback["values"], nan=-7.0), torch.nan_to_num(rec_rows["values"], nan=-7.0)), (order, nDep, nCoef)
+        # coefficients of magnitude 1e9: where the value cancels, any two evaluation orders differ by a few eps * max|coef|;
+        # the two row forms must agree to the strict bar widened by exactly that
+        big = bspy.Spline(1, nDep, (order,), (nCoef,), [np.array(s.knots[0])], 1e9 * np.asarray(s.coefs) + 1.0)
+        dbig = device_spline(big)
+        pb = _cuda.eval_points(dbig, u, 1, 1, N, values=True)["values"]
+        option("CURVE_POLY", 0)
+        rb = _cuda.eval_points(dbig, u, 1, 1, N, values=True)["values"]
+        option("CURVE_POLY", None)
+        slack = 32 * np.finfo(float).eps * float(np.abs(big.coefs).max())
+        both = torch.isfinite(pb) & torch.isfinite(rb)
+        assert bool((torch.isfinite(pb) == torch.isfinite(rb)).all()), (order, nDep, nCoef)
+        assert bool(((pb - rb).abs()[both] <= 1e-13 + 1e-12 * rb.abs()[both] + slack).all()), (order, nDep, nCoef, "magnitude 1e9")
+        # default dispatch (replicated rows for this N) against the oracle: spans bit-exact, values within tolerance
         r = _cuda.eval_points(ds, u, 1, 1, N, values=True, jacobian=True, spans=True)
         idx = np.concatenate((np.arange(0, min(3 * m, 6000)), rng.integers(0, N - 1, 4000)))
         so = O.OracleSpline.of(s)
@@ -670,6 +701,7 @@ def test_curve_replicated_rows_bit_identical(option):
         assert np.array_equal(r["spans"][0, idx].cpu().numpy(), sp[:, 0]), (order, nDep, nCoef)
         if not cluster:                                            # 1e-7 gaps make the derivative scale 1e7: condition-aware bar elsewhere
             assert close(r["values"][:, idx].cpu().numpy().T, ref)
+            assert close(poly_rows["values"][:, idx].cpu().numpy().T, ref)
             assert close(r["jacobian"][:, 0, idx].cpu().numpy().T, O.jacobian_vec(so, uh)[:, :, 0])
         # outside the domain: first offender reported, like the direct kernel
         bad = u.clone()
