@@ -42,7 +42,7 @@ def test_library_is_sm100a_with_dmma_and_lineinfo():
     sass = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN4bspy17grid2_dmma_kernelILi3ELi4ELb0EEEvNS_11Grid2ParamsE", _cuda.LIB_PATH],
                           capture_output=True, text=True).stdout
     assert "DMMA" in sass, "the grid kernel must run on the FP64 tensor pipe"
-    sass = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN4bspy21eval_curve_tab_kernelILi4ELi3ELb0ELi2EEEvNS_11CurveParamsENS_11TableLayoutE",
+    sass = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN4bspy21eval_curve_tab_kernelILi4ELi3ELb0ELi2ELb1EEEvNS_11CurveParamsENS_11TableLayoutE",
                            _cuda.LIB_PATH], capture_output=True, text=True).stdout
     assert "UBLKCP" in sass and "SYNCS" in sass, "the cached curve tables must arrive by bulk asynchronous copy (TMA) on an mbarrier"
 
