@@ -33,7 +33,8 @@ SYMBOLS = (
     "bspy_cuda_abi_version", "bspy_cuda_last_error_string", "bspy_cuda_launch_count", "bspy_cuda_set_option", "bspy_cuda_copy_2d",
     "bspy_cuda_spans", "bspy_cuda_basis", "bspy_cuda_eval_points", "bspy_cuda_eval_points_binned",
     "bspy_cuda_binned_workspace_bytes", "bspy_cuda_eval_points_aos", "bspy_cuda_aos_workspace_bytes", "bspy_cuda_curve_table_bytes", "bspy_cuda_curve_table_build", "bspy_cuda_eval_grid",
-    "bspy_cuda_eval_grid_batch", "bspy_cuda_eval_many", "bspy_cuda_probe_fp64", "bspy_cuda_probe_hbm",
+    "bspy_cuda_eval_grid_batch", "bspy_cuda_eval_many", "bspy_cuda_many_table_bytes", "bspy_cuda_many_table_build",
+    "bspy_cuda_eval_many_tab", "bspy_cuda_probe_fp64", "bspy_cuda_probe_hbm",
     "bspy_cuda_probe_tiles", "bspy_cuda_curvature", "bspy_cuda_curvature_points", "bspy_cuda_contract_axis", "bspy_cuda_block_accumulate",
     "bspy_cuda_normal_from_jacobian", "bspy_cuda_collocation",
 )
@@ -94,6 +95,8 @@ def library():
             "bspy_cuda_eval_grid": [C.POINTER(CSpline), C.POINTER(vp), C.POINTER(i64), u32, u32, vp, vp, vp, vp, vp],
             "bspy_cuda_eval_grid_batch": [C.POINTER(CSpline), i64, C.POINTER(i64), i64, C.POINTER(vp), C.POINTER(i64), u32, u32, vp, vp, vp, vp, vp],
             "bspy_cuda_eval_many": [i32, i32, i32, i64, vp, i64, vp, i64, vp, i32, vp, vp, vp, vp],
+            "bspy_cuda_many_table_build": [i32, i32, i32, i64, vp, i64, vp, i64, vp, i64, vp],
+            "bspy_cuda_eval_many_tab": [i32, i32, i32, i64, vp, i64, vp, i64, vp, i64, vp, i32, vp, vp, vp],
             "bspy_cuda_probe_fp64": [i32, i32, vp, C.POINTER(C.c_double), vp],
             "bspy_cuda_probe_hbm": [i32, vp, vp, i64, C.POINTER(C.c_double), vp],
             "bspy_cuda_probe_tiles": [vp, i32, i64, i64, i32, i32, C.POINTER(C.c_double), vp],
@@ -112,6 +115,8 @@ def library():
         lib.bspy_cuda_binned_workspace_bytes.restype = C.c_int64
         lib.bspy_cuda_curve_table_bytes.argtypes = [C.POINTER(CSpline)]
         lib.bspy_cuda_curve_table_bytes.restype = C.c_int64
+        lib.bspy_cuda_many_table_bytes.argtypes = [i32, i32, i32, i64]
+        lib.bspy_cuda_many_table_bytes.restype = C.c_int64
         lib.bspy_cuda_aos_workspace_bytes.argtypes = [C.POINTER(CSpline), i64]
         lib.bspy_cuda_aos_workspace_bytes.restype = C.c_int64
         if lib.bspy_cuda_abi_version() != 2:
@@ -380,6 +385,38 @@ def eval_many(order, nCoef, nDep, knots, coefs, u, *, deriv1=False, flag=None, o
                                            _ptr(coefs), int(coefs.stride(0)), _ptr(u), nPts, _ptr(out["values"]),
                                            _ptr(out.get("derivative")), _ptr(flag), _stream(dev))
     _check(rc, "bspy_cuda_eval_many")
+    return out
+
+
+def many_table(order, nCoef, nDep, knots, coefs):
+    """Build the cached per-curve images of a batch of curves (bspy_cuda_many_table_build): knots (S, order+nCoef) (stride 0
+    allowed), coefs (S, nDep, nCoef).  Returns a uint8 device tensor, or None when the shape has no tables."""
+    dev = coefs.device
+    S = int(coefs.shape[0])
+    lib = library()
+    need = int(lib.bspy_cuda_many_table_bytes(int(order), int(nCoef), int(nDep), S))
+    if need <= 0:
+        return None
+    table = torch.empty(need, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.bspy_cuda_many_table_build(int(order), int(nCoef), int(nDep), S, _ptr(knots), int(knots.stride(0)), _ptr(coefs),
+                                            int(coefs.stride(0)), _ptr(table), need, _stream(dev))
+    _check(rc, "bspy_cuda_many_table_build")
+    return table
+
+
+def eval_many_tab(order, nCoef, nDep, knots, coefs, table, u, *, flag=None, out=None):
+    """Launch bspy_cuda_eval_many_tab: values (S, nDep, nPts) of a batch of curves from its cached images."""
+    dev = u.device
+    S, nPts = int(u.shape[0]), int(u.shape[1])
+    _f64(knots, dev), _f64(coefs, dev), _f64(u, dev)
+    if out is None:
+        out = {"values": torch.empty((S, nDep, nPts), dtype=torch.float64, device=dev), "derivative": None}
+    with torch.cuda.device(dev):
+        rc = library().bspy_cuda_eval_many_tab(int(order), int(nCoef), int(nDep), S, _ptr(knots), int(knots.stride(0)), _ptr(coefs),
+                                               int(coefs.stride(0)), _ptr(table), int(table.numel()), _ptr(u), nPts,
+                                               _ptr(out["values"]), _ptr(flag), _stream(dev))
+    _check(rc, "bspy_cuda_eval_many_tab")
     return out
 
 

@@ -336,6 +336,65 @@ def test_many_curves_vs_oracle():
     assert close(r.values[4].T, O.evaluate_vec(so, uu[4][:, None]))
 
 
+def test_many_curves_cached_images():
+    """Value-only requests on a resident batch of curves read cached per-curve images (bucket table + per-span polynomial
+    rows, fetched by TMA; bspy_cuda_many_table_build / bspy_cuda_eval_many_tab): values inside the strict bar of the
+    recurrence kernel and of the oracle, the first offender outside the domain reported alike, ragged sizes (points per
+    curve not a multiple of 32 and above the prefetched 256, curves not a multiple of the warps per block), NaN parameters,
+    shared knots; a curve whose image is flagged invalid is evaluated by the recurrence inside the same kernel."""
+    bspy, _cuda, O, _ = _mods()
+    rng = np.random.default_rng(1703)
+    for order, nCoef, nDep, S, nPts, shared in ((4, 32, 3, 3001, 256, False), (3, 9, 2, 1500, 77, False), (6, 11, 1, 1100, 333, False),
+                                                (2, 5, 3, 1030, 40, True), (5, 40, 2, 1027, 300, False)):
+        def one():
+            w = rng.uniform(0.25, 1.75, nCoef - order + 1)
+            inner = np.concatenate(([0.0], np.cumsum(w))); inner /= inner[-1]
+            return np.concatenate((np.zeros(order - 1), inner, np.ones(order - 1)))
+        knots = one() if shared else np.stack([one() for _ in range(S)])
+        coefs = rng.standard_normal((S, nDep, nCoef))
+        u = rng.uniform(0, 1, (S, nPts))
+        u[0, 0], u[-1, -1] = 0.0, 1.0
+        kn1 = knots if shared else knots[1]
+        u[1, :3] = kn1[order:order + 3]
+        u[2, 5] = float("nan")
+        batch = bspy.SplineBatch(1, nDep, (order,), (nCoef,), [knots], coefs)
+        ut = torch.from_numpy(u).cuda()
+        batch.cache_tables = False
+        plain = batch.evaluate(ut).values
+        batch.cache_tables = "now"
+        cached = batch.evaluate(ut).values
+        table = batch.__dict__["_curve_images_cache"][0]
+        assert table is not None and table.numel() % S == 0
+        assert _close_t(cached, plain), (order, nCoef, nDep)
+        if order == 4:
+            assert not torch.equal(torch.nan_to_num(cached), torch.nan_to_num(plain)), "cached images not in use"
+        assert bool(torch.isnan(cached[2, :, 5]).all())
+        for s_ in range(0, S, max(1, S // 7)):
+            so = O.OracleSpline(1, nDep, (order,), (nCoef,), [knots if shared else knots[s_]], coefs[s_])
+            keep = np.isfinite(u[s_])
+            assert close(cached[s_].cpu().numpy().T[keep], O.evaluate_vec(so, u[s_][keep][:, None]))
+        # curves 3 and S-1 flagged invalid in their images: the kernel evaluates them with the recurrence (tolerance-equal
+        # to the plain kernel, which hoists the knot gaps into reciprocals)
+        per = table.numel() // S
+        for c in (3, S - 1):
+            table[c * per + 8:c * per + 12] = 0
+        again = batch.evaluate(ut).values
+        assert _close_t(again, plain)
+        assert torch.equal(torch.nan_to_num(again[:3]), torch.nan_to_num(cached[:3]))
+        # outside the domain: same first offender, same exception
+        u2 = ut.clone(); u2[S // 2, 1] = -0.5; u2[S - 1, 0] = 1.5
+        with pytest.raises(ValueError, match="outside domain"):
+            batch.evaluate(u2)
+        r = batch.evaluate(u2, check_domain="defer")
+        assert int(r.first_outside.item()) == (S // 2) * nPts + 1
+        # the images are made by the second value-only call of a batch, never by the first
+        lazy = bspy.SplineBatch(1, nDep, (order,), (nCoef,), [knots], coefs)
+        lazy.evaluate(ut)
+        assert "_curve_images_cache" not in lazy.__dict__
+        lazy.evaluate(ut)
+        assert "_curve_images_cache" in lazy.__dict__
+
+
 def test_large_sample_vs_c_oracle_and_properties():
     """Config-4-shaped spline at a size the C oracle finishes in seconds, plus size-independent
     properties at a larger size: partition of unity, linearity in the coefficients, jacobian of an
