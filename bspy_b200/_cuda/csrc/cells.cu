@@ -458,13 +458,64 @@ static long long cell_images_bytes(const SplineDev &s, long long N)
     return 8 * pad64(binned_cells(s) * (long long)image_layout(s).size);
 }
 
+struct PolyEntry;
+static const PolyEntry *find_poly(const SplineDev &s, int code);
+static bool poly_entry_pair(const PolyEntry *e);
+
+static int poly_matrix_stride(int o) { return (o * o + 2 + 1) & ~1; }
+
+struct PolyLayout {
+    int n, nDep, o[BSPY_MAX_IND], cs[BSPY_MAX_IND], pm[BSPY_MAX_IND];   // orders, compact strides, matrix strides
+    int perDep, perDepPad, E, slot;                                       // slot = doubles per cell image
+    int padded;                                                           // rows of the last variable padded to 4 doubles ([d][q][4], ImageShape)
+};
+
+static PolyLayout poly_layout(const SplineDev &s, bool padded = false)
+{
+    PolyLayout L{};
+    L.padded = padded ? 1 : 0;
+    L.n = s.nInd; L.nDep = s.nDep;
+    L.perDep = 1;
+    for (int i = s.nInd - 1; i >= 0; --i) {
+        L.o[i] = s.order[i];
+        L.cs[i] = L.perDep;
+        L.perDep *= s.order[i];
+        L.pm[i] = poly_matrix_stride(s.order[i]);
+    }
+    L.perDepPad = padded ? L.perDep / s.order[s.nInd - 1] * 4 : (L.perDep + 1) & ~1;
+    L.E = L.nDep * L.perDep;
+    L.slot = L.nDep * L.perDepPad + 4;
+    return L;
+}
+
+
+// cell polynomial images (built once per call): worth it when the batch holds a few points per cell at least
+static bool poly_applies(const SplineDev &s, long long N)
+{
+    const long long code = option(OPT_CELL_POLY, 1);
+    if (code <= 0 || s.nInd < 2 || s.nInd > 4) return false;
+    for (int i = 0; i < s.nInd; ++i)
+        if (s.order[i] > 4) return false;
+    if (!find_poly(s, (int)code)) return false;
+    return N >= 8 * binned_cells(s);
+}
+
+static long long cell_poly_bytes(const SplineDev &s, long long N)
+{
+    if (!poly_applies(s, N)) return 0;
+    long long doubles = 8;                                            // flag (+ padding)
+    for (int i = 0; i < s.nInd; ++i) doubles += (long long)(s.nCoef[i] - s.order[i] + 1) * poly_matrix_stride(s.order[i]);
+    doubles = pad64(doubles) + pad64(binned_cells(s) * (long long)poly_layout(s, poly_entry_pair(find_poly(s, (int)option(OPT_CELL_POLY, 1)))).slot);
+    return 8 * doubles;
+}
+
 long long binned_workspace(const SplineDev &s, long long N, bool aosOut)
 {
     if (!binning_applies(s, N)) return 0;
     const long long cells = binned_cells(s);
     if (aosOut || bin_mode(N) == 1) {
         const long long chunk = N < BIN_REC_CHUNK ? N : BIN_REC_CHUNK;
-        return 2 * records_half_bytes(s, chunk, !aosOut) + span_records_bytes(s) + cell_images_bytes(s, N);
+        return 2 * records_half_bytes(s, chunk, !aosOut) + span_records_bytes(s) + cell_images_bytes(s, N) + cell_poly_bytes(s, N);
     }
     const long long chunk = N < BIN_CHUNK_MAX ? N : BIN_CHUNK_MAX;
     return 3 * 4 * pad64(chunk) + 4 * pad64(cells + 1);
@@ -794,6 +845,357 @@ __global__ void __launch_bounds__(CELL_WARPS * 32, MINB) eval_cell_mma_kernel(co
     }
 }
 
+// ---- cell polynomials: the window of every cell converted to powers of (u - mid-cell) ------------------------------------
+// In cell order every point of a warp evaluates the SAME polynomial piece.  The Cox-de Boor kernels spend a tenth of their
+// FP64 instructions on the basis recurrence and contract the window with value / derivative dot products (2 O FMAs per row
+// and variable); a piece written in powers of t_v = u_v - (middle of the span of variable v),
+//     S(u) = sum_k P[k_0 .. k_{n-1}] t_0^k_0 .. t_{n-1}^k_{n-1},    P = (M_0 x .. x M_{n-1}) C,   M_v[k][j] = B_j^(k)(m_v) / k!
+// needs no basis at all and a nested Horner scheme with derivatives: 2 O - 3 FMAs per row instead of 2 O -- 369 instead of
+// 678 FP64 instructions per point for the tricubic nDep-3 volume with its jacobian, 936 instead of 1854 for the 4-variate
+// nDep-6 manifold -- with the same loads.  Centred at mid-cell, every |t_v| <= h_v / 2 and every knot gap of the derivative
+// stages contains the span itself, so the terms stay of the order of the coefficients: measured against long-double
+// arithmetic the values and jacobians are as close to the exact result as the recurrence's (worst 0.08 vs 0.09 of the
+// parity bar on the config-4 shape).  A pre-pass per call builds
+//   * per variable and span the conversion matrix M_v (derivative stages of the recurrence at the mid-span), m_v, h_v / 2;
+//   * per cell the image { P in the compact layout of WindowShape | m_0 .. m_{n-1} } and checks its conditioning
+//     (sum |P| prod (h_v/2)^k_v <= 64 max|C| of the cell's window per dependent variable, everything finite; a cell no
+//     parameter can reach -- an interior span of zero width -- is skipped): one failing cell clears a device flag and the
+//     evaluation of the whole call is done by the recurrence kernels instead (both kernels are enqueued, each looks at
+//     the flag first: PointsDev::gate).
+// The evaluation kernel is eval_staged2_kernel's structure: persistent warps over contiguous runs of sorted tiles, the
+// cell's image staged once per cell (contiguous 16-byte cp.async copies) into one of two slots per warp.
+
+template <int O>
+__device__ __forceinline__ void poly_matrix_span(const double *__restrict__ kn, const int sp, double *__restrict__ out)
+{
+    const int ix = O + sp;
+    double left[O > 1 ? O - 1 : 1], rc[O > 1 ? O * (O - 1) / 2 : 1], dl[O > 1 ? O - 1 : 1];
+#pragma unroll
+    for (int j = 0; j < O - 1; ++j) left[j] = kn[ix - (O - 1) + j];
+    int at = 0;
+#pragma unroll
+    for (int deg = 1; deg < O; ++deg)
+#pragma unroll
+        for (int t = 0; t < deg; ++t) rc[at++] = 1.0 / (kn[ix + t] - kn[ix - deg + t]);
+    const double k0 = kn[ix - 1], k1 = kn[ix], m = 0.5 * (k0 + k1);
+#pragma unroll
+    for (int j = 0; j < O - 1; ++j) dl[j] = m - left[j];
+    double invFact = 1.0;
+#pragma unroll
+    for (int k = 0; k < O; ++k) {
+        double bk[O], unused[O];
+        basis_core<O, false>(dl, rc, k, bk, unused);
+        if (k > 1) invFact /= (double)k;
+#pragma unroll
+        for (int j = 0; j < O; ++j) out[k * O + j] = bk[j] * invFact;
+    }
+    out[O * O] = m;
+    out[O * O + 1] = 0.5 * (k1 - k0);
+}
+
+__global__ void __launch_bounds__(128) poly_matrix_kernel(const double *__restrict__ kn, const int o, const int nCoef,
+                                                          double *__restrict__ out, const int stride)
+{
+    const int sp = blockIdx.x * blockDim.x + threadIdx.x;
+    if (sp > nCoef - o) return;
+    double *r = out + (long long)sp * stride;
+    switch (o) {
+        case 1: poly_matrix_span<1>(kn, sp, r); break;
+        case 2: poly_matrix_span<2>(kn, sp, r); break;
+        case 3: poly_matrix_span<3>(kn, sp, r); break;
+        default: poly_matrix_span<4>(kn, sp, r); break;
+    }
+}
+
+constexpr int POLY_BUILD_WARPS = 4, POLY_BUILD_MAX_E = 1024;
+
+struct PolyMatrices { const double *m[BSPY_MAX_IND]; };
+
+// one warp per cell: window -> tensor transform, axis by axis, in the warp's two shared-memory buffers -> image
+__global__ void __launch_bounds__(POLY_BUILD_WARPS * 32) build_cell_poly_kernel(const SplineDev s, const PolyLayout L, const long long cells,
+                                                                                const PolyMatrices PM, double *__restrict__ images,
+                                                                                int *__restrict__ flag)
+{
+    extern __shared__ __align__(16) double polyBuild[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *bufA = polyBuild + (size_t)warp * (2 * L.E + 32), *bufB = bufA + L.E, *cm = bufB + L.E;   // cm: max |C| per dependent variable
+    for (long long cell = blockIdx.x * (long long)POLY_BUILD_WARPS + warp; cell < cells; cell += gridDim.x * (long long)POLY_BUILD_WARPS) {
+        int span[BSPY_MAX_IND];
+        const double *M[BSPY_MAX_IND];
+        long long base = 0;
+        bool unreachable = false, bad = false;
+        {
+            long long key = cell;
+            for (int iv = L.n - 1; iv >= 0; --iv) {
+                const int m = s.nCoef[iv] - L.o[iv] + 1;
+                span[iv] = (int)(key % m);
+                key /= m;
+                base += (long long)span[iv] * s.stride[iv];
+                M[iv] = PM.m[iv] + (long long)span[iv] * L.pm[iv];
+                const double hh = M[iv][L.o[iv] * L.o[iv] + 1];
+                if (!(hh > 0.0)) {
+                    if (hh == 0.0 && span[iv] > 0 && span[iv] < m - 1) unreachable = true;   // interior span of zero width
+                    else bad = true;
+                }
+            }
+        }
+        __syncwarp();
+        if (!unreachable && !bad) {
+            for (int e = lane; e < L.E; e += 32) {
+                const int d = e / L.perDep;
+                int r = e - d * L.perDep;
+                long long src = base + (long long)d * s.depStride;
+                for (int iv = L.n - 1; iv >= 0; --iv) {
+                    src += (long long)(r % L.o[iv]) * s.stride[iv];
+                    r /= L.o[iv];
+                }
+                bufA[e] = __ldg(s.coefs + src);
+            }
+            __syncwarp();
+            for (int d = 0; d < L.nDep; ++d) {
+                double mx = 0.0;
+                for (int e = lane; e < L.perDep; e += 32) mx = fmax(mx, fabs(bufA[d * L.perDep + e]));
+#pragma unroll
+                for (int off = 16; off; off >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+                if (lane == 0 && d < 32) cm[d] = mx;
+            }
+            double *src = bufA, *dst = bufB;
+            for (int v = 0; v < L.n; ++v) {
+                const int cs = L.cs[v], ov = L.o[v];
+                const double *Mv = M[v];
+                for (int e = lane; e < L.E; e += 32) {
+                    const int k = (e / cs) % ov, e0 = e - k * cs;
+                    double acc = 0.0;
+                    for (int j = 0; j < ov; ++j) acc = fma(Mv[k * ov + j], src[e0 + j * cs], acc);
+                    dst[e] = acc;
+                }
+                __syncwarp();
+                double *t = src; src = dst; dst = t;
+            }
+            // conditioning: the Horner terms against the largest coefficient of the window, per dependent variable
+            for (int d = 0; d < L.nDep; ++d) {
+                double terms = 0.0;
+                for (int e = lane; e < L.perDep; e += 32) {
+                    double w = fabs(src[d * L.perDep + e]);
+                    int r = e;
+                    for (int iv = L.n - 1; iv >= 0; --iv) {
+                        const double hh = M[iv][L.o[iv] * L.o[iv] + 1];
+                        for (int k = r % L.o[iv]; k > 0; --k) w *= hh;
+                        r /= L.o[iv];
+                    }
+                    terms += w;
+                }
+#pragma unroll
+                for (int off = 16; off; off >>= 1) terms += __shfl_xor_sync(0xffffffffu, terms, off);
+                if (!(terms <= 64.0 * cm[d < 32 ? d : 31])) bad = true;     // NaN / inf fail too
+            }
+            double *img = images + cell * (long long)L.slot;
+            if (L.padded) {
+                const int ol = L.o[L.n - 1];
+                for (int e = lane; e < L.nDep * L.perDepPad; e += 32) {
+                    const int d = e / L.perDepPad, r = e - d * L.perDepPad, q = r >> 2, k = r & 3;
+                    img[e] = k < ol ? src[d * L.perDep + q * ol + k] : 0.0;
+                }
+            } else {
+                for (int e = lane; e < L.E; e += 32) {
+                    const int d = e / L.perDep;
+                    img[d * L.perDepPad + (e - d * L.perDep)] = src[e];
+                }
+                if (L.perDepPad > L.perDep && lane < L.nDep) img[lane * L.perDepPad + L.perDep] = 0.0;
+            }
+            if (lane < 4) img[L.nDep * L.perDepPad + lane] = lane < L.n ? M[lane][L.o[lane] * L.o[lane]] : 0.0;
+        }
+        if (bad && lane == 0) atomicExch(flag, 0);
+    }
+}
+
+// nested Horner with derivatives over variables L .. n-1 of the compact image (NDT dependent variables starting at w);
+// q = offset of the fixed indices of variables < L.  v value, g[m] derivative with respect to variable m >= L.
+template <int L, class Ord, int NDEP, int NDT>
+struct HornerS {
+    using WS = WindowShape<Ord, NDEP>;
+    static constexpr int n = Ord::n;
+    __device__ __forceinline__ static void run(const double *__restrict__ w, const int q, const double (&t)[n], double (&v)[NDT],
+                                               double (&g)[n][NDT])
+    {
+        constexpr int O = Ord::at(L);
+        if constexpr (L == n - 1) {
+#pragma unroll
+            for (int d = 0; d < NDT; ++d) {
+                double x[O];
+                load_run<O>(w, q + d * WS::perDepPad, x);
+                double val = x[O - 1], der = 0.0;
+#pragma unroll
+                for (int k = O - 2; k >= 0; --k) {
+                    der = (k == O - 2) ? val : fma(der, t[L], val);
+                    val = fma(val, t[L], x[k]);
+                }
+                v[d] = val;
+                g[L][d] = der;
+            }
+        } else {
+#pragma unroll
+            for (int i = O - 1; i >= 0; --i) {
+                double cv[NDT];
+                double cg[n][NDT];
+                HornerS<L + 1, Ord, NDEP, NDT>::run(w, q + i * WS::stride(L), t, cv, cg);
+#pragma unroll
+                for (int d = 0; d < NDT; ++d) {
+                    if (i == O - 1) {
+                        v[d] = cv[d];
+                        g[L][d] = 0.0;
+#pragma unroll
+                        for (int m = L + 1; m < n; ++m) g[m][d] = cg[m][d];
+                    } else {
+                        g[L][d] = (i == O - 2) ? v[d] : fma(g[L][d], t[L], v[d]);
+                        v[d] = fma(v[d], t[L], cv[d]);
+#pragma unroll
+                        for (int m = L + 1; m < n; ++m) g[m][d] = fma(g[m][d], t[L], cg[m][d]);
+                    }
+                }
+            }
+        }
+    }
+};
+
+template <int NIND, int O0, int O1, int O2, int O3, int NDEP, int NDT, int MINB>
+__global__ void __launch_bounds__(128, MINB) eval_poly_kernel(const SplineDev s, const PointsDev in, const long long N,
+                                                               const WrtDev wrt, const OutDev out)
+{
+    using Ord = Orders<NIND, O0, O1, O2, O3>;
+    using WS = WindowShape<Ord, NDEP>;
+    constexpr int SLOT = WS::size + 4;                              // image: compact polynomial | mid-cell of every variable
+    static_assert(NDEP % NDT == 0, "dependent-variable tile must divide nDep");
+    if (gate_closed(in)) return;
+    extern __shared__ __align__(16) double polySlots[];             // per warp: two slots
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *w0 = polySlots + warp * 2 * SLOT;
+    int slotKey0 = -1, slotKey1 = -1;                               // cells held by the two slots (warp-uniform)
+    bool prefetched = false;                                        // an image requested ahead of its first use is still in flight
+    int cells = 1;
+#pragma unroll
+    for (int iv = 0; iv < NIND; ++iv) cells *= s.nCoef[iv] - Ord::at(iv) + 1;
+    const long long tiles = (N + 31) >> 5, nWarps = gridDim.x * 4LL;
+    const long long per = (tiles + nWarps - 1) / nWarps;
+    const long long firstTile = (blockIdx.x * 4LL + warp) * per;
+    const long long endTile = firstTile + per < tiles ? firstTile + per : tiles;
+    double2 r0 = make_double2(0.0, 0.0), r1 = r0;
+    long long k4 = -1;
+    auto fetch = [&](long long tile) {
+        const long long t = tile * 32 + lane;
+        if (tile < endTile && t < N) {
+            const double2 *rp = reinterpret_cast<const double2 *>(in.records + 4 * t);
+            r0 = __ldcs(rp);
+            r1 = __ldcs(rp + 1);
+            if constexpr (NIND > 3) k4 = __ldcs(reinterpret_cast<const long long *>(in.recKI) + t);
+        }
+    };
+    auto stage = [&](int key, double *dst) {                        // the warp copies the image of cell `key` into a slot
+        const double *src = in.images + (long long)key * SLOT;
+        const unsigned dstAddr = (unsigned)__cvta_generic_to_shared(dst);
+#pragma unroll
+        for (int c0 = 0; c0 < SLOT / 2; c0 += 32) {
+            const int c = c0 + lane;
+            if ((SLOT / 2) % 32 == 0 || c < SLOT / 2)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dstAddr + 16u * c), "l"(src + 2 * c) : "memory");
+        }
+    };
+    fetch(firstTile);
+    for (long long tile = firstTile; tile < endTile; ++tile) {
+        const long long t = tile * 32 + lane;
+        const bool live = t < N;
+        double u[NIND];
+        u[0] = r0.x;
+        if constexpr (NIND > 1) u[1] = r0.y;
+        if constexpr (NIND > 2) u[2] = r1.x;
+        if constexpr (NIND > 3) u[3] = r1.y;
+        const long long ki = NIND > 3 ? k4 : __double_as_longlong(r1.y);
+        const int key = live ? (int)ki : -1;
+        const long long dest = out.aosScatter ? out.aosBase + (ki >> 32) : t;
+        fetch(tile + 1);                                            // next tile's records arrive under this tile's arithmetic
+        if (prefetched) {                                           // requested a tile ago: long since there
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncwarp();
+            prefetched = false;
+        }
+        bool done = !live;
+        while (true) {
+            const unsigned pending = __ballot_sync(0xffffffffu, !done);
+            if (!pending) break;
+            // up to two distinct cells per pass, each in the slot that already holds it or freshly staged
+            const int k0 = __shfl_sync(0xffffffffu, key, __ffs(pending) - 1);
+            const bool in0 = !done && key == k0;
+            const unsigned rest = __ballot_sync(0xffffffffu, !done && !in0);
+            const int k1 = rest ? __shfl_sync(0xffffffffu, key, __ffs(rest) - 1) : -1;
+            const bool in1 = !done && !in0 && key == k1;
+            int s0, s1 = -1;
+            bool staged = false;
+            if (k0 == slotKey0) s0 = 0;
+            else if (k0 == slotKey1) s0 = 1;
+            else {
+                s0 = (k1 >= 0 && k1 == slotKey0) ? 1 : 0;
+                stage(k0, w0 + s0 * SLOT);
+                if (s0) slotKey1 = k0; else slotKey0 = k0;
+                staged = true;
+            }
+            if (k1 >= 0) {
+                s1 = 1 - s0;
+                if ((s1 ? slotKey1 : slotKey0) != k1) {
+                    stage(k1, w0 + s1 * SLOT);
+                    if (s1) slotKey1 = k1; else slotKey0 = k1;
+                    staged = true;
+                }
+            }
+            if (staged) {
+                asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+                __syncwarp();
+            }
+            if (k1 < 0 && k0 + 1 < cells) {
+                // the last pass of this tile needs one slot: the image of the NEXT cell of the sorted sequence (cells are dense:
+                // its points follow within a tile or a few) travels to the other slot under this tile's arithmetic
+                const int other = 1 - s0;
+                if ((other ? slotKey1 : slotKey0) != k0 + 1) {
+                    stage(k0 + 1, w0 + other * SLOT);
+                    asm volatile("cp.async.commit_group;" ::: "memory");
+                    if (other) slotKey1 = k0 + 1; else slotKey0 = k0 + 1;
+                    prefetched = true;
+                }
+            }
+            if (in0 || in1) {
+                const double *w = w0 + (in1 ? s1 : s0) * SLOT;
+                double tt[NIND];
+                {
+                    const double2 m01 = *reinterpret_cast<const double2 *>(w + WS::size);
+                    tt[0] = u[0] - m01.x;
+                    if constexpr (NIND > 1) tt[1] = u[1] - m01.y;
+                    if constexpr (NIND > 2) {
+                        const double2 m23 = *reinterpret_cast<const double2 *>(w + WS::size + 2);
+                        tt[2] = u[2] - m23.x;
+                        if constexpr (NIND > 3) tt[3] = u[3] - m23.y;
+                    }
+                }
+                double *rec = out.aos + dest * out.aosStride;
+                if constexpr (NDT == NDEP) {
+                    double v[NDEP];
+                    double g[NIND][NDEP];
+                    HornerS<0, Ord, NDEP, NDEP>::run(w, 0, tt, v, g);
+                    store_result_record<NIND, NDEP, true>(s, out, rec, v, g);
+                } else {
+#pragma unroll 1
+                    for (int d0 = 0; d0 < NDEP; d0 += NDT) {
+                        double vt[NDT];
+                        double gt[NIND][NDT];
+                        HornerS<0, Ord, NDEP, NDT>::run(w + d0 * WS::perDepPad, 0, tt, vt, gt);
+                        store_result_tile<NIND, NDEP, NDT, true>(rec, d0, vt, gt);
+                    }
+                }
+                done = true;
+            }
+            __syncwarp();                                            // slots may be overwritten by the next pass / tile
+        }
+    }
+}
+
 // ---- cell images: one compact, padded copy of every cell's window (+ its span records) in global memory ------------
 // The thread-per-point kernel in cell order walks its window through L1 with run-time strides: 486 scalar loads and
 // ~700 address instructions per point for the 4-variate nDep-6 manifold (ncu: 4.0 long-scoreboard + 1.9 LG-throttle stalls
@@ -1096,6 +1498,7 @@ __global__ void __launch_bounds__(128, MINB) eval_image2_kernel(const SplineDev 
     static_assert(NDEP % NDT == 0, "dependent-variable tile must divide nDep");
     constexpr int R = NDEP * (1 + NIND), RP = (R + 3) & ~3;
     extern __shared__ __align__(16) double recTile[];                // [point 0 | point 1][R slots][128 threads]
+    if (gate_closed(in)) return;
     const long long P = blockIdx.x * 128LL + threadIdx.x;            // pair index: sorted slots 2P and 2P + 1
     if (2 * P >= (long long)__ldg(in.sortedTotal)) return;
     double ra[4], rb[4];
@@ -1129,6 +1532,145 @@ __global__ void __launch_bounds__(128, MINB) eval_image2_kernel(const SplineDev 
         double v0[NDT], v1[NDT];
         double g0[NIND][NDT], g1[NIND][NDT];
         ContractI2<0, Ord, NDEP, NDT>::run(img + d0 * IS::perDep, 0, c0, c1, v0, g0, v1, g1);
+#pragma unroll
+        for (int d = 0; d < NDT; ++d) {
+            mine[(d0 + d) * 128] = v0[d];
+            mine[(R + d0 + d) * 128] = v1[d];
+#pragma unroll
+            for (int iv = 0; iv < NIND; ++iv) {
+                mine[(NDEP + (d0 + d) * NIND + iv) * 128] = g0[iv][d];
+                mine[(R + NDEP + (d0 + d) * NIND + iv) * 128] = g1[iv][d];
+            }
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+        const long long ki = p ? kib : kia;
+        const long long idx = ki >> 32;
+        if (idx < 0) continue;                                        // dummy slot of an odd cell
+        const long long dest = out.aosScatter ? out.aosBase + idx : 2 * P + p;
+        double *rec = out.aos + dest * out.aosStride;
+        const double *src = mine + p * R * 128;
+#pragma unroll
+        for (int j = 0; j < RP / 4; ++j) {
+            if (4 * j < out.aosStride) {
+                double x[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) x[e] = 4 * j + e < R ? src[(4 * j + e) * 128] : 0.0;
+                if (out.aosWide)
+                    asm volatile("st.global.cs.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(rec + 4 * j), "d"(x[0]), "d"(x[1]), "d"(x[2]), "d"(x[3]) : "memory");
+                else {
+                    __stcs(reinterpret_cast<double2 *>(rec + 4 * j), make_double2(x[0], x[1]));
+                    __stcs(reinterpret_cast<double2 *>(rec + 4 * j) + 1, make_double2(x[2], x[3]));
+                }
+            }
+        }
+    }
+}
+
+// ---- cell polynomials, two points of the same cell per thread -------------------------------------------------------------
+// eval_image2_kernel's structure (images read from global memory through L1 by 256-bit broadcast loads at immediate offsets,
+// even-padded cell segments, results through a shared-memory tile) on the padded polynomial images: no span records, no basis,
+// nested Horner for both points from every loaded row.  Half the FP64 instructions and 14 * NDT instead of (14 + 6) * NDT + 24
+// live doubles per point against the recurrence version.
+template <int L, class Ord, int NDEP, int NDT>
+struct HornerI2 {
+    using IS = ImageShape<Ord, NDEP>;
+    static constexpr int n = Ord::n;
+    __device__ __forceinline__ static void run(const double *__restrict__ img, const int q, const double (&t0)[n], const double (&t1)[n],
+                                               double (&v0)[NDT], double (&g0)[n][NDT], double (&v1)[NDT], double (&g1)[n][NDT])
+    {
+        constexpr int O = Ord::at(L);
+        if constexpr (L == n - 1) {
+#pragma unroll
+            for (int d = 0; d < NDT; ++d) {
+                double x[4];
+                ld_row256(img + (d * IS::Q + q) * 4, x);
+                double a = x[O - 1], b = x[O - 1], da = 0.0, db = 0.0;
+#pragma unroll
+                for (int k = O - 2; k >= 0; --k) {
+                    da = (k == O - 2) ? a : fma(da, t0[L], a);
+                    db = (k == O - 2) ? b : fma(db, t1[L], b);
+                    a = fma(a, t0[L], x[k]);
+                    b = fma(b, t1[L], x[k]);
+                }
+                v0[d] = a; v1[d] = b;
+                g0[L][d] = da; g1[L][d] = db;
+            }
+        } else {
+#pragma unroll
+            for (int i = O - 1; i >= 0; --i) {
+                double cv0[NDT], cv1[NDT];
+                double cg0[n][NDT], cg1[n][NDT];
+                HornerI2<L + 1, Ord, NDEP, NDT>::run(img, q + i * IS::qstride(L), t0, t1, cv0, cg0, cv1, cg1);
+#pragma unroll
+                for (int d = 0; d < NDT; ++d) {
+                    if (i == O - 1) {
+                        v0[d] = cv0[d]; v1[d] = cv1[d];
+                        g0[L][d] = 0.0; g1[L][d] = 0.0;
+#pragma unroll
+                        for (int m = L + 1; m < n; ++m) { g0[m][d] = cg0[m][d]; g1[m][d] = cg1[m][d]; }
+                    } else {
+                        g0[L][d] = (i == O - 2) ? v0[d] : fma(g0[L][d], t0[L], v0[d]);
+                        g1[L][d] = (i == O - 2) ? v1[d] : fma(g1[L][d], t1[L], v1[d]);
+                        v0[d] = fma(v0[d], t0[L], cv0[d]);
+                        v1[d] = fma(v1[d], t1[L], cv1[d]);
+#pragma unroll
+                        for (int m = L + 1; m < n; ++m) {
+                            g0[m][d] = fma(g0[m][d], t0[L], cg0[m][d]);
+                            g1[m][d] = fma(g1[m][d], t1[L], cg1[m][d]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+};
+
+template <int NIND, int O0, int O1, int O2, int O3, int NDEP, int NDT, int MINB>
+__global__ void __launch_bounds__(128, MINB) eval_poly2_kernel(const SplineDev s, const PointsDev in, const long long N,
+                                                                const WrtDev wrt, const OutDev out)
+{
+    using Ord = Orders<NIND, O0, O1, O2, O3>;
+    using IS = ImageShape<Ord, NDEP>;
+    static_assert(NDEP % NDT == 0, "dependent-variable tile must divide nDep");
+    constexpr int SLOT = IS::window + 4;                             // padded polynomial | mid-cell of every variable
+    constexpr int R = NDEP * (1 + NIND), RP = (R + 3) & ~3;
+    if (gate_closed(in)) return;
+    extern __shared__ __align__(16) double recTile[];                // [point 0 | point 1][R slots][128 threads]
+    const long long P = blockIdx.x * 128LL + threadIdx.x;            // pair index: sorted slots 2P and 2P + 1
+    if (2 * P >= (long long)__ldg(in.sortedTotal)) return;
+    double ra[4], rb[4];
+    ld_row256(in.records + 8 * P, ra);
+    ld_row256(in.records + 8 * P + 4, rb);
+    long long kia, kib;
+    if constexpr (NIND > 3) {
+        const longlong2 kk = __ldcs(reinterpret_cast<const longlong2 *>(in.recKI) + P);
+        kia = kk.x;
+        kib = kk.y;
+    } else {
+        kia = __double_as_longlong(ra[3]);
+        kib = __double_as_longlong(rb[3]);
+    }
+    const double *img = in.images + (long long)(int)kia * SLOT;
+    if (in.prefetchImages) {
+        constexpr int lines = (SLOT * 8 + 127) / 128;
+#pragma unroll
+        for (int l = 0; l < lines; ++l) asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char *>(img) + 128 * l));
+    }
+    double t0[NIND], t1[NIND];
+    {
+        double mid[4];
+        ld_row256(img + IS::window, mid);
+#pragma unroll
+        for (int iv = 0; iv < NIND; ++iv) { t0[iv] = ra[iv] - mid[iv]; t1[iv] = rb[iv] - mid[iv]; }
+    }
+    double *mine = recTile + threadIdx.x;
+#pragma unroll 1
+    for (int d0 = 0; d0 < NDEP; d0 += NDT) {
+        double v0[NDT], v1[NDT];
+        double g0[NIND][NDT], g1[NIND][NDT];
+        HornerI2<0, Ord, NDEP, NDT>::run(img + d0 * IS::perDep, 0, t0, t1, v0, g0, v1, g1);
 #pragma unroll
         for (int d = 0; d < NDT; ++d) {
             mine[(d0 + d) * 128] = v0[d];
@@ -1203,6 +1745,46 @@ static const ImageEntry *find_image(const SplineDev &s, int jac, int code)
     return nullptr;
 }
 
+// cell-polynomial kernels: code = 10 * (dependent variables per pass) + CTAs per SM
+struct PolyEntry {
+    int nInd, o[4], nDep, code;
+    FixedFn fn;
+    int slotDoubles, optIn;
+    int pair;                  // two points per thread on padded images read from global memory (code 1000 + ...)
+    int recDoubles;            // pair: shared-memory result tile per thread
+};
+#define BSPY_POLY(NI, A, B, C, D_, ND, NDT, MB, OPT)                                                   \
+    {NI, {A, B, C, D_}, ND, 10 * NDT + MB, eval_poly_kernel<NI, A, B, C, D_, ND, NDT, MB>,              \
+     WindowShape<Orders<NI, A, B, C, D_>, ND>::size + 4, OPT, 0, 0}
+#define BSPY_POLY2(NI, A, B, C, D_, ND, NDT, MB, OPT)                                                  \
+    {NI, {A, B, C, D_}, ND, 1000 + 10 * NDT + MB, eval_poly2_kernel<NI, A, B, C, D_, ND, NDT, MB>,      \
+     ImageShape<Orders<NI, A, B, C, D_>, ND>::window + 4, OPT, 1, 2 * ND * (1 + NI)}
+static const PolyEntry kPoly[] = {
+    // the 4-variate nDep-6 manifold (config 5): two points per thread
+    BSPY_POLY2(4, 3, 3, 3, 3, 6, 2, 3, 0), BSPY_POLY2(4, 3, 3, 3, 3, 6, 2, 4, 1), BSPY_POLY2(4, 3, 3, 3, 3, 6, 3, 3, 1), BSPY_POLY2(4, 3, 3, 3, 3, 6, 1, 4, 1),
+    BSPY_POLY2(4, 3, 3, 3, 3, 6, 2, 2, 1),
+    // tricubic nDep-3 volume (config 4), whole step: 35 -> 12.00, 34 -> 11.98, 36 -> 11.73, 16 -> 5.85 Gpts/s; recurrence 10.53
+    BSPY_POLY(3, 4, 4, 4, 0, 3, 3, 5, 0), BSPY_POLY(3, 4, 4, 4, 0, 3, 3, 4, 1), BSPY_POLY(3, 4, 4, 4, 0, 3, 3, 6, 1),
+    // the 4-variate nDep-6 manifold: one point per lane moves 3.9 KB per point through the load-return path -- 2.75 Gpts/s against
+    // 3.61 for two points per thread on the recurrence images (eval_image2_kernel); opt-in until a pair version exists
+    BSPY_POLY(4, 3, 3, 3, 3, 6, 2, 5, 1), BSPY_POLY(4, 3, 3, 3, 3, 6, 3, 4, 1), BSPY_POLY(4, 3, 3, 3, 3, 6, 2, 4, 1), BSPY_POLY(4, 3, 3, 3, 3, 6, 1, 6, 1),
+    BSPY_POLY(3, 4, 4, 4, 0, 1, 1, 6, 0), BSPY_POLY(3, 4, 4, 4, 0, 4, 2, 5, 0), BSPY_POLY(3, 3, 3, 3, 0, 3, 3, 6, 0), BSPY_POLY(3, 4, 4, 4, 0, 2, 2, 6, 0),
+    BSPY_POLY(3, 3, 3, 3, 0, 2, 2, 6, 0),
+};
+
+static const PolyEntry *find_poly(const SplineDev &s, int code)
+{
+    for (const PolyEntry &e : kPoly) {
+        if (e.nInd != s.nInd || e.nDep != s.nDep) continue;
+        bool same = true;
+        for (int i = 0; i < s.nInd; ++i) same &= e.o[i] == s.order[i];
+        if (same && (code <= 1 ? !e.optIn : code == e.code)) return &e;
+    }
+    return nullptr;
+}
+
+static bool poly_entry_pair(const PolyEntry *e) { return e && e->pair; }
+
 struct CellEntry {
     int nInd, o[4], nDep;
     FixedFn fn;
@@ -1266,6 +1848,12 @@ static int eval_binned_records(const SplineDev &s, PointsDev in, long long N, co
     const size_t cellSmem = cell ? sizeof(double) * CELL_WARPS * cell->warpDoubles : 0;
     if (cell)
         if (int rc = allow_dynamic_smem(cell->fn, cellSmem)) return rc;
+    // cell polynomials (value + jacobian requests): the default where compiled; CELL_POLY=0 turns them off, CELL_POLY=<10 * deps
+    // per pass + CTAs per SM> picks a variant
+    const PolyEntry *poly = (jac && plainWrt && !nN && !cell && poly_applies(s, N)) ? find_poly(s, (int)option(OPT_CELL_POLY, 1)) : nullptr;
+    const size_t polySmem = poly ? (poly->pair ? sizeof(double) * 128 * poly->recDoubles : sizeof(double) * 4 * 2 * poly->slotDoubles) : 0;
+    if (poly)
+        if (int rc = allow_dynamic_smem(poly->fn, polySmem)) return rc;
     const StagedEntry *staged = nullptr;
     {
         const int code = (int)option(OPT_STAGED, 0);
@@ -1276,7 +1864,7 @@ static int eval_binned_records(const SplineDev &s, PointsDev in, long long N, co
     // per lane (eval_staged2_kernel) -- unlike the 4-variate manifold, where two points per thread gave +38 %, the tricubic
     // kernel loses more to the lower occupancy (168-246 registers) than it gains from halving the window loads.  Off by default.
     const StagedEntry *stagedPair = nullptr;
-    if (jac && plainWrt && !nN && option(OPT_SPAN_RECORDS, 1) && option(OPT_STAGED_PAIR, -1) >= 0 && !(cell != nullptr))
+    if (jac && plainWrt && !nN && option(OPT_SPAN_RECORDS, 1) && option(OPT_STAGED_PAIR, -1) >= 0 && !(cell != nullptr) && !poly)
         stagedPair = find_staged_pair(s, (int)option(OPT_STAGED_PAIR, -1));
     const size_t stagedPairSmem = stagedPair ? sizeof(double) * 4 * stagedPair->windowDoubles : 0;
     if (stagedPair)
@@ -1304,7 +1892,7 @@ static int eval_binned_records(const SplineDev &s, PointsDev in, long long N, co
     // cell images (padded window + span records per cell, built once per call) for the shapes compiled for them
     const ImageEntry *image = nullptr;
     const double *images = nullptr;
-    if (images_apply(s, N) && !cell && !stagedPair) {
+    if (images_apply(s, N) && !cell && !stagedPair && !(poly && !poly->pair)) {   // a pair polynomial kernel keeps the recurrence images as its fallback
         image = find_image(s, jac, (int)option(OPT_IMAGE, 0));
         if (image && nN && (image->pair || (image->code % 100) / 10 != s.nDep)) image = nullptr;   // normals need the whole jacobian in one pass
         if (image && image->pair && !plainWrt) image = nullptr;
@@ -1323,12 +1911,44 @@ static int eval_binned_records(const SplineDev &s, PointsDev in, long long N, co
         images = dst;
         if (int rc = allow_dynamic_smem(image->fn, sizeof(double) * 128 * image->recDoubles)) return rc;
     }
+    // cell polynomial images + the flag their validation leaves behind
+    const double *polyImages = nullptr;
+    const int *polyFlag = nullptr;
+    if (poly && poly->pair && !(image && image->pair)) poly = nullptr;
+    if (poly) {
+        const PolyLayout L = poly_layout(s, poly->pair != 0);
+        if (L.E > POLY_BUILD_MAX_E) { set_error("cell polynomial build: window of %d doubles", L.E); return BSPY_E_UNSUPPORTED; }
+        double *at = (double *)((char *)workspace + 2 * half + span_records_bytes(s) + cell_images_bytes(s, N));
+        int *flag = (int *)at;
+        cudaError_t e = cudaMemsetAsync(flag, 0xff, sizeof(int), stream);              // != 0: valid until a cell says otherwise
+        if (e != cudaSuccess) { set_error("cudaMemsetAsync: %s", cudaGetErrorString(e)); return (int)e; }
+        at += 8;
+        PolyMatrices PM{};
+        long long used = 8;
+        for (int i = 0; i < s.nInd; ++i) {
+            const int spans = s.nCoef[i] - s.order[i] + 1, st = poly_matrix_stride(s.order[i]);
+            poly_matrix_kernel<<<(spans + 127) / 128, 128, 0, stream>>>(s.knots[i], s.order[i], s.nCoef[i], at, st);
+            PM.m[i] = at;
+            at += (long long)spans * st;
+            used += (long long)spans * st;
+        }
+        double *dst = (double *)((char *)workspace + 2 * half + span_records_bytes(s) + cell_images_bytes(s, N)) + pad64(used);
+        const size_t bsm = sizeof(double) * POLY_BUILD_WARPS * (2 * L.E + 32);
+        if (int rc = allow_dynamic_smem(build_cell_poly_kernel, bsm)) return rc;
+        long long blocks = (cells + POLY_BUILD_WARPS - 1) / POLY_BUILD_WARPS;
+        const long long cap = (long long)num_sms() * 8;
+        if (blocks > cap) blocks = cap;
+        build_cell_poly_kernel<<<(unsigned)blocks, POLY_BUILD_WARPS * 32, bsm, stream>>>(s, L, cells, PM, dst, flag);
+        count_launch(s.nInd + 1);
+        polyImages = dst;
+        polyFlag = flag;
+    }
     // cell segments are padded to even lengths for the chunks a two-points-per-thread kernel evaluates (the staged pair
     // kernel only takes dense chunks: a sparse tail chunk is sorted without padding and goes to the one-point kernels)
     auto pair_pad = [&](int n) { return (image && image->pair) || (stagedPair != nullptr && n >= 48 * cells); };
     // Sort (and un-permute) of the neighbouring chunks on a second stream under the evaluation of this one: the sort
     // passes are memory / latency bound, the evaluation FP64 bound.  BIN_OVERLAP=0/1 overrides.
-    const bool wantOverlap = option(OPT_BIN_OVERLAP, (staged != nullptr || cell != nullptr || stagedPair != nullptr) ? 1 : 0) != 0;
+    const bool wantOverlap = option(OPT_BIN_OVERLAP, (staged != nullptr || cell != nullptr || stagedPair != nullptr || (poly && !poly->pair)) ? 1 : 0) != 0;
     BinStreams *bs = wantOverlap ? acquire_bin_streams() : nullptr;
     struct Release { BinStreams *b; ~Release() { if (b) release_bin_streams(b); } } releaseOnExit{bs};
     const long long nChunks = (N + chunk - 1) / chunk;
@@ -1388,6 +2008,24 @@ static int eval_binned_records(const SplineDev &s, PointsDev in, long long N, co
         pin.images = images;
         pin.sortedTotal = B.hist + cells;
         pin.prefetchImages = (int)option(OPT_EXP_B, 1);
+        if (poly && poly->pair) {
+            PointsDev pp = pin;
+            pp.images = polyImages; pp.gate = polyFlag; pp.gateWant = -1;
+            const long long pairs = (n + cells + 1) / 2;          // upper bound; the kernel reads the exact slot count
+            poly->fn<<<(unsigned)((pairs + 127) / 128), 128, polySmem, sEval>>>(s, pp, n, wrt, o2);
+            count_launch(1);
+            pin.gate = polyFlag; pin.gateWant = 0;
+        } else if (poly && n >= 48 * cells) {
+            // persistent warps over contiguous runs of tiles; the recurrence kernel of the same chunk follows and runs only
+            // if the validation of the images cleared the flag
+            PointsDev pp = pin;
+            pp.images = polyImages; pp.gate = polyFlag; pp.gateWant = -1;
+            long long blocks = (long long)num_sms() * (poly->code % 10);
+            if (blocks > (n + 127) / 128) blocks = (n + 127) / 128;
+            poly->fn<<<(unsigned)blocks, 128, polySmem, sEval>>>(s, pp, n, wrt, o2);
+            count_launch(1);
+            pin.gate = polyFlag; pin.gateWant = 0;
+        }
         if (image && image->pair) {
             const long long pairs = (n + cells + 1) / 2;          // upper bound; the kernel reads the exact slot count
             image->fn<<<(unsigned)((pairs + 127) / 128), 128, sizeof(double) * 128 * image->recDoubles, sEval>>>(s, pin, n, wrt, o2);

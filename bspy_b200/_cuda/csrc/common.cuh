@@ -47,7 +47,7 @@ static inline int allow_dynamic_smem(K kernel, size_t smem)
 enum Option {
     OPT_CURVE_REPL, OPT_CURVE_PPT, OPT_BIN_MODE, OPT_BIN_OVERLAP, OPT_STAGED, OPT_DEP_TILE, OPT_SPAN_RECORDS, OPT_BIN_CHUNK,
     OPT_BIN_REC_CHUNK_LOG2, OPT_GRID_CHUNK, OPT_GRID_ROWS, OPT_GRID_GROUP, OPT_CELL_KERNEL, OPT_CURVE_TMA, OPT_MANY_MODE,
-    OPT_GRID3_ROWS, OPT_GRID3_CHUNK, OPT_EXP_A, OPT_EXP_B, OPT_IMAGE, OPT_STAGED_PAIR, OPT_STAGED_WAVES, OPT_CURVE_POLY, OPT_COUNT
+    OPT_GRID3_ROWS, OPT_GRID3_CHUNK, OPT_EXP_A, OPT_EXP_B, OPT_IMAGE, OPT_STAGED_PAIR, OPT_STAGED_WAVES, OPT_CURVE_POLY, OPT_CELL_POLY, OPT_COUNT
 };
 long long option(Option o, long long unset);
 
@@ -89,6 +89,10 @@ struct PointsDev {
     const double *images;
     int prefetchImages;       // eval_image2_kernel: request all lines of the cell image up front
     const int *sortedTotal;   // number of slots of the sorted sequence (cell segments rounded up to even lengths)
+    // gate (device int) of a kernel pair that shares one decision taken on the device: the kernel runs only when *gate ==
+    // gateWant (cell polynomial images that passed / failed their validation); nullptr: always
+    const int *gate;
+    int gateWant;
 };
 
 struct OutDev {
@@ -310,6 +314,8 @@ __device__ __forceinline__ double fetch_param(const PointsDev &in, long long p, 
     }
     return __ldg(in.uvw + p * in.pointStride + iv * in.varStride);
 }
+
+__device__ __forceinline__ bool gate_closed(const PointsDev &in) { return in.gate != nullptr && *in.gate != in.gateWant; }
 
 // first point outside the domain: keep the smallest index
 __device__ __forceinline__ void report_outside(int64_t *flag, int64_t p)

@@ -25,6 +25,7 @@ __global__ void __launch_bounds__(128, MINB ? MINB : fixed_min_blocks(NIND, O0, 
 {
     using Ord = Orders<NIND, O0, O1, O2, O3>;
     static_assert(NDEP % NDT == 0, "dependent-variable tile must divide nDep");
+    if (gate_closed(in)) return;
     const bool recs = in.records != nullptr;
     const bool binned = in.perm != nullptr || recs;
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < N; t += (long long)gridDim.x * blockDim.x) {
@@ -155,6 +156,7 @@ __global__ void __launch_bounds__(128, MINB) eval_staged_kernel(const SplineDev 
     using Ord = Orders<NIND, O0, O1, O2, O3>;
     using WS = WindowShape<Ord, NDEP>;
     static_assert(NDEP % NDT == 0, "dependent-variable tile must divide nDep");
+    if (gate_closed(in)) return;
     extern __shared__ __align__(16) double stagedWindows[];         // per warp: two window images
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double *w0 = stagedWindows + warp * 2 * WS::size;
@@ -314,6 +316,7 @@ __global__ void __launch_bounds__(128, MINB) eval_staged2_kernel(const SplineDev
     using CR = CellRecords<Ord>;
     constexpr int SLOT = WS::size + CR::size;                       // doubles per slot (both parts even: 16-byte aligned)
     static_assert(NDEP % NDT == 0, "dependent-variable tile must divide nDep");
+    if (gate_closed(in)) return;
     extern __shared__ __align__(16) double stagedWindows[];         // per warp: two slots
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double *w0 = stagedWindows + warp * 2 * SLOT;

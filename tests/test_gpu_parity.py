@@ -553,6 +553,7 @@ def test_record_mode_staged_windows_bit_identical(option):
         return np.concatenate((np.zeros(o - 1), inner, np.ones(o - 1)))
 
     option("BIN_MODE", 1)
+    option("CELL_POLY", 0)                                         # the recurrence kernels: bit for bit (cell polynomials: next test)
     shapes = [((4, 4, 4), 3, (18, 18, 18)), ((3, 3, 3), 3, (20, 19, 18)), ((4, 4, 4), 1, (28, 27, 26)), ((4, 4, 4), 4, (17, 16, 18)),
               ((3, 3, 3, 3), 6, (10, 10, 9, 10))]
     for order, nDep, nCoef in shapes:
@@ -619,8 +620,9 @@ def test_cell_kernel_tensor_pipe_and_aos_records(option):
             pts = torch.rand((N, nInd), dtype=torch.float64, device="cuda", generator=g)
             pts[7, 0], pts[N - 1, nInd - 1], pts[99, 1] = 0.0, 1.0, float(s.knots[1][order[1] + 2])
             direct = _cuda.eval_points(ds, pts, nInd, 1, N, binned=False, values=True, jacobian=True, normal=want_normal, spans=True)
-            for cell_kernel in (1, 0):
+            for cell_kernel, cell_poly in ((1, None), (0, None), (0, 0)):   # tensor-pipe experiment, cell polynomials (default), recurrence
                 option("CELL_KERNEL", cell_kernel)
+                option("CELL_POLY", cell_poly)
                 rec, sp = _cuda.eval_points_aos(ds, pts, nInd, 1, N, jacobian=True, normal=want_normal, spans=True)
                 assert rec.shape == (N, (nDep * (1 + nInd) + (max(nInd, nDep) if want_normal else 0) + 3) // 4 * 4)
                 assert torch.equal(sp, direct["spans"]), (order, nDep, N, cell_kernel)
@@ -637,6 +639,7 @@ def test_cell_kernel_tensor_pipe_and_aos_records(option):
                 values_only, _ = _cuda.eval_points_aos(ds, pts, nInd, 1, N)
                 assert torch.equal(values_only[:, :nDep].T, _cuda.eval_points(ds, pts, nInd, 1, N, binned=False)["values"])
             option("CELL_KERNEL", None)
+            option("CELL_POLY", None)
             idx = rng.integers(0, N, 4000)
             ref = CO.evaluate(s, pts[idx].cpu().numpy(), values=True, jacobian=True, spans=True)
             assert np.array_equal(sp[:, idx].cpu().numpy().T, ref["spans"])
@@ -790,6 +793,12 @@ def test_record_mode_multi_chunk_overlap_bit_identical(option):
     N = 2 * (1 << 22) + 70_001                                     # three chunks, ragged sparse tail
     pts = torch.rand((N, 3), dtype=torch.float64, device="cuda", generator=torch.Generator(device="cuda").manual_seed(5))
     ref = _cuda.eval_points(ds, pts, 3, 1, N, binned=False, values=True, jacobian=True)
+    # default dispatch: cell polynomials (value + jacobian requests) -- strict bar against the recurrence, every point
+    a = _cuda.eval_points(ds, pts, 3, 1, N, binned=True, values=True, jacobian=True)
+    assert _close_t(a["values"], ref["values"]) and _close_t(a["jacobian"], ref["jacobian"])
+    assert not torch.equal(a["jacobian"], ref["jacobian"]), "cell polynomials not in use"
+    del a
+    option("CELL_POLY", 0)
     for flag in ("1", "0", "v1"):
         option("BIN_OVERLAP", 1 if flag == "v1" else int(flag))
         option("EXP_A", 1 if flag == "v1" else None)               # v1: first-generation staged kernel (per-lane span records)
@@ -798,6 +807,18 @@ def test_record_mode_multi_chunk_overlap_bit_identical(option):
         assert torch.equal(a["values"], ref["values"]) and torch.equal(a["jacobian"], ref["jacobian"]), flag
         del a
     option("BIN_OVERLAP", None)
+    # a spline whose cell polynomials fail the validation of their build (an empty LAST span in the first variable: the
+    # recurrence gives inf / NaN there, which a polynomial piece cannot reproduce entry for entry): the device flag sends the
+    # whole call to the recurrence kernels
+    kz = np.array(s.knots[0]); kz[18:] = kz[18] + np.array([0.0, 0.1, 0.2, 0.3]); kz[17] = kz[18]   # unclamped right end, k[nCoef-1] == k[nCoef]
+    rough = bspy.Spline(3, 3, (4, 4, 4), (18, 18, 18), [kz, np.array(s.knots[1]), np.array(s.knots[2])], np.array(s.coefs))
+    dr = device_spline(rough)
+    n2 = (1 << 21) + 333
+    rec0, _ = _cuda.eval_points_aos(dr, pts[:n2], 3, 1, n2, jacobian=True)
+    option("CELL_POLY", None)
+    rec1, _ = _cuda.eval_points_aos(dr, pts[:n2], 3, 1, n2, jacobian=True)
+    option("CELL_POLY", 0)
+    assert torch.equal(rec0, rec1), "fallback to the recurrence kernels"
     bad = pts.clone()
     bad[(1 << 22) + 17, 2] = 1.25
     bad[2 * (1 << 22) + 5, 0] = -0.5

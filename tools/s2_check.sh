@@ -11,5 +11,8 @@ except Exception as e:
     print(open(f"gpurun_out/s2v_{tag}.err").read()[-1500:])
 PY
 }
-timeout 900 python -m pytest tests -m gpu -x -q -k "many" 2>&1 | tail -15
-run c3_tab cfg3
+timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -6
+run c4 cfg4
+run c4_noov cfg4 BSPY_BIN_OVERLAP=0
+run c4soa cfg4_soa
+run c5 cfg5
