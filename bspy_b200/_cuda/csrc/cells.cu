@@ -1745,13 +1745,237 @@ static const ImageEntry *find_image(const SplineDev &s, int jac, int code)
     return nullptr;
 }
 
+// ---- cell polynomials, staged images, two points of the same cell per lane --------------------------------------------------
+// The global-image pair kernel above is latency-bound (ncu: 47 % of the warp time waits for image rows on their way from L2 /
+// HBM, FP64 pipe 29 %, 77 % of its instructions are FMAs): every CTA starts cold, and the 61 KB result tile of a CTA leaves L1
+// too small to keep prefetched images.  Here warps are persistent over contiguous runs of 64-slot tiles of the (even-padded)
+// sorted sequence, lane l takes slots 2l and 2l + 1; the cell's compact image is staged in shared memory once per cell (two
+// slots per warp) and the image of the NEXT cell of the sorted sequence is requested a tile ahead, so that the point loop
+// never waits for memory; results of the passes over the dependent variables are collected in the warp's [2][R][32] tile and
+// leave as whole 32-byte sectors.
+template <int L, class Ord, int NDEP, int NDT>
+struct HornerS2 {
+    using WS = WindowShape<Ord, NDEP>;
+    static constexpr int n = Ord::n;
+    __device__ __forceinline__ static void run(const double *__restrict__ w, const int q, const double (&t0)[n], const double (&t1)[n],
+                                               double (&v0)[NDT], double (&g0)[n][NDT], double (&v1)[NDT], double (&g1)[n][NDT])
+    {
+        constexpr int O = Ord::at(L);
+        if constexpr (L == n - 1) {
+#pragma unroll
+            for (int d = 0; d < NDT; ++d) {
+                double x[O];
+                load_run<O>(w, q + d * WS::perDepPad, x);
+                double a = x[O - 1], b = x[O - 1], da = 0.0, db = 0.0;
+#pragma unroll
+                for (int k = O - 2; k >= 0; --k) {
+                    da = (k == O - 2) ? a : fma(da, t0[L], a);
+                    db = (k == O - 2) ? b : fma(db, t1[L], b);
+                    a = fma(a, t0[L], x[k]);
+                    b = fma(b, t1[L], x[k]);
+                }
+                v0[d] = a; v1[d] = b;
+                g0[L][d] = da; g1[L][d] = db;
+            }
+        } else {
+#pragma unroll
+            for (int i = O - 1; i >= 0; --i) {
+                double cv0[NDT], cv1[NDT];
+                double cg0[n][NDT], cg1[n][NDT];
+                HornerS2<L + 1, Ord, NDEP, NDT>::run(w, q + i * WS::stride(L), t0, t1, cv0, cg0, cv1, cg1);
+#pragma unroll
+                for (int d = 0; d < NDT; ++d) {
+                    if (i == O - 1) {
+                        v0[d] = cv0[d]; v1[d] = cv1[d];
+                        g0[L][d] = 0.0; g1[L][d] = 0.0;
+#pragma unroll
+                        for (int m = L + 1; m < n; ++m) { g0[m][d] = cg0[m][d]; g1[m][d] = cg1[m][d]; }
+                    } else {
+                        g0[L][d] = (i == O - 2) ? v0[d] : fma(g0[L][d], t0[L], v0[d]);
+                        g1[L][d] = (i == O - 2) ? v1[d] : fma(g1[L][d], t1[L], v1[d]);
+                        v0[d] = fma(v0[d], t0[L], cv0[d]);
+                        v1[d] = fma(v1[d], t1[L], cv1[d]);
+#pragma unroll
+                        for (int m = L + 1; m < n; ++m) {
+                            g0[m][d] = fma(g0[m][d], t0[L], cg0[m][d]);
+                            g1[m][d] = fma(g1[m][d], t1[L], cg1[m][d]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+};
+
+template <int NIND, int O0, int O1, int O2, int O3, int NDEP, int NDT, int MINB>
+__global__ void __launch_bounds__(128, MINB) eval_poly_s2_kernel(const SplineDev s, const PointsDev in, const long long N,
+                                                                  const WrtDev wrt, const OutDev out)
+{
+    using Ord = Orders<NIND, O0, O1, O2, O3>;
+    using WS = WindowShape<Ord, NDEP>;
+    constexpr int SLOT = WS::size + 4;
+    constexpr int R = NDEP * (1 + NIND), RP = (R + 3) & ~3;
+    static_assert(NDEP % NDT == 0, "dependent-variable tile must divide nDep");
+    if (gate_closed(in)) return;
+    extern __shared__ __align__(16) double polyPair[];              // per warp: two slots | result tile [2][R][32]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *w0 = polyPair + warp * (2 * SLOT + 2 * R * 32);
+    double *mine = w0 + 2 * SLOT + lane;                            // results of this lane: mine[(p * R + slot) * 32]
+    int slotKey0 = -1, slotKey1 = -1;
+    bool prefetched = false;
+    int cells = 1;
+#pragma unroll
+    for (int iv = 0; iv < NIND; ++iv) cells *= s.nCoef[iv] - Ord::at(iv) + 1;
+    const long long total = __ldg(in.sortedTotal);                  // slots of the sorted sequence (segments padded to even)
+    const long long tiles = (total + 63) >> 6, nWarps = gridDim.x * 4LL;
+    const long long per = (tiles + nWarps - 1) / nWarps;
+    const long long firstTile = (blockIdx.x * 4LL + warp) * per;
+    const long long endTile = firstTile + per < tiles ? firstTile + per : tiles;
+    double2 ra0 = make_double2(0.0, 0.0), ra1 = ra0, rb0 = ra0, rb1 = ra0;
+    longlong2 kk = make_longlong2(-1, -1);
+    auto fetch = [&](long long tile) {
+        const long long t = tile * 64 + 2 * lane;
+        if (tile < endTile && t < total) {
+            const double2 *rp = reinterpret_cast<const double2 *>(in.records + 4 * t);
+            ra0 = __ldcs(rp); ra1 = __ldcs(rp + 1); rb0 = __ldcs(rp + 2); rb1 = __ldcs(rp + 3);
+            if constexpr (NIND > 3) kk = __ldcs(reinterpret_cast<const longlong2 *>(in.recKI + t));
+        }
+    };
+    auto stage = [&](int key, double *dst) {
+        const double *src = in.images + (long long)key * SLOT;
+        const unsigned dstAddr = (unsigned)__cvta_generic_to_shared(dst);
+#pragma unroll
+        for (int c0 = 0; c0 < SLOT / 2; c0 += 32) {
+            const int c = c0 + lane;
+            if ((SLOT / 2) % 32 == 0 || c < SLOT / 2)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dstAddr + 16u * c), "l"(src + 2 * c) : "memory");
+        }
+    };
+    fetch(firstTile);
+    for (long long tile = firstTile; tile < endTile; ++tile) {
+        const long long t = tile * 64 + 2 * lane;
+        const bool live = t < total;
+        double ua[NIND], ub[NIND];
+        ua[0] = ra0.x; ub[0] = rb0.x;
+        if constexpr (NIND > 1) { ua[1] = ra0.y; ub[1] = rb0.y; }
+        if constexpr (NIND > 2) { ua[2] = ra1.x; ub[2] = rb1.x; }
+        if constexpr (NIND > 3) { ua[3] = ra1.y; ub[3] = rb1.y; }
+        const long long kia = NIND > 3 ? kk.x : __double_as_longlong(ra1.y), kib = NIND > 3 ? kk.y : __double_as_longlong(rb1.y);
+        const int key = live ? (int)kia : -1;
+        fetch(tile + 1);
+        if (prefetched) {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncwarp();
+            prefetched = false;
+        }
+        bool done = !live;
+        while (true) {
+            const unsigned pending = __ballot_sync(0xffffffffu, !done);
+            if (!pending) break;
+            const int k0 = __shfl_sync(0xffffffffu, key, __ffs(pending) - 1);
+            const bool in0 = !done && key == k0;
+            const unsigned rest = __ballot_sync(0xffffffffu, !done && !in0);
+            const int k1 = rest ? __shfl_sync(0xffffffffu, key, __ffs(rest) - 1) : -1;
+            const bool in1 = !done && !in0 && key == k1;
+            int s0, s1 = -1;
+            bool staged = false;
+            if (k0 == slotKey0) s0 = 0;
+            else if (k0 == slotKey1) s0 = 1;
+            else {
+                s0 = (k1 >= 0 && k1 == slotKey0) ? 1 : 0;
+                stage(k0, w0 + s0 * SLOT);
+                if (s0) slotKey1 = k0; else slotKey0 = k0;
+                staged = true;
+            }
+            if (k1 >= 0) {
+                s1 = 1 - s0;
+                if ((s1 ? slotKey1 : slotKey0) != k1) {
+                    stage(k1, w0 + s1 * SLOT);
+                    if (s1) slotKey1 = k1; else slotKey0 = k1;
+                    staged = true;
+                }
+            }
+            if (staged) {
+                asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+                __syncwarp();
+            }
+            if (k1 < 0 && k0 + 1 < cells) {
+                const int other = 1 - s0;
+                if ((other ? slotKey1 : slotKey0) != k0 + 1) {
+                    stage(k0 + 1, w0 + other * SLOT);
+                    asm volatile("cp.async.commit_group;" ::: "memory");
+                    if (other) slotKey1 = k0 + 1; else slotKey0 = k0 + 1;
+                    prefetched = true;
+                }
+            }
+            if (in0 || in1) {
+                const double *w = w0 + (in1 ? s1 : s0) * SLOT;
+                double t0[NIND], t1[NIND];
+                {
+                    const double2 m01 = *reinterpret_cast<const double2 *>(w + WS::size);
+                    t0[0] = ua[0] - m01.x; t1[0] = ub[0] - m01.x;
+                    if constexpr (NIND > 1) { t0[1] = ua[1] - m01.y; t1[1] = ub[1] - m01.y; }
+                    if constexpr (NIND > 2) {
+                        const double2 m23 = *reinterpret_cast<const double2 *>(w + WS::size + 2);
+                        t0[2] = ua[2] - m23.x; t1[2] = ub[2] - m23.x;
+                        if constexpr (NIND > 3) { t0[3] = ua[3] - m23.y; t1[3] = ub[3] - m23.y; }
+                    }
+                }
+#pragma unroll 1
+                for (int d0 = 0; d0 < NDEP; d0 += NDT) {
+                    double v0[NDT], v1[NDT];
+                    double g0[NIND][NDT], g1[NIND][NDT];
+                    HornerS2<0, Ord, NDEP, NDT>::run(w + d0 * WS::perDepPad, 0, t0, t1, v0, g0, v1, g1);
+#pragma unroll
+                    for (int d = 0; d < NDT; ++d) {
+                        mine[(d0 + d) * 32] = v0[d];
+                        mine[(R + d0 + d) * 32] = v1[d];
+#pragma unroll
+                        for (int iv = 0; iv < NIND; ++iv) {
+                            mine[(NDEP + (d0 + d) * NIND + iv) * 32] = g0[iv][d];
+                            mine[(R + NDEP + (d0 + d) * NIND + iv) * 32] = g1[iv][d];
+                        }
+                    }
+                }
+#pragma unroll
+                for (int p = 0; p < 2; ++p) {
+                    const long long ki = p ? kib : kia;
+                    const long long idx = ki >> 32;
+                    if (idx < 0) continue;                          // dummy slot of an odd cell
+                    const long long dest = out.aosScatter ? out.aosBase + idx : t + p;
+                    double *rec = out.aos + dest * out.aosStride;
+                    const double *src = mine + p * R * 32;
+#pragma unroll
+                    for (int j = 0; j < RP / 4; ++j) {
+                        if (4 * j < out.aosStride) {
+                            double x[4];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) x[e] = 4 * j + e < R ? src[(4 * j + e) * 32] : 0.0;
+                            if (out.aosWide)
+                                asm volatile("st.global.cs.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(rec + 4 * j), "d"(x[0]), "d"(x[1]), "d"(x[2]), "d"(x[3]) : "memory");
+                            else {
+                                __stcs(reinterpret_cast<double2 *>(rec + 4 * j), make_double2(x[0], x[1]));
+                                __stcs(reinterpret_cast<double2 *>(rec + 4 * j) + 1, make_double2(x[2], x[3]));
+                            }
+                        }
+                    }
+                }
+                done = true;
+            }
+            __syncwarp();
+        }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
 // cell-polynomial kernels: code = 10 * (dependent variables per pass) + CTAs per SM
 struct PolyEntry {
     int nInd, o[4], nDep, code;
     FixedFn fn;
     int slotDoubles, optIn;
-    int pair;                  // two points per thread on padded images read from global memory (code 1000 + ...)
-    int recDoubles;            // pair: shared-memory result tile per thread
+    int pair;                  // 1: two points per thread on padded images read from global memory (code 1000 + ...);
+                               // 2: two points per lane on staged compact images, persistent warps (code 2000 + ...)
+    int recDoubles;            // pair 1: shared-memory result tile per thread; pair 2: doubles per warp (two slots + result tile)
 };
 #define BSPY_POLY(NI, A, B, C, D_, ND, NDT, MB, OPT)                                                   \
     {NI, {A, B, C, D_}, ND, 10 * NDT + MB, eval_poly_kernel<NI, A, B, C, D_, ND, NDT, MB>,              \
@@ -1759,7 +1983,16 @@ struct PolyEntry {
 #define BSPY_POLY2(NI, A, B, C, D_, ND, NDT, MB, OPT)                                                  \
     {NI, {A, B, C, D_}, ND, 1000 + 10 * NDT + MB, eval_poly2_kernel<NI, A, B, C, D_, ND, NDT, MB>,      \
      ImageShape<Orders<NI, A, B, C, D_>, ND>::window + 4, OPT, 1, 2 * ND * (1 + NI)}
+#define BSPY_POLYS2(NI, A, B, C, D_, ND, NDT, MB, OPT)                                                 \
+    {NI, {A, B, C, D_}, ND, 2000 + 10 * NDT + MB, eval_poly_s2_kernel<NI, A, B, C, D_, ND, NDT, MB>,    \
+     WindowShape<Orders<NI, A, B, C, D_>, ND>::size + 4, OPT, 2,                                       \
+     2 * (WindowShape<Orders<NI, A, B, C, D_>, ND>::size + 4) + 2 * ND * (1 + NI) * 32}
 static const PolyEntry kPoly[] = {
+    // staged images, two points per lane: measured on config 5 (whole step) 2022 -> 2.92, 2032 -> 2.92, 2062 -> 2.68 Gpts/s against 3.83
+    // for the global-image pair kernel -- 23 KB of shared memory per warp (two slots + the result tile) leave 8 warps per SM, too
+    // few to cover the dependent FMA chains and shared-memory latencies (ncu: issue 24 %, FP64 34 %, no memory stalls left);
+    // opt-in, kept with its parity test
+    BSPY_POLYS2(4, 3, 3, 3, 3, 6, 2, 2, 1), BSPY_POLYS2(4, 3, 3, 3, 3, 6, 3, 2, 1),
     // the 4-variate nDep-6 manifold (config 5): two points per thread
     BSPY_POLY2(4, 3, 3, 3, 3, 6, 2, 3, 0), BSPY_POLY2(4, 3, 3, 3, 3, 6, 2, 4, 1), BSPY_POLY2(4, 3, 3, 3, 3, 6, 3, 3, 1), BSPY_POLY2(4, 3, 3, 3, 3, 6, 1, 4, 1),
     BSPY_POLY2(4, 3, 3, 3, 3, 6, 2, 2, 1),
@@ -1783,7 +2016,7 @@ static const PolyEntry *find_poly(const SplineDev &s, int code)
     return nullptr;
 }
 
-static bool poly_entry_pair(const PolyEntry *e) { return e && e->pair; }
+static bool poly_entry_pair(const PolyEntry *e) { return e && e->pair == 1; }   // padded image layout
 
 struct CellEntry {
     int nInd, o[4], nDep;
@@ -1851,7 +2084,7 @@ static int eval_binned_records(const SplineDev &s, PointsDev in, long long N, co
     // cell polynomials (value + jacobian requests): the default where compiled; CELL_POLY=0 turns them off, CELL_POLY=<10 * deps
     // per pass + CTAs per SM> picks a variant
     const PolyEntry *poly = (jac && plainWrt && !nN && !cell && poly_applies(s, N)) ? find_poly(s, (int)option(OPT_CELL_POLY, 1)) : nullptr;
-    const size_t polySmem = poly ? (poly->pair ? sizeof(double) * 128 * poly->recDoubles : sizeof(double) * 4 * 2 * poly->slotDoubles) : 0;
+    const size_t polySmem = !poly ? 0 : poly->pair == 1 ? sizeof(double) * 128 * poly->recDoubles : poly->pair == 2 ? sizeof(double) * 4 * poly->recDoubles : sizeof(double) * 4 * 2 * poly->slotDoubles;
     if (poly)
         if (int rc = allow_dynamic_smem(poly->fn, polySmem)) return rc;
     const StagedEntry *staged = nullptr;
@@ -1916,7 +2149,7 @@ static int eval_binned_records(const SplineDev &s, PointsDev in, long long N, co
     const int *polyFlag = nullptr;
     if (poly && poly->pair && !(image && image->pair)) poly = nullptr;
     if (poly) {
-        const PolyLayout L = poly_layout(s, poly->pair != 0);
+        const PolyLayout L = poly_layout(s, poly->pair == 1);
         if (L.E > POLY_BUILD_MAX_E) { set_error("cell polynomial build: window of %d doubles", L.E); return BSPY_E_UNSUPPORTED; }
         double *at = (double *)((char *)workspace + 2 * half + span_records_bytes(s) + cell_images_bytes(s, N));
         int *flag = (int *)at;
@@ -2012,7 +2245,9 @@ static int eval_binned_records(const SplineDev &s, PointsDev in, long long N, co
             PointsDev pp = pin;
             pp.images = polyImages; pp.gate = polyFlag; pp.gateWant = -1;
             const long long pairs = (n + cells + 1) / 2;          // upper bound; the kernel reads the exact slot count
-            poly->fn<<<(unsigned)((pairs + 127) / 128), 128, polySmem, sEval>>>(s, pp, n, wrt, o2);
+            long long blocks = (pairs + 127) / 128;
+            if (poly->pair == 2 && blocks > (long long)num_sms() * (poly->code % 10)) blocks = (long long)num_sms() * (poly->code % 10);
+            poly->fn<<<(unsigned)blocks, 128, polySmem, sEval>>>(s, pp, n, wrt, o2);
             count_launch(1);
             pin.gate = polyFlag; pin.gateWant = 0;
         } else if (poly && n >= 48 * cells) {

@@ -620,7 +620,8 @@ def test_cell_kernel_tensor_pipe_and_aos_records(option):
             pts = torch.rand((N, nInd), dtype=torch.float64, device="cuda", generator=g)
             pts[7, 0], pts[N - 1, nInd - 1], pts[99, 1] = 0.0, 1.0, float(s.knots[1][order[1] + 2])
             direct = _cuda.eval_points(ds, pts, nInd, 1, N, binned=False, values=True, jacobian=True, normal=want_normal, spans=True)
-            for cell_kernel, cell_poly in ((1, None), (0, None), (0, 0)):   # tensor-pipe experiment, cell polynomials (default), recurrence
+            # tensor-pipe experiment, cell polynomials (default), recurrence, cell polynomials on staged images with two points per lane
+            for cell_kernel, cell_poly in ((1, None), (0, None), (0, 0), (0, 2022), (0, 1023)):
                 option("CELL_KERNEL", cell_kernel)
                 option("CELL_POLY", cell_poly)
                 rec, sp = _cuda.eval_points_aos(ds, pts, nInd, 1, N, jacobian=True, normal=want_normal, spans=True)
