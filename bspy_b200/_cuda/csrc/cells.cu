@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(128) bin_scatter_records_batched_kernel(const 
             r[j][iv] = (t < n && iv < s.nInd) ? __ldcs(in.uvw + (base + t) * in.pointStride + iv * in.varStride) : 0.0;
     }
 #pragma unroll
-    for (int j = 0; j < P; ++j) pos[j] += __ldg(offset + key[j]);
+    for (int j = 0; j < P; ++j) pos[j] += __ldg(offset + key[j]) & 0x7fffffff;   // sign bit: parity flag of an even-padded sort
 #pragma unroll
     for (int j = 0; j < P; ++j) {
         const int t = t0 + j * blockDim.x;
@@ -255,18 +255,18 @@ __global__ void __launch_bounds__(1024) bin_scan_kernel(int *__restrict__ hist, 
             if (i + 2 < cells) hist[i + 2] = o.z;
         }
         if (evenPad) {
-            const int cnt[4] = {raw.x, raw.y, raw.z, raw.w}, at[4] = {o.x, o.y, o.z, o.w};
+            // odd cells: the dummy record of the spare slot is written by bin_pad_kernel (all SMs; 19 000 scattered stores from
+            // this one CTA cost 36 us per chunk); the cell's parity travels in the sign bit of its offset
+            const int cnt[4] = {raw.x, raw.y, raw.z, raw.w};
+            int flagged[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (i + j < cells && (cnt[j] & 1)) {
-                    const long long pos = at[j] + cnt[j];
-                    const double nan = __longlong_as_double(0x7ff8000000000000LL);
-                    double2 *q = reinterpret_cast<double2 *>(records + 4 * pos);
-                    const long long ki = (-1LL << 32) | (unsigned)(i + j);
-                    q[0] = make_double2(nan, nan);
-                    q[1] = make_double2(nan, nInd <= 3 ? __longlong_as_double(ki) : nan);
-                    if (nInd > 3) recKI[pos] = make_int2(i + j, -1);
-                }
+            for (int j = 0; j < 4; ++j)
+                if (i + j < cells && (cnt[j] & 1)) flagged[j] |= (int)0x80000000;
+            if (i + 3 < cells) *reinterpret_cast<int4 *>(hist + i) = make_int4(flagged[0], flagged[1], flagged[2], flagged[3]);
+            else {
+                if (i < cells) hist[i] = flagged[0];
+                if (i + 1 < cells) hist[i + 1] = flagged[1];
+                if (i + 2 < cells) hist[i + 2] = flagged[2];
             }
         }
         __syncthreads();
@@ -274,6 +274,21 @@ __global__ void __launch_bounds__(1024) bin_scan_kernel(int *__restrict__ hist, 
         __syncthreads();
     }
     if (threadIdx.x == 0) hist[cells] = carry;
+}
+
+// dummy records of the odd cells of an even-padded sort (offsets flagged by bin_scan_kernel): NaN parameters, index -1
+__global__ void __launch_bounds__(256) bin_pad_kernel(const int *__restrict__ hist, const int cells, double *__restrict__ records,
+                                                      int2 *__restrict__ recKI, const int nInd)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cells || hist[c] >= 0) return;
+    const long long pos = (long long)(hist[c + 1] & 0x7fffffff) - 1;        // last slot of the cell's (even) segment; hist[cells] = total
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    double2 *q = reinterpret_cast<double2 *>(records + 4 * pos);
+    const long long ki = (-1LL << 32) | (unsigned)c;
+    q[0] = make_double2(nan, nan);
+    q[1] = make_double2(nan, nInd <= 3 ? __longlong_as_double(ki) : nan);
+    if (nInd > 3) recKI[pos] = make_int2(c, -1);
 }
 
 __global__ void __launch_bounds__(256) bin_scatter_kernel(const int *__restrict__ keys, int *__restrict__ cursor, const int n,
@@ -917,11 +932,30 @@ __global__ void __launch_bounds__(POLY_BUILD_WARPS * 32) build_cell_poly_kernel(
                                                                                 int *__restrict__ flag)
 {
     extern __shared__ __align__(16) double polyBuild[];
+    // per window position r (all variables, last fastest): its digits k_v (8 bits each) and its offset in the coefficient
+    // array -- computed once per CTA, so that the per-cell loops below are free of integer divisions
+    __shared__ unsigned digTab[256];
+    __shared__ long long offTab[256];
+    for (int r = threadIdx.x; r < L.perDep; r += blockDim.x) {
+        unsigned dig = 0;
+        long long off = 0;
+        int rr = r;
+        for (int iv = L.n - 1; iv >= 0; --iv) {
+            const int k = rr % L.o[iv];
+            rr /= L.o[iv];
+            dig |= (unsigned)k << (8 * iv);
+            off += (long long)k * s.stride[iv];
+        }
+        digTab[r] = dig;
+        offTab[r] = off;
+    }
+    __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double *bufA = polyBuild + (size_t)warp * (2 * L.E + 32), *bufB = bufA + L.E, *cm = bufB + L.E;   // cm: max |C| per dependent variable
     for (long long cell = blockIdx.x * (long long)POLY_BUILD_WARPS + warp; cell < cells; cell += gridDim.x * (long long)POLY_BUILD_WARPS) {
         int span[BSPY_MAX_IND];
         const double *M[BSPY_MAX_IND];
+        double hp[BSPY_MAX_IND];
         long long base = 0;
         bool unreachable = false, bad = false;
         {
@@ -933,6 +967,7 @@ __global__ void __launch_bounds__(POLY_BUILD_WARPS * 32) build_cell_poly_kernel(
                 base += (long long)span[iv] * s.stride[iv];
                 M[iv] = PM.m[iv] + (long long)span[iv] * L.pm[iv];
                 const double hh = M[iv][L.o[iv] * L.o[iv] + 1];
+                hp[iv] = hh;
                 if (!(hh > 0.0)) {
                     if (hh == 0.0 && span[iv] > 0 && span[iv] < m - 1) unreachable = true;   // interior span of zero width
                     else bad = true;
@@ -941,33 +976,32 @@ __global__ void __launch_bounds__(POLY_BUILD_WARPS * 32) build_cell_poly_kernel(
         }
         __syncwarp();
         if (!unreachable && !bad) {
-            for (int e = lane; e < L.E; e += 32) {
-                const int d = e / L.perDep;
-                int r = e - d * L.perDep;
-                long long src = base + (long long)d * s.depStride;
-                for (int iv = L.n - 1; iv >= 0; --iv) {
-                    src += (long long)(r % L.o[iv]) * s.stride[iv];
-                    r /= L.o[iv];
-                }
-                bufA[e] = __ldg(s.coefs + src);
-            }
-            __syncwarp();
             for (int d = 0; d < L.nDep; ++d) {
+                const double *gsrc = s.coefs + base + (long long)d * s.depStride;
                 double mx = 0.0;
-                for (int e = lane; e < L.perDep; e += 32) mx = fmax(mx, fabs(bufA[d * L.perDep + e]));
+                for (int r = lane; r < L.perDep; r += 32) {
+                    const double c = __ldg(gsrc + offTab[r]);
+                    bufA[d * L.perDep + r] = c;
+                    mx = fmax(mx, fabs(c));
+                }
 #pragma unroll
                 for (int off = 16; off; off >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, off));
                 if (lane == 0 && d < 32) cm[d] = mx;
             }
+            __syncwarp();
             double *src = bufA, *dst = bufB;
             for (int v = 0; v < L.n; ++v) {
                 const int cs = L.cs[v], ov = L.o[v];
                 const double *Mv = M[v];
-                for (int e = lane; e < L.E; e += 32) {
-                    const int k = (e / cs) % ov, e0 = e - k * cs;
-                    double acc = 0.0;
-                    for (int j = 0; j < ov; ++j) acc = fma(Mv[k * ov + j], src[e0 + j * cs], acc);
-                    dst[e] = acc;
+                for (int d = 0; d < L.nDep; ++d) {
+                    const double *sd = src + d * L.perDep;
+                    for (int r = lane; r < L.perDep; r += 32) {
+                        const int k = (digTab[r] >> (8 * v)) & 0xff;
+                        const double *col = sd + r - k * cs;
+                        double acc = 0.0;
+                        for (int j = 0; j < ov; ++j) acc = fma(Mv[k * ov + j], col[j * cs], acc);
+                        dst[d * L.perDep + r] = acc;
+                    }
                 }
                 __syncwarp();
                 double *t = src; src = dst; dst = t;
@@ -975,14 +1009,11 @@ __global__ void __launch_bounds__(POLY_BUILD_WARPS * 32) build_cell_poly_kernel(
             // conditioning: the Horner terms against the largest coefficient of the window, per dependent variable
             for (int d = 0; d < L.nDep; ++d) {
                 double terms = 0.0;
-                for (int e = lane; e < L.perDep; e += 32) {
-                    double w = fabs(src[d * L.perDep + e]);
-                    int r = e;
-                    for (int iv = L.n - 1; iv >= 0; --iv) {
-                        const double hh = M[iv][L.o[iv] * L.o[iv] + 1];
-                        for (int k = r % L.o[iv]; k > 0; --k) w *= hh;
-                        r /= L.o[iv];
-                    }
+                for (int r = lane; r < L.perDep; r += 32) {
+                    double w = fabs(src[d * L.perDep + r]);
+                    const unsigned dig = digTab[r];
+                    for (int iv = 0; iv < L.n; ++iv)
+                        for (int k = (dig >> (8 * iv)) & 0xff; k > 0; --k) w *= hp[iv];
                     terms += w;
                 }
 #pragma unroll
@@ -992,15 +1023,14 @@ __global__ void __launch_bounds__(POLY_BUILD_WARPS * 32) build_cell_poly_kernel(
             double *img = images + cell * (long long)L.slot;
             if (L.padded) {
                 const int ol = L.o[L.n - 1];
-                for (int e = lane; e < L.nDep * L.perDepPad; e += 32) {
-                    const int d = e / L.perDepPad, r = e - d * L.perDepPad, q = r >> 2, k = r & 3;
-                    img[e] = k < ol ? src[d * L.perDep + q * ol + k] : 0.0;
-                }
+                for (int d = 0; d < L.nDep; ++d)
+                    for (int r = lane; r < L.perDepPad; r += 32) {
+                        const int q = r >> 2, k = r & 3;
+                        img[d * L.perDepPad + r] = k < ol ? src[d * L.perDep + q * ol + k] : 0.0;
+                    }
             } else {
-                for (int e = lane; e < L.E; e += 32) {
-                    const int d = e / L.perDep;
-                    img[d * L.perDepPad + (e - d * L.perDep)] = src[e];
-                }
+                for (int d = 0; d < L.nDep; ++d)
+                    for (int r = lane; r < L.perDep; r += 32) img[d * L.perDepPad + r] = src[d * L.perDep + r];
                 if (L.perDepPad > L.perDep && lane < L.nDep) img[lane * L.perDepPad + L.perDep] = 0.0;
             }
             if (lane < 4) img[L.nDep * L.perDepPad + lane] = lane < L.n ? M[lane][L.o[lane] * L.o[lane]] : 0.0;
@@ -1993,6 +2023,8 @@ static const PolyEntry kPoly[] = {
     // few to cover the dependent FMA chains and shared-memory latencies (ncu: issue 24 %, FP64 34 %, no memory stalls left);
     // opt-in, kept with its parity test
     BSPY_POLYS2(4, 3, 3, 3, 3, 6, 2, 2, 1), BSPY_POLYS2(4, 3, 3, 3, 3, 6, 3, 2, 1),
+    // (config 4 with IMAGE=1013 for the even-padded sort: 2033 -> 11.26, 2032 -> 11.00, 2014 -> 11.23 Gpts/s against 12.1 for one point per lane;
+    //  a bucket table instead of the bisection in the keys pass: 87 us either way -- the pass is bound by its atomics, not by the search)
     // the 4-variate nDep-6 manifold (config 5): two points per thread
     BSPY_POLY2(4, 3, 3, 3, 3, 6, 2, 3, 0), BSPY_POLY2(4, 3, 3, 3, 3, 6, 2, 4, 1), BSPY_POLY2(4, 3, 3, 3, 3, 6, 3, 3, 1), BSPY_POLY2(4, 3, 3, 3, 3, 6, 1, 4, 1),
     BSPY_POLY2(4, 3, 3, 3, 3, 6, 2, 2, 1),
@@ -2214,7 +2246,11 @@ static int eval_binned_records(const SplineDev &s, PointsDev in, long long N, co
         // four points per thread in flight (measured against one point per thread at full occupancy: keys 106 -> 95 us,
         // scatter 88 -> 71 us per 4 Mi points)
         bin_keys_batched_kernel<4><<<(n + 511) / 512, 128, 0, sSort>>>(s, in, base, n, B.keys, B.hist, B.inv, o1);
-        if (pair_pad(n)) bin_scan_kernel<<<1, 1024, 0, sSort>>>(B.hist, (int)cells, 1, B.records, B.recKI, s.nInd);
+        if (pair_pad(n)) {
+            bin_scan_kernel<<<1, 1024, 0, sSort>>>(B.hist, (int)cells, 1, B.records, B.recKI, s.nInd);
+            bin_pad_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, sSort>>>(B.hist, (int)cells, B.records, B.recKI, s.nInd);
+            count_launch(1);
+        }
         else bin_scan_kernel<<<1, 1024, 0, sSort>>>(B.hist, (int)cells);
         bin_scatter_records_batched_kernel<4><<<(n + 511) / 512, 128, 0, sSort>>>(s, in, base, n, B.keys, B.hist, B.records, B.recKI,
                                                                                  B.inv, userAos ? 0 : 1);
