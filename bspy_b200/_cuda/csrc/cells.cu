@@ -1951,6 +1951,19 @@ __global__ void __launch_bounds__(128, MINB) eval_poly_s2_kernel(const SplineDev
                         if constexpr (NIND > 3) { t0[3] = ua[3] - m23.y; t1[3] = ub[3] - m23.y; }
                     }
                 }
+                if constexpr (NDT == NDEP) {
+                    // one pass: both records leave from registers as whole sectors, no result tile
+                    double v0[NDEP], v1[NDEP];
+                    double g0[NIND][NDEP], g1[NIND][NDEP];
+                    HornerS2<0, Ord, NDEP, NDEP>::run(w, 0, t0, t1, v0, g0, v1, g1);
+                    if ((kia >> 32) >= 0)
+                        store_result_record<NIND, NDEP, true>(s, out, out.aos + (out.aosScatter ? out.aosBase + (kia >> 32) : t) * out.aosStride, v0, g0);
+                    if ((kib >> 32) >= 0)
+                        store_result_record<NIND, NDEP, true>(s, out, out.aos + (out.aosScatter ? out.aosBase + (kib >> 32) : t + 1) * out.aosStride, v1, g1);
+                    done = true;
+                    __syncwarp();
+                    continue;
+                }
 #pragma unroll 1
                 for (int d0 = 0; d0 < NDEP; d0 += NDT) {
                     double v0[NDT], v1[NDT];
@@ -2023,7 +2036,8 @@ static const PolyEntry kPoly[] = {
     // few to cover the dependent FMA chains and shared-memory latencies (ncu: issue 24 %, FP64 34 %, no memory stalls left);
     // opt-in, kept with its parity test
     BSPY_POLYS2(4, 3, 3, 3, 3, 6, 2, 2, 1), BSPY_POLYS2(4, 3, 3, 3, 3, 6, 3, 2, 1),
-    // (config 4 with IMAGE=1013 for the even-padded sort: 2033 -> 11.26, 2032 -> 11.00, 2014 -> 11.23 Gpts/s against 12.1 for one point per lane;
+    // (config 4, records stored from registers without the result tile: 2033 -> 11.56 Gpts/s, 242 us per chunk against 213 for one point
+    //  per lane -- 168 registers, 12 warps per SM; with the tile and IMAGE=1013 for the even-padded sort: 2033 -> 11.26, 2032 -> 11.00, 2014 -> 11.23 Gpts/s against 12.1 for one point per lane;
     //  a bucket table instead of the bisection in the keys pass: 87 us either way -- the pass is bound by its atomics, not by the search)
     // the 4-variate nDep-6 manifold (config 5): two points per thread
     BSPY_POLY2(4, 3, 3, 3, 3, 6, 2, 3, 0), BSPY_POLY2(4, 3, 3, 3, 3, 6, 2, 4, 1), BSPY_POLY2(4, 3, 3, 3, 3, 6, 3, 3, 1), BSPY_POLY2(4, 3, 3, 3, 3, 6, 1, 4, 1),
@@ -2157,7 +2171,7 @@ static int eval_binned_records(const SplineDev &s, PointsDev in, long long N, co
     // cell images (padded window + span records per cell, built once per call) for the shapes compiled for them
     const ImageEntry *image = nullptr;
     const double *images = nullptr;
-    if (images_apply(s, N) && !cell && !stagedPair && !(poly && !poly->pair)) {   // a pair polynomial kernel keeps the recurrence images as its fallback
+    if (images_apply(s, N) && !cell && !stagedPair && !(poly && poly->pair != 1)) {   // the global-image pair polynomial kernel keeps the recurrence images as its fallback
         image = find_image(s, jac, (int)option(OPT_IMAGE, 0));
         if (image && nN && (image->pair || (image->code % 100) / 10 != s.nDep)) image = nullptr;   // normals need the whole jacobian in one pass
         if (image && image->pair && !plainWrt) image = nullptr;
@@ -2179,7 +2193,7 @@ static int eval_binned_records(const SplineDev &s, PointsDev in, long long N, co
     // cell polynomial images + the flag their validation leaves behind
     const double *polyImages = nullptr;
     const int *polyFlag = nullptr;
-    if (poly && poly->pair && !(image && image->pair)) poly = nullptr;
+    if (poly && poly->pair == 1 && !(image && image->pair)) poly = nullptr;
     if (poly) {
         const PolyLayout L = poly_layout(s, poly->pair == 1);
         if (L.E > POLY_BUILD_MAX_E) { set_error("cell polynomial build: window of %d doubles", L.E); return BSPY_E_UNSUPPORTED; }
@@ -2210,7 +2224,7 @@ static int eval_binned_records(const SplineDev &s, PointsDev in, long long N, co
     }
     // cell segments are padded to even lengths for the chunks a two-points-per-thread kernel evaluates (the staged pair
     // kernel only takes dense chunks: a sparse tail chunk is sorted without padding and goes to the one-point kernels)
-    auto pair_pad = [&](int n) { return (image && image->pair) || (stagedPair != nullptr && n >= 48 * cells); };
+    auto pair_pad = [&](int n) { return (image && image->pair) || (poly && poly->pair == 2) || (stagedPair != nullptr && n >= 48 * cells); };
     // Sort (and un-permute) of the neighbouring chunks on a second stream under the evaluation of this one: the sort
     // passes are memory / latency bound, the evaluation FP64 bound.  BIN_OVERLAP=0/1 overrides.
     const bool wantOverlap = option(OPT_BIN_OVERLAP, (staged != nullptr || cell != nullptr || stagedPair != nullptr || (poly && !poly->pair)) ? 1 : 0) != 0;
@@ -2311,7 +2325,7 @@ static int eval_binned_records(const SplineDev &s, PointsDev in, long long N, co
             const long long most = (n + 32 * CELL_WARPS - 1) / (32 * CELL_WARPS);
             if (blocks > most) blocks = most;
             cell->fn<<<(unsigned)blocks, CELL_WARPS * 32, cellSmem, sEval>>>(s, pin, n, wrt, o2);
-        } else if (staged && n >= 48 * cells) {
+        } else if (staged && n >= 48 * cells && !(poly && poly->pair == 2)) {
             // persistent warps over contiguous runs of tiles (window reuse between consecutive tiles)
             // STAGED_WAVES > 1: that many times more, shorter CTAs (runs of tiles stay long enough for the window reuse), so
             // that CTAs retire all along the kernel and the high-priority sort stream finds room before the tail
@@ -2319,8 +2333,11 @@ static int eval_binned_records(const SplineDev &s, PointsDev in, long long N, co
             if (blocks > (n + 127) / 128) blocks = (n + 127) / 128;
             stagedFn<<<(unsigned)blocks, 128, stagedSmem, sEval>>>(s, pin, n, wrt, o2);
         }
-        else
-            fn<<<(unsigned)((n + 127) / 128), 128, 0, sEval>>>(s, pin, n, wrt, o2);
+        else {
+            // even-padded records (staged pair polynomial kernels): up to one spare slot per cell, the kernel reads the exact count
+            const long long upTo = (poly && poly->pair == 2) ? (long long)n + cells : n;
+            fn<<<(unsigned)((upTo + 127) / 128), 128, 0, sEval>>>(s, pin, upTo, wrt, o2);
+        }
         if (overlap) cudaEventRecord(bs->evaluated[c & 1], sEval);
         count_launch(1);
         return check_launch("bspy_cuda_eval_points_binned(eval)");

@@ -28,7 +28,10 @@ __global__ void __launch_bounds__(128, MINB ? MINB : fixed_min_blocks(NIND, O0, 
     if (gate_closed(in)) return;
     const bool recs = in.records != nullptr;
     const bool binned = in.perm != nullptr || recs;
-    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < N; t += (long long)gridDim.x * blockDim.x) {
+    // sorted records of an even-padded sort: the slot count is on the device (<= N, the caller's upper bound), spare slots
+    // hold dummy records (index -1) that are skipped
+    const long long limit = (recs && in.sortedTotal) ? min(N, (long long)__ldg(in.sortedTotal)) : N;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < limit; t += (long long)gridDim.x * blockDim.x) {
         FixedCtx<Ord, NDT, JAC> c;
         int ix[NIND];
         double u[NIND];
@@ -45,6 +48,7 @@ __global__ void __launch_bounds__(128, MINB ? MINB : fixed_min_blocks(NIND, O0, 
                 if constexpr (NIND > 3) u[3] = r1.y;
                 const long long ki = NIND > 3 ? __ldcs(reinterpret_cast<const long long *>(in.recKI) + t) : __double_as_longlong(r1.y);
                 key = (int)ki;
+                if ((ki >> 32) < 0) continue;                 // dummy slot
                 dest = out.aosScatter ? out.aosBase + (ki >> 32) : t;
             } else {
                 p = in.base + __ldg(in.perm + t);
