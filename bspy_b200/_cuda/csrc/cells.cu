@@ -1529,8 +1529,9 @@ __global__ void __launch_bounds__(128, MINB) eval_image2_kernel(const SplineDev 
     constexpr int R = NDEP * (1 + NIND), RP = (R + 3) & ~3;
     extern __shared__ __align__(16) double recTile[];                // [point 0 | point 1][R slots][128 threads]
     if (gate_closed(in)) return;
-    const long long P = blockIdx.x * 128LL + threadIdx.x;            // pair index: sorted slots 2P and 2P + 1
-    if (2 * P >= (long long)__ldg(in.sortedTotal)) return;
+    // one pair per thread; a launch with fewer CTAs than pairs / 128 (the fallback behind a gate: cheap to skip) strides over them
+    const long long total = (long long)__ldg(in.sortedTotal);
+    for (long long P = blockIdx.x * 128LL + threadIdx.x; 2 * P < total; P += gridDim.x * 128LL) {   // pair index: sorted slots 2P and 2P + 1
     double ra[4], rb[4];
     ld_row256(in.records + 8 * P, ra);
     ld_row256(in.records + 8 * P + 4, rb);
@@ -1595,6 +1596,7 @@ __global__ void __launch_bounds__(128, MINB) eval_image2_kernel(const SplineDev 
                 }
             }
         }
+    }
     }
 }
 
@@ -2313,7 +2315,9 @@ static int eval_binned_records(const SplineDev &s, PointsDev in, long long N, co
         }
         if (image && image->pair) {
             const long long pairs = (n + cells + 1) / 2;          // upper bound; the kernel reads the exact slot count
-            image->fn<<<(unsigned)((pairs + 127) / 128), 128, sizeof(double) * 128 * image->recDoubles, sEval>>>(s, pin, n, wrt, o2);
+            long long blocks = (pairs + 127) / 128;
+            if (pin.gate && blocks > (long long)num_sms() * 2) blocks = (long long)num_sms() * 2;   // behind a gate: normally skipped
+            image->fn<<<(unsigned)blocks, 128, sizeof(double) * 128 * image->recDoubles, sEval>>>(s, pin, n, wrt, o2);
         } else if (image) {
             image->fn<<<(unsigned)((n + 127) / 128), 128, sizeof(double) * 128 * image->recDoubles, sEval>>>(s, pin, n, wrt, o2);
         } else if (stagedPair && n >= 48 * cells) {

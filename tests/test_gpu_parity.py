@@ -820,6 +820,18 @@ def test_record_mode_multi_chunk_overlap_bit_identical(option):
     rec1, _ = _cuda.eval_points_aos(dr, pts[:n2], 3, 1, n2, jacobian=True)
     option("CELL_POLY", 0)
     assert torch.equal(rec0, rec1), "fallback to the recurrence kernels"
+    # the same for the 4-variate nDep-6 shape, whose fallback is the two-points-per-thread recurrence kernel on even-padded
+    # records (launched with a small grid behind the gate: it strides over the pairs)
+    k4 = [K(3, 10), K(3, 10), K(3, 9), K(3, 10)]
+    k4[0][10:] = k4[0][10] + np.array([0.0, 0.1, 0.2]); k4[0][9] = k4[0][10]
+    man = bspy.Spline(4, 6, (3, 3, 3, 3), (10, 10, 9, 10), k4, rng.standard_normal((6, 10, 10, 9, 10)))
+    dm = device_spline(man)
+    p4 = torch.rand((n2, 4), dtype=torch.float64, device="cuda", generator=torch.Generator(device="cuda").manual_seed(6))
+    m0, _ = _cuda.eval_points_aos(dm, p4, 4, 1, n2, jacobian=True)
+    option("CELL_POLY", None)
+    m1, _ = _cuda.eval_points_aos(dm, p4, 4, 1, n2, jacobian=True)
+    option("CELL_POLY", 0)
+    assert torch.equal(m0, m1), "fallback to the recurrence pair kernel"
     bad = pts.clone()
     bad[(1 << 22) + 17, 2] = 1.25
     bad[2 * (1 << 22) + 5, 0] = -0.5
