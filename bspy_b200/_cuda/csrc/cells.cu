@@ -190,6 +190,34 @@ __global__ void __launch_bounds__(128) bin_scatter_records_batched_kernel(const 
     }
 }
 
+// the same without the records: only the (cell key, index in the chunk) pair of every point goes to its sorted slot (8 bytes into
+// an array that stays in L2) -- the evaluation kernel gathers the parameters of its points itself, from the chunk the keys
+// pass has just read.  Saves the second read of the points and the 32-byte record write of every point.
+template <int P>
+__global__ void __launch_bounds__(128) bin_scatter_pairs_batched_kernel(const int n, const int *__restrict__ keys,
+                                                                        const int *__restrict__ offset, int2 *__restrict__ recKI,
+                                                                        int *__restrict__ inv, const int writeInv)
+{
+    const int t0 = blockIdx.x * (blockDim.x * P) + threadIdx.x;
+    int key[P], pos[P];
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+        const int t = t0 + j * blockDim.x;
+        key[j] = t < n ? keys[t] : 0;
+        pos[j] = t < n ? inv[t] : 0;
+    }
+#pragma unroll
+    for (int j = 0; j < P; ++j) pos[j] += __ldg(offset + key[j]) & 0x7fffffff;
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+        const int t = t0 + j * blockDim.x;
+        if (t < n) {
+            recKI[pos[j]] = make_int2(key[j], t);
+            if (writeInv) inv[t] = pos[j];
+        }
+    }
+}
+
 // warp-aggregated slot claim: the lanes of a warp that share a cell take consecutive slots with one atomic
 __device__ __forceinline__ int claim_slot(int *cursor, int key, unsigned active)
 {
@@ -1110,9 +1138,29 @@ __global__ void __launch_bounds__(128, MINB) eval_poly_kernel(const SplineDev s,
     const long long firstTile = (blockIdx.x * 4LL + warp) * per;
     const long long endTile = firstTile + per < tiles ? firstTile + per : tiles;
     double2 r0 = make_double2(0.0, 0.0), r1 = r0;
-    long long k4 = -1;
+    long long k4 = -1, k4next = -1;
+    // records == nullptr: the sorted sequence holds (cell key, index) pairs only and the lane gathers its point's parameters from
+    // the caller's array (one 32-byte sector of a chunk that is still in L2 from the keys pass); the pair of tile + 2 and the
+    // point of tile + 1 are requested under tile's arithmetic
+    const bool gather = in.records == nullptr;
+    auto fetchKey = [&](long long tile) {
+        const long long t = tile * 32 + lane;
+        k4next = (tile < endTile && t < N) ? __ldcs(reinterpret_cast<const long long *>(in.recKI) + t) : -1;
+    };
     auto fetch = [&](long long tile) {
         const long long t = tile * 32 + lane;
+        if (gather) {
+            k4 = k4next;                                            // requested a tile ago
+            fetchKey(tile + 1);
+            if (tile < endTile && t < N) {
+                const double *up = in.uvw + (in.base + (k4 >> 32)) * in.pointStride;
+                r0.x = __ldg(up);
+                if constexpr (NIND > 1) r0.y = __ldg(up + in.varStride);
+                if constexpr (NIND > 2) r1.x = __ldg(up + 2 * in.varStride);
+                if constexpr (NIND > 3) r1.y = __ldg(up + 3 * in.varStride);
+            }
+            return;
+        }
         if (tile < endTile && t < N) {
             const double2 *rp = reinterpret_cast<const double2 *>(in.records + 4 * t);
             r0 = __ldcs(rp);
@@ -1130,6 +1178,7 @@ __global__ void __launch_bounds__(128, MINB) eval_poly_kernel(const SplineDev s,
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dstAddr + 16u * c), "l"(src + 2 * c) : "memory");
         }
     };
+    if (gather) fetchKey(firstTile);
     fetch(firstTile);
     for (long long tile = firstTile; tile < endTile; ++tile) {
         const long long t = tile * 32 + lane;
@@ -1139,7 +1188,7 @@ __global__ void __launch_bounds__(128, MINB) eval_poly_kernel(const SplineDev s,
         if constexpr (NIND > 1) u[1] = r0.y;
         if constexpr (NIND > 2) u[2] = r1.x;
         if constexpr (NIND > 3) u[3] = r1.y;
-        const long long ki = NIND > 3 ? k4 : __double_as_longlong(r1.y);
+        const long long ki = (NIND > 3 || gather) ? k4 : __double_as_longlong(r1.y);
         const int key = live ? (int)ki : -1;
         const long long dest = out.aosScatter ? out.aosBase + (ki >> 32) : t;
         fetch(tile + 1);                                            // next tile's records arrive under this tile's arithmetic
@@ -2226,6 +2275,10 @@ static int eval_binned_records(const SplineDev &s, PointsDev in, long long N, co
     }
     // cell segments are padded to even lengths for the chunks a two-points-per-thread kernel evaluates (the staged pair
     // kernel only takes dense chunks: a sparse tail chunk is sorted without padding and goes to the one-point kernels)
+    // BIN_PERM=1: (cell key, index) pairs instead of point records for the staged polynomial kernel -- no record scatter (64 -> 34 us
+    // per chunk), but the kernel's own gather of the points costs its load path more than that (213 -> 276 us): 11.54 against
+    // 12.17 Gpts/s on config 4.  Off by default, kept with its bit-for-bit test.
+    const bool usePairs = poly && !poly->pair && option(OPT_BIN_PERM, 0) != 0;
     auto pair_pad = [&](int n) { return (image && image->pair) || (poly && poly->pair == 2) || (stagedPair != nullptr && n >= 48 * cells); };
     // Sort (and un-permute) of the neighbouring chunks on a second stream under the evaluation of this one: the sort
     // passes are memory / latency bound, the evaluation FP64 bound.  BIN_OVERLAP=0/1 overrides.
@@ -2268,8 +2321,11 @@ static int eval_binned_records(const SplineDev &s, PointsDev in, long long N, co
             count_launch(1);
         }
         else bin_scan_kernel<<<1, 1024, 0, sSort>>>(B.hist, (int)cells);
-        bin_scatter_records_batched_kernel<4><<<(n + 511) / 512, 128, 0, sSort>>>(s, in, base, n, B.keys, B.hist, B.records, B.recKI,
-                                                                                 B.inv, userAos ? 0 : 1);
+        if (usePairs)
+            bin_scatter_pairs_batched_kernel<4><<<(n + 511) / 512, 128, 0, sSort>>>(n, B.keys, B.hist, B.recKI, B.inv, userAos ? 0 : 1);
+        else
+            bin_scatter_records_batched_kernel<4><<<(n + 511) / 512, 128, 0, sSort>>>(s, in, base, n, B.keys, B.hist, B.records, B.recKI,
+                                                                                     B.inv, userAos ? 0 : 1);
         if (overlap) cudaEventRecord(bs->sorted[c & 1], sSort);
         count_launch(3);
         return check_launch("bspy_cuda_eval_points_binned(sort)");
@@ -2280,7 +2336,8 @@ static int eval_binned_records(const SplineDev &s, PointsDev in, long long N, co
         const int n = (int)(N - base < chunk ? N - base : chunk);
         if (overlap) cudaStreamWaitEvent(sEval, bs->sorted[c & 1], 0);
         PointsDev pin{};
-        pin.records = B.records; pin.recKI = B.recKI;
+        pin.records = usePairs ? nullptr : B.records; pin.recKI = B.recKI;
+        if (usePairs) { pin.uvw = in.uvw; pin.pointStride = in.pointStride; pin.varStride = in.varStride; pin.base = base; }
         for (int i = 0; i < s.nInd; ++i) pin.spanRec[i] = spanRec[i];
         OutDev o2 = out;
         o2.spans = nullptr; o2.firstOutside = nullptr;
@@ -2329,7 +2386,7 @@ static int eval_binned_records(const SplineDev &s, PointsDev in, long long N, co
             const long long most = (n + 32 * CELL_WARPS - 1) / (32 * CELL_WARPS);
             if (blocks > most) blocks = most;
             cell->fn<<<(unsigned)blocks, CELL_WARPS * 32, cellSmem, sEval>>>(s, pin, n, wrt, o2);
-        } else if (staged && n >= 48 * cells && !(poly && poly->pair == 2)) {
+        } else if (staged && n >= 48 * cells && !(poly && poly->pair == 2) && !usePairs) {
             // persistent warps over contiguous runs of tiles (window reuse between consecutive tiles)
             // STAGED_WAVES > 1: that many times more, shorter CTAs (runs of tiles stay long enough for the window reuse), so
             // that CTAs retire all along the kernel and the high-priority sort stream finds room before the tail
@@ -2340,7 +2397,9 @@ static int eval_binned_records(const SplineDev &s, PointsDev in, long long N, co
         else {
             // even-padded records (staged pair polynomial kernels): up to one spare slot per cell, the kernel reads the exact count
             const long long upTo = (poly && poly->pair == 2) ? (long long)n + cells : n;
-            fn<<<(unsigned)((upTo + 127) / 128), 128, 0, sEval>>>(s, pin, upTo, wrt, o2);
+            long long blocks = (upTo + 127) / 128;
+            if (pin.gate && blocks > (long long)num_sms() * 4) blocks = (long long)num_sms() * 4;   // behind a gate: normally skipped (grid-stride kernel)
+            fn<<<(unsigned)blocks, 128, 0, sEval>>>(s, pin, upTo, wrt, o2);
         }
         if (overlap) cudaEventRecord(bs->evaluated[c & 1], sEval);
         count_launch(1);

@@ -47,7 +47,7 @@ static inline int allow_dynamic_smem(K kernel, size_t smem)
 enum Option {
     OPT_CURVE_REPL, OPT_CURVE_PPT, OPT_BIN_MODE, OPT_BIN_OVERLAP, OPT_STAGED, OPT_DEP_TILE, OPT_SPAN_RECORDS, OPT_BIN_CHUNK,
     OPT_BIN_REC_CHUNK_LOG2, OPT_GRID_CHUNK, OPT_GRID_ROWS, OPT_GRID_GROUP, OPT_CELL_KERNEL, OPT_CURVE_TMA, OPT_MANY_MODE,
-    OPT_GRID3_ROWS, OPT_GRID3_CHUNK, OPT_EXP_A, OPT_EXP_B, OPT_IMAGE, OPT_STAGED_PAIR, OPT_STAGED_WAVES, OPT_CURVE_POLY, OPT_CELL_POLY, OPT_COUNT
+    OPT_GRID3_ROWS, OPT_GRID3_CHUNK, OPT_EXP_A, OPT_EXP_B, OPT_IMAGE, OPT_STAGED_PAIR, OPT_STAGED_WAVES, OPT_CURVE_POLY, OPT_CELL_POLY, OPT_BIN_PERM, OPT_COUNT
 };
 long long option(Option o, long long unset);
 
@@ -81,7 +81,8 @@ struct PointsDev {
     // span key (cell) and the point's index inside its chunk are the low / high 32 bits of the bit pattern of
     // records[4t+3] for nInd <= 3, recKI[t] = (key, index) for nInd == 4
     const double *records;
-    const int2 *recKI;
+    const int2 *recKI;         // records == nullptr && recKI != nullptr: sorted (cell key, index) pairs only -- the kernel gathers
+                               // the parameters of slot t from uvw[(base + index) * pointStride ..] itself (no record scatter pass)
     // per-span records of variable i (left knots | reciprocal knot gaps, SpanRec<order>::stride doubles per span), built
     // once per call by span_records_kernel for the binned path; nullptr: gaps are divided per point
     const double *spanRec[BSPY_MAX_IND];

@@ -28,7 +28,7 @@ void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 static const char *const kOptionNames[OPT_COUNT] = {
     "CURVE_REPL", "CURVE_PPT", "BIN_MODE", "BIN_OVERLAP", "STAGED", "DEP_TILE", "SPAN_RECORDS", "BIN_CHUNK",
     "BIN_REC_CHUNK_LOG2", "GRID_CHUNK", "GRID_ROWS", "GRID_GROUP", "CELL_KERNEL", "CURVE_TMA", "MANY_MODE",
-    "GRID3_ROWS", "GRID3_CHUNK", "EXP_A", "EXP_B", "IMAGE", "STAGED_PAIR", "STAGED_WAVES", "CURVE_POLY", "CELL_POLY",
+    "GRID3_ROWS", "GRID3_CHUNK", "EXP_A", "EXP_B", "IMAGE", "STAGED_PAIR", "STAGED_WAVES", "CURVE_POLY", "CELL_POLY", "BIN_PERM",
 };
 constexpr long long kOptionUnset = INT64_MIN;
 static std::atomic<long long> g_options[OPT_COUNT];

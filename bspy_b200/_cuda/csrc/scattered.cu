@@ -27,10 +27,11 @@ __global__ void __launch_bounds__(128, MINB ? MINB : fixed_min_blocks(NIND, O0, 
     static_assert(NDEP % NDT == 0, "dependent-variable tile must divide nDep");
     if (gate_closed(in)) return;
     const bool recs = in.records != nullptr;
-    const bool binned = in.perm != nullptr || recs;
+    const bool pairs = !recs && in.recKI != nullptr;              // sorted (cell key, index) pairs: parameters gathered here
+    const bool binned = in.perm != nullptr || recs || pairs;
     // sorted records of an even-padded sort: the slot count is on the device (<= N, the caller's upper bound), spare slots
     // hold dummy records (index -1) that are skipped
-    const long long limit = (recs && in.sortedTotal) ? min(N, (long long)__ldg(in.sortedTotal)) : N;
+    const long long limit = ((recs || pairs) && in.sortedTotal) ? min(N, (long long)__ldg(in.sortedTotal)) : N;
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < limit; t += (long long)gridDim.x * blockDim.x) {
         FixedCtx<Ord, NDT, JAC> c;
         int ix[NIND];
@@ -50,6 +51,12 @@ __global__ void __launch_bounds__(128, MINB ? MINB : fixed_min_blocks(NIND, O0, 
                 key = (int)ki;
                 if ((ki >> 32) < 0) continue;                 // dummy slot
                 dest = out.aosScatter ? out.aosBase + (ki >> 32) : t;
+            } else if (pairs) {
+                const int2 ki = __ldcs(in.recKI + t);
+                key = ki.x;
+                if (ki.y < 0) continue;                       // dummy slot
+                p = in.base + ki.y;
+                dest = out.aosScatter ? out.aosBase + ki.y : t;
             } else {
                 p = in.base + __ldg(in.perm + t);
                 key = __ldg(in.cellKey + t);

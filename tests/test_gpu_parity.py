@@ -798,7 +798,15 @@ def test_record_mode_multi_chunk_overlap_bit_identical(option):
     a = _cuda.eval_points(ds, pts, 3, 1, N, binned=True, values=True, jacobian=True)
     assert _close_t(a["values"], ref["values"]) and _close_t(a["jacobian"], ref["jacobian"])
     assert not torch.equal(a["jacobian"], ref["jacobian"]), "cell polynomials not in use"
-    del a
+    # BIN_PERM=1: the kernel gathers its points through sorted (cell key, index) pairs instead of reading point records: the
+    # same bits
+    option("BIN_PERM", 1)
+    b = _cuda.eval_points(ds, pts, 3, 1, N, binned=True, values=True, jacobian=True)
+    option("BIN_PERM", None)
+    assert torch.equal(a["values"], b["values"]) and torch.equal(a["jacobian"], b["jacobian"])
+    ra, _ = _cuda.eval_points_aos(ds, pts, 3, 1, N, jacobian=True)
+    assert torch.equal(ra[:, :3].T, a["values"]) and torch.equal(ra[:, 3:12].T.reshape(3, 3, N), a["jacobian"])
+    del a, b, ra
     option("CELL_POLY", 0)
     for flag in ("1", "0", "v1"):
         option("BIN_OVERLAP", 1 if flag == "v1" else int(flag))
