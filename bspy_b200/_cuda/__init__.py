@@ -96,7 +96,7 @@ def library():
             "bspy_cuda_eval_grid_batch": [C.POINTER(CSpline), i64, C.POINTER(i64), i64, C.POINTER(vp), C.POINTER(i64), u32, u32, vp, vp, vp, vp, vp],
             "bspy_cuda_eval_many": [i32, i32, i32, i64, vp, i64, vp, i64, vp, i32, vp, vp, vp, vp],
             "bspy_cuda_many_table_build": [i32, i32, i32, i64, vp, i64, vp, i64, vp, i64, vp],
-            "bspy_cuda_eval_many_tab": [i32, i32, i32, i64, vp, i64, vp, i64, vp, i64, vp, i32, vp, vp, vp],
+            "bspy_cuda_eval_many_tab": [i32, i32, i32, i64, vp, i64, vp, i64, vp, i64, vp, i32, vp, vp, vp, vp],
             "bspy_cuda_probe_fp64": [i32, i32, vp, C.POINTER(C.c_double), vp],
             "bspy_cuda_probe_hbm": [i32, vp, vp, i64, C.POINTER(C.c_double), vp],
             "bspy_cuda_probe_tiles": [vp, i32, i64, i64, i32, i32, C.POINTER(C.c_double), vp],
@@ -405,17 +405,18 @@ def many_table(order, nCoef, nDep, knots, coefs):
     return table
 
 
-def eval_many_tab(order, nCoef, nDep, knots, coefs, table, u, *, flag=None, out=None):
-    """Launch bspy_cuda_eval_many_tab: values (S, nDep, nPts) of a batch of curves from its cached images."""
+def eval_many_tab(order, nCoef, nDep, knots, coefs, table, u, *, deriv1=False, flag=None, out=None):
+    """Launch bspy_cuda_eval_many_tab: values (S, nDep, nPts) [, first derivatives] of a batch of curves from its cached images."""
     dev = u.device
     S, nPts = int(u.shape[0]), int(u.shape[1])
     _f64(knots, dev), _f64(coefs, dev), _f64(u, dev)
     if out is None:
-        out = {"values": torch.empty((S, nDep, nPts), dtype=torch.float64, device=dev), "derivative": None}
+        out = {"values": torch.empty((S, nDep, nPts), dtype=torch.float64, device=dev),
+               "derivative": torch.empty((S, nDep, nPts), dtype=torch.float64, device=dev) if deriv1 else None}
     with torch.cuda.device(dev):
         rc = library().bspy_cuda_eval_many_tab(int(order), int(nCoef), int(nDep), S, _ptr(knots), int(knots.stride(0)), _ptr(coefs),
                                                int(coefs.stride(0)), _ptr(table), int(table.numel()), _ptr(u), nPts,
-                                               _ptr(out["values"]), _ptr(flag), _stream(dev))
+                                               _ptr(out["values"]), _ptr(out.get("derivative")), _ptr(flag), _stream(dev))
     _check(rc, "bspy_cuda_eval_many_tab")
     return out
 

@@ -210,15 +210,14 @@ __device__ __forceinline__ void build_repl_tables(const double *__restrict__ kno
 // The point loop of the replicated-row kernels: REPL_U points per thread and round; the parameters of the next round
 // are requested before this round's arithmetic (the loop is otherwise a chain DRAM load -> table -> row -> arithmetic ->
 // store per point).  un[] holds the first round's parameters, requested by the caller before the tables were ready.
-// POLY (value-only requests on a validated table image, see curve_table_kernel): the row of a span is its polynomial in
-// powers of (u - mid-span) -- { c_0[d], .., c_{O-1}[d], m } -- and a point is one row fetch and a Horner evaluation.
+// POLY (validated table image, see curve_table_kernel): the row of a span is its polynomial in powers of (u - mid-span) --
+// { c_0[d], .., c_{O-1}[d], m } -- and a point is one row fetch and a Horner evaluation (with its derivative when DER).
 template <int O, int NDEP, bool DER, int REPL_U, bool POLY = false>
 __device__ __forceinline__ void repl_point_loop(const CurveParams &P, const int buckets, const double *rows, const double *kn,
                                                 const unsigned short *tab, double (&un)[REPL_U], const double *up,
                                                 const long long pfirst, const long long pstep, const long long rstep)
 {
     using R = SpanRec<O>;
-    static_assert(!(POLY && DER), "polynomial rows serve value-only requests");
     constexpr int ROW = POLY ? poly_row_doubles(O, NDEP) : ((O - 1) + O * (O - 1) / 2 + O * NDEP + 1) & ~1, CH = ROW / 2;
     constexpr int CP = REPL_COPIES, KC = REPL_KNOT_COPIES;
     const int lane = threadIdx.x & 31;
@@ -262,11 +261,14 @@ __device__ __forceinline__ void repl_point_loop(const CurveParams &P, const int 
                 const double t = uk - r[O * NDEP];
 #pragma unroll
                 for (int d = 0; d < NDEP; ++d) {
-                    double h = r[(O - 1) * NDEP + d];
+                    double h = r[(O - 1) * NDEP + d], dh = 0.0;
 #pragma unroll
-                    for (int k = O - 2; k >= 0; --k) h = fma(h, t, r[k * NDEP + d]);
+                    for (int k = O - 2; k >= 0; --k) {
+                        if (DER) dh = (k == O - 2) ? h : fma(dh, t, h);
+                        h = fma(h, t, r[k * NDEP + d]);
+                    }
                     v[d] = h;
-                    g[d] = 0.0;
+                    g[d] = dh;
                 }
             } else {
                 double dl[O > 1 ? O - 1 : 1], rc[O > 1 ? O * (O - 1) / 2 : 1];
@@ -388,8 +390,8 @@ __global__ void __launch_bounds__(512) curve_table_kernel(const double *__restri
     // One failing span clears the flag and value-only requests keep the recurrence rows.
     constexpr int PROW = poly_row_doubles(O, NDEP), PCH = PROW / 2;
     double *gPoly = reinterpret_cast<double *>(image + T.cdbBytes);
-    __shared__ int polyOk;
-    if (threadIdx.x == 0) polyOk = 1;
+    __shared__ int polyOk, polyDerOk;
+    if (threadIdx.x == 0) { polyOk = 1; polyDerOk = 1; }
     __syncthreads();
     for (int sp = threadIdx.x; sp < spans; sp += blockDim.x) {
         const int ix = O + sp;
@@ -427,7 +429,7 @@ __global__ void __launch_bounds__(512) curve_table_kernel(const double *__restri
 #pragma unroll
             for (int q = 0; q < CP; ++q)
                 *reinterpret_cast<double2 *>(gPoly + 2 * ((sp * PCH + j) * CP + q)) = make_double2(row[2 * j], row[2 * j + 1]);
-        bool ok = true;
+        bool ok = true, okDer = true;
         double cmax[NDEP];
 #pragma unroll
         for (int d = 0; d < NDEP; ++d) {
@@ -450,26 +452,39 @@ __global__ void __launch_bounds__(512) curve_table_kernel(const double *__restri
                 for (int j = 0; j < O - 1; ++j) du[j] = u - left[j];
                 basis_core<O, false>(du, rc, 0, b0, unused);
                 const double t = u - m;
+                double b1[O];
+                basis_core<O, false>(du, rc, 1, b1, unused);        // first-derivative basis of the recurrence
 #pragma unroll
                 for (int d = 0; d < NDEP; ++d) {
-                    double ref = 0.0;
+                    double ref = 0.0, dref = 0.0, dterms = 0.0;
 #pragma unroll
-                    for (int j = 0; j < O; ++j) ref = fma(raw[d * nCoef + sp + j], b0[j], ref);
-                    double hv = row[(O - 1) * NDEP + d];
+                    for (int j = 0; j < O; ++j) {
+                        const double cj = raw[d * nCoef + sp + j];
+                        ref = fma(cj, b0[j], ref);
+                        dref = fma(cj, b1[j], dref);
+                        dterms = fma(fabs(cj), fabs(b1[j]), dterms);
+                    }
+                    double hv = row[(O - 1) * NDEP + d], dv = 0.0;
 #pragma unroll
-                    for (int k = O - 2; k >= 0; --k) hv = fma(hv, t, row[k * NDEP + d]);
+                    for (int k = O - 2; k >= 0; --k) {
+                        dv = (k == O - 2) ? hv : fma(dv, t, hv);
+                        hv = fma(hv, t, row[k * NDEP + d]);
+                    }
                     if (!(fabs(hv - ref) <= 0.25 * (1e-13 + 1e-12 * fabs(ref)) + 8.9e-16 * cmax[d])) ok = false;   // NaN / inf fail too
+                    // derivative: the same bar, widened by 4 eps times the terms the recurrence itself sums
+                    if (!(fabs(dv - dref) <= 0.25 * (1e-13 + 1e-12 * fabs(dref)) + 8.9e-16 * dterms)) okDer = false;
                 }
             }
         } else if (sp == 0 || sp == spans - 1 || !(h == 0.0)) {
             ok = false;                                   // empty end span, or knots that are not ascending / not finite
         }
         if (!ok) polyOk = 0;
+        if (!ok || !okDer) polyDerOk = 0;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
         int *flag = reinterpret_cast<int *>(image + T.cdbBytes + T.polyBytes);
-        flag[0] = polyOk; flag[1] = 0; flag[2] = 0; flag[3] = 0;
+        flag[0] = polyOk; flag[1] = polyDerOk; flag[2] = 0; flag[3] = 0;   // values / values + first derivative
     }
 }
 
@@ -523,7 +538,7 @@ __global__ void __launch_bounds__(TAB_THREADS, 1) eval_curve_tab_kernel(const Cu
     for (int k = 0; k < U; ++k) un[k] = pfirst + k * pstep < P.N ? __ldcs(up + k * pstep * P.in.pointStride) : 0.0;
     mbar_wait(bar, 0);
     if constexpr (POLY) {
-        const bool valid = *reinterpret_cast<const int *>(image + T.polyFetch - 16) != 0;
+        const bool valid = reinterpret_cast<const int *>(image + T.polyFetch - 16)[DER ? 1 : 0] != 0;
         if (valid) {
             const double *kn = reinterpret_cast<const double *>(image);
             const unsigned short *tab = reinterpret_cast<const unsigned short *>(image + T.knotBytes);
@@ -562,12 +577,14 @@ static int launch_curve3(const CurveParams &P, size_t smem, cudaStream_t stream)
             if (blocks > cap) blocks = cap;
             // (eight points per thread requested up front for short batches were measured slower at 1e6 points:
             // 19.0 against 16.7 us)
-            if constexpr (!DER && O >= 2) {
-                // value-only requests: polynomial rows (CURVE_POLY=0: recurrence rows, bit-identical to the other curve kernels)
-                if (option(OPT_CURVE_POLY, 1)) {
+            if constexpr (O >= 2) {
+                // polynomial rows: values, and values + first derivative (CURVE_POLY=0: recurrence rows, bit-identical to the other
+                // curve kernels; CURVE_POLY=2: value-only requests only)
+                const long long cp = option(OPT_CURVE_POLY, 1);
+                if (cp == 1 || (cp == 2 && !DER)) {
                     const size_t smem = T.polyFetch > T.cdbBytes ? T.polyFetch : T.cdbBytes;   // room for the fallback
-                    if (int rc = allow_dynamic_smem(eval_curve_tab_kernel<O, NDEP, false, REPL_U, true>, smem)) return rc;
-                    eval_curve_tab_kernel<O, NDEP, false, REPL_U, true><<<(unsigned)blocks, TAB_THREADS, smem, stream>>>(P, T);
+                    if (int rc = allow_dynamic_smem(eval_curve_tab_kernel<O, NDEP, DER, REPL_U, true>, smem)) return rc;
+                    eval_curve_tab_kernel<O, NDEP, DER, REPL_U, true><<<(unsigned)blocks, TAB_THREADS, smem, stream>>>(P, T);
                     count_launch();
                     return check_launch("bspy_cuda_eval_points(curve, cached polynomial rows)");
                 }

@@ -320,7 +320,8 @@ __global__ void __launch_bounds__(256, 5) many_poly_kernel(const ManyParams P)
 // per batch into a caller-owned image, one per curve:
 //     header { scale of the bucket function, flag: rows validated } | knots | bucket table of the span search | one row per span
 //     with the span's polynomial in powers of (u - mid-span): { c_0[d], .., c_{O-1}[d], m }
-// (value-only requests; the rows are validated against the recurrence when they are built, exactly as in curve.cu).  The
+// (values, or values + first derivative by Horner's rule with derivative; the rows are validated against the recurrence for
+// both when they are built, exactly as in curve.cu).  The
 // evaluation kernel is then, per curve and warp: one bulk asynchronous copy of the image into the warp's slice of shared
 // memory (cp.async.bulk + mbarrier, double-buffered: the next curve's image and parameters travel under this curve's points),
 // and per point a bucket look-up + short advance (bit-exact span), ONE row of O*nDep+1 doubles and a Horner evaluation.
@@ -402,7 +403,7 @@ __global__ void __launch_bounds__(256) many_table_kernel(const ManyTableParams P
                 run += __shfl_sync(0xffffffffu, incl, 31);
             }
         }
-        bool ok = true;
+        bool ok = true, okDer = true;
         for (int sp = lane; sp < spans; sp += 32) {
             const int ix = O + sp;
             double left[O - 1], rc[O * (O - 1) / 2];
@@ -454,18 +455,27 @@ __global__ void __launch_bounds__(256) many_table_kernel(const ManyTableParams P
                     if (!(terms <= 16.0 * cmax)) ok = false;
                     for (int sidx = 0; sidx <= 8; ++sidx) {
                         const double u = sidx == 8 ? k1 : k0 + h * (0.125 * sidx);
-                        double du[O - 1], b0[O], unused[O];
+                        double du[O - 1], b0[O], b1[O], unused[O];
 #pragma unroll
                         for (int j = 0; j < O - 1; ++j) du[j] = u - left[j];
                         basis_core<O, false>(du, rc, 0, b0, unused);
-                        double ref = 0.0;
+                        basis_core<O, false>(du, rc, 1, b1, unused);
+                        double ref = 0.0, dref = 0.0, dterms = 0.0;
 #pragma unroll
-                        for (int j = 0; j < O; ++j) ref = fma(cw[j][d], b0[j], ref);
+                        for (int j = 0; j < O; ++j) {
+                            ref = fma(cw[j][d], b0[j], ref);
+                            dref = fma(cw[j][d], b1[j], dref);
+                            dterms = fma(fabs(cw[j][d]), fabs(b1[j]), dterms);
+                        }
                         const double t = u - m;
-                        double hv = row[(O - 1) * NDEP + d];
+                        double hv = row[(O - 1) * NDEP + d], dv = 0.0;
 #pragma unroll
-                        for (int k = O - 2; k >= 0; --k) hv = fma(hv, t, row[k * NDEP + d]);
+                        for (int k = O - 2; k >= 0; --k) {
+                            dv = (k == O - 2) ? hv : fma(dv, t, hv);
+                            hv = fma(hv, t, row[k * NDEP + d]);
+                        }
                         if (!(fabs(hv - ref) <= 0.25 * (1e-13 + 1e-12 * fabs(ref)) + 8.9e-16 * cmax)) ok = false;
+                        if (!(fabs(dv - dref) <= 0.25 * (1e-13 + 1e-12 * fabs(dref)) + 8.9e-16 * dterms)) okDer = false;
                     }
                 }
             } else if (sp == 0 || sp == spans - 1 || !(h == 0.0)) {
@@ -473,10 +483,11 @@ __global__ void __launch_bounds__(256) many_table_kernel(const ManyTableParams P
             }
         }
         ok = __all_sync(0xffffffffu, ok);
+        okDer = __all_sync(0xffffffffu, ok && okDer);
         if (lane == 0) {
             *reinterpret_cast<double *>(img) = scale;
-            reinterpret_cast<int *>(img)[2] = ok ? 1 : 0;
-            reinterpret_cast<int *>(img)[3] = 0;
+            reinterpret_cast<int *>(img)[2] = ok ? 1 : 0;          // rows validated for values ...
+            reinterpret_cast<int *>(img)[3] = okDer ? 1 : 0;       // ... and for values + first derivative
         }
     }
 }
@@ -489,7 +500,7 @@ struct ManyTabParams {
 
 constexpr int MANY_TAB_WARPS = 8;
 
-template <int O, int NDEP>
+template <int O, int NDEP, bool DER>
 __global__ void __launch_bounds__(MANY_TAB_WARPS * 32, 3) many_tab_kernel(const ManyTabParams Q)
 {
     extern __shared__ __align__(128) unsigned char smraw[];
@@ -540,18 +551,19 @@ __global__ void __launch_bounds__(MANY_TAB_WARPS * 32, 3) many_tab_kernel(const 
         }
         const unsigned char *img = slot + (size_t)b * L.image;
         const double scale = *reinterpret_cast<const double *>(img);
-        const bool valid = reinterpret_cast<const int *>(img)[2] != 0;
+        const bool valid = reinterpret_cast<const int *>(img)[DER ? 3 : 2] != 0;
         const double *kn = reinterpret_cast<const double *>(img + 16);
         const unsigned short *tab = reinterpret_cast<const unsigned short *>(img + 16 + 8 * L.knotDoubles);
         const double *rows = reinterpret_cast<const double *>(img + 16 + 8 * L.knotDoubles + L.tabBytes) - O * PROW;
         const double lo = kn[O - 1], hi = kn[P.nCoef];
         double *ov = P.values + s * NDEP * P.nPts;
+        double *og = DER ? P.deriv1 + s * NDEP * P.nPts : nullptr;
         auto point = [&](int p, double u) {
             if (((u < lo) | (u > hi)) && P.firstOutside) report_outside((int64_t *)P.firstOutside, s * P.nPts + p);
             int ix = tab[many_bucket_of(u, lo, scale, L.buckets - 1)];
             while (ix < P.nCoef && kn[ix] <= u) ++ix;
             if (u != u) ix = P.nCoef;
-            double v[NDEP];
+            double v[NDEP], g[NDEP];
             if (valid) {
                 double r[PROW];
                 const double2 *rp = reinterpret_cast<const double2 *>(rows + ix * PROW);
@@ -564,28 +576,40 @@ __global__ void __launch_bounds__(MANY_TAB_WARPS * 32, 3) many_tab_kernel(const 
                 const double t = u - r[O * NDEP];
 #pragma unroll
                 for (int d = 0; d < NDEP; ++d) {
-                    double h = r[(O - 1) * NDEP + d];
+                    double h = r[(O - 1) * NDEP + d], dh = 0.0;
 #pragma unroll
-                    for (int k = O - 2; k >= 0; --k) h = fma(h, t, r[k * NDEP + d]);
+                    for (int k = O - 2; k >= 0; --k) {
+                        if (DER) dh = (k == O - 2) ? h : fma(dh, t, h);
+                        h = fma(h, t, r[k * NDEP + d]);
+                    }
                     v[d] = h;
+                    g[d] = dh;
                 }
             } else {
                 // rows that failed their validation (rare): the recurrence on the curve's own knots and coefficients
                 double kw[2 * (O - 1)], b0[O], b1[O];
 #pragma unroll
                 for (int j = 0; j < 2 * (O - 1); ++j) kw[j] = kn[ix - (O - 1) + j];
-                basis_regs<O, false>(kw, u, 0, b0, b1);
+                basis_regs<O, DER>(kw, u, 0, b0, b1);
                 const double *gc = P.coefs + s * P.coefStride;
 #pragma unroll
                 for (int d = 0; d < NDEP; ++d) {
-                    double acc = 0.0;
+                    double acc = 0.0, dacc = 0.0;
 #pragma unroll
-                    for (int j = 0; j < O; ++j) acc = fma(__ldg(gc + d * P.nCoef + ix - O + j), b0[j], acc);
+                    for (int j = 0; j < O; ++j) {
+                        const double cj = __ldg(gc + d * P.nCoef + ix - O + j);
+                        acc = fma(cj, b0[j], acc);
+                        if (DER) dacc = fma(cj, b1[j], dacc);
+                    }
                     v[d] = acc;
+                    g[d] = dacc;
                 }
             }
 #pragma unroll
-            for (int d = 0; d < NDEP; ++d) __stcs(ov + d * P.nPts + p, v[d]);
+            for (int d = 0; d < NDEP; ++d) {
+                __stcs(ov + d * P.nPts + p, v[d]);
+                if (DER) __stcs(og + d * P.nPts + p, g[d]);
+            }
         };
 #pragma unroll
         for (int k = 0; k < MANY_PF; ++k)
@@ -608,18 +632,24 @@ static int launch_many_table(const ManyTableParams &T, cudaStream_t stream)
     return check_launch("bspy_cuda_many_table_build");
 }
 
-template <int O, int NDEP>
-static int launch_many_tab(const ManyTabParams &Q, cudaStream_t stream)
+template <int O, int NDEP, bool DER>
+static int launch_many_tab2(const ManyTabParams &Q, cudaStream_t stream)
 {
     const size_t smem = (size_t)MANY_TAB_WARPS * 2 * Q.L.image;
-    if (int rc = allow_dynamic_smem(many_tab_kernel<O, NDEP>, smem)) return rc;
+    if (int rc = allow_dynamic_smem(many_tab_kernel<O, NDEP, DER>, smem)) return rc;
     long long blocks = (Q.P.nSplines + MANY_TAB_WARPS - 1) / MANY_TAB_WARPS;
     const long long perSm = (220 * 1024) / (long long)(smem + 1024);
     const long long cap = (long long)num_sms() * (perSm < 1 ? 1 : perSm > 3 ? 3 : perSm);
     if (blocks > cap) blocks = cap;
-    many_tab_kernel<O, NDEP><<<(unsigned)blocks, MANY_TAB_WARPS * 32, smem, stream>>>(Q);
+    many_tab_kernel<O, NDEP, DER><<<(unsigned)blocks, MANY_TAB_WARPS * 32, smem, stream>>>(Q);
     count_launch();
     return check_launch("bspy_cuda_eval_many_tab");
+}
+
+template <int O, int NDEP>
+static int launch_many_tab(const ManyTabParams &Q, cudaStream_t stream)
+{
+    return Q.P.deriv1 ? launch_many_tab2<O, NDEP, true>(Q, stream) : launch_many_tab2<O, NDEP, false>(Q, stream);
 }
 
 #define BSPY_MANY_TAB_DISPATCH(FN, ARG)                                                             \
@@ -764,7 +794,7 @@ extern "C" int bspy_cuda_many_table_build(int32_t order, int32_t nCoef, int32_t 
 
 extern "C" int bspy_cuda_eval_many_tab(int32_t order, int32_t nCoef, int32_t nDep, int64_t nSplines, const double *knots,
                                        int64_t knotStride, const double *coefs, int64_t coefStride, const void *table,
-                                       int64_t tableBytes, const double *u, int32_t nPts, double *values,
+                                       int64_t tableBytes, const double *u, int32_t nPts, double *values, double *deriv1,
                                        int64_t *firstOutside, void *stream)
 {
     const ManyTableLayout L = many_table_layout(order, nCoef, nDep);
@@ -778,7 +808,7 @@ extern "C" int bspy_cuda_eval_many_tab(int32_t order, int32_t nCoef, int32_t nDe
     Q.P.nCoef = nCoef; Q.P.nDep = nDep; Q.P.nPts = nPts; Q.P.nSplines = nSplines;
     Q.P.knots = knots; Q.P.coefs = coefs; Q.P.u = u;
     Q.P.knotStride = knotStride; Q.P.coefStride = coefStride;
-    Q.P.values = values; Q.P.deriv1 = nullptr;
+    Q.P.values = values; Q.P.deriv1 = deriv1;
     Q.P.firstOutside = (long long *)firstOutside;
     Q.table = (const unsigned char *)table; Q.L = L;
     cudaStream_t st = (cudaStream_t)stream;

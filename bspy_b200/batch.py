@@ -154,11 +154,12 @@ class SplineBatch:
             k = k.unsqueeze(0).expand(self.nSplines, -1)       # stride 0: every warp stages the same knots
         flag = _cuda.new_flag(self.device) if check_domain else None
         coefs = self.coefs.reshape(self.nSplines, self.nDep, self.nCoef[0])
-        table = None if derivative else self._curve_images(k, coefs)
+        table = self._curve_images(k, coefs)
         if self.order[0] > _cuda.MANY_MAX_ORDER:
             res = self._evaluate_per_spline(k, coefs, ut, derivative, flag, out)
         elif table is not None:
-            res = _cuda.eval_many_tab(self.order[0], self.nCoef[0], self.nDep, _ExpandedKnots(k), coefs, table, ut, flag=flag, out=out)
+            res = _cuda.eval_many_tab(self.order[0], self.nCoef[0], self.nDep, _ExpandedKnots(k), coefs, table, ut, deriv1=derivative,
+                                      flag=flag, out=out)
         else:
             res = _cuda.eval_many(self.order[0], self.nCoef[0], self.nDep, _ExpandedKnots(k), coefs, ut, deriv1=derivative,
                                   flag=flag, out=out)
@@ -175,15 +176,15 @@ class SplineBatch:
         return EvalResult(values=vals, derivative=der, first_outside=flag if defer else None)
 
     def _curve_images(self, k, coefs):
-        """Cached per-curve images of a batch of curves (value-only requests): built by the first evaluation on the device the
+        """Cached per-curve images of a batch of curves (values and first derivatives): built by the first evaluation on the device the
         batch lives on and kept with the batch -- like the knots and coefficients they are derived from, a batch is immutable
         once uploaded.  They cost 3-4x the memory of the raw curves and one pass to build, so they are made by the SECOND
-        value-only evaluation of a batch; ``batch.cache_tables = False`` turns them off, ``= "now"`` builds them at once."""
+        evaluation of a batch; ``batch.cache_tables = False`` turns them off, ``= "now"`` builds them at once."""
         if not getattr(self, "cache_tables", True) or self.nSplines < 1024 or not coefs.is_cuda:
             return None
         hit = self.__dict__.get("_curve_images_cache")
         if hit is None:
-            # a batch that is evaluated once never pays for the build: the images are made by the second value-only call
+            # a batch that is evaluated once never pays for the build: the images are made by the second call
             seen = self.__dict__.get("_curve_images_calls", 0)
             self.__dict__["_curve_images_calls"] = seen + 1
             if seen < 1 and getattr(self, "cache_tables", True) != "now":

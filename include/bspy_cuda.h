@@ -186,14 +186,14 @@ int bspy_cuda_eval_many(int32_t order, int32_t nCoef, int32_t nDep, int64_t nSpl
                         const double *u, int32_t nPts, double *values, double *deriv1,
                         int64_t *firstOutside, void *stream);
 
-/*      Cached per-curve images for VALUE-ONLY requests on a resident batch of curves (nothing in the reference: what
+/*      Cached per-curve images for a resident batch of curves (values; deriv1 != NULL: + first derivatives) (nothing in the reference: what
  *      bspline_values, bspy/_spline_evaluation.py:4-27, recomputes per point -- span search, knot gaps, the recurrence --
  *      precomputed once per curve): per curve { bucket scale, flag | knots | bucket table of the span search | one row per span
  *      with the span's polynomial in powers of (u - mid-span) }, rows validated against the Cox-de Boor recurrence when they are
  *      built (a curve that fails keeps the recurrence, decided per curve inside the kernel).  The caller owns the buffer.
  *      bspy_cuda_many_table_bytes: bytes for nSplines curves (0: shape without tables -- order outside 2..6, nDep > 3, image
  *      of a curve above 12 KB); bspy_cuda_many_table_build fills it (16-byte aligned); bspy_cuda_eval_many_tab evaluates
- *      values (nSplines, nDep, nPts) from it -- tableBytes must be exactly what _bytes returned for this batch.            */
+ *      values (and deriv1, may be NULL), both (nSplines, nDep, nPts), from it -- tableBytes must be exactly what _bytes returned for this batch.            */
 int64_t bspy_cuda_many_table_bytes(int32_t order, int32_t nCoef, int32_t nDep, int64_t nSplines);
 int bspy_cuda_many_table_build(int32_t order, int32_t nCoef, int32_t nDep, int64_t nSplines,
                                const double *knots, int64_t knotStride, const double *coefs, int64_t coefStride,
@@ -201,7 +201,7 @@ int bspy_cuda_many_table_build(int32_t order, int32_t nCoef, int32_t nDep, int64
 int bspy_cuda_eval_many_tab(int32_t order, int32_t nCoef, int32_t nDep, int64_t nSplines,
                             const double *knots, int64_t knotStride, const double *coefs, int64_t coefStride,
                             const void *table, int64_t tableBytes, const double *u, int32_t nPts,
-                            double *values, int64_t *firstOutside, void *stream);
+                            double *values, double *deriv1, int64_t *firstOutside, void *stream);
 
 /* ---- curvature: replaces curvature, bspy/_spline_evaluation.py:80-107, for N points
  *      from batched derivatives produced by bspy_cuda_eval_points.

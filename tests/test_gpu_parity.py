@@ -361,8 +361,21 @@ def test_many_curves_cached_images():
         ut = torch.from_numpy(u).cuda()
         batch.cache_tables = False
         plain = batch.evaluate(ut).values
+        plain_d = batch.evaluate(ut, derivative=True)
         batch.cache_tables = "now"
         cached = batch.evaluate(ut).values
+        cached_d = batch.evaluate(ut, derivative=True)                  # Horner with derivative on the same rows
+        assert _close_t(cached_d.values, plain_d.values), (order, nCoef, nDep)
+        assert torch.equal(torch.nan_to_num(cached_d.values, nan=-7.0), torch.nan_to_num(cached, nan=-7.0))
+
+        def close_der(x, y):
+            # where a derivative cancels, two evaluation orders differ by a few eps times the terms they sum: the strict bar
+            # widened by 32 eps times the curve's largest derivative
+            scale = torch.nan_to_num(y).abs().amax(dim=(1, 2), keepdim=True)
+            both = torch.isfinite(x) & torch.isfinite(y)
+            return bool((torch.isfinite(x) == torch.isfinite(y)).all()) and \
+                bool((((x - y).abs() <= 1e-13 + 1e-12 * y.abs() + 32 * np.finfo(float).eps * scale) | ~both).all())
+        assert close_der(cached_d.derivative, plain_d.derivative), (order, nCoef, nDep)
         table = batch.__dict__["_curve_images_cache"][0]
         assert table is not None and table.numel() % S == 0
         assert _close_t(cached, plain), (order, nCoef, nDep)
@@ -373,13 +386,16 @@ def test_many_curves_cached_images():
             so = O.OracleSpline(1, nDep, (order,), (nCoef,), [knots if shared else knots[s_]], coefs[s_])
             keep = np.isfinite(u[s_])
             assert close(cached[s_].cpu().numpy().T[keep], O.evaluate_vec(so, u[s_][keep][:, None]))
+            assert close_cond(cached_d.derivative[s_].cpu().numpy().T[keep], O.derivative_vec(so, [1], u[s_][keep][:, None]),
+                              O.derivative_abs_vec(so, [1], u[s_][keep][:, None]))
         # curves 3 and S-1 flagged invalid in their images: the kernel evaluates them with the recurrence (tolerance-equal
         # to the plain kernel, which hoists the knot gaps into reciprocals)
         per = table.numel() // S
         for c in (3, S - 1):
-            table[c * per + 8:c * per + 12] = 0
+            table[c * per + 8:c * per + 16] = 0
         again = batch.evaluate(ut).values
-        assert _close_t(again, plain)
+        again_d = batch.evaluate(ut, derivative=True)
+        assert _close_t(again, plain) and close_der(again_d.derivative, plain_d.derivative)
         assert torch.equal(torch.nan_to_num(again[:3]), torch.nan_to_num(cached[:3]))
         # outside the domain: same first offender, same exception
         u2 = ut.clone(); u2[S // 2, 1] = -0.5; u2[S - 1, 0] = 1.5
@@ -387,7 +403,7 @@ def test_many_curves_cached_images():
             batch.evaluate(u2)
         r = batch.evaluate(u2, check_domain="defer")
         assert int(r.first_outside.item()) == (S // 2) * nPts + 1
-        # the images are made by the second value-only call of a batch, never by the first
+        # the images are made by the second call of a batch, never by the first
         lazy = bspy.SplineBatch(1, nDep, (order,), (nCoef,), [knots], coefs)
         lazy.evaluate(ut)
         assert "_curve_images_cache" not in lazy.__dict__
@@ -734,15 +750,27 @@ def test_curve_replicated_rows_bit_identical(option):
         assert _close_t(poly_rows["values"], rec_rows["values"]), (order, nDep, nCoef)
         if (order, nDep, nCoef, clamp, cluster) == (4, 3, 64, True, False):       # the shape of config 1: the rows must be in use
             assert not torch.equal(torch.nan_to_num(poly_rows["values"]), torch.nan_to_num(rec_rows["values"])), "polynomial rows not in use"
+        # the same rows serve requests with the first derivative (Horner with derivative; validated separately at the build)
+        option("CURVE_POLY", 0)
+        rec_der = _cuda.eval_points(ds, u, 1, 1, N, values=True, jacobian=True)
+        option("CURVE_POLY", None)
+        poly_der = _cuda.eval_points(ds, u, 1, 1, N, values=True, jacobian=True)
+        assert _close_t(poly_der["values"], rec_der["values"]), (order, nDep, nCoef)
+        if not cluster:
+            assert _close_t(poly_der["jacobian"], rec_der["jacobian"]), (order, nDep, nCoef)
+        if (order, nDep, nCoef, clamp, cluster) == (4, 3, 64, True, False):
+            assert not torch.equal(torch.nan_to_num(poly_der["jacobian"]), torch.nan_to_num(rec_der["jacobian"])), "polynomial rows not in use"
         if ds.curve_table is not None:
-            # a table whose rows failed the validation of the build (flag in the image's 16-byte trailer cleared): the kernel
+            # a table whose rows failed the validation of the build (flags in the image's 16-byte trailer cleared): the kernel
             # fetches the recurrence rows instead -- bit-identical to them
             saved = ds.curve_table[-16:].clone()
             ds.curve_table[-16:] = 0
             fallback = _cuda.eval_points(ds, u, 1, 1, N, values=True, spans=True)
+            fallback_der = _cuda.eval_points(ds, u, 1, 1, N, values=True, jacobian=True)
             ds.curve_table[-16:] = saved
             assert torch.equal(fallback["spans"], rec_rows["spans"])
             assert torch.equal(torch.nan_to_num(fallback["values"], nan=-7.0), torch.nan_to_num(rec_rows["values"], nan=-7.0)), (order, nDep, nCoef)
+            assert torch.equal(torch.nan_to_num(fallback_der["jacobian"], nan=-7.0), torch.nan_to_num(rec_der["jacobian"], nan=-7.0)), (order, nDep, nCoef)
         # coefficients of magnitude 1e9: where the value cancels, any two evaluation orders differ by a few eps * max|coef|;
         # the two row forms must agree to the strict bar widened by exactly that
         big = bspy.Spline(1, nDep, (order,), (nCoef,), [np.array(s.knots[0])], 1e9 * np.asarray(s.coefs) + 1.0)
