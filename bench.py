@@ -365,7 +365,7 @@ class Cfg1Curve1e8(Cfg1Curve):
 
 class Cfg4Volume(ScatteredBase):
     name = "cfg4: trivariate order-4 volume (nInd 3, nDep 3, 32^3 coefficients), 1e8 scattered points, value + jacobian, array-of-structs records"
-    kernel = "cell-sorted pipeline: bin_keys, bin_scan, bin_scatter_records, cell evaluation kernel writing [values|jacobian] records in place (whole step)"
+    kernel = "cell-sorted pipeline: bin_keys, bin_scan, bin_scatter_records, eval_poly_kernel<3,4,4,4,0,3,3,5> (cell polynomials) writing [values|jacobian] records in place (whole step)"
     bytes_per_point, flops_per_point, seed, N, jac, bound = 120.0, 1320.0, 1004, 100_000_000, True, "fp64"
     layout = "aos"
     cpu_calls = ("evaluate", "jacobian")
@@ -383,7 +383,7 @@ class Cfg4VolumeSoA(Cfg4Volume):
 
 class Cfg5Manifold(ScatteredBase):
     name = "cfg5: nInd 4 / nDep 6 order-3 manifold (16^4 coefficients), 1.25e8 scattered points per GPU, value + first derivatives, array-of-structs records"
-    kernel = "cell-sorted pipeline: bin_keys, bin_scan, bin_scatter_records, cell evaluation kernel writing [values|jacobian] records in place (whole step)"
+    kernel = "cell-sorted pipeline: bin_keys, bin_scan, bin_pad, bin_scatter_records, eval_poly2_kernel<4,3,3,3,3,6,2,3> (cell polynomials, two points per thread) writing [values|jacobian] records in place (whole step)"
     bytes_per_point, flops_per_point, seed, N, jac, bound = 272.0, 3650.0, 1005, 125_000_000, True, "fp64"
     layout = "aos"
     cpu_calls = ("evaluate", "jacobian")
