@@ -81,10 +81,14 @@ class Spline(Manifold):
     def _ufunc_style(self, uvw, kwargs, with_respect_to):
         """numpy-ufunc calling convention of the reference: ``nInd`` broadcastable arrays in, a tuple
         of ``nDep`` arrays (or one array when nDep == 1) out, cast to ``coefs.dtype``."""
+        kwargs = dict(kwargs)
+        where, outs = kwargs.pop("where", True), kwargs.pop("out", None)
         if kwargs:
-            raise NotImplementedError(f"ufunc keyword arguments are not supported by the CUDA path: {sorted(kwargs)}")
+            raise NotImplementedError(f"ufunc keyword arguments other than where= / out= are not supported by the CUDA path: {sorted(kwargs)}")
         if len(uvw) != self.nInd:
             raise ValueError("invalid number of arguments")
+        if where is not True or outs is not None:
+            return self._ufunc_where_out(uvw, where, outs, with_respect_to)
         arrays = np.broadcast_arrays(*[np.asarray(a, dtype=np.float64) for a in uvw])
         shape = arrays[0].shape
         pts = np.stack([a.reshape(-1) for a in arrays], axis=1)
@@ -99,6 +103,41 @@ class Spline(Manifold):
             # entry 0 of each; reproduced so that callers see the same shape
             out = out[:, 0][..., None]
         return np.array(out, dt)
+
+    def _ufunc_where_out(self, uvw, where, outs, with_respect_to):
+        """``where=`` / ``out=`` of the reference's ``np.frompyfunc`` ufunc (bspy/spline.py:940-947): only the selected points
+        are evaluated (and domain-checked); results land in the ``out`` arrays -- object arrays as ``frompyfunc`` produces
+        them when none are given, so that entries left out by ``where`` stay ``None`` and the final cast to ``coefs.dtype``
+        raises exactly where the reference's does."""
+        arrays = np.broadcast_arrays(*[np.asarray(a, dtype=np.float64) for a in uvw], np.asarray(where, dtype=bool))
+        mask = arrays[-1]
+        shape = mask.shape
+        if outs is None:
+            outs = tuple(np.empty(shape, dtype=object) for _ in range(self.nDep))
+        elif not isinstance(outs, tuple):
+            outs = (outs,)
+        if len(outs) != self.nDep:
+            raise ValueError("The 'out' tuple must have exactly one entry per ufunc output")
+        for o in outs:
+            if o.shape != shape:
+                raise ValueError(f"non-broadcastable output operand with shape {o.shape} doesn't match the broadcast shape {shape}")
+        sel = np.nonzero(mask.reshape(-1))[0]
+        if sel.size:
+            pts = np.stack([a.reshape(-1)[sel] for a in arrays[:-1]], axis=1)
+            res = _ev.evaluate_points(self, pts, values=with_respect_to is None, with_respect_to=with_respect_to)
+            soa = res.values if with_respect_to is None else res.derivative
+            for d, o in enumerate(outs):
+                o[mask] = soa[d]
+        dt = self.coefs.dtype
+        if self.nDep > 1:
+            return tuple(o.astype(dt, copy=False) for o in outs)
+        # nDep == 1: the reference iterates the first axis of the result and keeps entry 0 (a 1-tuple) of each row (spline.py:947);
+        # an entry left out by where= is None there and cannot be subscripted
+        if outs[0].ndim >= 2:
+            return np.array([[x[0]] for x in outs[0]], dt)
+        if any(x is None for x in outs[0]):
+            raise TypeError("'NoneType' object is not subscriptable")
+        return np.array(outs[0], dt)
 
     def evaluate(self, *uvw, **kwargs):
         """Value of the spline.  ``s(0.2, 0.3)``, ``s([0.2, 0.3])`` -> ``ndarray (nDep,)``;

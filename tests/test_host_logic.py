@@ -147,10 +147,42 @@ def test_ufunc_style_dispatch():
     assert close(scalar(0.5), d["scalar_point"])
     r = scalar(d["uu2d"])
     assert r.shape == d["scalar_ufunc_2d"].shape and close(r, d["scalar_ufunc_2d"])
+    # where= / out= of the reference's np.frompyfunc ufunc (bspy/spline.py:940-947), against the same construction around this
+    # package's single-point evaluate: only selected points are evaluated, results land in the out arrays
+    def as_reference(sp, args, **kw):
+        uf = np.frompyfunc(lambda *p: tuple(sp.evaluate(*p)), sp.nInd, sp.nDep)
+        if sp.nDep > 1:
+            return tuple(a.astype(sp.coefs.dtype, copy=False) for a in uf(*args, **kw))
+        return np.array([x[0] for x in uf(*args, **kw)], sp.coefs.dtype)
+    mask = (np.add.outer(np.arange(d["U"].shape[0]), np.arange(d["U"].shape[1])) % 3) != 0
+    outs_a = tuple(np.full(d["U"].shape, -5.0, dtype=object) for _ in range(3))
+    outs_b = tuple(np.full(d["U"].shape, -5.0, dtype=object) for _ in range(3))
+    ra = surf(d["U"], d["V"], where=mask, out=outs_a)
+    rb = as_reference(surf, (d["U"], d["V"]), where=mask, out=outs_b)
+    assert isinstance(ra, tuple) and len(ra) == 3
+    for a, b in zip(ra, rb):
+        assert a.dtype == b.dtype and a.shape == b.shape and close(a[mask], b[mask]) and np.all(a[~mask] == -5.0) and np.all(b[~mask] == -5.0)
+    bad = d["U"].copy(); bad[~mask] = 7.0                                   # outside the domain, but never evaluated
+    assert close(np.array(surf(bad, d["V"], where=mask, out=tuple(np.zeros(d["U"].shape, dtype=object) for _ in range(3))))[:, mask],
+                 np.array(rb)[:, mask])
+    ra, rb = surf(d["U"], d["V"], where=mask), as_reference(surf, (d["U"], d["V"]), where=mask)   # entries left out: None -> nan in the cast
+    for a, b in zip(ra, rb):
+        assert close(a[mask], b[mask]) and np.isnan(a[~mask]).all() and np.isnan(b[~mask]).all()
+    with pytest.raises(TypeError):                                           # nDep == 1: None cannot be subscripted, there as here
+        scalar(d["uu"], where=np.arange(d["uu"].shape[0]) % 2 == 0)
+    with pytest.raises(TypeError):
+        as_reference(scalar, (d["uu"],), where=np.arange(d["uu"].shape[0]) % 2 == 0)
+    m1 = np.arange(d["uu"].shape[0]) % 2 == 0
+    o1, o2 = np.full(d["uu"].shape, None, dtype=object), np.full(d["uu"].shape, None, dtype=object)
+    o1[~m1] = 0.0
+    for i in np.nonzero(~m1)[0]:
+        o2[i] = (0.0,)                                                       # what the reference's ufunc leaves in its out array: 1-tuples
+    assert close(scalar(d["uu"], where=m1, out=o1), as_reference(scalar, (d["uu"],), where=m1, out=o2))
+    with pytest.raises(NotImplementedError):
+        surf(d["U"], d["V"], casting="unsafe")
     with pytest.raises(ValueError, match="invalid number of arguments"):
         surf(d["uu"])                                                        # one array for two variables
-    with pytest.raises(NotImplementedError):
-        curve(d["uu"], out=None)
+    assert close(np.array(curve(d["uu"], out=None)), d["curve_ufunc"])         # numpy's default
     with pytest.raises(ValueError, match="outside domain"):
         curve(np.array([0.1, 1.5, 0.2]))
 
