@@ -199,6 +199,14 @@ def test_dispatch_forms():
     if "scalar_ufunc_2d" in d:
         r = scalar(d["uu2d"])
         assert r.shape == d["scalar_ufunc_2d"].shape and close(r, d["scalar_ufunc_2d"])
+    # where= / out= of the reference's frompyfunc ufunc: only the selected points are evaluated (the others may lie outside)
+    mask = (np.add.outer(np.arange(d["U"].shape[0]), np.arange(d["U"].shape[1])) % 3) != 0
+    bad = d["U"].copy(); bad[~mask] = 7.0
+    outs = tuple(np.full(d["U"].shape, -5.0, dtype=object) for _ in range(3))
+    r = surf(bad, d["V"], where=mask, out=outs)
+    assert close(np.array(r)[:, mask], d["surf_ufunc"][:, mask]) and np.all(np.array(r)[:, ~mask] == -5.0)
+    r = surf(d["U"], d["V"], where=mask)
+    assert close(np.array(r)[:, mask], d["surf_ufunc"][:, mask]) and np.isnan(np.array(r)[:, ~mask]).all()
 
 
 def test_errors_match_reference():
