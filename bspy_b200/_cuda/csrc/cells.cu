@@ -539,7 +539,10 @@ static bool poly_applies(const SplineDev &s, long long N)
     if (code <= 0 || s.nInd < 2 || s.nInd > 4) return false;
     for (int i = 0; i < s.nInd; ++i)
         if (s.order[i] > 4) return false;
-    if (!find_poly(s, (int)code)) return false;
+    const PolyEntry *e = find_poly(s, (int)code);
+    if (!e) return false;
+    // one image per cell in the caller's workspace: not for splines whose images would pass 1 GiB
+    if (binned_cells(s) * (long long)poly_layout(s, poly_entry_pair(e)).slot * 8 > (1LL << 30)) return false;
     return N >= 8 * binned_cells(s);
 }
 
