@@ -307,8 +307,11 @@ def contract(self, uvw):
     removed = 0
     for iv in fixed:
         u = torch.tensor([float(uvw[iv])], dtype=torch.float64, device=dev)
-        sp, b = _cuda.basis(ds.knots[iv], int(self.order[iv]), u, 0, False, None)
-        ix = int(sp[0].item())
+        _, b = _cuda.basis(ds.knots[iv], int(self.order[iv]), u, 0, False, None)
+        # the span on the host, as the reference finds it (np.searchsorted 'right' + clamp, _spline_evaluation.py:7-8; the kernel's
+        # own span is bit-exact with it): no device read-back between the launches of the fixed variables
+        kn = np.asarray(self.knots[iv], dtype=np.float64)
+        ix = int(min(max(np.searchsorted(kn, float(uvw[iv]), side="right"), self.order[iv]), len(kn) - self.order[iv]))
         coefs = _cuda.contract_axis(coefs, 1 + iv - removed, ix - self.order[iv], self.order[iv], b.reshape(-1))
         removed += 1
     keep = [iv for iv in range(self.nInd) if uvw[iv] is None]
